@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope='session')
+def tables():
+    import numpy as np
+    t = np.load(os.path.join(GOLDEN, 'tables.npz'))
+    return t['window'], t['mel']
+
+
+@pytest.fixture(scope='session')
+def manifest():
+    import json
+    with open(os.path.join(GOLDEN, 'manifest.json')) as f:
+        return json.load(f)
