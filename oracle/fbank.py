@@ -138,5 +138,5 @@ def fbank(wave, num_mel_bins=80, sample_frequency=16000.0, frame_length=25.0, fr
     mel = np.asarray(mel, dtype=dtype)
     melp = np.concatenate([mel, np.zeros((mel.shape[0], 1), dtype=dtype)], axis=1)  # kaldi.py:627
     energies = power @ melp.T                           # kaldi.py:630
-    eps = dtype(EPS_F32) if dtype == np.float32 else np.float64(np.finfo(np.float64).eps)
+    eps = dtype(EPS_F32)  # kaldi.py:31-37: EPSILON is finfo(float32).eps cast to the waveform dtype
     return np.log(np.maximum(energies, eps)).astype(dtype)  # kaldi.py:631-633
