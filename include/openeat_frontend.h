@@ -1,0 +1,147 @@
+/* openeat_frontend.h -- C ABI of the B200-native OpenEAT acoustic front-end.
+ *
+ * The reference (TongtongSong/OpenEAT) has no native code and no FFI: its front-end is
+ * Python calling torchaudio on the CPU, one utterance at a time.  This header is the
+ * boundary a native replacement exposes instead; every entry point names the reference
+ * code it replaces (paths relative to the reference tree, `kaldi.py` =
+ * torchaudio/compliance/kaldi.py 2.11.0, the third-party function the reference calls).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns an int status (OE_OK == 0); nothing throws or aborts across
+ *     the ABI; oe_last_error() returns a thread-local message for the last failure.
+ *   - the CALLER owns every buffer.  `d_` pointers are device memory on the handle's
+ *     device; all others are host memory.  The library owns only the immutable tables
+ *     inside the opaque handle (window, twiddles, sparse mel matrix, resampler taps).
+ *   - all work is enqueued on the given cudaStream_t; no device-wide synchronisation and
+ *     no allocation happens inside the batch calls (the caller passes a workspace whose
+ *     size it queries first).  Host metadata arrays may be reused as soon as a call
+ *     returns (they are copied to the workspace with a stream-ordered memcpy).
+ *   - batches are ragged: one call handles B utterances of different lengths with ONE
+ *     launch sequence (device-side work list), never one launch per utterance.
+ */
+#ifndef OPENEAT_FRONTEND_H_
+#define OPENEAT_FRONTEND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OE_ABI_VERSION 1
+
+enum { OE_OK = 0, OE_ERR_INVALID = 1, OE_ERR_UNSUPPORTED = 2, OE_ERR_CUDA = 3, OE_ERR_WORKSPACE = 4 };
+/* OE_WAV_I16: PCM int16.  OE_WAV_F32: fp32 on the int16 scale (dataset.py:75).
+ * OE_FEATS_F32: the input already is log-mel features (rows x num_mel_bins fp32, data_type != 'wav',
+ * dataset.py:190-191): wav_offsets / wav_lens then count ROWS, and only the post-fbank chain runs. */
+enum { OE_WAV_I16 = 0, OE_WAV_F32 = 1, OE_FEATS_F32 = 2 };
+enum { OE_NORM_NONE = 0, OE_NORM_PER_UTT = 1 };
+
+typedef struct oe_frontend oe_frontend; /* opaque */
+typedef void* oe_stream;                /* cudaStream_t */
+
+/* Front-end parameters: the keyword arguments of the kaldi.fbank call at
+ * openeat/dataset/dataset.py:93-100 (everything else is torchaudio's default). */
+typedef struct {
+    int32_t sample_rate;   /* sample_frequency                      (16000) */
+    int32_t frame_length;  /* samples: sr*25 ms                     (400)   */
+    int32_t frame_shift;   /* samples: sr*10 ms                     (160)   */
+    int32_t fft_size;      /* round_to_power_of_two(frame_length)   (512)   */
+    int32_t num_mel_bins;  /* feature_extraction_conf['mel_bins']   (80)    */
+    float preemph;         /* preemphasis_coefficient               (0.97)  */
+    float low_freq;        /* low_freq                              (20)    */
+    float high_freq;       /* high_freq, <= 0: offset from Nyquist  (0)     */
+    float log_floor;       /* torch.finfo(float32).eps, kaldi.py:31-37,631-633 */
+} oe_config;
+
+/* One ragged batch.  Replaces the per-utterance loop of _extract_feature
+ * (dataset.py:53-111) plus the numeric part of audio_collate_func.__call__
+ * (dataset.py:195-218) and GlobalCMVN.forward (openeat/modules/cmvn.py:35-46). */
+typedef struct {
+    int32_t batch;               /* B */
+    int32_t wav_dtype;           /* OE_WAV_* of d_wav */
+    const int64_t* wav_offsets;  /* [B] sample offset of each utterance in d_wav; multiple of 8 */
+    const int32_t* wav_lens;     /* [B] samples.  < frame_length -> 0 frames: the reference drops
+                                    such utterances (kaldi.py:142 raises, dataset.py:108-111) */
+    const int64_t* out_rows;     /* [B] first output row of each utterance */
+    const int32_t* out_nrows;    /* [B] rows to write (>= frames; the excess is padding, the zeros of
+                                    pad_sequence at dataset.py:217-218), or NULL = frames */
+    int64_t out_pitch;           /* floats between rows; 0 = num_mel_bins */
+    int32_t norm_mode;           /* OE_NORM_PER_UTT = _normalization, feature_processor.py:5-8 */
+    int32_t n_tmask;             /* time masks per utterance  (_spec_augmentation, :31-35) */
+    int32_t n_fmask;             /* freq masks per utterance  (:37-41) */
+    const int32_t* tmask;        /* [B][n_tmask][2] half-open frame ranges, or NULL */
+    const int32_t* fmask;        /* [B][n_fmask][2] half-open bin ranges, or NULL */
+    const int32_t* frame_map;    /* composed _spec_substitute index map (:44-64): output frame t of
+                                    utterance b is source frame frame_map[frame_map_offsets[b]+t];
+                                    NULL = identity */
+    const int64_t* frame_map_offsets; /* [B] */
+    const float* d_cmvn_mean;    /* DEVICE [num_mel_bins] or NULL (GlobalCMVN buffers) */
+    const float* d_cmvn_istd;    /* DEVICE [num_mel_bins] or NULL (norm_var=False) */
+    int32_t cmvn_on_padding;     /* 1: padding rows become (0-mean)*istd, what GlobalCMVN does to the
+                                    zero-padded batch inside the encoder (encoder.py:221-222) */
+    double* d_stats;             /* DEVICE [2*num_mel_bins+1] or NULL: += sum, sum of squares and
+                                    frame count of the RAW log-mel frames (compute_cmvn_stats; the
+                                    reference only ships the consumer, openeat/utils/cmvn.py:30-35) */
+    int32_t* out_frames;         /* [B] out, or NULL: frames per utterance, 1+(N-400)//160 (kaldi.py:67) */
+} oe_batch;
+
+/* One ragged resampling batch (speed perturb).  Replaces _speed_perturb
+ * (openeat/dataset/audio_processor.py:19-35): `speed s` + `rate sr` == resample from
+ * int(s*sr) to sr.  table_ids come from oe_add_resampler; -1 copies the utterance. */
+typedef struct {
+    int32_t batch;
+    int32_t wav_dtype;           /* dtype of d_in; the output is always fp32 */
+    const int64_t* in_offsets;   /* [B] */
+    const int32_t* in_lens;      /* [B] */
+    const int32_t* table_ids;    /* [B] */
+    const int64_t* out_offsets;  /* [B] sample offsets in d_out (keep them multiples of 8) */
+    int32_t* out_lens;           /* [B] out, or NULL: ceil(new*N/orig) */
+} oe_resample_batch;
+
+const char* oe_last_error(void);
+int oe_abi_version(void);
+
+int oe_config_default(oe_config* cfg);
+
+/* window: [frame_length] or NULL; mel: [num_mel_bins][fft_size/2] row-major or NULL.
+ * NULL tables are computed in double precision and rounded to fp32; pass the tables built
+ * with torch's own fp32 expressions (kaldi.py:98-100, 436-511) for bit-identical constants.
+ * `device` is the CUDA ordinal; -1 = current device. */
+int oe_frontend_create(const oe_config* cfg, const float* window, const float* mel, int device,
+                       oe_frontend** out);
+int oe_frontend_destroy(oe_frontend* fe);
+/* copies the tables in use back to the host (window[frame_length], mel[bins][fft/2]) */
+int oe_frontend_get_tables(const oe_frontend* fe, float* window, float* mel);
+
+/* 1 + (n - frame_length) / frame_shift, 0 when n < frame_length  (kaldi.py:63-67) */
+int32_t oe_num_frames(const oe_frontend* fe, int64_t num_samples);
+
+/* workspace bytes needed by oe_fbank_batch for this batch (depends on lengths and options) */
+int oe_fbank_workspace_bytes(const oe_frontend* fe, const oe_batch* batch, size_t* bytes);
+
+/* waveform -> [per-utt norm] -> [spec_sub] -> [spec_aug] -> [global CMVN] -> padded/ragged rows.
+ * d_out may be NULL when only d_stats is wanted. */
+int oe_fbank_batch(oe_frontend* fe, const oe_batch* batch, const void* d_wav, float* d_out,
+                   void* d_workspace, size_t workspace_bytes, oe_stream stream);
+
+/* GlobalCMVN.forward (openeat/modules/cmvn.py:43-46): y = (x - mean) [* istd], rows x dim fp32. */
+int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
+                  const float* d_istd, oe_stream stream);
+
+/* Registers a polyphase table: kernel[new_rate][taps], taps = 2*width + orig_rate
+ * (torchaudio functional.py:1343-1398 layout), or NULL = hann-windowed sinc, lowpass width 6,
+ * rolloff 0.99 computed in double.  Returns the table id in *table_id. */
+int oe_add_resampler(oe_frontend* fe, int32_t orig_rate, int32_t new_rate, const float* kernel,
+                     int32_t taps, int32_t* table_id);
+int64_t oe_resample_out_len(int64_t n, int32_t orig_rate, int32_t new_rate);
+int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* batch, size_t* bytes);
+int oe_resample(oe_frontend* fe, const oe_resample_batch* batch, const void* d_in, float* d_out,
+                void* d_workspace, size_t workspace_bytes, oe_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENEAT_FRONTEND_H_ */

@@ -1,0 +1,1222 @@
+// B200 (sm_100a) acoustic front-end kernels + the C ABI declared in include/openeat_frontend.h.
+//
+// Reference behaviour being replaced (see DESIGN.md for the full map):
+//   openeat/dataset/dataset.py:39-118, 155-239     _extract_feature / audio_collate_func
+//   torchaudio/compliance/kaldi.py:514-645          fbank (third-party, called at dataset.py:93-100)
+//   openeat/dataset/feature_processor.py:5-64       _normalization / _spec_augmentation / _spec_substitute
+//   openeat/dataset/audio_processor.py:19-35        _speed_perturb
+//   openeat/modules/cmvn.py:35-46                   GlobalCMVN.forward
+//
+// Kernel inventory
+//   oe_fbank_kernel     ragged batch, one CTA per 32-frame tile, persistent grid:
+//                       stage waveform -> smem (pre-emphasis folded in, block sums for DC removal)
+//                       -> per-frame 512-pt real FFT as 256-pt complex FFT split 16x16 over 16 threads
+//                       (registers + half-warp smem exchange) -> power -> sparse mel -> log
+//                       -> [mask, CMVN] -> coalesced rows; optional per-tile column statistics.
+//   oe_utt_stats_kernel per-utterance mean/std from tile statistics (Chan merge, fp64).
+//   oe_finalize_kernel  per-utt normalisation + spec_sub gather + spec_aug masks + CMVN + padding.
+//   oe_global_stats_kernel  += sum / sumsq / count for compute_cmvn_stats.
+//   oe_cmvn_kernel      GlobalCMVN.forward.
+//   oe_resample_kernel  polyphase sinc resampler (speed perturb).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/openeat_frontend.h"
+#include "oe_fft.h"
+
+namespace oe {
+
+constexpr int kWin = 400;           // frame_length
+constexpr int kShift = 160;         // frame_shift
+constexpr int kFft = 512;
+constexpr int kBins = 256;          // fft bins carrying mel weight (kaldi.py:627 pads Nyquist with 0)
+constexpr int kTileFrames = 32;
+constexpr int kThreads = 256;
+constexpr int kTileSamples = kShift * (kTileFrames - 1) + kWin;   // 5360
+constexpr int kChunks = 672;        // 8-sample chunks staged per tile (5376 samples, 16 of slack)
+constexpr int kMaxMel = 128;
+constexpr int kMaxNnz = 2048;
+constexpr int kRowE = 18;           // complex per exchange row: 16 + 2 pad -> 144 B (conflict-free LDS.128)
+constexpr int kRowP = 36;           // floats per power-spectrum row: 32 frames + 4 pad
+constexpr int kRowO = 81;           // floats per output-tile row (80 + 1 pad); generic: F + 1
+
+struct DevTables {
+    float window[kFft];             // zero beyond frame_length
+    float2 twA[16 * kRowE];         // W256^(tau*k1) = (cos, -sin)
+    float2 twU[9 * kRowE];          // (cos, sin)(2 pi k / 512), k = u + 16*k2; row 8 = u 8
+    int mel_start[kMaxMel];
+    int mel_len[kMaxMel];
+    int mel_off[kMaxMel];
+    int group_begin[9];
+    int n_mel;
+    int nnz;
+    float log_floor;
+    float preemph;
+    float mel_w[kMaxNnz];           // already multiplied by 1/4 (see untangle_power)
+};
+
+struct FbankParams {
+    const void* wav;
+    const int64_t* wav_off;
+    const int32_t* wav_len;
+    const int32_t* n_frames;
+    const int32_t* n_rows;
+    const int32_t* tile_prefix;     // [B+1]
+    const int64_t* out_row;
+    float* out;
+    int64_t pitch;
+    int B;
+    int total_tiles;
+    const int32_t* tmask;
+    const int32_t* fmask;
+    int n_tmask;
+    int n_fmask;
+    const float* cmvn_mean;
+    const float* cmvn_istd;
+    int cmvn_on_pad;
+    float* tile_stats;              // [total_tiles][2][F]: column sum, sum of squared deviations
+    const DevTables* tab;
+};
+
+// ------------------------------------------------------------------------------------------
+// shared memory map of oe_fbank_kernel (bytes)
+constexpr int kSmP = 0;                                    // float p[5376]      | out tile (32 x (F+1))
+constexpr int kSmS8 = kSmP + 5376 * 4;                     // float s8[672]
+constexpr int kSmCm = kSmS8 + kChunks * 4;                 // float cmean[32]
+constexpr int kSmE = kSmCm + 32 * 4;                       // float2 E[16][2][16][18] | float P[256][36]
+constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
+constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
+constexpr int kSmMelIdx = kSmTwU + 9 * kRowE * 8;          // int start/len/off [3][128], group_begin[9] (+pad)
+constexpr int kSmMisc = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // int b, t0; uchar rowmask[32], colmask[128]
+constexpr int kSmMelW = kSmMisc + 16 + 32 + kMaxMel;       // float mel_w[nnz]
+static_assert(kSmE % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0, "align");
+static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
+
+__device__ __forceinline__ int find_utt(const int32_t* __restrict__ prefix, int B, int tile) {
+    int lo = 0, hi = B;                       // prefix[lo] <= tile < prefix[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool kF32>
+__device__ __forceinline__ void load8(const void* wav, int64_t base, int s, int wlen, float (&x)[8], float& prev) {
+    if (kF32) {
+        const float* w = reinterpret_cast<const float*>(wav) + base;
+        if (s + 8 <= wlen) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w + s));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(w + s + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+            x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (s + i < wlen) ? __ldg(w + s + i) : 0.0f;
+        }
+        prev = (s > 0) ? ((s - 1 < wlen) ? __ldg(w + s - 1) : 0.0f) : x[0];
+    } else {
+        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + base;
+        if (s + 8 <= wlen) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(w + s));
+            x[0] = (float)(int16_t)(v.x & 0xffff); x[1] = (float)(v.x >> 16);
+            x[2] = (float)(int16_t)(v.y & 0xffff); x[3] = (float)(v.y >> 16);
+            x[4] = (float)(int16_t)(v.z & 0xffff); x[5] = (float)(v.z >> 16);
+            x[6] = (float)(int16_t)(v.w & 0xffff); x[7] = (float)(v.w >> 16);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (s + i < wlen) ? (float)__ldg(w + s + i) : 0.0f;
+        }
+        prev = (s > 0) ? ((s - 1 < wlen) ? (float)__ldg(w + s - 1) : 0.0f) : x[0];
+    }
+}
+
+template <bool kF32>
+__global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* const sp = reinterpret_cast<float*>(smem + kSmP);
+    float* const s8 = reinterpret_cast<float*>(smem + kSmS8);
+    float* const cmean = reinterpret_cast<float*>(smem + kSmCm);
+    float2* const sE = reinterpret_cast<float2*>(smem + kSmE);
+    float* const sPw = reinterpret_cast<float*>(smem + kSmE);
+    float2* const sTwA = reinterpret_cast<float2*>(smem + kSmTwA);
+    float2* const sTwU = reinterpret_cast<float2*>(smem + kSmTwU);
+    int* const sMelStart = reinterpret_cast<int*>(smem + kSmMelIdx);
+    int* const sMelLen = sMelStart + kMaxMel;
+    int* const sMelOff = sMelLen + kMaxMel;
+    int* const sGroup = sMelOff + kMaxMel;
+    int* const sTile = reinterpret_cast<int*>(smem + kSmMisc);
+    unsigned char* const sRowMask = smem + kSmMisc + 16;
+    unsigned char* const sColMask = sRowMask + 32;
+    float* const sMelW = reinterpret_cast<float*>(smem + kSmMelW);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tau = tid & 15, grp = tid >> 4;
+    const DevTables* __restrict__ tab = P.tab;
+    const int F = tab->n_mel;
+    const int rowO = F + 1;
+
+    // ---- one-time table staging ----
+    for (int i = tid; i < 16 * kRowE; i += kThreads) sTwA[i] = tab->twA[i];
+    for (int i = tid; i < 9 * kRowE; i += kThreads) sTwU[i] = tab->twU[i];
+    for (int i = tid; i < kMaxMel; i += kThreads) {
+        sMelStart[i] = tab->mel_start[i];
+        sMelLen[i] = tab->mel_len[i];
+        sMelOff[i] = tab->mel_off[i];
+    }
+    if (tid < 9) sGroup[tid] = tab->group_begin[tid];
+    for (int i = tid; i < tab->nnz; i += kThreads) sMelW[i] = tab->mel_w[i];
+    float wv0[13], wv1[13];                    // window taps of this lane: w[32 n1 + 2 tau (+1)]
+#pragma unroll
+    for (int n1 = 0; n1 < 13; ++n1) {
+        wv0[n1] = tab->window[32 * n1 + 2 * tau];
+        wv1[n1] = tab->window[32 * n1 + 2 * tau + 1];
+    }
+    const float preemph = tab->preemph;
+    const float dc_coef = 1.0f - preemph;
+    const float log_floor = tab->log_floor;
+    const bool fused = (P.n_tmask | P.n_fmask) != 0;
+
+    int slot = 0;                                  // tile descriptor is double-buffered: padding-only
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, slot ^= 2) {   // tiles have no barrier but (1)
+        if (tid == 0) {
+            const int b = find_utt(P.tile_prefix, P.B, tile);
+            sTile[slot] = b;
+            sTile[slot + 1] = (tile - P.tile_prefix[b]) * kTileFrames;
+        }
+        __syncthreads();                                           // (1) also fences the previous tile
+        const int b = sTile[slot], t0 = sTile[slot + 1];
+        const int nfr = P.n_frames[b];
+        const int nrows = P.n_rows[b];
+        const int nvalid = min(kTileFrames, nfr - t0);             // <= 0: padding-only tile
+        if (fused) {
+            if (tid < 32) {
+                const int t = t0 + tid;
+                bool m = false;
+                for (int j = 0; j < P.n_tmask; ++j) {
+                    const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
+                    m |= (t >= r[0]) & (t < r[1]);
+                }
+                sRowMask[tid] = m;
+            } else if (tid < 32 + F) {
+                const int f = tid - 32;
+                bool m = false;
+                for (int j = 0; j < P.n_fmask; ++j) {
+                    const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
+                    m |= (f >= r[0]) & (f < r[1]);
+                }
+                sColMask[f] = m;
+            }
+        }
+        if (nvalid > 0) {
+            // ---- stage the waveform: p[j] = x[j] - preemph * x[j-1], 8-sample block sums ----
+            {
+                const int64_t woff = P.wav_off[b];
+                const int wlen = P.wav_len[b];
+                const int s_base = t0 * kShift;
+                for (int c = tid; c < kChunks; c += kThreads) {
+                    float x[8], prev;
+                    load8<kF32>(P.wav, woff, s_base + 8 * c, wlen, x, prev);
+                    float4 lo, hi;
+                    lo.x = fmaf(-preemph, prev, x[0]);
+                    lo.y = fmaf(-preemph, x[0], x[1]);
+                    lo.z = fmaf(-preemph, x[1], x[2]);
+                    lo.w = fmaf(-preemph, x[2], x[3]);
+                    hi.x = fmaf(-preemph, x[3], x[4]);
+                    hi.y = fmaf(-preemph, x[4], x[5]);
+                    hi.z = fmaf(-preemph, x[5], x[6]);
+                    hi.w = fmaf(-preemph, x[6], x[7]);
+                    reinterpret_cast<float4*>(sp)[2 * c] = lo;
+                    reinterpret_cast<float4*>(sp)[2 * c + 1] = hi;
+                    s8[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+                }
+            }
+            __syncthreads();                                       // (2)
+            if (tid < kTileFrames) {                               // frame mean (kaldi.py:183-186)
+                const float* q = s8 + 20 * tid;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 50; i += 2) {
+                    a0 += q[i];
+                    a1 += q[i + 1];
+                }
+                cmean[tid] = dc_coef * ((a0 + a1) / (float)kWin);
+            }
+            __syncthreads();                                       // (3)
+
+            // ---- stage A: 16-point FFTs of z[16 n1 + tau] for the group's two frames ----
+            float zr[2][16], zi[2][16];
+#pragma unroll
+            for (int fr = 0; fr < 2; ++fr) {
+                const float* base = sp + kShift * (2 * grp + fr) + 2 * tau;
+                const float c = cmean[2 * grp + fr];
+#pragma unroll
+                for (int n1 = 0; n1 < 13; ++n1) {
+                    const float2 v = *reinterpret_cast<const float2*>(base + 32 * n1);
+                    zr[fr][n1] = (v.x - c) * wv0[n1];
+                    zi[fr][n1] = (v.y - c) * wv1[n1];
+                }
+#pragma unroll
+                for (int n1 = 13; n1 < 16; ++n1) {
+                    zr[fr][n1] = 0.f;
+                    zi[fr][n1] = 0.f;
+                }
+            }
+            fft_dif<16, 13>(zr[0], zi[0]);
+            fft_dif<16, 13>(zr[1], zi[1]);
+            {
+                float2* const e0 = sE + ((grp * 2 + 0) * 16) * kRowE + tau;
+                float2* const e1 = sE + ((grp * 2 + 1) * 16) * kRowE + tau;
+                const float4* const tw4 = reinterpret_cast<const float4*>(sTwA + tau * kRowE);
+                static_for<0, 8>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    const float4 t = tw4[i];                       // k1 = 2i: (t.x, t.y), 2i+1: (t.z, t.w)
+                    constexpr int p0 = bitrev<16>(2 * i), p1 = bitrev<16>(2 * i + 1);
+                    if constexpr (i == 0) {
+                        e0[0] = make_float2(zr[0][p0], zi[0][p0]);
+                        e1[0] = make_float2(zr[1][p0], zi[1][p0]);
+                    } else {
+                        e0[(2 * i) * kRowE] = make_float2(zr[0][p0] * t.x - zi[0][p0] * t.y, zr[0][p0] * t.y + zi[0][p0] * t.x);
+                        e1[(2 * i) * kRowE] = make_float2(zr[1][p0] * t.x - zi[1][p0] * t.y, zr[1][p0] * t.y + zi[1][p0] * t.x);
+                    }
+                    e0[(2 * i + 1) * kRowE] = make_float2(zr[0][p1] * t.z - zi[0][p1] * t.w, zr[0][p1] * t.w + zi[0][p1] * t.z);
+                    e1[(2 * i + 1) * kRowE] = make_float2(zr[1][p1] * t.z - zi[1][p1] * t.w, zr[1][p1] * t.w + zi[1][p1] * t.z);
+                });
+            }
+            __syncwarp();
+
+            // ---- stage B: lane (fsel, u) transforms rows u and 16-u (0 and 8 for u == 0) ----
+            const int fsel = tau >> 3, u = tau & 7;
+            float ar[16], ai[16], br[16], bi[16];
+            {
+                const int ra = stage_b_row_a(u), rb = stage_b_row_b(u);
+                const float4* const pa = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + ra) * kRowE);
+                const float4* const pb = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + rb) * kRowE);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 va = pa[i], vb = pb[i];
+                    ar[2 * i] = va.x; ai[2 * i] = va.y; ar[2 * i + 1] = va.z; ai[2 * i + 1] = va.w;
+                    br[2 * i] = vb.x; bi[2 * i] = vb.y; br[2 * i + 1] = vb.z; bi[2 * i + 1] = vb.w;
+                }
+            }
+            __syncthreads();                                       // (4) exchange buffer is dead -> power tile
+            fft_dif<16>(ar, ai);
+            fft_dif<16>(br, bi);
+            {
+                float* const pcol = sPw + (2 * grp + fsel);
+                if (u != 0) {
+                    const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
+                    static_for<0, 8>([&](auto ii) {
+                        constexpr int i = decltype(ii)::value;
+                        const float4 t = tw4[i];
+                        {
+                            constexpr int k2 = 2 * i;
+                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                            float pk, pnk;
+                            untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
+                            const int k = u + 16 * k2;
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                        {
+                            constexpr int k2 = 2 * i + 1;
+                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                            float pk, pnk;
+                            untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
+                            const int k = u + 16 * k2;
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                    });
+                } else {
+                    const float2* const tw0 = sTwU;                 // k = 16 k2
+                    const float2* const tw8 = sTwU + 8 * kRowE;     // k = 8 + 16 k2
+                    static_for<0, 9>([&](auto kk) {                 // row 0: P = Z[16 k2], Q = Z[16 (16-k2)]
+                        constexpr int k2 = decltype(kk)::value;
+                        constexpr int p = bitrev<16>(k2), q = bitrev<16>((16 - k2) & 15);
+                        const float2 t = tw0[k2];
+                        float pk, pnk;
+                        untangle_power(ar[p], ai[p], ar[q], ai[q], t.x, t.y, pk, pnk);
+                        pcol[(16 * k2) * kRowP] = pk;
+                        if constexpr (k2 != 0) pcol[(256 - 16 * k2) * kRowP] = pnk;   // bin 256 has no mel weight
+                    });
+                    static_for<0, 8>([&](auto kk) {                 // row 8: P = Z[8+16 k2], Q = Z[8+16 (15-k2)]
+                        constexpr int k2 = decltype(kk)::value;
+                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                        const float2 t = tw8[k2];
+                        float pk, pnk;
+                        untangle_power(br[p], bi[p], br[q], bi[q], t.x, t.y, pk, pnk);
+                        pcol[(8 + 16 * k2) * kRowP] = pk;
+                        pcol[(248 - 16 * k2) * kRowP] = pnk;
+                    });
+                }
+            }
+            __syncthreads();                                       // (5) power tile complete
+
+            // ---- sparse mel + log: warp = mel-bin group, lane = frame ----
+            {
+                const float* const pcol = sPw + lane;
+                for (int bin = sGroup[warp]; bin < sGroup[warp + 1]; ++bin) {
+                    const int k0 = sMelStart[bin], len = sMelLen[bin];
+                    const float* const w = sMelW + sMelOff[bin];
+                    float acc = 0.f;
+                    for (int i = 0; i < len; ++i) acc = fmaf(w[i], pcol[(k0 + i) * kRowP], acc);
+                    sp[lane * rowO + bin] = __logf(fmaxf(acc, log_floor));
+                }
+            }
+            __syncthreads();                                       // (6) output tile complete
+            if (P.tile_stats != nullptr && tid < F) {
+                float s = 0.f;
+                for (int r = 0; r < nvalid; ++r) s += sp[r * rowO + tid];
+                const float mean = s / (float)nvalid;
+                float m2 = 0.f;
+                for (int r = 0; r < nvalid; ++r) {
+                    const float d = sp[r * rowO + tid] - mean;
+                    m2 = fmaf(d, d, m2);
+                }
+                float* const st = P.tile_stats + (int64_t)tile * 2 * F;
+                st[tid] = s;
+                st[F + tid] = m2;
+            }
+        }
+
+        // ---- rows out: [mask] -> [CMVN] -> coalesced stores; padding rows are 0 / (0-mean)*istd ----
+        if (P.out != nullptr) {
+            const bool has_cmvn = P.cmvn_mean != nullptr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = warp + 8 * i;
+                const int t = t0 + r;
+                if (t >= nrows) continue;
+                const bool real = t < nfr;
+                const bool rmask = fused && real && sRowMask[r];
+                float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
+                for (int f = lane; f < F; f += 32) {
+                    float v = real ? sp[r * rowO + f] : 0.f;
+                    if (rmask || (fused && real && sColMask[f])) v = 0.f;
+                    if (has_cmvn && (real || P.cmvn_on_pad)) {
+                        v = v - __ldg(P.cmvn_mean + f);
+                        if (P.cmvn_istd != nullptr) v = v * __ldg(P.cmvn_istd + f);
+                    }
+                    dst[f] = v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct UttStatsParams {
+    const float* tile_stats;
+    const int32_t* tile_prefix;
+    const int32_t* n_frames;
+    float* utt_mean;     // [B][F]
+    float* utt_std;      // [B][F]
+    int F;
+};
+
+// feature_processor.py:5-8: mean and population std over the frames of one utterance.
+__global__ void oe_utt_stats_kernel(const UttStatsParams P) {
+    const int b = blockIdx.x, f = threadIdx.x;
+    if (f >= P.F) return;
+    const int nfr = P.n_frames[b];
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    const int tb = P.tile_prefix[b];
+    const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
+    for (int i = 0; i < ntiles; ++i) {
+        const float* st = P.tile_stats + (int64_t)(tb + i) * 2 * P.F;
+        const double nb = (double)min(kTileFrames, nfr - i * kTileFrames);
+        const double mb = (double)st[f] / nb;
+        const double delta = mb - mean;
+        const double nn = n + nb;
+        mean += delta * nb / nn;
+        m2 += (double)st[P.F + f] + delta * delta * n * nb / nn;
+        n = nn;
+    }
+    P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
+    P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / n);
+}
+
+struct GlobalStatsParams {
+    const float* tile_stats;
+    const int32_t* tile_prefix;
+    const int32_t* n_frames;
+    double* stats;       // [2F+1] accumulated in place
+    int B;
+    int F;
+};
+
+// compute_cmvn_stats: sum, sum of squares, count of the raw log-mel frames (fixed summation order).
+__global__ void oe_global_stats_kernel(const GlobalStatsParams P) {
+    const int f = threadIdx.x;
+    if (f < P.F) {
+        double s = 0.0, q = 0.0;
+        for (int b = 0; b < P.B; ++b) {
+            const int nfr = P.n_frames[b];
+            const int tb = P.tile_prefix[b];
+            const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
+            for (int i = 0; i < ntiles; ++i) {
+                const float* st = P.tile_stats + (int64_t)(tb + i) * 2 * P.F;
+                const double nb = (double)min(kTileFrames, nfr - i * kTileFrames);
+                const double sb = (double)st[f];
+                s += sb;
+                q += (double)st[P.F + f] + sb * sb / nb;
+            }
+        }
+        P.stats[f] += s;
+        P.stats[P.F + f] += q;
+    } else if (f == P.F) {
+        double cnt = 0.0;
+        for (int b = 0; b < P.B; ++b) cnt += (double)P.n_frames[b];
+        P.stats[2 * P.F] += cnt;
+    }
+}
+
+struct FeatStatsParams {
+    const float* feats;          // ragged rows, pitch F
+    const int64_t* row_off;      // [B] first row of each utterance
+    const int32_t* n_frames;
+    const int32_t* tile_prefix;
+    float* tile_stats;
+    int B, F, total_tiles;
+};
+
+// Same per-tile column statistics as the fbank kernel's epilogue, for batches that arrive as
+// features (data_type != 'wav', dataset.py:190-191, or the numpy-level processor mirrors).
+__global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
+    const int f = threadIdx.x;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int b = find_utt(P.tile_prefix, P.B, tile);
+        const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
+        const int nvalid = min(kTileFrames, P.n_frames[b] - t0);
+        if (f >= P.F || nvalid <= 0) continue;
+        const float* src = P.feats + (P.row_off[b] + t0) * P.F + f;
+        float s = 0.f;
+        for (int r = 0; r < nvalid; ++r) s += src[(int64_t)r * P.F];
+        const float mean = s / (float)nvalid;
+        float m2 = 0.f;
+        for (int r = 0; r < nvalid; ++r) {
+            const float d = src[(int64_t)r * P.F] - mean;
+            m2 = fmaf(d, d, m2);
+        }
+        float* const st = P.tile_stats + (int64_t)tile * 2 * P.F;
+        st[f] = s;
+        st[P.F + f] = m2;
+    }
+}
+
+struct FinalizeParams {
+    const float* raw;            // ragged raw log-mel, pitch F
+    const int64_t* frame_prefix; // [B+1]
+    const int64_t* row_prefix;   // [B+1]
+    const int32_t* n_frames;
+    const int64_t* out_row;
+    float* out;
+    int64_t pitch;
+    const float* utt_mean;
+    const float* utt_std;
+    const int32_t* frame_map;
+    const int64_t* map_off;
+    const int32_t* tmask;
+    const int32_t* fmask;
+    int n_tmask, n_fmask;
+    const float* cmvn_mean;
+    const float* cmvn_istd;
+    int cmvn_on_pad;
+    int B, F;
+    int64_t total_rows;
+};
+
+// dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
+__global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < P.total_rows; row += nwarps) {
+        int lo = 0, hi = P.B;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (P.row_prefix[mid] <= row) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int t = (int)(row - P.row_prefix[b]);
+        const int nfr = P.n_frames[b];
+        const bool real = t < nfr;
+        float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
+        bool rmask = false;
+        const float* src = nullptr;
+        if (real) {
+            for (int j = 0; j < P.n_tmask; ++j) {
+                const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
+                rmask |= (t >= r[0]) & (t < r[1]);
+            }
+            const int ts = P.frame_map ? P.frame_map[P.map_off[b] + t] : t;
+            src = P.raw + (P.frame_prefix[b] + ts) * P.F;
+        }
+        for (int f = lane; f < P.F; f += 32) {
+            float v = 0.f;
+            if (real) {
+                v = src[f];
+                if (P.utt_mean) v = (v - P.utt_mean[(int64_t)b * P.F + f]) / P.utt_std[(int64_t)b * P.F + f];
+                bool m = rmask;
+                for (int j = 0; j < P.n_fmask; ++j) {
+                    const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
+                    m |= (f >= r[0]) & (f < r[1]);
+                }
+                if (m) v = 0.f;
+            }
+            if (P.cmvn_mean && (real || P.cmvn_on_pad)) {
+                v = v - P.cmvn_mean[f];
+                if (P.cmvn_istd) v = v * P.cmvn_istd[f];
+            }
+            dst[f] = v;
+        }
+    }
+}
+
+// openeat/modules/cmvn.py:43-46
+__global__ void __launch_bounds__(256) oe_cmvn_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                      int64_t n, int dim, const float* __restrict__ mean,
+                                                      const float* __restrict__ istd) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int f = (int)(i % dim);
+        float v = x[i] - mean[f];
+        if (istd) v = v * istd[f];
+        y[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct RsTable {
+    int orig, neu, taps, width, coef_off;
+};
+constexpr int kMaxRsTables = 16;
+constexpr int kMaxRsCoefs = 16384;
+
+struct ResampleParams {
+    const void* in;
+    float* out;
+    const int64_t* in_off;
+    const int32_t* in_len;
+    const int32_t* table_id;
+    const int64_t* out_off;
+    const int32_t* out_len;
+    const RsTable* tables;
+    const float* coefs;
+};
+
+// torchaudio functional.py:1401-1432: y[m*new + p] = sum_q k[p][q] * xpad[m*orig + q], xpad = x shifted by width.
+template <bool kF32>
+__global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P) {
+    const int b = blockIdx.y;
+    const int n_out = P.out_len[b];
+    const int n_in = P.in_len[b];
+    const int tid_ = P.table_id[b];
+    float* const out = P.out + P.out_off[b];
+    const int64_t ioff = P.in_off[b];
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+        float acc = 0.f;
+        if (tid_ < 0) {
+            acc = kF32 ? reinterpret_cast<const float*>(P.in)[ioff + i]
+                       : (float)reinterpret_cast<const int16_t*>(P.in)[ioff + i];
+        } else {
+            const RsTable t = P.tables[tid_];
+            const int m = i / t.neu, ph = i - m * t.neu;
+            const float* const k = P.coefs + t.coef_off + ph * t.taps;
+            const int x0 = m * t.orig - t.width;
+            for (int q = 0; q < t.taps; ++q) {
+                const int xi = x0 + q;
+                if (xi >= 0 && xi < n_in) {
+                    const float xv = kF32 ? reinterpret_cast<const float*>(P.in)[ioff + xi]
+                                          : (float)reinterpret_cast<const int16_t*>(P.in)[ioff + xi];
+                    acc = fmaf(k[q], xv, acc);
+                }
+            }
+        }
+        out[i] = acc;
+    }
+}
+
+}  // namespace oe
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+struct oe_frontend {
+    oe_config cfg;
+    int device;
+    int sm_count;
+    oe::DevTables* d_tab;
+    std::vector<float> window, mel;
+    std::vector<oe::RsTable> rs;
+    std::vector<float> rs_coefs;
+    oe::RsTable* d_rs;
+    float* d_rs_coefs;
+    size_t fbank_smem;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define OE_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(OE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// kaldi.py:98-100 in double, rounded once
+void default_window(int n, std::vector<float>& w) {
+    w.assign(n, 0.f);
+    for (int j = 0; j < n; ++j) {
+        double h = 0.5 - 0.5 * std::cos(2.0 * oe::kPi * j / (n - 1));
+        if (j == 0 || j == n - 1) h = 0.0;
+        w[j] = (float)std::pow(h, 0.85);
+    }
+}
+
+// kaldi.py:436-511 (vtln_warp 1.0): scalar limits in double, per-bin arithmetic in fp32 like torch
+void default_mel(const oe_config& c, std::vector<float>& m) {
+    const int nb = c.num_mel_bins, nf = c.fft_size / 2;
+    const double nyq = 0.5 * c.sample_rate;
+    double high = c.high_freq;
+    if (high <= 0.0) high += nyq;
+    const double mel_lo = 1127.0 * std::log(1.0 + (double)c.low_freq / 700.0);
+    const double mel_hi = 1127.0 * std::log(1.0 + high / 700.0);
+    const double delta = (mel_hi - mel_lo) / (nb + 1);
+    const float bw = (float)((double)c.sample_rate / c.fft_size);
+    m.assign((size_t)nb * nf, 0.f);
+    for (int b = 0; b < nb; ++b) {
+        const float left = (float)mel_lo + (float)b * (float)delta;
+        const float center = (float)mel_lo + ((float)b + 1.0f) * (float)delta;
+        const float right = (float)mel_lo + ((float)b + 2.0f) * (float)delta;
+        for (int k = 0; k < nf; ++k) {
+            const float mel = 1127.0f * std::log(1.0f + (bw * (float)k) / 700.0f);
+            const float up = (mel - left) / (center - left);
+            const float down = (right - mel) / (right - center);
+            m[(size_t)b * nf + k] = std::max(0.0f, std::min(up, down));
+        }
+    }
+}
+
+struct Meta {               // device-side metadata block layout (byte offsets into the workspace)
+    size_t wav_off, out_row, frame_prefix, row_prefix, map_off;          // int64 arrays
+    size_t wav_len, n_frames, n_rows, tile_prefix, tmask, fmask, fmap;   // int32 arrays
+    size_t meta_bytes;
+    size_t raw, tile_stats, utt_mean, utt_std, total;
+    int64_t total_frames, total_rows, total_map;
+    int total_tiles;
+    bool two_phase, need_stats, feats;
+};
+
+int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t>* frames_out) {
+    if (!fe || !bt) return fail(OE_ERR_INVALID, "null frontend or batch");
+    if (bt->batch < 0) return fail(OE_ERR_INVALID, "negative batch");
+    if (bt->batch > 0 && (!bt->wav_offsets || !bt->wav_lens || !bt->out_rows))
+        return fail(OE_ERR_INVALID, "wav_offsets, wav_lens and out_rows are required");
+    if (bt->wav_dtype != OE_WAV_I16 && bt->wav_dtype != OE_WAV_F32 && bt->wav_dtype != OE_FEATS_F32)
+        return fail(OE_ERR_INVALID, "bad wav_dtype");
+    const bool feats = bt->wav_dtype == OE_FEATS_F32;
+    if (bt->n_tmask < 0 || bt->n_fmask < 0 || (bt->n_tmask > 0 && !bt->tmask) || (bt->n_fmask > 0 && !bt->fmask))
+        return fail(OE_ERR_INVALID, "mask counts / pointers inconsistent");
+    if (bt->frame_map && !bt->frame_map_offsets) return fail(OE_ERR_INVALID, "frame_map without offsets");
+    const int B = bt->batch, F = fe->cfg.num_mel_bins;
+    const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
+    if (pitch < F) return fail(OE_ERR_INVALID, "out_pitch smaller than num_mel_bins");
+    M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr;
+    M.feats = feats;
+    M.need_stats = bt->norm_mode != OE_NORM_NONE || bt->d_stats != nullptr;
+    M.total_frames = M.total_rows = M.total_map = 0;
+    int64_t tiles = 0;
+    if (frames_out) frames_out->resize(B);
+    for (int b = 0; b < B; ++b) {
+        if (bt->wav_lens[b] < 0) return fail(OE_ERR_INVALID, "negative wav_len at %d", b);
+        if (bt->wav_offsets[b] < 0 || (!feats && (bt->wav_offsets[b] & 7)))
+            return fail(OE_ERR_INVALID, "wav_offsets[%d] must be a non-negative multiple of 8 samples", b);
+        const int nfr = feats ? bt->wav_lens[b] : oe_num_frames(fe, bt->wav_lens[b]);
+        const int nrows = bt->out_nrows ? bt->out_nrows[b] : nfr;
+        if (nrows < nfr) return fail(OE_ERR_INVALID, "out_nrows[%d]=%d < frames %d", b, nrows, nfr);
+        if (frames_out) (*frames_out)[b] = nfr;
+        M.total_frames += nfr;
+        M.total_rows += nrows;
+        const int cover = M.two_phase ? nfr : nrows;
+        tiles += (cover + oe::kTileFrames - 1) / oe::kTileFrames;
+        if (bt->frame_map) M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
+    }
+    if (tiles > INT32_MAX) return fail(OE_ERR_INVALID, "batch too large");
+    M.total_tiles = (int)tiles;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 16); return r; };
+    M.wav_off = take(8 * (size_t)B);
+    M.out_row = take(8 * (size_t)B);
+    M.frame_prefix = take(8 * (size_t)(B + 1));
+    M.row_prefix = take(8 * (size_t)(B + 1));
+    M.map_off = take(8 * (size_t)B);
+    M.wav_len = take(4 * (size_t)B);
+    M.n_frames = take(4 * (size_t)B);
+    M.n_rows = take(4 * (size_t)B);
+    M.tile_prefix = take(4 * (size_t)(B + 1));
+    M.tmask = take(8 * (size_t)B * bt->n_tmask);
+    M.fmask = take(8 * (size_t)B * bt->n_fmask);
+    M.fmap = take(4 * (size_t)M.total_map);
+    M.meta_bytes = o;
+    M.raw = take(M.two_phase && !feats ? 4 * (size_t)M.total_frames * F : 0);
+    M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 2 * F : 0);
+    M.utt_mean = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
+    M.utt_std = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
+    M.total = o;
+    return OE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* oe_last_error(void) { return g_err; }
+int oe_abi_version(void) { return OE_ABI_VERSION; }
+
+int oe_config_default(oe_config* cfg) {
+    if (!cfg) return fail(OE_ERR_INVALID, "null cfg");
+    cfg->sample_rate = 16000;
+    cfg->frame_length = 400;
+    cfg->frame_shift = 160;
+    cfg->fft_size = 512;
+    cfg->num_mel_bins = 80;
+    cfg->preemph = 0.97f;
+    cfg->low_freq = 20.0f;
+    cfg->high_freq = 0.0f;
+    cfg->log_floor = 1.1920928955078125e-07f;
+    return OE_OK;
+}
+
+int32_t oe_num_frames(const oe_frontend* fe, int64_t n) {
+    const int win = fe ? fe->cfg.frame_length : oe::kWin, shift = fe ? fe->cfg.frame_shift : oe::kShift;
+    if (n < win) return 0;
+    return (int32_t)(1 + (n - win) / shift);
+}
+
+int oe_frontend_create(const oe_config* cfg, const float* window, const float* mel, int device, oe_frontend** out) {
+    if (!cfg || !out) return fail(OE_ERR_INVALID, "null cfg/out");
+    *out = nullptr;
+    if (cfg->frame_length != oe::kWin || cfg->frame_shift != oe::kShift || cfg->fft_size != oe::kFft)
+        return fail(OE_ERR_UNSUPPORTED, "only 25 ms / 10 ms framing at 16 kHz (400/160/512 samples) is built; got %d/%d/%d",
+                    cfg->frame_length, cfg->frame_shift, cfg->fft_size);
+    if (cfg->num_mel_bins < 4 || cfg->num_mel_bins > oe::kMaxMel)
+        return fail(OE_ERR_UNSUPPORTED, "num_mel_bins must be in [4, %d]", oe::kMaxMel);
+    if (!(cfg->preemph >= 0.f && cfg->preemph <= 1.f)) return fail(OE_ERR_INVALID, "preemph must be in [0,1]");
+    if (device < 0) OE_CUDA(cudaGetDevice(&device));
+    OE_CUDA(cudaSetDevice(device));
+    oe_frontend* fe = new oe_frontend();
+    fe->cfg = *cfg;
+    fe->device = device;
+    fe->d_tab = nullptr;
+    fe->d_rs = nullptr;
+    fe->d_rs_coefs = nullptr;
+    const int nb = cfg->num_mel_bins, nf = cfg->fft_size / 2;
+    if (window) fe->window.assign(window, window + cfg->frame_length); else default_window(cfg->frame_length, fe->window);
+    if (mel) fe->mel.assign(mel, mel + (size_t)nb * nf); else default_mel(*cfg, fe->mel);
+    if (fe->window[0] != 0.f) {
+        delete fe;
+        return fail(OE_ERR_UNSUPPORTED, "window[0] must be 0 (povey): pre-emphasis is folded into the staged waveform");
+    }
+    std::vector<oe::DevTables> hv(1);
+    oe::DevTables& h = hv[0];
+    memset(&h, 0, sizeof(h));
+    for (int j = 0; j < cfg->frame_length; ++j) h.window[j] = fe->window[j];
+    for (int tau = 0; tau < 16; ++tau)
+        for (int k1 = 0; k1 < 16; ++k1) {
+            const double a = 2.0 * oe::kPi * (double)((tau * k1) % 256) / 256.0;
+            h.twA[tau * oe::kRowE + k1] = make_float2((float)std::cos(a), (float)-std::sin(a));
+        }
+    for (int u = 0; u < 9; ++u)
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const double a = 2.0 * oe::kPi * (double)(u + 16 * k2) / 512.0;
+            h.twU[u * oe::kRowE + k2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    int nnz = 0;
+    for (int b = 0; b < nb; ++b) {
+        int first = -1, last = -1;
+        for (int k = 0; k < nf; ++k)
+            if (fe->mel[(size_t)b * nf + k] != 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        h.mel_start[b] = first < 0 ? 0 : first;
+        h.mel_len[b] = first < 0 ? 0 : last - first + 1;
+        h.mel_off[b] = nnz;
+        if (nnz + h.mel_len[b] > oe::kMaxNnz) {
+            delete fe;
+            return fail(OE_ERR_UNSUPPORTED, "mel matrix too dense (> %d stored weights)", oe::kMaxNnz);
+        }
+        for (int i = 0; i < h.mel_len[b]; ++i) h.mel_w[nnz + i] = 0.25f * fe->mel[(size_t)b * nf + h.mel_start[b] + i];
+        nnz += h.mel_len[b];
+    }
+    h.nnz = nnz;
+    h.n_mel = nb;
+    h.log_floor = cfg->log_floor;
+    h.preemph = cfg->preemph;
+    {   // contiguous mel-bin groups for the 8 warps, balanced by stored weights (+2 per bin of overhead)
+        const double total = nnz + 2.0 * nb;
+        int b = 0;
+        double acc = 0.0;
+        h.group_begin[0] = 0;
+        for (int g = 1; g < 8; ++g) {
+            while (b < nb && acc + 0.5 * (h.mel_len[b] + 2) <= total * g / 8.0) acc += h.mel_len[b++] + 2;
+            h.group_begin[g] = b;
+        }
+        h.group_begin[8] = nb;
+    }
+    cudaError_t e = cudaMalloc(&fe->d_tab, sizeof(oe::DevTables));
+    if (e == cudaSuccess) e = cudaMemcpy(fe->d_tab, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&fe->d_rs, sizeof(oe::RsTable) * oe::kMaxRsTables);
+    if (e == cudaSuccess) e = cudaMalloc(&fe->d_rs_coefs, sizeof(float) * oe::kMaxRsCoefs);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    fe->fbank_smem = align_up((size_t)oe::kSmMelW + 4 * (size_t)nnz, 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    if (e != cudaSuccess) {
+        if (fe->d_tab) cudaFree(fe->d_tab);
+        if (fe->d_rs) cudaFree(fe->d_rs);
+        if (fe->d_rs_coefs) cudaFree(fe->d_rs_coefs);
+        delete fe;
+        return fail(OE_ERR_CUDA, "frontend setup failed: %s", cudaGetErrorString(e));
+    }
+    fe->sm_count = prop.multiProcessorCount;
+    *out = fe;
+    return OE_OK;
+}
+
+int oe_frontend_destroy(oe_frontend* fe) {
+    if (!fe) return OE_OK;
+    cudaFree(fe->d_tab);
+    cudaFree(fe->d_rs);
+    cudaFree(fe->d_rs_coefs);
+    delete fe;
+    return OE_OK;
+}
+
+int oe_frontend_get_tables(const oe_frontend* fe, float* window, float* mel) {
+    if (!fe) return fail(OE_ERR_INVALID, "null frontend");
+    if (window) memcpy(window, fe->window.data(), fe->window.size() * sizeof(float));
+    if (mel) memcpy(mel, fe->mel.data(), fe->mel.size() * sizeof(float));
+    return OE_OK;
+}
+
+int oe_fbank_workspace_bytes(const oe_frontend* fe, const oe_batch* batch, size_t* bytes) {
+    if (!bytes) return fail(OE_ERR_INVALID, "null bytes");
+    Meta M;
+    const int rc = plan(fe, batch, M, nullptr);
+    if (rc != OE_OK) return rc;
+    *bytes = M.total + 256;
+    return OE_OK;
+}
+
+int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float* d_out, void* d_ws,
+                   size_t ws_bytes, oe_stream stream_) {
+    Meta M;
+    std::vector<int32_t> frames;
+    int rc = plan(fe, bt, M, &frames);
+    if (rc != OE_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = bt->batch, F = fe->cfg.num_mel_bins;
+    if (bt->out_frames) for (int b = 0; b < B; ++b) bt->out_frames[b] = frames[b];
+    if (B == 0) return OE_OK;
+    if (!d_wav) return fail(OE_ERR_INVALID, "null d_wav");
+    if (!d_out && !bt->d_stats) return fail(OE_ERR_INVALID, "nothing to produce: d_out and d_stats are both null");
+    if (!d_ws || ws_bytes < M.total) return fail(OE_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", M.total, ws_bytes);
+    if ((reinterpret_cast<uintptr_t>(d_ws) & 15) || (reinterpret_cast<uintptr_t>(d_wav) & 15))
+        return fail(OE_ERR_INVALID, "d_wav and d_workspace must be 16-byte aligned");
+    OE_CUDA(cudaSetDevice(fe->device));
+
+    // ---- pack metadata on the host, one stream-ordered copy to the workspace ----
+    std::vector<unsigned char> hm(M.meta_bytes, 0);
+    auto i64 = [&](size_t off) { return reinterpret_cast<int64_t*>(hm.data() + off); };
+    auto i32 = [&](size_t off) { return reinterpret_cast<int32_t*>(hm.data() + off); };
+    int64_t fp = 0, rp = 0;
+    int tp = 0;
+    for (int b = 0; b < B; ++b) {
+        const int nfr = frames[b];
+        const int nrows = bt->out_nrows ? bt->out_nrows[b] : nfr;
+        i64(M.wav_off)[b] = bt->wav_offsets[b];
+        i64(M.out_row)[b] = bt->out_rows[b];
+        i64(M.frame_prefix)[b] = fp;
+        i64(M.row_prefix)[b] = rp;
+        i64(M.map_off)[b] = bt->frame_map ? bt->frame_map_offsets[b] : 0;
+        i32(M.wav_len)[b] = bt->wav_lens[b];
+        i32(M.n_frames)[b] = nfr;
+        i32(M.n_rows)[b] = M.two_phase ? nfr : nrows;
+        i32(M.tile_prefix)[b] = tp;
+        fp += nfr;
+        rp += nrows;
+        tp += ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
+    }
+    i64(M.frame_prefix)[B] = fp;
+    i64(M.row_prefix)[B] = rp;
+    i32(M.tile_prefix)[B] = tp;
+    if (bt->n_tmask) memcpy(i32(M.tmask), bt->tmask, 8 * (size_t)B * bt->n_tmask);
+    if (bt->n_fmask) memcpy(i32(M.fmask), bt->fmask, 8 * (size_t)B * bt->n_fmask);
+    if (bt->frame_map) {
+        for (int b = 0; b < B; ++b)
+            for (int t = 0; t < frames[b]; ++t) {
+                const int32_t s = bt->frame_map[bt->frame_map_offsets[b] + t];
+                if (s < 0 || s >= frames[b]) return fail(OE_ERR_INVALID, "frame_map[%d][%d]=%d out of range", b, t, s);
+            }
+        memcpy(i32(M.fmap), bt->frame_map, 4 * (size_t)M.total_map);
+    }
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    OE_CUDA(cudaMemcpyAsync(ws, hm.data(), M.meta_bytes, cudaMemcpyHostToDevice, stream));
+
+    const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
+    oe::FbankParams P;
+    memset(&P, 0, sizeof(P));
+    P.wav = d_wav;
+    P.wav_off = reinterpret_cast<const int64_t*>(ws + M.wav_off);
+    P.wav_len = reinterpret_cast<const int32_t*>(ws + M.wav_len);
+    P.n_frames = reinterpret_cast<const int32_t*>(ws + M.n_frames);
+    P.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
+    P.tile_prefix = reinterpret_cast<const int32_t*>(ws + M.tile_prefix);
+    P.B = B;
+    P.total_tiles = M.total_tiles;
+    P.tab = fe->d_tab;
+    P.tile_stats = M.need_stats ? reinterpret_cast<float*>(ws + M.tile_stats) : nullptr;
+    if (M.two_phase) {
+        P.out = reinterpret_cast<float*>(ws + M.raw);
+        P.out_row = reinterpret_cast<const int64_t*>(ws + M.frame_prefix);
+        P.pitch = F;
+    } else {
+        P.out = d_out;
+        P.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        P.pitch = pitch;
+        P.tmask = reinterpret_cast<const int32_t*>(ws + M.tmask);
+        P.fmask = reinterpret_cast<const int32_t*>(ws + M.fmask);
+        P.n_tmask = bt->n_tmask;
+        P.n_fmask = bt->n_fmask;
+        P.cmvn_mean = bt->d_cmvn_mean;
+        P.cmvn_istd = bt->d_cmvn_istd;
+        P.cmvn_on_pad = bt->cmvn_on_padding;
+    }
+    if (M.feats) {
+        if (M.need_stats && M.total_tiles > 0) {
+            oe::FeatStatsParams S;
+            S.feats = reinterpret_cast<const float*>(d_wav);
+            S.row_off = P.wav_off;
+            S.n_frames = P.n_frames;
+            S.tile_prefix = P.tile_prefix;
+            S.tile_stats = P.tile_stats;
+            S.B = B;
+            S.F = F;
+            S.total_tiles = M.total_tiles;
+            oe::oe_feat_tile_stats_kernel<<<std::min(M.total_tiles, fe->sm_count * 8), oe::kMaxMel, 0, stream>>>(S);
+            OE_CUDA(cudaGetLastError());
+        }
+    } else if (M.total_tiles > 0) {
+        const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
+        if (bt->wav_dtype == OE_WAV_F32)
+            oe::oe_fbank_kernel<true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+        else
+            oe::oe_fbank_kernel<false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+        OE_CUDA(cudaGetLastError());
+    }
+    if (bt->norm_mode != OE_NORM_NONE) {
+        oe::UttStatsParams U;
+        U.tile_stats = P.tile_stats;
+        U.tile_prefix = P.tile_prefix;
+        U.n_frames = P.n_frames;
+        U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
+        U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
+        U.F = F;
+        oe::oe_utt_stats_kernel<<<B, oe::kMaxMel, 0, stream>>>(U);
+        OE_CUDA(cudaGetLastError());
+    }
+    if (bt->d_stats) {
+        oe::GlobalStatsParams G;
+        G.tile_stats = P.tile_stats;
+        G.tile_prefix = P.tile_prefix;
+        G.n_frames = P.n_frames;
+        G.stats = bt->d_stats;
+        G.B = B;
+        G.F = F;
+        oe::oe_global_stats_kernel<<<1, oe::kMaxMel + 32, 0, stream>>>(G);
+        OE_CUDA(cudaGetLastError());
+    }
+    if (M.two_phase && d_out && M.total_rows > 0) {
+        oe::FinalizeParams Z;
+        memset(&Z, 0, sizeof(Z));
+        Z.raw = M.feats ? reinterpret_cast<const float*>(d_wav) : reinterpret_cast<const float*>(ws + M.raw);
+        Z.frame_prefix = reinterpret_cast<const int64_t*>(ws + (M.feats ? M.wav_off : M.frame_prefix));
+        Z.row_prefix = reinterpret_cast<const int64_t*>(ws + M.row_prefix);
+        Z.n_frames = P.n_frames;
+        Z.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        Z.out = d_out;
+        Z.pitch = pitch;
+        if (bt->norm_mode != OE_NORM_NONE) {
+            Z.utt_mean = reinterpret_cast<const float*>(ws + M.utt_mean);
+            Z.utt_std = reinterpret_cast<const float*>(ws + M.utt_std);
+        }
+        if (bt->frame_map) {
+            Z.frame_map = reinterpret_cast<const int32_t*>(ws + M.fmap);
+            Z.map_off = reinterpret_cast<const int64_t*>(ws + M.map_off);
+        }
+        Z.tmask = reinterpret_cast<const int32_t*>(ws + M.tmask);
+        Z.fmask = reinterpret_cast<const int32_t*>(ws + M.fmask);
+        Z.n_tmask = bt->n_tmask;
+        Z.n_fmask = bt->n_fmask;
+        Z.cmvn_mean = bt->d_cmvn_mean;
+        Z.cmvn_istd = bt->d_cmvn_istd;
+        Z.cmvn_on_pad = bt->cmvn_on_padding;
+        Z.B = B;
+        Z.F = F;
+        Z.total_rows = M.total_rows;
+        const int64_t blocks = std::min<int64_t>((M.total_rows + 7) / 8, (int64_t)fe->sm_count * 8);
+        oe::oe_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(Z);
+        OE_CUDA(cudaGetLastError());
+    }
+    return OE_OK;
+}
+
+int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
+                  const float* d_istd, oe_stream stream) {
+    if (rows < 0 || dim <= 0) return fail(OE_ERR_INVALID, "bad shape");
+    if (rows == 0) return OE_OK;
+    if (!d_x || !d_y || !d_mean) return fail(OE_ERR_INVALID, "null pointer");
+    const int64_t n = rows * dim;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    oe::oe_cmvn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n, dim, d_mean, d_istd);
+    OE_CUDA(cudaGetLastError());
+    return OE_OK;
+}
+
+int64_t oe_resample_out_len(int64_t n, int32_t orig, int32_t neu) {
+    if (orig <= 0 || neu <= 0 || n < 0) return -1;
+    return (neu * n + orig - 1) / orig;          // ceil(new*n/orig), functional.py:1427
+}
+
+int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* kernel, int32_t taps, int32_t* table_id) {
+    if (!fe || !table_id) return fail(OE_ERR_INVALID, "null pointer");
+    if (orig <= 0 || neu <= 0) return fail(OE_ERR_INVALID, "rates must be positive");
+    for (size_t i = 0; i < fe->rs.size(); ++i)
+        if (fe->rs[i].orig == orig && fe->rs[i].neu == neu && !kernel) {
+            *table_id = (int)i;
+            return OE_OK;
+        }
+    if ((int)fe->rs.size() >= oe::kMaxRsTables) return fail(OE_ERR_UNSUPPORTED, "too many resampler tables");
+    // functional.py:1343-1398
+    const double lowpass = 6.0, rolloff = 0.99;
+    const double base = std::min(orig, neu) * rolloff;
+    const int width = (int)std::ceil(lowpass * orig / base);
+    const int ntaps = 2 * width + orig;
+    if (kernel && taps != ntaps) return fail(OE_ERR_INVALID, "taps must be 2*width+orig = %d", ntaps);
+    if (fe->rs_coefs.size() + (size_t)neu * ntaps > (size_t)oe::kMaxRsCoefs) return fail(OE_ERR_UNSUPPORTED, "resampler table too large");
+    oe::RsTable t;
+    t.orig = orig;
+    t.neu = neu;
+    t.taps = ntaps;
+    t.width = width;
+    t.coef_off = (int)fe->rs_coefs.size();
+    for (int p = 0; p < neu; ++p)
+        for (int q = 0; q < ntaps; ++q) {
+            float v;
+            if (kernel) {
+                v = kernel[(size_t)p * ntaps + q];
+            } else {
+                double tt = (-(double)p / neu + (double)(q - width) / orig) * base;
+                tt = std::max(-lowpass, std::min(lowpass, tt));
+                const double win = std::pow(std::cos(tt * oe::kPi / lowpass / 2.0), 2.0);
+                const double ang = tt * oe::kPi;
+                const double sinc = ang == 0.0 ? 1.0 : std::sin(ang) / ang;
+                v = (float)(sinc * win * (base / orig));
+            }
+            fe->rs_coefs.push_back(v);
+        }
+    fe->rs.push_back(t);
+    OE_CUDA(cudaSetDevice(fe->device));
+    OE_CUDA(cudaMemcpy(fe->d_rs, fe->rs.data(), sizeof(oe::RsTable) * fe->rs.size(), cudaMemcpyHostToDevice));
+    OE_CUDA(cudaMemcpy(fe->d_rs_coefs, fe->rs_coefs.data(), sizeof(float) * fe->rs_coefs.size(), cudaMemcpyHostToDevice));
+    *table_id = (int)fe->rs.size() - 1;
+    return OE_OK;
+}
+
+int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* bt, size_t* bytes) {
+    if (!fe || !bt || !bytes) return fail(OE_ERR_INVALID, "null pointer");
+    const size_t B = (size_t)std::max(bt->batch, 0);
+    *bytes = align_up(8 * B, 16) * 2 + align_up(4 * B, 16) * 3 + 256;
+    return OE_OK;
+}
+
+int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, float* d_out, void* d_ws,
+                size_t ws_bytes, oe_stream stream_) {
+    if (!fe || !bt) return fail(OE_ERR_INVALID, "null pointer");
+    const int B = bt->batch;
+    if (B < 0) return fail(OE_ERR_INVALID, "negative batch");
+    if (B == 0) return OE_OK;
+    if (!bt->in_offsets || !bt->in_lens || !bt->table_ids || !bt->out_offsets) return fail(OE_ERR_INVALID, "null metadata");
+    if (!d_in || !d_out) return fail(OE_ERR_INVALID, "null buffer");
+    size_t need;
+    oe_resample_workspace_bytes(fe, bt, &need);
+    if (!d_ws || ws_bytes < need) return fail(OE_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+    const size_t a8 = align_up(8 * (size_t)B, 16), a4 = align_up(4 * (size_t)B, 16);
+    std::vector<unsigned char> hm(2 * a8 + 3 * a4, 0);
+    int64_t* in_off = reinterpret_cast<int64_t*>(hm.data());
+    int64_t* out_off = reinterpret_cast<int64_t*>(hm.data() + a8);
+    int32_t* in_len = reinterpret_cast<int32_t*>(hm.data() + 2 * a8);
+    int32_t* tab = reinterpret_cast<int32_t*>(hm.data() + 2 * a8 + a4);
+    int32_t* out_len = reinterpret_cast<int32_t*>(hm.data() + 2 * a8 + 2 * a4);
+    int max_out = 0;
+    for (int b = 0; b < B; ++b) {
+        const int id = bt->table_ids[b];
+        if (id >= (int)fe->rs.size()) return fail(OE_ERR_INVALID, "table_ids[%d]=%d is not registered", b, id);
+        if (bt->in_lens[b] < 0) return fail(OE_ERR_INVALID, "negative length");
+        in_off[b] = bt->in_offsets[b];
+        out_off[b] = bt->out_offsets[b];
+        in_len[b] = bt->in_lens[b];
+        tab[b] = id;
+        out_len[b] = id < 0 ? bt->in_lens[b] : (int32_t)oe_resample_out_len(bt->in_lens[b], fe->rs[id].orig, fe->rs[id].neu);
+        if (bt->out_lens) bt->out_lens[b] = out_len[b];
+        max_out = std::max(max_out, out_len[b]);
+    }
+    if (max_out == 0) return OE_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    OE_CUDA(cudaSetDevice(fe->device));
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    OE_CUDA(cudaMemcpyAsync(ws, hm.data(), hm.size(), cudaMemcpyHostToDevice, stream));
+    oe::ResampleParams P;
+    P.in = d_in;
+    P.out = d_out;
+    P.in_off = reinterpret_cast<const int64_t*>(ws);
+    P.out_off = reinterpret_cast<const int64_t*>(ws + a8);
+    P.in_len = reinterpret_cast<const int32_t*>(ws + 2 * a8);
+    P.table_id = reinterpret_cast<const int32_t*>(ws + 2 * a8 + a4);
+    P.out_len = reinterpret_cast<const int32_t*>(ws + 2 * a8 + 2 * a4);
+    P.tables = fe->d_rs;
+    P.coefs = fe->d_rs_coefs;
+    dim3 grid((unsigned)std::min((max_out + 1023) / 1024, 1024), (unsigned)B);
+    if (bt->wav_dtype == OE_WAV_F32)
+        oe::oe_resample_kernel<true><<<grid, 256, 0, stream>>>(P);
+    else
+        oe::oe_resample_kernel<false><<<grid, 256, 0, stream>>>(P);
+    OE_CUDA(cudaGetLastError());
+    return OE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+"""Host-side driver of the CUDA front-end: owns the handle, packs ragged batches, launches.
+
+PyTorch is used here only for device memory, streams and pinned staging; all numeric work
+happens in ``csrc/oe_frontend.cu`` through the C ABI (``include/openeat_frontend.h``).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (OE_FEATS_F32, OE_NORM_NONE, OE_NORM_PER_UTT, OE_WAV_F32, OE_WAV_I16, FrontendError,
+                   OeBatch, OeConfig, OeResampleBatch, c_f32p, c_i32p, c_i64p, check)
+
+ALIGN = 8  # samples; the kernels read 16-byte vectors (include/openeat_frontend.h: wav_offsets)
+
+
+def torch_povey_window(n=400):
+    """kaldi.py:98-100 with torch's own fp32 ops -> bit-identical to torchaudio's table."""
+    return torch.hann_window(n, periodic=False, dtype=torch.float32).pow(0.85)
+
+
+def torch_mel_banks(num_bins=80, padded=512, sample_freq=16000.0, low_freq=20.0, high_freq=0.0):
+    """kaldi.py:436-511 (vtln_warp_factor == 1.0) with torch's own fp32 ops."""
+    num_fft_bins = padded / 2
+    nyquist = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyquist
+    fft_bin_width = sample_freq / padded
+    mel_low = 1127.0 * math.log(1.0 + low_freq / 700.0)
+    mel_high = 1127.0 * math.log(1.0 + high_freq / 700.0)
+    delta = (mel_high - mel_low) / (num_bins + 1)
+    b = torch.arange(num_bins).unsqueeze(1)
+    left = mel_low + b * delta
+    center = mel_low + (b + 1.0) * delta
+    right = mel_low + (b + 2.0) * delta
+    mel = (1127.0 * (1.0 + (fft_bin_width * torch.arange(num_fft_bins)) / 700.0).log()).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    return torch.max(torch.zeros(1), torch.min(up, down))
+
+
+def torch_sinc_kernel(orig, new, lowpass_filter_width=6, rolloff=0.99):
+    """torchaudio functional.py:1343-1398 (sinc_interp_hann) on an fp32 grid, as the reference's
+    substitute speed oracle evaluates it for fp32 waveforms.  Returns (kernel[new, taps], width)."""
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float32)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float32)[:, None, None] / new + idx
+    t *= base
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    return kernels[:, 0, :].contiguous(), width
+
+
+def speed_ratio(speed, sample_rate=16000):
+    """torchaudio functional.py:2408-2413: 0.9 -> (9, 10), 1.1 -> (11, 10)."""
+    src, dst = int(speed * sample_rate), int(sample_rate)
+    g = math.gcd(src, dst)
+    return src // g, dst // g
+
+
+def aligned_offsets(lens, align=ALIGN):
+    """Packed sample offsets with every utterance starting on an `align`-sample boundary."""
+    lens = np.asarray(lens, dtype=np.int64)
+    padded = (lens + align - 1) // align * align
+    offs = np.zeros(len(lens), dtype=np.int64)
+    if len(lens) > 1:
+        offs[1:] = np.cumsum(padded[:-1])
+    total = int(padded.sum())
+    return offs, total
+
+
+def pack_waveforms(waves, dtype=np.int16, pinned=True):
+    """list of 1-D arrays -> (pinned packed host tensor, offsets, lens)."""
+    lens = np.array([len(w) for w in waves], dtype=np.int32)
+    offs, total = aligned_offsets(lens)
+    tdt = torch.int16 if dtype == np.int16 else torch.float32
+    buf = torch.zeros(max(total, ALIGN), dtype=tdt)
+    if pinned and torch.cuda.is_available():
+        buf = buf.pin_memory()
+    view = buf.numpy()
+    for w, o in zip(waves, offs):
+        view[o:o + len(w)] = w
+    return buf, offs, lens
+
+
+def _ptr(arr, ptype):
+    return arr.ctypes.data_as(ptype) if arr is not None else None
+
+
+class Frontend(object):
+    """One CUDA front-end handle (tables + resampler taps) on one device."""
+
+    def __init__(self, mel_bins=80, sample_rate=16000, device=None, torch_tables=True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise FrontendError('openeat_b200 needs a CUDA device: the front-end has no CPU path')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        cfg = OeConfig()
+        check(self.lib.oe_config_default(ctypes.byref(cfg)))
+        cfg.sample_rate = int(sample_rate)
+        cfg.frame_length = int(sample_rate * 25.0 * 0.001)     # kaldi.py:138-140
+        cfg.frame_shift = int(sample_rate * 10.0 * 0.001)
+        cfg.fft_size = 1 if cfg.frame_length == 0 else 2 ** (cfg.frame_length - 1).bit_length()
+        cfg.num_mel_bins = int(mel_bins)
+        self.cfg = cfg
+        self.mel_bins = int(mel_bins)
+        self.sample_rate = int(sample_rate)
+        win = mel = None
+        if torch_tables:
+            win = np.ascontiguousarray(torch_povey_window(cfg.frame_length).numpy())
+            mel = np.ascontiguousarray(torch_mel_banks(mel_bins, cfg.fft_size, float(sample_rate)).numpy())
+        handle = ctypes.c_void_p()
+        check(self.lib.oe_frontend_create(ctypes.byref(cfg), _ptr(win, c_f32p), _ptr(mel, c_f32p),
+                                          self.device.index, ctypes.byref(handle)))
+        self.handle = handle
+        self.torch_tables = torch_tables
+        self._resamplers = {}
+        self._ws = {}
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.oe_frontend_destroy(h)
+            self.handle = None
+
+    # ------------------------------------------------------------------ helpers
+    def tables(self):
+        win = np.zeros(self.cfg.frame_length, np.float32)
+        mel = np.zeros((self.mel_bins, self.cfg.fft_size // 2), np.float32)
+        check(self.lib.oe_frontend_get_tables(self.handle, _ptr(win, c_f32p), _ptr(mel, c_f32p)))
+        return win, mel
+
+    def num_frames(self, n):
+        return int(self.lib.oe_num_frames(self.handle, int(n)))
+
+    def _stream(self, stream):
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        return s, ctypes.c_void_p(s.cuda_stream)
+
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ speed perturb
+    def resampler_id(self, orig, new):
+        key = (int(orig), int(new))
+        if key not in self._resamplers:
+            tid = ctypes.c_int32(-1)
+            if self.torch_tables:
+                k, _ = torch_sinc_kernel(*key)
+                k = np.ascontiguousarray(k.numpy())
+                check(self.lib.oe_add_resampler(self.handle, key[0], key[1], _ptr(k, c_f32p), k.shape[1],
+                                                ctypes.byref(tid)))
+            else:
+                check(self.lib.oe_add_resampler(self.handle, key[0], key[1], None, 0, ctypes.byref(tid)))
+            self._resamplers[key] = tid.value
+        return self._resamplers[key]
+
+    def resample_out_len(self, n, orig, new):
+        return int(self.lib.oe_resample_out_len(int(n), int(orig), int(new)))
+
+    def resample(self, wav, offsets, lens, ratios, out=None, out_offsets=None, stream=None):
+        """Ragged polyphase resampling.  ``ratios[b]`` is (orig, new) or None (plain copy to fp32).
+        Returns (fp32 device tensor, out_offsets, out_lens)."""
+        B = len(lens)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        ids = np.array([-1 if r is None else self.resampler_id(*r) for r in ratios], dtype=np.int32)
+        olens = np.array([n if r is None else self.resample_out_len(n, *r) for n, r in zip(lens, ratios)],
+                         dtype=np.int32)
+        if out_offsets is None:
+            out_offsets, total = aligned_offsets(olens)
+        else:
+            out_offsets = np.ascontiguousarray(out_offsets, dtype=np.int64)
+            total = int((out_offsets + olens).max()) if B else 0
+        if out is None:
+            out = torch.zeros(max(total, ALIGN), dtype=torch.float32, device=self.device)
+        rb = OeResampleBatch(B, OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16, _ptr(offsets, c_i64p),
+                             _ptr(lens, c_i32p), _ptr(ids, c_i32p), _ptr(out_offsets, c_i64p), None)
+        need = ctypes.c_size_t()
+        check(self.lib.oe_resample_workspace_bytes(self.handle, ctypes.byref(rb), ctypes.byref(need)))
+        s, sp = self._stream(stream)
+        ws = self._workspace(('rs', s.cuda_stream), need.value)
+        check(self.lib.oe_resample(self.handle, ctypes.byref(rb), ctypes.c_void_p(wav.data_ptr()),
+                                   ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
+                                   ws.numel(), sp))
+        return out, out_offsets, olens
+
+    # ------------------------------------------------------------------ fbank (+ fused chain)
+    def fbank(self, wav, offsets, lens, *, layout='padded', out=None, max_rows=None, out_rows=None,
+              normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
+              cmvn_on_padding=False, stats=None, stream=None, features_in=False, want_out=True):
+        """Runs one ragged batch.
+
+        wav       packed device tensor: int16 PCM, fp32 on the int16 scale, or (features_in) a
+                  (rows, mel_bins) fp32 feature matrix.
+        offsets   [B] sample (row) offsets, lens [B] samples (rows).
+        layout    'padded' -> (B, Tmax, F) zero padded like pad_sequence (dataset.py:217-218);
+                  'ragged' -> (sum T_b, F).
+        tmask / fmask   int32 [B, n, 2] half-open ranges (spec_aug plan) or None.
+        frame_maps      list of int32 index maps (spec_sub plan) or None.
+        cmvn      (mean, istd) fp32 device tensors, istd may be None (norm_var=False).
+        stats     float64 device tensor [2F+1] accumulating sum / sumsq / count of raw frames.
+        Returns (out tensor or None, frames int32 ndarray).
+        """
+        B = len(lens)
+        F = self.mel_bins
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        if features_in:
+            dtype = OE_FEATS_F32
+            frames = lens.copy()
+        else:
+            dtype = OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16
+            if wav.dtype not in (torch.float32, torch.int16):
+                raise FrontendError('waveform must be int16 or float32, got %s' % wav.dtype)
+            frames = np.array([self.num_frames(n) for n in lens], dtype=np.int32)
+        nrows = None
+        if not want_out:
+            out = None
+            out_rows = np.zeros(B, dtype=np.int64)
+        elif layout == 'padded':
+            tmax = int(frames.max()) if B else 0
+            if max_rows is not None:
+                tmax = max(tmax, int(max_rows))
+            if out is None:
+                out = torch.empty((B, tmax, F), dtype=torch.float32, device=self.device)
+            else:
+                tmax = out.shape[1]
+            out_rows = np.arange(B, dtype=np.int64) * tmax
+            nrows = np.full(B, tmax, dtype=np.int32)
+        elif layout == 'ragged':
+            if out_rows is None:
+                out_rows = np.zeros(B, dtype=np.int64)
+                if B > 1:
+                    out_rows[1:] = np.cumsum(frames[:-1].astype(np.int64))
+            else:
+                out_rows = np.ascontiguousarray(out_rows, dtype=np.int64)
+            if out is None:
+                out = torch.empty((int(frames.sum()), F), dtype=torch.float32, device=self.device)
+        else:
+            raise ValueError(layout)
+        tm = fm = None
+        n_t = n_f = 0
+        if tmask is not None and np.size(tmask):
+            tm = np.ascontiguousarray(tmask, dtype=np.int32).reshape(B, -1, 2)
+            n_t = tm.shape[1]
+        if fmask is not None and np.size(fmask):
+            fm = np.ascontiguousarray(fmask, dtype=np.int32).reshape(B, -1, 2)
+            n_f = fm.shape[1]
+        fmap = fmap_off = None
+        if frame_maps is not None:
+            fmap_off = np.zeros(B, dtype=np.int64)
+            if B > 1:
+                fmap_off[1:] = np.cumsum(frames[:-1].astype(np.int64))
+            fmap = np.concatenate([np.asarray(m, dtype=np.int32) for m in frame_maps]) if B else np.zeros(0, np.int32)
+            fmap = np.ascontiguousarray(fmap, dtype=np.int32)
+            if fmap.shape[0] != int(frames.sum()):
+                raise FrontendError('frame_maps must have one entry per frame')
+        mean_p = istd_p = None
+        if cmvn is not None:
+            mean, istd = cmvn
+            mean_p = ctypes.c_void_p(mean.data_ptr())
+            istd_p = ctypes.c_void_p(istd.data_ptr()) if istd is not None else None
+        out_frames = np.zeros(B, dtype=np.int32)
+        bt = OeBatch(B, dtype, _ptr(offsets, c_i64p), _ptr(lens, c_i32p), _ptr(out_rows, c_i64p),
+                     _ptr(nrows, c_i32p), 0, OE_NORM_PER_UTT if normalization else OE_NORM_NONE, n_t, n_f,
+                     _ptr(tm, c_i32p), _ptr(fm, c_i32p), _ptr(fmap, c_i32p), _ptr(fmap_off, c_i64p),
+                     mean_p, istd_p, 1 if cmvn_on_padding else 0,
+                     ctypes.c_void_p(stats.data_ptr()) if stats is not None else None,
+                     _ptr(out_frames, c_i32p))
+        need = ctypes.c_size_t()
+        check(self.lib.oe_fbank_workspace_bytes(self.handle, ctypes.byref(bt), ctypes.byref(need)))
+        s, sp = self._stream(stream)
+        ws = self._workspace(('fb', s.cuda_stream), need.value)
+        check(self.lib.oe_fbank_batch(self.handle, ctypes.byref(bt), ctypes.c_void_p(wav.data_ptr()),
+                                      ctypes.c_void_p(out.data_ptr()) if out is not None else None,
+                                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
+        return out, out_frames
+
+    def cmvn_apply(self, x, mean, istd=None, out=None, stream=None):
+        """GlobalCMVN.forward on a contiguous fp32 device tensor (..., F)."""
+        x = x.contiguous()
+        if out is None:
+            out = torch.empty_like(x)
+        _, sp = self._stream(stream)
+        check(self.lib.oe_cmvn_apply(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                     x.numel() // x.shape[-1], x.shape[-1], ctypes.c_void_p(mean.data_ptr()),
+                                     ctypes.c_void_p(istd.data_ptr()) if istd is not None else None, sp))
+        return out
+
+
+_default = {}
+
+
+def default_frontend(mel_bins=80, sample_rate=16000, device=None):
+    """Process-wide cache of handles keyed by (mel_bins, sample_rate, device)."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    key = (int(mel_bins), int(sample_rate), dev)
+    if key not in _default:
+        _default[key] = Frontend(mel_bins, sample_rate, torch.device('cuda', dev))
+    return _default[key]

@@ -1,0 +1,245 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star):
+  log-mel  max-abs <= 1e-3 vs the fp32 oracle/golden on noise- and speech-like signals, and
+           <= max(1e-3, fp32-vs-fp64 oracle gap) vs the fp64 golden on tonal signals;
+  masks / substitution indices / padding: bit-exact; run-to-run: bit-identical.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import augment as A      # noqa: E402
+from oracle import cmvn as C         # noqa: E402
+from oracle import fbank as F        # noqa: E402
+from oracle import signals           # noqa: E402
+
+CASES = ['fbank_white_400', 'fbank_white_559', 'fbank_white_560', 'fbank_white_8000', 'fbank_white_80000',
+         'fbank_white_560000', 'fbank_speech_8000', 'fbank_speech_80000', 'fbank_lsb_8000', 'fbank_zero_8000',
+         'fbank_dcsine_8000', 'fbank_square_8000']
+
+
+@pytest.fixture(scope='module')
+def fe():
+    from openeat_b200.frontend import Frontend
+    return Frontend(mel_bins=80, sample_rate=16000)
+
+
+def run_raw(fe, waves, dtype=np.int16, **kw):
+    from openeat_b200.frontend import pack_waveforms
+    buf, offs, lens = pack_waveforms([np.asarray(w, dtype=dtype) for w in waves], dtype=dtype)
+    out, frames = fe.fbank(buf.cuda(), offs, lens, **kw)
+    torch.cuda.synchronize()
+    return (out.cpu().numpy() if out is not None else None), frames
+
+
+def test_tables_are_torchaudios(fe, tables):
+    win, mel = fe.tables()
+    assert np.array_equal(win, tables[0]) and np.array_equal(mel, tables[1])
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('dtype', [np.int16, np.float32])
+def test_fbank_matches_golden(fe, name, dtype, golden_dir, manifest):
+    meta = manifest[name]
+    x = signals.make(meta['kind'], meta['samples'], meta['seed'])
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    stride = int(g['stride'])
+    y, frames = run_raw(fe, [x], dtype=dtype, layout='ragged')
+    assert frames.tolist() == [meta['frames']] and y.shape == (meta['frames'], 80)
+    assert np.isfinite(y).all()
+    tol = max(1e-3, meta['gap32_64'])
+    assert np.abs(y[::stride] - g['y64']).max() <= tol, 'vs fp64 torchaudio'
+    if meta['kind'] in ('white', 'speech', 'lsb', 'zero', 'square'):
+        assert np.abs(y[::stride] - g['y32']).max() <= 1e-3, 'vs fp32 torchaudio'
+    np.testing.assert_allclose(y.astype(np.float64).sum(0), g['colsum64'], rtol=0, atol=2e-4 * meta['frames'])
+
+
+def test_zero_signal_is_exactly_log_eps(fe):
+    y, _ = run_raw(fe, [np.zeros(8000, np.int16)], layout='ragged')
+    assert np.abs(y - np.log(F.EPS_F32)).max() < 2e-6
+
+
+def test_ragged_batch_padded_layout_and_drop(fe, tables):
+    """Mixed lengths in one launch, incl. < 400 samples (0 frames: the reference drops it),
+    exactly one frame, tile-boundary lengths; padding must be exactly 0."""
+    lens = [399, 400, 559, 560, 160 * 31 + 400, 160 * 32 + 400, 160 * 33 + 399, 12345, 0, 80000]
+    waves = [signals.make('speech' if i % 2 else 'white', n, 100 + i) for i, n in enumerate(lens)]
+    y, frames = run_raw(fe, waves, layout='padded')
+    exp = [F.num_frames(n) for n in lens]
+    assert frames.tolist() == exp
+    assert y.shape == (len(lens), max(exp), 80)
+    for i, w in enumerate(waves):
+        if exp[i]:
+            ref = F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1])
+            assert np.abs(y[i, :exp[i]] - ref).max() <= 1e-3
+        assert np.all(y[i, exp[i]:] == 0.0)
+
+
+def test_run_to_run_bitwise_stable(fe):
+    waves = [signals.make('speech', n, 7 + i) for i, n in enumerate([30000, 5000, 77777])]
+    a, _ = run_raw(fe, waves, layout='padded', normalization=True)
+    for _ in range(3):
+        b, _ = run_raw(fe, waves, layout='padded', normalization=True)
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_frames_independent_streaming_windows(fe):
+    """BASELINE config 5: a stream cut into 16-frame windows (2800 samples, 240 overlap)
+    gives exactly the whole-stream features."""
+    x = signals.make('speech', 160 * 16 * 40 + 240, 5)
+    whole, fr = run_raw(fe, [x], layout='ragged')
+    wins = [x[2560 * i: 2560 * i + 2800] for i in range(40)]
+    parts, frames = run_raw(fe, wins, layout='ragged')
+    assert frames.tolist() == [16] * 40 and fr[0] == 640
+    assert np.array_equal(parts, whole)
+
+
+def _plans(frames, seed, n_t=3, n_f=2, max_t=50, max_f=10, sub=False):
+    random.seed(seed)
+    subs = [A.plan_spec_substitute(int(t), max_t=30, num_t_sub=3) for t in frames] if sub else None
+    plans = [A.plan_spec_augmentation(int(t), 80, n_t, n_f, max_t, max_f) for t in frames]
+    tm = np.array([p[0] for p in plans], dtype=np.int32)
+    fm = np.array([p[1] for p in plans], dtype=np.int32)
+    return subs, plans, tm, fm
+
+
+def test_fused_specaug_cmvn_single_pass(fe, tables, golden_dir):
+    lens = [16000, 9000, 5200, 12345]
+    waves = [signals.make('speech', n, 200 + i) for i, n in enumerate(lens)]
+    frames = [F.num_frames(n) for n in lens]
+    _, plans, tm, fm = _plans(frames, 11)
+    mean, istd = C.load_cmvn(os.path.join(golden_dir, 'cmvn_stats.json'), True)
+    mean_d = torch.from_numpy(mean).float().cuda()
+    istd_d = torch.from_numpy(istd).float().cuda()
+    for on_pad in (False, True):
+        y, _ = run_raw(fe, waves, layout='padded', tmask=tm, fmask=fm, cmvn=(mean_d, istd_d),
+                       cmvn_on_padding=on_pad)
+        for i, w in enumerate(waves):
+            raw = F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1])
+            aug = A.apply_spec_augmentation(raw, *plans[i])
+            ref = C.global_cmvn(aug, mean, istd)
+            got = y[i, :frames[i]]
+            masked = aug == 0
+            assert np.array_equal(got[masked], ref[masked])            # masked cells: exactly (0-mean)*istd
+            assert np.abs(got - ref).max() <= 1e-3 * float(istd.max())
+            pad = y[i, frames[i]:]
+            if on_pad:
+                assert np.array_equal(pad, np.broadcast_to(C.global_cmvn(np.zeros(80), mean, istd), pad.shape))
+            else:
+                assert np.all(pad == 0)
+
+
+@pytest.mark.parametrize('sub', [False, True])
+def test_two_phase_norm_sub_aug(fe, tables, sub):
+    lens = [16000, 9000, 5200, 12345, 700, 48000]
+    waves = [signals.make('speech' if i % 2 else 'white', n, 300 + i) for i, n in enumerate(lens)]
+    frames = [F.num_frames(n) for n in lens]
+    subs, plans, tm, fm = _plans(frames, 12, sub=sub)
+    maps = [A.substitute_index_map(t, s) for t, s in zip(frames, subs)] if sub else None
+    y, _ = run_raw(fe, waves, layout='padded', normalization=True, tmask=tm, fmask=fm, frame_maps=maps)
+    for i, w in enumerate(waves):
+        raw = F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1])
+        ref = A.normalization(raw)
+        if sub:
+            ref = A.apply_spec_substitute(ref, subs[i])
+        ref = A.apply_spec_augmentation(ref, *plans[i])
+        got = y[i, :frames[i]]
+        assert np.array_equal(got == 0, ref == 0)                      # masks bit-exact
+        assert np.abs(got - ref).max() <= 2e-3                         # 1e-3 log-mel / std(~0.5+)
+        assert np.all(y[i, frames[i]:] == 0)
+
+
+def test_normalization_zero_variance_is_nan_like_reference(fe):
+    y, _ = run_raw(fe, [np.zeros(4000, np.int16)], layout='padded', normalization=True)
+    assert np.isnan(y).all()                                           # feature_processor.py:8 has no epsilon
+
+
+def test_cmvn_stats_accumulate(fe, tables):
+    lens = [16000, 9000, 300, 5200, 80000]
+    waves = [signals.make('speech', n, 400 + i) for i, n in enumerate(lens)]
+    stats = torch.zeros(161, dtype=torch.float64, device='cuda')
+    _, frames = run_raw(fe, waves[:2], layout='ragged', stats=stats, want_out=False)
+    y, frames2 = run_raw(fe, waves[2:], layout='ragged', stats=stats)
+    feats = [F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1]) for w in waves if len(w) >= 400]
+    s, q, n = C.compute_cmvn_stats(feats)
+    got = stats.cpu().numpy()
+    assert got[160] == n
+    np.testing.assert_allclose(got[:80], s, rtol=1e-4)                 # north_star: 1e-4 relative
+    np.testing.assert_allclose(got[80:160], q, rtol=1e-4)
+    # and against the device features themselves (tight): the reduction adds no error of its own
+    s2, q2, _ = C.compute_cmvn_stats([y])
+    rest = C.compute_cmvn_stats(feats[:2])
+    np.testing.assert_allclose(got[:80] - rest[0], s2, rtol=1e-5)
+
+
+def test_features_in_mode_matches_reference_processors(fe, golden_dir):
+    """The numpy-level reference processors through the device finalize path (features in)."""
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    xs = [g['x0'], g['x1'], g['x2']]
+    rows = np.array([x.shape[0] for x in xs], dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(rows[:-1])]).astype(np.int64)
+    feats = torch.from_numpy(np.concatenate(xs)).cuda()
+    plans, maps = [], []
+    for i, x in enumerate(xs):
+        random.seed(3000 + i)
+        subs = A.plan_spec_substitute(x.shape[0], max_t=30, num_t_sub=3)
+        maps.append(A.substitute_index_map(x.shape[0], subs))
+        plans.append(A.plan_spec_augmentation(x.shape[0], 80, 3, 2, 50, 10))
+    tm = np.array([p[0] for p in plans], dtype=np.int32)
+    fm = np.array([p[1] for p in plans], dtype=np.int32)
+    out, _ = fe.fbank(feats, offs, rows, layout='padded', features_in=True, tmask=tm, fmask=fm, frame_maps=maps)
+    out = out.cpu().numpy()
+    for i, x in enumerate(xs):
+        assert np.array_equal(out[i, :rows[i]], g['subaug%d' % i])     # bit-exact vs the reference's own output
+    out, _ = fe.fbank(feats, offs, rows, layout='padded', features_in=True, normalization=True)
+    out = out.cpu().numpy()
+    for i, x in enumerate(xs):
+        assert np.abs(out[i, :rows[i]] - g['norm%d' % i]).max() < 1e-5
+
+
+def test_speed_perturb_resampler(fe, golden_dir):
+    from openeat_b200.frontend import pack_waveforms
+    g = np.load(os.path.join(golden_dir, 'speed.npz'))
+    x = g['x']
+    buf, offs, lens = pack_waveforms([x, x, x, x.astype(np.int16)[:3000]], dtype=np.float32)
+    out, ooffs, olens = fe.resample(buf.cuda(), offs, lens, [(9, 10), (11, 10), None, (9, 10)])
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    assert olens.tolist() == [8889, 7273, 8000, 3334]
+    y090 = out[ooffs[0]:ooffs[0] + olens[0]]
+    y110 = out[ooffs[1]:ooffs[1] + olens[1]]
+    assert np.abs(y090 - g['y090']).max() < 0.05                        # int16 scale: stated resampler tolerance
+    assert np.abs(y110 - g['y110']).max() < 0.05
+    assert np.array_equal(out[ooffs[2]:ooffs[2] + 8000], x)
+    # int16 input path + fbank of the perturbed audio vs torchaudio speed -> fbank
+    buf16, o16, l16 = pack_waveforms([x.astype(np.int16)], dtype=np.int16)
+    r, ro, rl = fe.resample(buf16.cuda(), o16, l16, [(9, 10)])
+    y, frames = fe.fbank(r, ro, rl, layout='ragged')
+    assert np.abs(y.cpu().numpy() - g['fb090']).max() < 2e-3
+
+
+def test_global_cmvn_apply(fe, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'cmvn.npz'))
+    mean = torch.from_numpy(g['mean_json']).float().cuda()
+    istd = torch.from_numpy(g['istd_json']).float().cuda()
+    x = torch.from_numpy(g['x']).cuda()
+    assert np.array_equal(fe.cmvn_apply(x, mean, istd).cpu().numpy(), g['y'])
+    assert np.array_equal(fe.cmvn_apply(x, mean, None).cpu().numpy(), g['y_novar'])
+
+
+def test_errors_are_reported_not_fatal(fe):
+    from openeat_b200 import FrontendError
+    buf = torch.zeros(1000, dtype=torch.int16, device='cuda')
+    with pytest.raises(FrontendError):
+        fe.fbank(buf, np.array([3]), np.array([500]))                   # misaligned offset
+    with pytest.raises(FrontendError):
+        fe.fbank(buf.double(), np.array([0]), np.array([500]))          # unsupported dtype
+    from openeat_b200.frontend import Frontend
+    with pytest.raises(FrontendError):
+        Frontend(mel_bins=80, sample_rate=8000)                         # unsupported framing says so
