@@ -1,0 +1,488 @@
+// oe_fbank_kernel: ragged-batch Kaldi fbank for sm_100a (included by oe_frontend.cu).
+//
+// One CTA (256 threads) per 32-frame tile, persistent grid, 2 CTAs / SM.  Per tile:
+//   (1) wait for the tile's raw samples (cp.async prefetch issued during the previous tile)
+//   (2) convert int16/fp32 -> fp32, fold pre-emphasis (kaldi.py:193-198) into the staged signal,
+//       8-sample block sums for the per-frame DC removal (kaldi.py:183-186)
+//   (3) stage A  16 threads x 2 frames: mean (half-warp shuffles), window, 16-point DIF FFT in registers,
+//       twiddle, half-warp exchange through shared memory
+//   (4) stage B  two 16-point FFTs per lane, real-FFT untangle, |X|^2 -> power tile [256 bins][32 frames]
+//   (5) sparse mel + log (kaldi.py:621-633): warp = bin group, lane = frame -> output tile
+//   (6) [per-tile column statistics]  [mask -> CMVN]  coalesced row stores
+// See DESIGN.md for the data layout and the per-phase instruction budget.
+#pragma once
+
+namespace oe {
+
+struct FbankParams {
+    const void* wav;
+    const int64_t* wav_off;
+    const int32_t* wav_len;
+    const int32_t* n_frames;
+    const int32_t* n_rows;
+    const int2* tiles;              // [total_tiles] (utterance, first frame), built on the host
+    const int64_t* out_row;
+    float* out;
+    int64_t pitch;
+    int total_tiles;
+    const int32_t* tmask;
+    const int32_t* fmask;
+    int n_tmask;
+    int n_fmask;
+    const float* cmvn_mean;
+    const float* cmvn_istd;
+    int cmvn_on_pad;
+    float* tile_stats;              // [total_tiles][3][2][F]: per row-group column sum and sum of squared deviations
+    const DevTables* tab;
+    float mel_w[512];               // standard-structure fast path: weights (x 1/4) in mel80::kOff order;
+                                    // lives in the kernel-parameter constant bank -> FFMA constant operands
+};
+
+// rows of a 32-frame tile covered by statistics row-group rg (0..2): [11 rg, min(nvalid, 11 rg + 11))
+__host__ __device__ __forceinline__ int stats_rows(int nvalid, int rg) {
+    const int lo = 11 * rg, hi = nvalid < lo + 11 ? nvalid : lo + 11;
+    return hi > lo ? hi - lo : 0;
+}
+
+__device__ __forceinline__ int find_utt(const int32_t* __restrict__ prefix, int B, int tile) {
+    int lo = 0, hi = B;                       // prefix[lo] <= tile < prefix[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory map (bytes)
+constexpr int kSmP = 0;                                    // float p[5376]      | out tile (32 x (F+1))
+constexpr int kSmS8 = kSmP + 5376 * 4;                     // float s8[672]
+constexpr int kSmE = kSmS8 + kChunks * 4;                  // float2 E[16][2][16][18] | float P[256][36] + raw prefetch
+constexpr int kSmRaw = kSmE + kBins * kRowP * 4;           // next tile's raw samples: 673 chunks of 8 (i16: 16 B, f32: 32 B)
+constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
+constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
+constexpr int kSmMask = kSmTwU + 9 * kRowE * 8;            // uchar rowmask[32], colmask[128]
+constexpr int kSmStd = kSmMask + 32 + kMaxMel;             // end of the standard-mel layout
+constexpr int kSmMelIdx = kSmStd;                          // generic mel only: int start/len/off [3][128], group_begin[9] (+pad)
+constexpr int kSmMelW = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // generic mel only: float mel_w[nnz]
+static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0, "align");
+static_assert(kSmRaw + 673 * 32 <= kSmTwA, "raw prefetch buffer must fit behind the power tile");
+static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Asynchronously stages the raw samples [s_base - 8, s_base + 5376) of one utterance into shared memory,
+// zero-filling everything outside [0, wlen) (cp.async src-size form), so the waveform's HBM latency
+// overlaps the previous tile's FFT.  Chunk j of the buffer holds samples s_base - 8 + 8 j.
+template <bool kF32>
+__device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, int64_t woff, int wlen,
+                                              int s_base, int tid) {
+    if (kF32) {
+        const float* w = reinterpret_cast<const float*>(wav) + woff;
+        for (int q = tid; q < 673 * 2; q += kThreads) {
+            const int s = s_base - 8 + 4 * q;
+            int valid = wlen - s;
+            valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+            if (s < 0) valid = 0;
+            cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 4 * valid);
+        }
+    } else {
+        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + woff;
+        for (int q = tid; q < 673; q += kThreads) {
+            const int s = s_base - 8 + 8 * q;
+            int valid = wlen - s;
+            valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
+            if (s < 0) valid = 0;
+            cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 2 * valid);
+        }
+    }
+    cp_async_commit();
+}
+
+// ln(x) for x >= the log floor (a normal number): lg2.approx.ftz (max abs error 2^-22.6 on the mantissa's
+// log2, i.e. ~1.2e-7 absolute on ln) without the denormal guard __logf carries.
+__device__ __forceinline__ float fast_ln(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.693147180559945309f;
+}
+
+// Standard-structure mel projection of one warp's bin group: every index is a compile-time constant,
+// the weights are kernel-parameter constants, repeated power-spectrum loads are CSE'd by the compiler.
+template <int G>
+__device__ __forceinline__ void mel_group_std(const float* __restrict__ pcol, const FbankParams& P,
+                                              float* __restrict__ orow, float log_floor) {
+    constexpr int b0 = mel80::kGroup[G], b1 = mel80::kGroup[G + 1];
+    float acc[b1 - b0];
+    static_for<b0, b1>([&](auto bb) {
+        constexpr int b = decltype(bb)::value;
+        constexpr int k0 = mel80::kStart[b], off = mel80::kOff[b];
+        float a = 0.f;
+        static_for<0, mel80::kLen[b]>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            a = fmaf(P.mel_w[off + i], pcol[(k0 + i) * kRowP], a);
+        });
+        acc[b - b0] = a;
+    });
+    static_for<b0, b1>([&](auto bb) {
+        constexpr int b = decltype(bb)::value;
+        orow[b] = fast_ln(fmaxf(acc[b - b0], log_floor));
+    });
+}
+
+template <bool kF32, bool kStdMel>
+__global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* const sp = reinterpret_cast<float*>(smem + kSmP);
+    float* const s8 = reinterpret_cast<float*>(smem + kSmS8);
+    float2* const sE = reinterpret_cast<float2*>(smem + kSmE);
+    float* const sPw = reinterpret_cast<float*>(smem + kSmE);
+    unsigned char* const sRaw = smem + kSmRaw;
+    float2* const sTwA = reinterpret_cast<float2*>(smem + kSmTwA);
+    float2* const sTwU = reinterpret_cast<float2*>(smem + kSmTwU);
+    unsigned char* const sRowMask = smem + kSmMask;
+    unsigned char* const sColMask = sRowMask + 32;
+    int* const sMelStart = reinterpret_cast<int*>(smem + kSmMelIdx);
+    int* const sMelLen = sMelStart + kMaxMel;
+    int* const sMelOff = sMelLen + kMaxMel;
+    int* const sGroup = sMelOff + kMaxMel;
+    float* const sMelW = reinterpret_cast<float*>(smem + kSmMelW);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tau = tid & 15, grp = tid >> 4;
+    const DevTables* __restrict__ tab = P.tab;
+    const int F = kStdMel ? mel80::kBins : tab->n_mel;
+    const int rowO = F + 1;
+
+    // ---- first tile's waveform starts moving before anything else ----
+    int tile = blockIdx.x;
+    if (tile < P.total_tiles) {
+        const int2 d = P.tiles[tile];
+        if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+    }
+    // ---- one-time table staging ----
+    for (int i = tid; i < 16 * kRowE; i += kThreads) sTwA[i] = tab->twA[i];
+    for (int i = tid; i < 9 * kRowE; i += kThreads) sTwU[i] = tab->twU[i];
+    if (!kStdMel) {
+        for (int i = tid; i < kMaxMel; i += kThreads) {
+            sMelStart[i] = tab->mel_start[i];
+            sMelLen[i] = tab->mel_len[i];
+            sMelOff[i] = tab->mel_off[i];
+        }
+        if (tid < 9) sGroup[tid] = tab->group_begin[tid];
+        for (int i = tid; i < tab->nnz; i += kThreads) sMelW[i] = tab->mel_w[i];
+    }
+    float wv0[13], wv1[13];                    // window taps of this lane: w[32 n1 + 2 tau (+1)]
+#pragma unroll
+    for (int n1 = 0; n1 < 13; ++n1) {
+        wv0[n1] = tab->window[32 * n1 + 2 * tau];
+        wv1[n1] = tab->window[32 * n1 + 2 * tau + 1];
+    }
+    const float preemph = tab->preemph;
+    const float dc_coef = 1.0f - preemph;
+    const float log_floor = tab->log_floor;
+    const bool fused = (P.n_tmask | P.n_fmask) != 0;
+
+    for (; tile < P.total_tiles; tile += gridDim.x) {
+        const int2 desc = P.tiles[tile];
+        const int b = desc.x, t0 = desc.y;
+        const int nfr = P.n_frames[b];
+        const int nrows = P.n_rows[b];
+        const int nvalid = min(kTileFrames, nfr - t0);             // <= 0: padding-only tile
+        const int next = tile + gridDim.x;
+        cp_async_wait_all();
+        __syncthreads();               // (1) raw samples visible; previous tile's rows are out of smem
+        if (fused) {
+            if (tid < 32) {
+                const int t = t0 + tid;
+                bool m = false;
+                for (int j = 0; j < P.n_tmask; ++j) {
+                    const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
+                    m |= (t >= r[0]) & (t < r[1]);
+                }
+                sRowMask[tid] = m;
+            } else if (tid < 32 + F) {
+                const int f = tid - 32;
+                bool m = false;
+                for (int j = 0; j < P.n_fmask; ++j) {
+                    const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
+                    m |= (f >= r[0]) & (f < r[1]);
+                }
+                sColMask[f] = m;
+            }
+        }
+        if (nvalid > 0) {
+            // ---- convert: p[j] = x[j] - preemph * x[j-1] (kaldi.py:193-198), 8-sample block sums ----
+            {
+                const bool utt_start = t0 == 0;
+                for (int blk = warp; blk < 21; blk += 8) {
+                    const int i0 = blk * 256 + 4 * lane, i1 = i0 + 128;
+                    float xa[4], xb[4], edge;
+                    if (kF32) {
+                        const float* r = reinterpret_cast<const float*>(sRaw) + 8;
+                        const float4 a = *reinterpret_cast<const float4*>(r + i0);
+                        const float4 c = *reinterpret_cast<const float4*>(r + i1);
+                        xa[0] = a.x; xa[1] = a.y; xa[2] = a.z; xa[3] = a.w;
+                        xb[0] = c.x; xb[1] = c.y; xb[2] = c.z; xb[3] = c.w;
+                        edge = r[blk * 256 - 1];
+                    } else {
+                        const int16_t* r = reinterpret_cast<const int16_t*>(sRaw) + 8;
+                        const int2 a = *reinterpret_cast<const int2*>(r + i0);
+                        const int2 c = *reinterpret_cast<const int2*>(r + i1);
+                        xa[0] = (float)(int16_t)(a.x & 0xffff); xa[1] = (float)(a.x >> 16);
+                        xa[2] = (float)(int16_t)(a.y & 0xffff); xa[3] = (float)(a.y >> 16);
+                        xb[0] = (float)(int16_t)(c.x & 0xffff); xb[1] = (float)(c.x >> 16);
+                        xb[2] = (float)(int16_t)(c.y & 0xffff); xb[3] = (float)(c.y >> 16);
+                        edge = (float)r[blk * 256 - 1];
+                    }
+                    const float upa = __shfl_sync(0xffffffffu, xa[3], (lane + 31) & 31);
+                    const float upb = __shfl_sync(0xffffffffu, xb[3], (lane + 31) & 31);
+                    const float pva = lane ? upa : ((utt_start && blk == 0) ? xa[0] : edge);
+                    const float pvb = lane ? upb : upa;
+                    float4 pa, pb;
+                    pa.x = fmaf(-preemph, pva, xa[0]);
+                    pa.y = fmaf(-preemph, xa[0], xa[1]);
+                    pa.z = fmaf(-preemph, xa[1], xa[2]);
+                    pa.w = fmaf(-preemph, xa[2], xa[3]);
+                    pb.x = fmaf(-preemph, pvb, xb[0]);
+                    pb.y = fmaf(-preemph, xb[0], xb[1]);
+                    pb.z = fmaf(-preemph, xb[1], xb[2]);
+                    pb.w = fmaf(-preemph, xb[2], xb[3]);
+                    *reinterpret_cast<float4*>(sp + i0) = pa;
+                    *reinterpret_cast<float4*>(sp + i1) = pb;
+                    float sa = (xa[0] + xa[1]) + (xa[2] + xa[3]);
+                    float sb = (xb[0] + xb[1]) + (xb[2] + xb[3]);
+                    sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                    if (!(lane & 1)) {
+                        s8[blk * 32 + (lane >> 1)] = sa;
+                        s8[blk * 32 + 16 + (lane >> 1)] = sb;
+                    }
+                }
+            }
+            __syncthreads();                                       // (2)
+
+            // ---- stage A: frame means (kaldi.py:183-186), then 16-point FFTs of z[16 n1 + tau] ----
+            float zr[2][16], zi[2][16];
+            {
+                const float* q0 = s8 + 20 * (2 * grp) + tau;
+                float m0 = (q0[0] + q0[16]) + q0[32], m1 = (q0[20] + q0[36]) + q0[52];
+                if (tau < 2) {
+                    m0 += q0[48];
+                    m1 += q0[68];
+                }
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) {
+                    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+                    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+                }
+                const float c0 = dc_coef * (m0 / (float)kWin), c1 = dc_coef * (m1 / (float)kWin);
+                const float* base = sp + kShift * (2 * grp) + 2 * tau;
+#pragma unroll
+                for (int n1 = 0; n1 < 13; ++n1) {
+                    const float2 v0 = *reinterpret_cast<const float2*>(base + 32 * n1);
+                    const float2 v1 = *reinterpret_cast<const float2*>(base + kShift + 32 * n1);
+                    zr[0][n1] = (v0.x - c0) * wv0[n1];
+                    zi[0][n1] = (v0.y - c0) * wv1[n1];
+                    zr[1][n1] = (v1.x - c1) * wv0[n1];
+                    zi[1][n1] = (v1.y - c1) * wv1[n1];
+                }
+#pragma unroll
+                for (int n1 = 13; n1 < 16; ++n1) {
+                    zr[0][n1] = zi[0][n1] = zr[1][n1] = zi[1][n1] = 0.f;
+                }
+            }
+            fft_dif<16, 13>(zr[0], zi[0]);
+            fft_dif<16, 13>(zr[1], zi[1]);
+            {
+                float2* const e0 = sE + ((grp * 2 + 0) * 16) * kRowE + tau;
+                float2* const e1 = sE + ((grp * 2 + 1) * 16) * kRowE + tau;
+                const float4* const tw4 = reinterpret_cast<const float4*>(sTwA + tau * kRowE);
+                static_for<0, 8>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    const float4 t = tw4[i];                       // k1 = 2i: (t.x, t.y), 2i+1: (t.z, t.w)
+                    constexpr int p0 = bitrev<16>(2 * i), p1 = bitrev<16>(2 * i + 1);
+                    if constexpr (i == 0) {
+                        e0[0] = make_float2(zr[0][p0], zi[0][p0]);
+                        e1[0] = make_float2(zr[1][p0], zi[1][p0]);
+                    } else {
+                        e0[(2 * i) * kRowE] = make_float2(zr[0][p0] * t.x - zi[0][p0] * t.y, zr[0][p0] * t.y + zi[0][p0] * t.x);
+                        e1[(2 * i) * kRowE] = make_float2(zr[1][p0] * t.x - zi[1][p0] * t.y, zr[1][p0] * t.y + zi[1][p0] * t.x);
+                    }
+                    e0[(2 * i + 1) * kRowE] = make_float2(zr[0][p1] * t.z - zi[0][p1] * t.w, zr[0][p1] * t.w + zi[0][p1] * t.z);
+                    e1[(2 * i + 1) * kRowE] = make_float2(zr[1][p1] * t.z - zi[1][p1] * t.w, zr[1][p1] * t.w + zi[1][p1] * t.z);
+                });
+            }
+            __syncwarp();
+
+            // ---- stage B: lane (fsel, u) transforms rows u and 16-u (0 and 8 for u == 0) ----
+            const int fsel = tau >> 3, u = tau & 7;
+            float ar[16], ai[16], br[16], bi[16];
+            {
+                const int ra = stage_b_row_a(u), rb = stage_b_row_b(u);
+                const float4* const pa = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + ra) * kRowE);
+                const float4* const pb = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + rb) * kRowE);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 va = pa[i], vb = pb[i];
+                    ar[2 * i] = va.x; ai[2 * i] = va.y; ar[2 * i + 1] = va.z; ai[2 * i + 1] = va.w;
+                    br[2 * i] = vb.x; bi[2 * i] = vb.y; br[2 * i + 1] = vb.z; bi[2 * i + 1] = vb.w;
+                }
+            }
+            __syncthreads();           // (3) exchange buffer is dead -> power tile + next tile's raw samples
+            if (next < P.total_tiles) {
+                const int2 d = P.tiles[next];
+                if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+            }
+            fft_dif<16>(ar, ai);
+            fft_dif<16>(br, bi);
+            {
+                float* const pcol = sPw + (2 * grp + fsel);
+                if (u != 0) {
+                    const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
+                    static_for<0, 8>([&](auto ii) {
+                        constexpr int i = decltype(ii)::value;
+                        const float4 t = tw4[i];
+                        {
+                            constexpr int k2 = 2 * i;
+                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                            float pk, pnk;
+                            untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
+                            const int k = u + 16 * k2;
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                        {
+                            constexpr int k2 = 2 * i + 1;
+                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                            float pk, pnk;
+                            untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
+                            const int k = u + 16 * k2;
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                    });
+                } else {
+                    const float2* const tw0 = sTwU;                 // k = 16 k2
+                    const float2* const tw8 = sTwU + 8 * kRowE;     // k = 8 + 16 k2
+                    static_for<0, 9>([&](auto kk) {                 // row 0: P = Z[16 k2], Q = Z[16 (16-k2)]
+                        constexpr int k2 = decltype(kk)::value;
+                        constexpr int p = bitrev<16>(k2), q = bitrev<16>((16 - k2) & 15);
+                        const float2 t = tw0[k2];
+                        float pk, pnk;
+                        untangle_power(ar[p], ai[p], ar[q], ai[q], t.x, t.y, pk, pnk);
+                        pcol[(16 * k2) * kRowP] = pk;
+                        if constexpr (k2 != 0) pcol[(256 - 16 * k2) * kRowP] = pnk;   // bin 256 has no mel weight
+                    });
+                    static_for<0, 8>([&](auto kk) {                 // row 8: P = Z[8+16 k2], Q = Z[8+16 (15-k2)]
+                        constexpr int k2 = decltype(kk)::value;
+                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                        const float2 t = tw8[k2];
+                        float pk, pnk;
+                        untangle_power(br[p], bi[p], br[q], bi[q], t.x, t.y, pk, pnk);
+                        pcol[(8 + 16 * k2) * kRowP] = pk;
+                        pcol[(248 - 16 * k2) * kRowP] = pnk;
+                    });
+                }
+            }
+            __syncthreads();                                       // (4) power tile complete
+
+            // ---- sparse mel + log: warp = mel-bin group, lane = frame ----
+            if (kStdMel) {
+                const float* const pcol = sPw + lane;
+                float* const orow = sp + lane * rowO;
+                switch (warp) {
+                    case 0: mel_group_std<0>(pcol, P, orow, log_floor); break;
+                    case 1: mel_group_std<1>(pcol, P, orow, log_floor); break;
+                    case 2: mel_group_std<2>(pcol, P, orow, log_floor); break;
+                    case 3: mel_group_std<3>(pcol, P, orow, log_floor); break;
+                    case 4: mel_group_std<4>(pcol, P, orow, log_floor); break;
+                    case 5: mel_group_std<5>(pcol, P, orow, log_floor); break;
+                    case 6: mel_group_std<6>(pcol, P, orow, log_floor); break;
+                    default: mel_group_std<7>(pcol, P, orow, log_floor); break;
+                }
+            } else {
+                const float* const pcol = sPw + lane;
+                for (int bin = sGroup[warp]; bin < sGroup[warp + 1]; ++bin) {
+                    const int k0 = sMelStart[bin], len = sMelLen[bin];
+                    const float* const w = sMelW + sMelOff[bin];
+                    float acc = 0.f;
+                    for (int i = 0; i < len; ++i) acc = fmaf(w[i], pcol[(k0 + i) * kRowP], acc);
+                    sp[lane * rowO + bin] = fast_ln(fmaxf(acc, log_floor));
+                }
+            }
+            __syncthreads();                                       // (5) output tile complete
+            if (P.tile_stats != nullptr) {
+                for (int idx = tid; idx < 3 * F; idx += kThreads) {
+                    const int rg = idx / F, f = idx - rg * F;
+                    const int n = stats_rows(nvalid, rg);
+                    float s = 0.f, m2 = 0.f;
+                    if (n > 0) {
+                        const float* col = sp + (11 * rg) * rowO + f;
+                        for (int r = 0; r < n; ++r) s += col[r * rowO];
+                        const float mean = s / (float)n;
+                        for (int r = 0; r < n; ++r) {
+                            const float d = col[r * rowO] - mean;
+                            m2 = fmaf(d, d, m2);
+                        }
+                    }
+                    float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * F;
+                    st[f] = s;
+                    st[F + f] = m2;
+                }
+            }
+        } else if (next < P.total_tiles) {
+            const int2 d = P.tiles[next];
+            if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+        }
+
+        // ---- rows out: [mask] -> [CMVN] -> coalesced stores; padding rows are 0 / (0-mean)*istd ----
+        if (P.out != nullptr) {
+            const bool has_cmvn = P.cmvn_mean != nullptr;
+            const int rows_here = min(kTileFrames, nrows - t0);
+            const int pitch = (int)P.pitch;
+            float* const dst0 = P.out + (P.out_row[b] + t0) * P.pitch;
+            if (!fused && !has_cmvn) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = warp + 8 * i;
+                    if (r < rows_here) {
+                        const bool real = r < nvalid;
+                        const float* const srow = sp + r * rowO;
+                        float* const dst = dst0 + r * pitch;
+                        for (int f = lane; f < F; f += 32) dst[f] = real ? srow[f] : 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = warp + 8 * i;
+                    if (r < rows_here) {
+                        const bool real = r < nvalid;
+                        const bool rmask = fused && real && sRowMask[r];
+                        const bool do_cmvn = has_cmvn && (real || P.cmvn_on_pad);
+                        const float* const srow = sp + r * rowO;
+                        float* const dst = dst0 + r * pitch;
+                        for (int f = lane; f < F; f += 32) {
+                            float v = real ? srow[f] : 0.f;
+                            if (rmask || (fused && real && sColMask[f])) v = 0.f;
+                            if (do_cmvn) {
+                                v = v - __ldg(P.cmvn_mean + f);
+                                if (P.cmvn_istd != nullptr) v = v * __ldg(P.cmvn_istd + f);
+                            }
+                            dst[f] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+}  // namespace oe

@@ -62,355 +62,12 @@ struct DevTables {
     float mel_w[kMaxNnz];           // already multiplied by 1/4 (see untangle_power)
 };
 
-struct FbankParams {
-    const void* wav;
-    const int64_t* wav_off;
-    const int32_t* wav_len;
-    const int32_t* n_frames;
-    const int32_t* n_rows;
-    const int32_t* tile_prefix;     // [B+1]
-    const int64_t* out_row;
-    float* out;
-    int64_t pitch;
-    int B;
-    int total_tiles;
-    const int32_t* tmask;
-    const int32_t* fmask;
-    int n_tmask;
-    int n_fmask;
-    const float* cmvn_mean;
-    const float* cmvn_istd;
-    int cmvn_on_pad;
-    float* tile_stats;              // [total_tiles][2][F]: column sum, sum of squared deviations
-    const DevTables* tab;
-};
+}  // namespace oe
 
-// ------------------------------------------------------------------------------------------
-// shared memory map of oe_fbank_kernel (bytes)
-constexpr int kSmP = 0;                                    // float p[5376]      | out tile (32 x (F+1))
-constexpr int kSmS8 = kSmP + 5376 * 4;                     // float s8[672]
-constexpr int kSmCm = kSmS8 + kChunks * 4;                 // float cmean[32]
-constexpr int kSmE = kSmCm + 32 * 4;                       // float2 E[16][2][16][18] | float P[256][36]
-constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
-constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
-constexpr int kSmMelIdx = kSmTwU + 9 * kRowE * 8;          // int start/len/off [3][128], group_begin[9] (+pad)
-constexpr int kSmMisc = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // int b, t0; uchar rowmask[32], colmask[128]
-constexpr int kSmMelW = kSmMisc + 16 + 32 + kMaxMel;       // float mel_w[nnz]
-static_assert(kSmE % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0, "align");
-static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
+#include "oe_mel80.h"
+#include "oe_fbank_kernel.cuh"
 
-__device__ __forceinline__ int find_utt(const int32_t* __restrict__ prefix, int B, int tile) {
-    int lo = 0, hi = B;                       // prefix[lo] <= tile < prefix[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= tile) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-template <bool kF32>
-__device__ __forceinline__ void load8(const void* wav, int64_t base, int s, int wlen, float (&x)[8], float& prev) {
-    if (kF32) {
-        const float* w = reinterpret_cast<const float*>(wav) + base;
-        if (s + 8 <= wlen) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(w + s));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(w + s + 4));
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-            x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = (s + i < wlen) ? __ldg(w + s + i) : 0.0f;
-        }
-        prev = (s > 0) ? ((s - 1 < wlen) ? __ldg(w + s - 1) : 0.0f) : x[0];
-    } else {
-        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + base;
-        if (s + 8 <= wlen) {
-            const int4 v = __ldg(reinterpret_cast<const int4*>(w + s));
-            x[0] = (float)(int16_t)(v.x & 0xffff); x[1] = (float)(v.x >> 16);
-            x[2] = (float)(int16_t)(v.y & 0xffff); x[3] = (float)(v.y >> 16);
-            x[4] = (float)(int16_t)(v.z & 0xffff); x[5] = (float)(v.z >> 16);
-            x[6] = (float)(int16_t)(v.w & 0xffff); x[7] = (float)(v.w >> 16);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = (s + i < wlen) ? (float)__ldg(w + s + i) : 0.0f;
-        }
-        prev = (s > 0) ? ((s - 1 < wlen) ? (float)__ldg(w + s - 1) : 0.0f) : x[0];
-    }
-}
-
-template <bool kF32>
-__global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    float* const sp = reinterpret_cast<float*>(smem + kSmP);
-    float* const s8 = reinterpret_cast<float*>(smem + kSmS8);
-    float* const cmean = reinterpret_cast<float*>(smem + kSmCm);
-    float2* const sE = reinterpret_cast<float2*>(smem + kSmE);
-    float* const sPw = reinterpret_cast<float*>(smem + kSmE);
-    float2* const sTwA = reinterpret_cast<float2*>(smem + kSmTwA);
-    float2* const sTwU = reinterpret_cast<float2*>(smem + kSmTwU);
-    int* const sMelStart = reinterpret_cast<int*>(smem + kSmMelIdx);
-    int* const sMelLen = sMelStart + kMaxMel;
-    int* const sMelOff = sMelLen + kMaxMel;
-    int* const sGroup = sMelOff + kMaxMel;
-    int* const sTile = reinterpret_cast<int*>(smem + kSmMisc);
-    unsigned char* const sRowMask = smem + kSmMisc + 16;
-    unsigned char* const sColMask = sRowMask + 32;
-    float* const sMelW = reinterpret_cast<float*>(smem + kSmMelW);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tau = tid & 15, grp = tid >> 4;
-    const DevTables* __restrict__ tab = P.tab;
-    const int F = tab->n_mel;
-    const int rowO = F + 1;
-
-    // ---- one-time table staging ----
-    for (int i = tid; i < 16 * kRowE; i += kThreads) sTwA[i] = tab->twA[i];
-    for (int i = tid; i < 9 * kRowE; i += kThreads) sTwU[i] = tab->twU[i];
-    for (int i = tid; i < kMaxMel; i += kThreads) {
-        sMelStart[i] = tab->mel_start[i];
-        sMelLen[i] = tab->mel_len[i];
-        sMelOff[i] = tab->mel_off[i];
-    }
-    if (tid < 9) sGroup[tid] = tab->group_begin[tid];
-    for (int i = tid; i < tab->nnz; i += kThreads) sMelW[i] = tab->mel_w[i];
-    float wv0[13], wv1[13];                    // window taps of this lane: w[32 n1 + 2 tau (+1)]
-#pragma unroll
-    for (int n1 = 0; n1 < 13; ++n1) {
-        wv0[n1] = tab->window[32 * n1 + 2 * tau];
-        wv1[n1] = tab->window[32 * n1 + 2 * tau + 1];
-    }
-    const float preemph = tab->preemph;
-    const float dc_coef = 1.0f - preemph;
-    const float log_floor = tab->log_floor;
-    const bool fused = (P.n_tmask | P.n_fmask) != 0;
-
-    int slot = 0;                                  // tile descriptor is double-buffered: padding-only
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, slot ^= 2) {   // tiles have no barrier but (1)
-        if (tid == 0) {
-            const int b = find_utt(P.tile_prefix, P.B, tile);
-            sTile[slot] = b;
-            sTile[slot + 1] = (tile - P.tile_prefix[b]) * kTileFrames;
-        }
-        __syncthreads();                                           // (1) also fences the previous tile
-        const int b = sTile[slot], t0 = sTile[slot + 1];
-        const int nfr = P.n_frames[b];
-        const int nrows = P.n_rows[b];
-        const int nvalid = min(kTileFrames, nfr - t0);             // <= 0: padding-only tile
-        if (fused) {
-            if (tid < 32) {
-                const int t = t0 + tid;
-                bool m = false;
-                for (int j = 0; j < P.n_tmask; ++j) {
-                    const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
-                    m |= (t >= r[0]) & (t < r[1]);
-                }
-                sRowMask[tid] = m;
-            } else if (tid < 32 + F) {
-                const int f = tid - 32;
-                bool m = false;
-                for (int j = 0; j < P.n_fmask; ++j) {
-                    const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
-                    m |= (f >= r[0]) & (f < r[1]);
-                }
-                sColMask[f] = m;
-            }
-        }
-        if (nvalid > 0) {
-            // ---- stage the waveform: p[j] = x[j] - preemph * x[j-1], 8-sample block sums ----
-            {
-                const int64_t woff = P.wav_off[b];
-                const int wlen = P.wav_len[b];
-                const int s_base = t0 * kShift;
-                for (int c = tid; c < kChunks; c += kThreads) {
-                    float x[8], prev;
-                    load8<kF32>(P.wav, woff, s_base + 8 * c, wlen, x, prev);
-                    float4 lo, hi;
-                    lo.x = fmaf(-preemph, prev, x[0]);
-                    lo.y = fmaf(-preemph, x[0], x[1]);
-                    lo.z = fmaf(-preemph, x[1], x[2]);
-                    lo.w = fmaf(-preemph, x[2], x[3]);
-                    hi.x = fmaf(-preemph, x[3], x[4]);
-                    hi.y = fmaf(-preemph, x[4], x[5]);
-                    hi.z = fmaf(-preemph, x[5], x[6]);
-                    hi.w = fmaf(-preemph, x[6], x[7]);
-                    reinterpret_cast<float4*>(sp)[2 * c] = lo;
-                    reinterpret_cast<float4*>(sp)[2 * c + 1] = hi;
-                    s8[c] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-                }
-            }
-            __syncthreads();                                       // (2)
-            if (tid < kTileFrames) {                               // frame mean (kaldi.py:183-186)
-                const float* q = s8 + 20 * tid;
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 50; i += 2) {
-                    a0 += q[i];
-                    a1 += q[i + 1];
-                }
-                cmean[tid] = dc_coef * ((a0 + a1) / (float)kWin);
-            }
-            __syncthreads();                                       // (3)
-
-            // ---- stage A: 16-point FFTs of z[16 n1 + tau] for the group's two frames ----
-            float zr[2][16], zi[2][16];
-#pragma unroll
-            for (int fr = 0; fr < 2; ++fr) {
-                const float* base = sp + kShift * (2 * grp + fr) + 2 * tau;
-                const float c = cmean[2 * grp + fr];
-#pragma unroll
-                for (int n1 = 0; n1 < 13; ++n1) {
-                    const float2 v = *reinterpret_cast<const float2*>(base + 32 * n1);
-                    zr[fr][n1] = (v.x - c) * wv0[n1];
-                    zi[fr][n1] = (v.y - c) * wv1[n1];
-                }
-#pragma unroll
-                for (int n1 = 13; n1 < 16; ++n1) {
-                    zr[fr][n1] = 0.f;
-                    zi[fr][n1] = 0.f;
-                }
-            }
-            fft_dif<16, 13>(zr[0], zi[0]);
-            fft_dif<16, 13>(zr[1], zi[1]);
-            {
-                float2* const e0 = sE + ((grp * 2 + 0) * 16) * kRowE + tau;
-                float2* const e1 = sE + ((grp * 2 + 1) * 16) * kRowE + tau;
-                const float4* const tw4 = reinterpret_cast<const float4*>(sTwA + tau * kRowE);
-                static_for<0, 8>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    const float4 t = tw4[i];                       // k1 = 2i: (t.x, t.y), 2i+1: (t.z, t.w)
-                    constexpr int p0 = bitrev<16>(2 * i), p1 = bitrev<16>(2 * i + 1);
-                    if constexpr (i == 0) {
-                        e0[0] = make_float2(zr[0][p0], zi[0][p0]);
-                        e1[0] = make_float2(zr[1][p0], zi[1][p0]);
-                    } else {
-                        e0[(2 * i) * kRowE] = make_float2(zr[0][p0] * t.x - zi[0][p0] * t.y, zr[0][p0] * t.y + zi[0][p0] * t.x);
-                        e1[(2 * i) * kRowE] = make_float2(zr[1][p0] * t.x - zi[1][p0] * t.y, zr[1][p0] * t.y + zi[1][p0] * t.x);
-                    }
-                    e0[(2 * i + 1) * kRowE] = make_float2(zr[0][p1] * t.z - zi[0][p1] * t.w, zr[0][p1] * t.w + zi[0][p1] * t.z);
-                    e1[(2 * i + 1) * kRowE] = make_float2(zr[1][p1] * t.z - zi[1][p1] * t.w, zr[1][p1] * t.w + zi[1][p1] * t.z);
-                });
-            }
-            __syncwarp();
-
-            // ---- stage B: lane (fsel, u) transforms rows u and 16-u (0 and 8 for u == 0) ----
-            const int fsel = tau >> 3, u = tau & 7;
-            float ar[16], ai[16], br[16], bi[16];
-            {
-                const int ra = stage_b_row_a(u), rb = stage_b_row_b(u);
-                const float4* const pa = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + ra) * kRowE);
-                const float4* const pb = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + rb) * kRowE);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 va = pa[i], vb = pb[i];
-                    ar[2 * i] = va.x; ai[2 * i] = va.y; ar[2 * i + 1] = va.z; ai[2 * i + 1] = va.w;
-                    br[2 * i] = vb.x; bi[2 * i] = vb.y; br[2 * i + 1] = vb.z; bi[2 * i + 1] = vb.w;
-                }
-            }
-            __syncthreads();                                       // (4) exchange buffer is dead -> power tile
-            fft_dif<16>(ar, ai);
-            fft_dif<16>(br, bi);
-            {
-                float* const pcol = sPw + (2 * grp + fsel);
-                if (u != 0) {
-                    const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
-                    static_for<0, 8>([&](auto ii) {
-                        constexpr int i = decltype(ii)::value;
-                        const float4 t = tw4[i];
-                        {
-                            constexpr int k2 = 2 * i;
-                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                            float pk, pnk;
-                            untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
-                            const int k = u + 16 * k2;
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                        {
-                            constexpr int k2 = 2 * i + 1;
-                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                            float pk, pnk;
-                            untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
-                            const int k = u + 16 * k2;
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                    });
-                } else {
-                    const float2* const tw0 = sTwU;                 // k = 16 k2
-                    const float2* const tw8 = sTwU + 8 * kRowE;     // k = 8 + 16 k2
-                    static_for<0, 9>([&](auto kk) {                 // row 0: P = Z[16 k2], Q = Z[16 (16-k2)]
-                        constexpr int k2 = decltype(kk)::value;
-                        constexpr int p = bitrev<16>(k2), q = bitrev<16>((16 - k2) & 15);
-                        const float2 t = tw0[k2];
-                        float pk, pnk;
-                        untangle_power(ar[p], ai[p], ar[q], ai[q], t.x, t.y, pk, pnk);
-                        pcol[(16 * k2) * kRowP] = pk;
-                        if constexpr (k2 != 0) pcol[(256 - 16 * k2) * kRowP] = pnk;   // bin 256 has no mel weight
-                    });
-                    static_for<0, 8>([&](auto kk) {                 // row 8: P = Z[8+16 k2], Q = Z[8+16 (15-k2)]
-                        constexpr int k2 = decltype(kk)::value;
-                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                        const float2 t = tw8[k2];
-                        float pk, pnk;
-                        untangle_power(br[p], bi[p], br[q], bi[q], t.x, t.y, pk, pnk);
-                        pcol[(8 + 16 * k2) * kRowP] = pk;
-                        pcol[(248 - 16 * k2) * kRowP] = pnk;
-                    });
-                }
-            }
-            __syncthreads();                                       // (5) power tile complete
-
-            // ---- sparse mel + log: warp = mel-bin group, lane = frame ----
-            {
-                const float* const pcol = sPw + lane;
-                for (int bin = sGroup[warp]; bin < sGroup[warp + 1]; ++bin) {
-                    const int k0 = sMelStart[bin], len = sMelLen[bin];
-                    const float* const w = sMelW + sMelOff[bin];
-                    float acc = 0.f;
-                    for (int i = 0; i < len; ++i) acc = fmaf(w[i], pcol[(k0 + i) * kRowP], acc);
-                    sp[lane * rowO + bin] = __logf(fmaxf(acc, log_floor));
-                }
-            }
-            __syncthreads();                                       // (6) output tile complete
-            if (P.tile_stats != nullptr && tid < F) {
-                float s = 0.f;
-                for (int r = 0; r < nvalid; ++r) s += sp[r * rowO + tid];
-                const float mean = s / (float)nvalid;
-                float m2 = 0.f;
-                for (int r = 0; r < nvalid; ++r) {
-                    const float d = sp[r * rowO + tid] - mean;
-                    m2 = fmaf(d, d, m2);
-                }
-                float* const st = P.tile_stats + (int64_t)tile * 2 * F;
-                st[tid] = s;
-                st[F + tid] = m2;
-            }
-        }
-
-        // ---- rows out: [mask] -> [CMVN] -> coalesced stores; padding rows are 0 / (0-mean)*istd ----
-        if (P.out != nullptr) {
-            const bool has_cmvn = P.cmvn_mean != nullptr;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = warp + 8 * i;
-                const int t = t0 + r;
-                if (t >= nrows) continue;
-                const bool real = t < nfr;
-                const bool rmask = fused && real && sRowMask[r];
-                float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
-                for (int f = lane; f < F; f += 32) {
-                    float v = real ? sp[r * rowO + f] : 0.f;
-                    if (rmask || (fused && real && sColMask[f])) v = 0.f;
-                    if (has_cmvn && (real || P.cmvn_on_pad)) {
-                        v = v - __ldg(P.cmvn_mean + f);
-                        if (P.cmvn_istd != nullptr) v = v * __ldg(P.cmvn_istd + f);
-                    }
-                    dst[f] = v;
-                }
-            }
-        }
-    }
-}
+namespace oe {
 
 // ------------------------------------------------------------------------------------------
 struct UttStatsParams {
@@ -431,14 +88,19 @@ __global__ void oe_utt_stats_kernel(const UttStatsParams P) {
     const int tb = P.tile_prefix[b];
     const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
     for (int i = 0; i < ntiles; ++i) {
-        const float* st = P.tile_stats + (int64_t)(tb + i) * 2 * P.F;
-        const double nb = (double)min(kTileFrames, nfr - i * kTileFrames);
-        const double mb = (double)st[f] / nb;
-        const double delta = mb - mean;
-        const double nn = n + nb;
-        mean += delta * nb / nn;
-        m2 += (double)st[P.F + f] + delta * delta * n * nb / nn;
-        n = nn;
+        const int nvalid = min(kTileFrames, nfr - i * kTileFrames);
+        for (int rg = 0; rg < 3; ++rg) {
+            const int rows = stats_rows(nvalid, rg);
+            if (rows == 0) continue;
+            const float* st = P.tile_stats + ((int64_t)(tb + i) * 3 + rg) * 2 * P.F;
+            const double nb = (double)rows;
+            const double mb = (double)st[f] / nb;
+            const double delta = mb - mean;
+            const double nn = n + nb;
+            mean += delta * nb / nn;
+            m2 += (double)st[P.F + f] + delta * delta * n * nb / nn;
+            n = nn;
+        }
     }
     P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
     P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / n);
@@ -463,11 +125,15 @@ __global__ void oe_global_stats_kernel(const GlobalStatsParams P) {
             const int tb = P.tile_prefix[b];
             const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
             for (int i = 0; i < ntiles; ++i) {
-                const float* st = P.tile_stats + (int64_t)(tb + i) * 2 * P.F;
-                const double nb = (double)min(kTileFrames, nfr - i * kTileFrames);
-                const double sb = (double)st[f];
-                s += sb;
-                q += (double)st[P.F + f] + sb * sb / nb;
+                const int nvalid = min(kTileFrames, nfr - i * kTileFrames);
+                for (int rg = 0; rg < 3; ++rg) {
+                    const int rows = stats_rows(nvalid, rg);
+                    if (rows == 0) continue;
+                    const float* st = P.tile_stats + ((int64_t)(tb + i) * 3 + rg) * 2 * P.F;
+                    const double sb = (double)st[f];
+                    s += sb;
+                    q += (double)st[P.F + f] + sb * sb / (double)rows;
+                }
             }
         }
         P.stats[f] += s;
@@ -497,18 +163,22 @@ __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
         const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
         const int nvalid = min(kTileFrames, P.n_frames[b] - t0);
         if (f >= P.F || nvalid <= 0) continue;
-        const float* src = P.feats + (P.row_off[b] + t0) * P.F + f;
-        float s = 0.f;
-        for (int r = 0; r < nvalid; ++r) s += src[(int64_t)r * P.F];
-        const float mean = s / (float)nvalid;
-        float m2 = 0.f;
-        for (int r = 0; r < nvalid; ++r) {
-            const float d = src[(int64_t)r * P.F] - mean;
-            m2 = fmaf(d, d, m2);
+        for (int rg = 0; rg < 3; ++rg) {
+            const int n = stats_rows(nvalid, rg);
+            const float* src = P.feats + (P.row_off[b] + t0 + 11 * rg) * P.F + f;
+            float s = 0.f, m2 = 0.f;
+            if (n > 0) {
+                for (int r = 0; r < n; ++r) s += src[(int64_t)r * P.F];
+                const float mean = s / (float)n;
+                for (int r = 0; r < n; ++r) {
+                    const float d = src[(int64_t)r * P.F] - mean;
+                    m2 = fmaf(d, d, m2);
+                }
+            }
+            float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * P.F;
+            st[f] = s;
+            st[P.F + f] = m2;
         }
-        float* const st = P.tile_stats + (int64_t)tile * 2 * P.F;
-        st[f] = s;
-        st[P.F + f] = m2;
     }
 }
 
@@ -662,6 +332,8 @@ struct oe_frontend {
     oe::RsTable* d_rs;
     float* d_rs_coefs;
     size_t fbank_smem;
+    bool std_mel;                  // the mel matrix has the baked mel80 structure -> fast kernel
+    float mel_w_std[512];
 };
 
 namespace {
@@ -721,7 +393,7 @@ void default_mel(const oe_config& c, std::vector<float>& m) {
 
 struct Meta {               // device-side metadata block layout (byte offsets into the workspace)
     size_t wav_off, out_row, frame_prefix, row_prefix, map_off;          // int64 arrays
-    size_t wav_len, n_frames, n_rows, tile_prefix, tmask, fmask, fmap;   // int32 arrays
+    size_t wav_len, n_frames, n_rows, tile_prefix, tmask, fmask, fmap, tiles;   // int32 arrays
     size_t meta_bytes;
     size_t raw, tile_stats, utt_mean, utt_std, total;
     int64_t total_frames, total_rows, total_map;
@@ -779,9 +451,10 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.tmask = take(8 * (size_t)B * bt->n_tmask);
     M.fmask = take(8 * (size_t)B * bt->n_fmask);
     M.fmap = take(4 * (size_t)M.total_map);
+    M.tiles = take(8 * (size_t)M.total_tiles);
     M.meta_bytes = o;
     M.raw = take(M.two_phase && !feats ? 4 * (size_t)M.total_frames * F : 0);
-    M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 2 * F : 0);
+    M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 3 * 2 * F : 0);
     M.utt_mean = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
     M.utt_std = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
     M.total = o;
@@ -892,9 +565,16 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     if (e == cudaSuccess) e = cudaMalloc(&fe->d_rs_coefs, sizeof(float) * oe::kMaxRsCoefs);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    fe->fbank_smem = align_up((size_t)oe::kSmMelW + 4 * (size_t)nnz, 16);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    fe->std_mel = nb == oe::mel80::kBins && nnz == oe::mel80::kNnz;
+    for (int b = 0; fe->std_mel && b < nb; ++b)
+        fe->std_mel = h.mel_start[b] == oe::mel80::kStart[b] && h.mel_len[b] == oe::mel80::kLen[b];
+    memset(fe->mel_w_std, 0, sizeof(fe->mel_w_std));
+    if (fe->std_mel) memcpy(fe->mel_w_std, h.mel_w, sizeof(float) * nnz);
+    fe->fbank_smem = fe->std_mel ? align_up((size_t)oe::kSmStd, 16) : align_up((size_t)oe::kSmMelW + 4 * (size_t)nnz, 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
     if (e != cudaSuccess) {
         if (fe->d_tab) cudaFree(fe->d_tab);
         if (fe->d_rs) cudaFree(fe->d_rs);
@@ -969,7 +649,12 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         i32(M.tile_prefix)[b] = tp;
         fp += nfr;
         rp += nrows;
-        tp += ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
+        const int ntiles = ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
+        for (int i = 0; i < ntiles; ++i) {
+            i32(M.tiles)[2 * (tp + i)] = b;
+            i32(M.tiles)[2 * (tp + i) + 1] = i * oe::kTileFrames;
+        }
+        tp += ntiles;
     }
     i64(M.frame_prefix)[B] = fp;
     i64(M.row_prefix)[B] = rp;
@@ -995,9 +680,10 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     P.wav_len = reinterpret_cast<const int32_t*>(ws + M.wav_len);
     P.n_frames = reinterpret_cast<const int32_t*>(ws + M.n_frames);
     P.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
-    P.tile_prefix = reinterpret_cast<const int32_t*>(ws + M.tile_prefix);
-    P.B = B;
+    P.tiles = reinterpret_cast<const int2*>(ws + M.tiles);
+    const int32_t* d_tile_prefix = reinterpret_cast<const int32_t*>(ws + M.tile_prefix);
     P.total_tiles = M.total_tiles;
+    if (fe->std_mel) memcpy(P.mel_w, fe->mel_w_std, sizeof(P.mel_w));
     P.tab = fe->d_tab;
     P.tile_stats = M.need_stats ? reinterpret_cast<float*>(ws + M.tile_stats) : nullptr;
     if (M.two_phase) {
@@ -1022,7 +708,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             S.feats = reinterpret_cast<const float*>(d_wav);
             S.row_off = P.wav_off;
             S.n_frames = P.n_frames;
-            S.tile_prefix = P.tile_prefix;
+            S.tile_prefix = d_tile_prefix;
             S.tile_stats = P.tile_stats;
             S.B = B;
             S.F = F;
@@ -1032,16 +718,20 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         }
     } else if (M.total_tiles > 0) {
         const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
-        if (bt->wav_dtype == OE_WAV_F32)
-            oe::oe_fbank_kernel<true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-        else
-            oe::oe_fbank_kernel<false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+        const bool f32 = bt->wav_dtype == OE_WAV_F32;
+        if (fe->std_mel) {
+            if (f32) oe::oe_fbank_kernel<true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else oe::oe_fbank_kernel<false, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+        } else {
+            if (f32) oe::oe_fbank_kernel<true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else oe::oe_fbank_kernel<false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+        }
         OE_CUDA(cudaGetLastError());
     }
     if (bt->norm_mode != OE_NORM_NONE) {
         oe::UttStatsParams U;
         U.tile_stats = P.tile_stats;
-        U.tile_prefix = P.tile_prefix;
+        U.tile_prefix = d_tile_prefix;
         U.n_frames = P.n_frames;
         U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
         U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
@@ -1052,7 +742,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     if (bt->d_stats) {
         oe::GlobalStatsParams G;
         G.tile_stats = P.tile_stats;
-        G.tile_prefix = P.tile_prefix;
+        G.tile_prefix = d_tile_prefix;
         G.n_frames = P.n_frames;
         G.stats = bt->d_stats;
         G.B = B;

@@ -18,7 +18,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 lens = np.round(rng.uniform(2, 10, B) * 16000).astype(np.int32)
 offs, total = aligned_offsets(lens)
 pool = [torch.randint(-3000, 3000, (total,), dtype=torch.int16, device='cuda') for _ in range(6)]
-frames = np.array([fe.num_frames(n) for n in lens])
+frames = fe.num_frames_array(lens)
 out = torch.empty((int(frames.sum()), 80), device='cuda')
 alg_bytes = 2 * int(lens.sum()) + 320 * int(frames.sum())
 for mode, kw in [('raw', {}), ('norm', dict(normalization=True))]:
