@@ -14,14 +14,24 @@
 
 namespace oe {
 
+// Everything one tile needs, self-contained (no dependent loads): built on the device by
+// oe_tile_desc_kernel and pulled into shared memory one tile ahead with cp.async.
+struct __align__(16) TileDesc {
+    int b;                  // utterance
+    int t0;                 // first frame of the tile
+    int nvalid;             // real frames in the tile (<= 0: padding-only tile)
+    int rows_here;          // rows to write (real + padding)
+    long long wav_start;    // element index of sample 160*t0 in the waveform buffer
+    int wav_remain;         // samples from there to the end of the utterance
+    int pad0;
+    long long out_start;    // first output row of the tile
+    long long pad1;
+};
+static_assert(sizeof(TileDesc) == 48, "TileDesc is three 16-byte cp.async pieces");
+
 struct FbankParams {
     const void* wav;
-    const int64_t* wav_off;
-    const int32_t* wav_len;
-    const int32_t* n_frames;
-    const int32_t* n_rows;
-    const int2* tiles;              // [total_tiles] (utterance, first frame), built on the host
-    const int64_t* out_row;
+    const TileDesc* tiles;          // [total_tiles]
     float* out;
     int64_t pitch;
     int total_tiles;
@@ -62,10 +72,13 @@ constexpr int kSmRaw = kSmE + kBins * kRowP * 4;           // next tile's raw sa
 constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
 constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
 constexpr int kSmMask = kSmTwU + 9 * kRowE * 8;            // uchar rowmask[32], colmask[128]
-constexpr int kSmStd = kSmMask + 32 + kMaxMel;             // end of the standard-mel layout
+constexpr int kSmDesc = kSmMask + 32 + kMaxMel;            // TileDesc[2]
+constexpr int kSmStd = kSmDesc + 2 * 48;                   // end of the standard-mel layout
 constexpr int kSmMelIdx = kSmStd;                          // generic mel only: int start/len/off [3][128], group_begin[9] (+pad)
 constexpr int kSmMelW = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // generic mel only: float mel_w[nnz]
-static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0, "align");
+static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0 &&
+              kSmDesc % 16 == 0, "align");
+constexpr int kRowS = 34;           // float2 per frame of the self-conjugate-row scratch (32 + 2 pad = 272 B), in the p area
 static_assert(kSmRaw + 673 * 32 <= kSmTwA, "raw prefetch buffer must fit behind the power tile");
 static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
 
@@ -79,29 +92,35 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Asynchronously stages the raw samples [s_base - 8, s_base + 5376) of one utterance into shared memory,
 // zero-filling everything outside [0, wlen) (cp.async src-size form), so the waveform's HBM latency
 // overlaps the previous tile's FFT.  Chunk j of the buffer holds samples s_base - 8 + 8 j.
+// `start` = element index of the tile's first sample, `remain` = samples left in the utterance from there,
+// `utt_start` = the tile begins the utterance (nothing before it may be read).
 template <bool kF32>
-__device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, int64_t woff, int wlen,
-                                              int s_base, int tid) {
+__device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, long long start, int remain,
+                                              bool utt_start, int tid) {
     if (kF32) {
-        const float* w = reinterpret_cast<const float*>(wav) + woff;
+        const float* w = reinterpret_cast<const float*>(wav) + start;
         for (int q = tid; q < 673 * 2; q += kThreads) {
-            const int s = s_base - 8 + 4 * q;
-            int valid = wlen - s;
+            const int s = 4 * q - 8;                       // relative to the tile's first sample
+            int valid = remain - s;
             valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-            if (s < 0) valid = 0;
+            if (s < 0 && utt_start) valid = 0;
             cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 4 * valid);
         }
     } else {
-        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + woff;
+        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + start;
         for (int q = tid; q < 673; q += kThreads) {
-            const int s = s_base - 8 + 8 * q;
-            int valid = wlen - s;
+            const int s = 8 * q - 8;
+            int valid = remain - s;
             valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
-            if (s < 0) valid = 0;
+            if (s < 0 && utt_start) valid = 0;
             cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 2 * valid);
         }
     }
-    cp_async_commit();
+}
+
+__device__ __forceinline__ void prefetch_desc(TileDesc* dst, const TileDesc* src, int tid) {
+    if (tid < 3) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16 * tid,
+                            reinterpret_cast<const unsigned char*>(src) + 16 * tid, 16);
 }
 
 // ln(x) for x >= the log floor (a normal number): lg2.approx.ftz (max abs error 2^-22.6 on the mantissa's
@@ -159,11 +178,19 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     const int F = kStdMel ? mel80::kBins : tab->n_mel;
     const int rowO = F + 1;
 
-    // ---- first tile's waveform starts moving before anything else ----
+    TileDesc* const sDesc = reinterpret_cast<TileDesc*>(smem + kSmDesc);
+
+    // ---- first tile: descriptor, then its waveform starts moving before anything else ----
     int tile = blockIdx.x;
+    int slot = 0;
     if (tile < P.total_tiles) {
-        const int2 d = P.tiles[tile];
-        if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+        prefetch_desc(sDesc, P.tiles + tile, tid);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        const TileDesc d = sDesc[0];
+        if (d.nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, d.wav_start, d.wav_remain, d.t0 == 0, tid);
+        cp_async_commit();
     }
     // ---- one-time table staging ----
     for (int i = tid; i < 16 * kRowE; i += kThreads) sTwA[i] = tab->twA[i];
@@ -188,15 +215,17 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     const float log_floor = tab->log_floor;
     const bool fused = (P.n_tmask | P.n_fmask) != 0;
 
-    for (; tile < P.total_tiles; tile += gridDim.x) {
-        const int2 desc = P.tiles[tile];
-        const int b = desc.x, t0 = desc.y;
-        const int nfr = P.n_frames[b];
-        const int nrows = P.n_rows[b];
-        const int nvalid = min(kTileFrames, nfr - t0);             // <= 0: padding-only tile
+    for (; tile < P.total_tiles; tile += gridDim.x, slot ^= 1) {
         const int next = tile + gridDim.x;
         cp_async_wait_all();
-        __syncthreads();               // (1) raw samples visible; previous tile's rows are out of smem
+        __syncthreads();               // (1) raw samples + descriptor visible; previous tile's rows are out of smem
+        const TileDesc* const dp = sDesc + slot;
+        const int b = dp->b, t0 = dp->t0;
+        const int nvalid = dp->nvalid;                             // <= 0: padding-only tile
+        const int rows_here = dp->rows_here;
+        const long long out_start = dp->out_start;
+        if (next < P.total_tiles) prefetch_desc(sDesc + (slot ^ 1), P.tiles + next, tid);
+        cp_async_commit();
         if (fused) {
             if (tid < 32) {
                 const int t = t0 + tid;
@@ -334,60 +363,75 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                     br[2 * i] = vb.x; bi[2 * i] = vb.y; br[2 * i + 1] = vb.z; bi[2 * i + 1] = vb.w;
                 }
             }
+            cp_async_wait_all();       // next tile's descriptor has landed (this thread's pieces)
             __syncthreads();           // (3) exchange buffer is dead -> power tile + next tile's raw samples
             if (next < P.total_tiles) {
-                const int2 d = P.tiles[next];
-                if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+                const TileDesc* const dn = sDesc + (slot ^ 1);
+                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn->wav_start, dn->wav_remain, dn->t0 == 0, tid);
             }
+            cp_async_commit();
             fft_dif<16>(ar, ai);
             fft_dif<16>(br, bi);
             {
+                // Lanes u = 1..7 own the conjugate row pair (u, 16-u).  Lane u = 0 owns the two self-conjugate
+                // rows 0 and 8: it runs the same code (results discarded) and hands its rows to the frame's 8
+                // lanes through a small scratch, two conjugate pairs per lane -> no divergent second path.
                 float* const pcol = sPw + (2 * grp + fsel);
-                if (u != 0) {
-                    const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
-                    static_for<0, 8>([&](auto ii) {
-                        constexpr int i = decltype(ii)::value;
-                        const float4 t = tw4[i];
-                        {
-                            constexpr int k2 = 2 * i;
-                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                            float pk, pnk;
-                            untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
-                            const int k = u + 16 * k2;
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                        {
-                            constexpr int k2 = 2 * i + 1;
-                            constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                            float pk, pnk;
-                            untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
-                            const int k = u + 16 * k2;
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                    });
-                } else {
-                    const float2* const tw0 = sTwU;                 // k = 16 k2
-                    const float2* const tw8 = sTwU + 8 * kRowE;     // k = 8 + 16 k2
-                    static_for<0, 9>([&](auto kk) {                 // row 0: P = Z[16 k2], Q = Z[16 (16-k2)]
-                        constexpr int k2 = decltype(kk)::value;
-                        constexpr int p = bitrev<16>(k2), q = bitrev<16>((16 - k2) & 15);
-                        const float2 t = tw0[k2];
-                        float pk, pnk;
-                        untangle_power(ar[p], ai[p], ar[q], ai[q], t.x, t.y, pk, pnk);
-                        pcol[(16 * k2) * kRowP] = pk;
-                        if constexpr (k2 != 0) pcol[(256 - 16 * k2) * kRowP] = pnk;   // bin 256 has no mel weight
-                    });
-                    static_for<0, 8>([&](auto kk) {                 // row 8: P = Z[8+16 k2], Q = Z[8+16 (15-k2)]
-                        constexpr int k2 = decltype(kk)::value;
+                float2* const sc = reinterpret_cast<float2*>(sp) + (2 * grp + fsel) * kRowS;
+                if (u == 0) {
+                    float4* const sc4 = reinterpret_cast<float4*>(sc);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        sc4[i] = make_float4(ar[2 * i], ai[2 * i], ar[2 * i + 1], ai[2 * i + 1]);      // position j: Z[16 * bitrev(j)]
+                        sc4[8 + i] = make_float4(br[2 * i], bi[2 * i], br[2 * i + 1], bi[2 * i + 1]);  // position j: Z[8 + 16 * bitrev(j)]
+                    }
+                }
+                const bool own = u != 0;
+                const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
+                static_for<0, 8>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    const float4 t = tw4[i];
+                    {
+                        constexpr int k2 = 2 * i;
                         constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                        const float2 t = tw8[k2];
                         float pk, pnk;
-                        untangle_power(br[p], bi[p], br[q], bi[q], t.x, t.y, pk, pnk);
-                        pcol[(8 + 16 * k2) * kRowP] = pk;
-                        pcol[(248 - 16 * k2) * kRowP] = pnk;
-                    });
+                        untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
+                        const int k = u + 16 * k2;
+                        if (own) {
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                    }
+                    {
+                        constexpr int k2 = 2 * i + 1;
+                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
+                        float pk, pnk;
+                        untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
+                        const int k = u + 16 * k2;
+                        if (own) {
+                            pcol[k * kRowP] = pk;
+                            pcol[(256 - k) * kRowP] = pnk;
+                        }
+                    }
+                });
+                __syncwarp();
+                {
+                    // row 8: P = Z[8 + 16 u], Q = Z[8 + 16 (15 - u)]  -> bins 8 + 16 u and 248 - 16 u
+                    const int ru = __brev((unsigned)u) >> 28, rq = __brev((unsigned)(15 - u)) >> 28;
+                    const float2 p8 = sc[16 + ru], q8 = sc[16 + rq];
+                    const float2 t8 = sTwU[8 * kRowE + u];
+                    float pk, pnk;
+                    untangle_power(p8.x, p8.y, q8.x, q8.y, t8.x, t8.y, pk, pnk);
+                    pcol[(8 + 16 * u) * kRowP] = pk;
+                    pcol[(248 - 16 * u) * kRowP] = pnk;
+                    // row 0: P = Z[16 (u+1)], Q = Z[16 (15 - u)]      -> bins 16 (u+1) and 256 - 16 (u+1)
+                    // (bin 0 and bin 256 carry no mel weight for any low_freq >= 0 and are never formed)
+                    const int r1 = __brev((unsigned)((u + 1) & 15)) >> 28;
+                    const float2 p0 = sc[r1], q0 = sc[rq];
+                    const float2 t0w = sTwU[u + 1];
+                    untangle_power(p0.x, p0.y, q0.x, q0.y, t0w.x, t0w.y, pk, pnk);
+                    pcol[(16 * (u + 1)) * kRowP] = pk;
+                    if (u != 7) pcol[(240 - 16 * u) * kRowP] = pnk;
                 }
             }
             __syncthreads();                                       // (4) power tile complete
@@ -436,17 +480,21 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                     st[F + f] = m2;
                 }
             }
-        } else if (next < P.total_tiles) {
-            const int2 d = P.tiles[next];
-            if (d.y < P.n_frames[d.x]) prefetch_tile<kF32>(sRaw, P.wav, P.wav_off[d.x], P.wav_len[d.x], d.y * kShift, tid);
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+            if (next < P.total_tiles) {
+                const TileDesc* const dn = sDesc + (slot ^ 1);
+                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn->wav_start, dn->wav_remain, dn->t0 == 0, tid);
+            }
+            cp_async_commit();
         }
 
         // ---- rows out: [mask] -> [CMVN] -> coalesced stores; padding rows are 0 / (0-mean)*istd ----
         if (P.out != nullptr) {
             const bool has_cmvn = P.cmvn_mean != nullptr;
-            const int rows_here = min(kTileFrames, nrows - t0);
             const int pitch = (int)P.pitch;
-            float* const dst0 = P.out + (P.out_row[b] + t0) * P.pitch;
+            float* const dst0 = P.out + out_start * P.pitch;
             if (!fused && !has_cmvn) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

@@ -70,6 +70,38 @@ struct DevTables {
 namespace oe {
 
 // ------------------------------------------------------------------------------------------
+struct TileDescParams {
+    const int32_t* tile_prefix;  // [B+1]
+    const int64_t* wav_off;
+    const int32_t* wav_len;
+    const int32_t* n_frames;
+    const int32_t* n_rows;
+    const int64_t* out_row;
+    TileDesc* tiles;
+    int B, total_tiles;
+    int shift;                   // samples per frame step (160), or 1 when the input already is features
+};
+
+// Expands the per-utterance metadata into one self-contained descriptor per 32-frame tile.
+__global__ void oe_tile_desc_kernel(const TileDescParams P) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= P.total_tiles) return;
+    const int b = find_utt(P.tile_prefix, P.B, tile);
+    const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
+    TileDesc d;
+    d.b = b;
+    d.t0 = t0;
+    d.nvalid = min(kTileFrames, P.n_frames[b] - t0);
+    d.rows_here = min(kTileFrames, P.n_rows[b] - t0);
+    d.wav_start = P.wav_off[b] + (long long)t0 * P.shift;
+    d.wav_remain = P.wav_len[b] - t0 * P.shift;
+    d.pad0 = 0;
+    d.out_start = P.out_row[b] + t0;
+    d.pad1 = 0;
+    P.tiles[tile] = d;
+}
+
+// ------------------------------------------------------------------------------------------
 struct UttStatsParams {
     const float* tile_stats;
     const int32_t* tile_prefix;
@@ -79,79 +111,88 @@ struct UttStatsParams {
     int F;
 };
 
-// feature_processor.py:5-8: mean and population std over the frames of one utterance.
+// feature_processor.py:5-8: mean and population std over the frames of one utterance, merged from the
+// per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2].
 __global__ void oe_utt_stats_kernel(const UttStatsParams P) {
     const int b = blockIdx.x, f = threadIdx.x;
     if (f >= P.F) return;
     const int nfr = P.n_frames[b];
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    const int tb = P.tile_prefix[b];
     const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
+    const float* base = P.tile_stats + (int64_t)P.tile_prefix[b] * 3 * 2 * P.F;
+    double S = 0.0;
+    for (int i = 0; i < 3 * ntiles; ++i) S += (double)base[(int64_t)i * 2 * P.F + f];
+    const double mean = S / (double)nfr;
+    double m2 = 0.0;
     for (int i = 0; i < ntiles; ++i) {
         const int nvalid = min(kTileFrames, nfr - i * kTileFrames);
+#pragma unroll
         for (int rg = 0; rg < 3; ++rg) {
             const int rows = stats_rows(nvalid, rg);
-            if (rows == 0) continue;
-            const float* st = P.tile_stats + ((int64_t)(tb + i) * 3 + rg) * 2 * P.F;
-            const double nb = (double)rows;
-            const double mb = (double)st[f] / nb;
-            const double delta = mb - mean;
-            const double nn = n + nb;
-            mean += delta * nb / nn;
-            m2 += (double)st[P.F + f] + delta * delta * n * nb / nn;
-            n = nn;
+            const float* st = base + (int64_t)(3 * i + rg) * 2 * P.F;
+            const float inv = rows > 0 ? 1.0f / (float)rows : 0.f;     // rows <= 11: one fp32 rounding on a partial mean
+            const double d = (double)(st[f] * inv) - mean;
+            m2 += (double)st[P.F + f] + (double)rows * d * d;
         }
     }
     P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
-    P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / n);
+    P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / (double)nfr);
 }
 
 struct GlobalStatsParams {
     const float* tile_stats;
-    const int32_t* tile_prefix;
-    const int32_t* n_frames;
+    const TileDesc* tiles;
+    double* partial;     // [kStatBlocks][2F]
     double* stats;       // [2F+1] accumulated in place
-    int B;
+    double count;
+    int total_tiles;
     int F;
 };
+constexpr int kStatBlocks = 64;
 
-// compute_cmvn_stats: sum, sum of squares, count of the raw log-mel frames (fixed summation order).
-__global__ void oe_global_stats_kernel(const GlobalStatsParams P) {
+// compute_cmvn_stats, stage 1: block g sums a contiguous range of tiles in a fixed order (fp64).
+__global__ void oe_global_stats_partial_kernel(const GlobalStatsParams P) {
+    const int f = threadIdx.x, g = blockIdx.x;
+    if (f >= P.F) return;
+    const int per = (P.total_tiles + kStatBlocks - 1) / kStatBlocks;
+    const int t_lo = g * per, t_hi = min(P.total_tiles, t_lo + per);
+    double s = 0.0, q = 0.0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int nvalid = P.tiles[t].nvalid;
+#pragma unroll
+        for (int rg = 0; rg < 3; ++rg) {
+            const int rows = stats_rows(nvalid, rg);
+            if (rows == 0) continue;
+            const float* st = P.tile_stats + ((int64_t)t * 3 + rg) * 2 * P.F;
+            const double sb = (double)st[f];
+            s += sb;
+            q += (double)st[P.F + f] + sb * sb / (double)rows;
+        }
+    }
+    P.partial[(int64_t)g * 2 * P.F + f] = s;
+    P.partial[(int64_t)g * 2 * P.F + P.F + f] = q;
+}
+
+// stage 2: += sum, sum of squares and frame count into the caller's accumulator.
+__global__ void oe_global_stats_final_kernel(const GlobalStatsParams P) {
     const int f = threadIdx.x;
     if (f < P.F) {
         double s = 0.0, q = 0.0;
-        for (int b = 0; b < P.B; ++b) {
-            const int nfr = P.n_frames[b];
-            const int tb = P.tile_prefix[b];
-            const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
-            for (int i = 0; i < ntiles; ++i) {
-                const int nvalid = min(kTileFrames, nfr - i * kTileFrames);
-                for (int rg = 0; rg < 3; ++rg) {
-                    const int rows = stats_rows(nvalid, rg);
-                    if (rows == 0) continue;
-                    const float* st = P.tile_stats + ((int64_t)(tb + i) * 3 + rg) * 2 * P.F;
-                    const double sb = (double)st[f];
-                    s += sb;
-                    q += (double)st[P.F + f] + sb * sb / (double)rows;
-                }
-            }
+        for (int g = 0; g < kStatBlocks; ++g) {
+            s += P.partial[(int64_t)g * 2 * P.F + f];
+            q += P.partial[(int64_t)g * 2 * P.F + P.F + f];
         }
         P.stats[f] += s;
         P.stats[P.F + f] += q;
     } else if (f == P.F) {
-        double cnt = 0.0;
-        for (int b = 0; b < P.B; ++b) cnt += (double)P.n_frames[b];
-        P.stats[2 * P.F] += cnt;
+        P.stats[2 * P.F] += P.count;
     }
 }
 
 struct FeatStatsParams {
     const float* feats;          // ragged rows, pitch F
-    const int64_t* row_off;      // [B] first row of each utterance
-    const int32_t* n_frames;
-    const int32_t* tile_prefix;
+    const TileDesc* tiles;
     float* tile_stats;
-    int B, F, total_tiles;
+    int F, total_tiles;
 };
 
 // Same per-tile column statistics as the fbank kernel's epilogue, for batches that arrive as
@@ -159,20 +200,18 @@ struct FeatStatsParams {
 __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
     const int f = threadIdx.x;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int b = find_utt(P.tile_prefix, P.B, tile);
-        const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
-        const int nvalid = min(kTileFrames, P.n_frames[b] - t0);
-        if (f >= P.F || nvalid <= 0) continue;
+        const TileDesc d = P.tiles[tile];
+        if (f >= P.F || d.nvalid <= 0) continue;
         for (int rg = 0; rg < 3; ++rg) {
-            const int n = stats_rows(nvalid, rg);
-            const float* src = P.feats + (P.row_off[b] + t0 + 11 * rg) * P.F + f;
+            const int n = stats_rows(d.nvalid, rg);
+            const float* src = P.feats + (d.wav_start + 11 * rg) * P.F + f;   // feats mode: wav_start counts rows
             float s = 0.f, m2 = 0.f;
             if (n > 0) {
                 for (int r = 0; r < n; ++r) s += src[(int64_t)r * P.F];
                 const float mean = s / (float)n;
                 for (int r = 0; r < n; ++r) {
-                    const float d = src[(int64_t)r * P.F] - mean;
-                    m2 = fmaf(d, d, m2);
+                    const float dd = src[(int64_t)r * P.F] - mean;
+                    m2 = fmaf(dd, dd, m2);
                 }
             }
             float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * P.F;
@@ -184,8 +223,8 @@ __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
 
 struct FinalizeParams {
     const float* raw;            // ragged raw log-mel, pitch F
-    const int64_t* frame_prefix; // [B+1]
-    const int64_t* row_prefix;   // [B+1]
+    const int64_t* frame_prefix; // [B] first raw row of each utterance
+    const int64_t* row_prefix;   // [B+1] output rows
     const int32_t* n_frames;
     const int64_t* out_row;
     float* out;
@@ -200,54 +239,75 @@ struct FinalizeParams {
     const float* cmvn_mean;
     const float* cmvn_istd;
     int cmvn_on_pad;
-    int B, F;
-    int64_t total_rows;
+    int F;
 };
 
 // dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
+// grid = (utterances, 32-row chunks); 8 threads per row; VEC = float4 path (F, pitch, bases 16-byte friendly).
+template <int VEC>
 __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = warp0; row < P.total_rows; row += nwarps) {
-        int lo = 0, hi = P.B;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (P.row_prefix[mid] <= row) lo = mid; else hi = mid;
+    __shared__ float sMean[kMaxMel], sStd[kMaxMel], sCm[kMaxMel], sCi[kMaxMel];
+    __shared__ unsigned char sCol[kMaxMel];
+    const int b = blockIdx.x;
+    const int r0 = blockIdx.y * 32;
+    const int nrows = (int)(P.row_prefix[b + 1] - P.row_prefix[b]);
+    if (r0 >= nrows) return;
+    const int tid = threadIdx.x;
+    const int F = P.F;
+    if (tid < F) {
+        sMean[tid] = P.utt_mean ? P.utt_mean[(int64_t)b * F + tid] : 0.f;
+        sStd[tid] = P.utt_std ? P.utt_std[(int64_t)b * F + tid] : 1.f;
+        sCm[tid] = P.cmvn_mean ? P.cmvn_mean[tid] : 0.f;
+        sCi[tid] = P.cmvn_istd ? P.cmvn_istd[tid] : 1.f;
+        bool m = false;
+        for (int j = 0; j < P.n_fmask; ++j) {
+            const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
+            m |= (tid >= r[0]) & (tid < r[1]);
         }
-        const int b = lo;
-        const int t = (int)(row - P.row_prefix[b]);
-        const int nfr = P.n_frames[b];
-        const bool real = t < nfr;
-        float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
-        bool rmask = false;
-        const float* src = nullptr;
-        if (real) {
-            for (int j = 0; j < P.n_tmask; ++j) {
-                const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
-                rmask |= (t >= r[0]) & (t < r[1]);
-            }
-            const int ts = P.frame_map ? P.frame_map[P.map_off[b] + t] : t;
-            src = P.raw + (P.frame_prefix[b] + ts) * P.F;
+        sCol[tid] = m;
+    }
+    __syncthreads();
+    const int t = r0 + (tid >> 3), t8 = tid & 7;
+    if (t >= nrows) return;
+    const int nfr = P.n_frames[b];
+    const bool real = t < nfr;
+    bool rmask = false;
+    const float* src = P.raw;
+    if (real) {
+        for (int j = 0; j < P.n_tmask; ++j) {
+            const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
+            rmask |= (t >= r[0]) & (t < r[1]);
         }
-        for (int f = lane; f < P.F; f += 32) {
-            float v = 0.f;
+        const int ts = P.frame_map ? P.frame_map[P.map_off[b] + t] : t;
+        src = P.raw + (P.frame_prefix[b] + ts) * F;
+    }
+    float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
+    const bool norm = P.utt_mean != nullptr;
+    const bool cm = P.cmvn_mean != nullptr && (real || P.cmvn_on_pad);
+    const bool ci = P.cmvn_istd != nullptr;
+    for (int c = t8 * VEC; c < F; c += 8 * VEC) {
+        float v[VEC];
+        if (VEC == 4) {
+            const float4 x = real ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[0] = x.x; v[1 % VEC] = x.y; v[2 % VEC] = x.z; v[3 % VEC] = x.w;
+        } else {
+            v[0] = real ? src[c] : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            float y = v[e];
             if (real) {
-                v = src[f];
-                if (P.utt_mean) v = (v - P.utt_mean[(int64_t)b * P.F + f]) / P.utt_std[(int64_t)b * P.F + f];
-                bool m = rmask;
-                for (int j = 0; j < P.n_fmask; ++j) {
-                    const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
-                    m |= (f >= r[0]) & (f < r[1]);
-                }
-                if (m) v = 0.f;
+                if (norm) y = (y - sMean[c + e]) / sStd[c + e];
+                if (rmask || sCol[c + e]) y = 0.f;
             }
-            if (P.cmvn_mean && (real || P.cmvn_on_pad)) {
-                v = v - P.cmvn_mean[f];
-                if (P.cmvn_istd) v = v * P.cmvn_istd[f];
+            if (cm) {
+                y = y - sCm[c + e];
+                if (ci) y = y * sCi[c + e];
             }
-            dst[f] = v;
+            v[e] = y;
         }
+        if (VEC == 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        else dst[c] = v[0];
     }
 }
 
@@ -395,7 +455,8 @@ struct Meta {               // device-side metadata block layout (byte offsets i
     size_t wav_off, out_row, frame_prefix, row_prefix, map_off;          // int64 arrays
     size_t wav_len, n_frames, n_rows, tile_prefix, tmask, fmask, fmap, tiles;   // int32 arrays
     size_t meta_bytes;
-    size_t raw, tile_stats, utt_mean, utt_std, total;
+    size_t raw, tile_stats, utt_mean, utt_std, stat_partial, total;
+    int max_rows;
     int64_t total_frames, total_rows, total_map;
     int total_tiles;
     bool two_phase, need_stats, feats;
@@ -419,6 +480,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || bt->d_stats != nullptr;
     M.total_frames = M.total_rows = M.total_map = 0;
+    M.max_rows = 0;
     int64_t tiles = 0;
     if (frames_out) frames_out->resize(B);
     for (int b = 0; b < B; ++b) {
@@ -431,6 +493,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
         if (frames_out) (*frames_out)[b] = nfr;
         M.total_frames += nfr;
         M.total_rows += nrows;
+        M.max_rows = std::max(M.max_rows, nrows);
         const int cover = M.two_phase ? nfr : nrows;
         tiles += (cover + oe::kTileFrames - 1) / oe::kTileFrames;
         if (bt->frame_map) M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
@@ -451,12 +514,13 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.tmask = take(8 * (size_t)B * bt->n_tmask);
     M.fmask = take(8 * (size_t)B * bt->n_fmask);
     M.fmap = take(4 * (size_t)M.total_map);
-    M.tiles = take(8 * (size_t)M.total_tiles);
     M.meta_bytes = o;
+    M.tiles = take(sizeof(oe::TileDesc) * (size_t)M.total_tiles);
     M.raw = take(M.two_phase && !feats ? 4 * (size_t)M.total_frames * F : 0);
     M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 3 * 2 * F : 0);
     M.utt_mean = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
     M.utt_std = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
+    M.stat_partial = take(bt->d_stats ? 8 * (size_t)oe::kStatBlocks * 2 * F : 0);
     M.total = o;
     return OE_OK;
 }
@@ -508,6 +572,11 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     const int nb = cfg->num_mel_bins, nf = cfg->fft_size / 2;
     if (window) fe->window.assign(window, window + cfg->frame_length); else default_window(cfg->frame_length, fe->window);
     if (mel) fe->mel.assign(mel, mel + (size_t)nb * nf); else default_mel(*cfg, fe->mel);
+    for (int b = 0; b < nb; ++b)
+        if (fe->mel[(size_t)b * nf] != 0.f) {
+            delete fe;
+            return fail(OE_ERR_UNSUPPORTED, "mel weight on fft bin 0 is not supported (Kaldi banks never have one)");
+        }
     if (fe->window[0] != 0.f) {
         delete fe;
         return fail(OE_ERR_UNSUPPORTED, "window[0] must be 0 (povey): pre-emphasis is folded into the staged waveform");
@@ -649,12 +718,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         i32(M.tile_prefix)[b] = tp;
         fp += nfr;
         rp += nrows;
-        const int ntiles = ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
-        for (int i = 0; i < ntiles; ++i) {
-            i32(M.tiles)[2 * (tp + i)] = b;
-            i32(M.tiles)[2 * (tp + i) + 1] = i * oe::kTileFrames;
-        }
-        tp += ntiles;
+        tp += ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
     }
     i64(M.frame_prefix)[B] = fp;
     i64(M.row_prefix)[B] = rp;
@@ -676,23 +740,22 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     oe::FbankParams P;
     memset(&P, 0, sizeof(P));
     P.wav = d_wav;
-    P.wav_off = reinterpret_cast<const int64_t*>(ws + M.wav_off);
-    P.wav_len = reinterpret_cast<const int32_t*>(ws + M.wav_len);
-    P.n_frames = reinterpret_cast<const int32_t*>(ws + M.n_frames);
-    P.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
-    P.tiles = reinterpret_cast<const int2*>(ws + M.tiles);
+    const int64_t* d_wav_off = reinterpret_cast<const int64_t*>(ws + M.wav_off);
+    const int32_t* d_n_frames = reinterpret_cast<const int32_t*>(ws + M.n_frames);
+    P.tiles = reinterpret_cast<const oe::TileDesc*>(ws + M.tiles);
     const int32_t* d_tile_prefix = reinterpret_cast<const int32_t*>(ws + M.tile_prefix);
     P.total_tiles = M.total_tiles;
     if (fe->std_mel) memcpy(P.mel_w, fe->mel_w_std, sizeof(P.mel_w));
     P.tab = fe->d_tab;
     P.tile_stats = M.need_stats ? reinterpret_cast<float*>(ws + M.tile_stats) : nullptr;
+    const int64_t* d_tile_out_row;
     if (M.two_phase) {
         P.out = reinterpret_cast<float*>(ws + M.raw);
-        P.out_row = reinterpret_cast<const int64_t*>(ws + M.frame_prefix);
+        d_tile_out_row = reinterpret_cast<const int64_t*>(ws + M.frame_prefix);
         P.pitch = F;
     } else {
         P.out = d_out;
-        P.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        d_tile_out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
         P.pitch = pitch;
         P.tmask = reinterpret_cast<const int32_t*>(ws + M.tmask);
         P.fmask = reinterpret_cast<const int32_t*>(ws + M.fmask);
@@ -702,15 +765,27 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         P.cmvn_istd = bt->d_cmvn_istd;
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
+    if (M.total_tiles > 0) {
+        oe::TileDescParams T;
+        T.tile_prefix = d_tile_prefix;
+        T.wav_off = d_wav_off;
+        T.wav_len = reinterpret_cast<const int32_t*>(ws + M.wav_len);
+        T.n_frames = d_n_frames;
+        T.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
+        T.out_row = d_tile_out_row;
+        T.tiles = reinterpret_cast<oe::TileDesc*>(ws + M.tiles);
+        T.B = B;
+        T.total_tiles = M.total_tiles;
+        T.shift = M.feats ? 1 : oe::kShift;
+        oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
+        OE_CUDA(cudaGetLastError());
+    }
     if (M.feats) {
         if (M.need_stats && M.total_tiles > 0) {
             oe::FeatStatsParams S;
             S.feats = reinterpret_cast<const float*>(d_wav);
-            S.row_off = P.wav_off;
-            S.n_frames = P.n_frames;
-            S.tile_prefix = d_tile_prefix;
+            S.tiles = P.tiles;
             S.tile_stats = P.tile_stats;
-            S.B = B;
             S.F = F;
             S.total_tiles = M.total_tiles;
             oe::oe_feat_tile_stats_kernel<<<std::min(M.total_tiles, fe->sm_count * 8), oe::kMaxMel, 0, stream>>>(S);
@@ -732,22 +807,24 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         oe::UttStatsParams U;
         U.tile_stats = P.tile_stats;
         U.tile_prefix = d_tile_prefix;
-        U.n_frames = P.n_frames;
+        U.n_frames = d_n_frames;
         U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
         U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
         U.F = F;
         oe::oe_utt_stats_kernel<<<B, oe::kMaxMel, 0, stream>>>(U);
         OE_CUDA(cudaGetLastError());
     }
-    if (bt->d_stats) {
+    if (bt->d_stats && M.total_tiles > 0) {
         oe::GlobalStatsParams G;
         G.tile_stats = P.tile_stats;
-        G.tile_prefix = d_tile_prefix;
-        G.n_frames = P.n_frames;
+        G.tiles = P.tiles;
+        G.partial = reinterpret_cast<double*>(ws + M.stat_partial);
         G.stats = bt->d_stats;
-        G.B = B;
+        G.count = (double)M.total_frames;
+        G.total_tiles = M.total_tiles;
         G.F = F;
-        oe::oe_global_stats_kernel<<<1, oe::kMaxMel + 32, 0, stream>>>(G);
+        oe::oe_global_stats_partial_kernel<<<oe::kStatBlocks, oe::kMaxMel, 0, stream>>>(G);
+        oe::oe_global_stats_final_kernel<<<1, oe::kMaxMel + 32, 0, stream>>>(G);
         OE_CUDA(cudaGetLastError());
     }
     if (M.two_phase && d_out && M.total_rows > 0) {
@@ -756,7 +833,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         Z.raw = M.feats ? reinterpret_cast<const float*>(d_wav) : reinterpret_cast<const float*>(ws + M.raw);
         Z.frame_prefix = reinterpret_cast<const int64_t*>(ws + (M.feats ? M.wav_off : M.frame_prefix));
         Z.row_prefix = reinterpret_cast<const int64_t*>(ws + M.row_prefix);
-        Z.n_frames = P.n_frames;
+        Z.n_frames = d_n_frames;
         Z.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
         Z.out = d_out;
         Z.pitch = pitch;
@@ -775,11 +852,12 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         Z.cmvn_mean = bt->d_cmvn_mean;
         Z.cmvn_istd = bt->d_cmvn_istd;
         Z.cmvn_on_pad = bt->cmvn_on_padding;
-        Z.B = B;
         Z.F = F;
-        Z.total_rows = M.total_rows;
-        const int64_t blocks = std::min<int64_t>((M.total_rows + 7) / 8, (int64_t)fe->sm_count * 8);
-        oe::oe_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(Z);
+        const bool vec = (F % 4 == 0) && (pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(Z.raw) & 15) &&
+                         !(reinterpret_cast<uintptr_t>(d_out) & 15);
+        dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + 31) / 32));
+        if (vec) oe::oe_finalize_kernel<4><<<zgrid, 256, 0, stream>>>(Z);
+        else oe::oe_finalize_kernel<1><<<zgrid, 256, 0, stream>>>(Z);
         OE_CUDA(cudaGetLastError());
     }
     return OE_OK;
