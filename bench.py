@@ -1,0 +1,347 @@
+"""Benchmark of the acoustic front-end hot path (BASELINE.json metric: fbank audio-sec/sec, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A "step" is one pass of the hot path over one batch of synthetic 16 kHz int16 audio:
+BASELINE config[1] -- AISHELL front-end + online speed perturb {0.9, 1.0, 1.1} + per-utterance
+normalisation (the recipe default) + SpecAugment (3, 2, 50, 10) + global CMVN, batch 256 of 2-10 s
+utterances -- plus accumulation of the CMVN statistics.  With N > 1 every rank runs the same
+workload on its own utterances (weak scaling, no data-path collective) and the one collective of the
+path, the 161-double CMVN-stats all-reduce, closes the timed region.
+
+Keys of the JSON line (see the task contract): value = device-resident whole-job throughput; e2e = same
+metric through the public collate API from pinned HOST memory (H2D + D2H inside the timed region);
+roofline = the fbank kernel alone against the measured HBM peak; cpu_baseline = the reference CPU path
+(oracle collate port calling torchaudio.compliance.kaldi.fbank) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = ('configs[1]: AISHELL front-end, batch 256 x U[2,10] s 16 kHz int16, online speed perturb '
+            '{0.9,1.0,1.1}, per-utt norm, spec_aug(3,2,50,10), global CMVN + CMVN-stats accumulation')
+BATCH = 256
+POOL = 8            # distinct batches cycled so the inputs (~0.4 GB) exceed the 126 MB L2
+CONF = {'resample_rate': 16000, 'speed_perturb_rate': 0, 'speeds': [0.9, 1.1, 0.1], 'wav_dither': 0.0,
+        'mel_bins': 80}
+AUG = dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10)
+SPEEDS = (0.9, 1.0, 1.1)
+
+
+def workload(rank):
+    """Lengths (seed 1002), speeds (seed 1003) -- BASELINE.md section 4; per-rank offsets for weak scaling."""
+    rng_l = np.random.default_rng(1002 + 7919 * rank)
+    rng_s = np.random.default_rng(1003 + 7919 * rank)
+    lens = np.round(rng_l.uniform(2.0, 10.0, BATCH) * 16000).astype(np.int32)
+    speeds = [SPEEDS[i] for i in rng_s.integers(0, 3, BATCH)]
+    return lens, speeds
+
+
+def synth_pool_host(lens, rank, count):
+    """int16 Gaussian sigma=3000 (clipped) packed batches in pinned host memory."""
+    import torch
+    from openeat_b200.frontend import aligned_offsets
+    offs, total = aligned_offsets(lens)
+    gen = torch.Generator().manual_seed(1001 + rank)
+    pool = []
+    for _ in range(count):
+        x = (torch.randn(total, generator=gen) * 3000.0).round_().clamp_(-32768, 32767).to(torch.int16)
+        pool.append(x.pin_memory())
+    return pool, offs
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference CPU path (also the cpu_baseline leg)
+_CPU = {}
+
+
+def _cpu_init(pcm, lens, offs, speeds):
+    import torch
+    torch.set_num_threads(1)
+    _CPU.update(pcm=pcm, lens=lens, offs=offs, speeds=speeds)
+    from oracle import collate
+    _CPU['collate'] = collate.AudioCollate(feature_extraction_conf=CONF, normalization=True, spec_aug=True,
+                                           spec_aug_conf=AUG, speed_fn=collate.default_speed_fn())
+
+
+def _cpu_work(idx):
+    """The reference's per-utterance chain on one core: speed perturb -> kaldi.fbank -> _normalization ->
+    _spec_augmentation (oracle/collate.py restates dataset.py:39-118,185-209)."""
+    pcm, lens, offs, speeds = _CPU['pcm'], _CPU['lens'], _CPU['offs'], _CPU['speeds']
+    batch = [('u%d' % i, (pcm[offs[i]:offs[i] + lens[i]].astype(np.float32), 16000), [1], speeds[i]) for i in idx]
+    random.seed(1234 + int(idx[0]))
+    _, out = _CPU['collate'](batch)
+    return float(sum(lens[i] for i in idx)) / 16000.0, int(out['features_length'].sum())
+
+
+def cpu_reference_throughput(lens, speeds, steps, warmup):
+    """Audio-sec/sec of the reference CPU pipeline on all host cores; each step = the same 256-utterance
+    batch split over `cores` worker processes (16-utterance sub-batches, like the recipe's batch 16)."""
+    import multiprocessing as mp
+    from openeat_b200.frontend import aligned_offsets
+    cores = len(os.sched_getaffinity(0))
+    offs, total = aligned_offsets(lens)
+    rng = np.random.default_rng(1001)
+    pcm = np.clip(np.round(rng.normal(0.0, 3000.0, total)), -32768, 32767).astype(np.int16)
+    from oracle import collate
+    impl = collate.default_fbank_fn()[1]
+    chunks = [list(range(i, min(i + 16, len(lens)))) for i in range(0, len(lens), 16)]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(pcm, lens, offs, speeds)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_work, chunks)
+        t0 = time.perf_counter()
+        secs = 0.0
+        for _ in range(steps):
+            secs += sum(r[0] for r in pool.map(_cpu_work, chunks))
+        dt = time.perf_counter() - t0
+    return secs / dt, cores, dt / steps * 1e3, impl
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    lens, speeds = workload(0)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    steps = min(steps, 10)                       # bounded: each step is ~1-2 s of 16-core CPU work
+    value, cores, ms, impl = cpu_reference_throughput(lens, speeds, steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': 'fbank_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch': BATCH, 'note': 'CPU reference path, rank 0 only'},
+        'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+                         'sample': 'one 256-utterance batch (%.0f audio-s) per step, %d steps; oracle collate port '
+                                   'calling %s (the function the reference calls at dataset.py:93-100), torchaudio.functional.speed '
+                                   '(libsox substitute), numpy norm/spec_aug; %d worker processes x 1 thread'
+                                   % (lens.sum() / 16000.0, steps, impl, cores)},
+        'e2e': {'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from openeat_b200.cmvn import all_reduce_stats
+    from openeat_b200.dataset import _plan_batch, _run_plan, audio_collate_func
+    from openeat_b200.feature_processor import plan_spec_augmentation
+    from openeat_b200.frontend import default_frontend
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    fe = default_frontend(80, 16000, dev)
+    lens, speeds = workload(rank)
+    host_pool, offs = synth_pool_host(lens, rank, POOL)
+    dev_pool = [h.to(dev) for h in host_pool]
+    keys = ['utt%d' % i for i in range(BATCH)]
+    labels = [[1, 2, 3]] * BATCH
+    audio_s = float(lens.sum()) / 16000.0
+    # synthetic global CMVN (any finite vectors exercise the same arithmetic)
+    mean = torch.linspace(8.0, 12.0, 80, device=dev)
+    istd = torch.linspace(0.4, 0.6, 80, device=dev)
+    stats = torch.zeros(161, dtype=torch.float64, device=dev)
+
+    # ---- plans: the host RNG work is done once per pool entry and reused (value leg) ----
+    random.seed(4242 + rank)
+    plans = []
+    for _ in range(POOL):
+        plan = _plan_batch(keys, labels, lens, [16000] * BATCH, speeds, CONF)
+        aug = [plan_spec_augmentation(int(t), 80, **AUG) for t in plan.frames]
+        plans.append((plan, np.array([a[0] for a in aug], np.int32), np.array([a[1] for a in aug], np.int32)))
+
+    def step_resident(i):
+        plan, tm, fm = plans[i % POOL]
+        _run_plan(plan, 80, dev_pool[i % POOL], offs, lens, normalization=True, tmask=tm, fmask=fm,
+                  cmvn=(mean, istd), cmvn_on_padding=True, stats=stats)
+
+    collate = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=True, spec_aug=True,
+                                 spec_aug_conf=AUG, global_cmvn=(mean, istd), cmvn_stats=stats)
+
+    def step_e2e(i):
+        """Public API from pinned host memory: H2D of the PCM, all kernels, D2H of the step's result
+        (frame counts + the running CMVN statistics; the features stay on the GPU for the model)."""
+        _, out = collate.collate_packed(host_pool[i % POOL], offs, lens, keys, labels, speeds)
+        return out['features_length'].cpu(), stats.cpu()
+
+    def timed(fn, steps, warmup, with_allreduce):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = fe.launches
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        if with_allreduce:
+            all_reduce_stats(stats)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), fe.launches - l0
+
+    warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, warmup, world > 1)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * audio_s * args.steps / (ms_total * 1e-3)
+    stats.zero_()
+    random.seed(99 + rank)
+    ms_e2e, _ = timed(step_e2e, args.steps, warmup, world > 1)
+    e2e_value = world * audio_s * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (oe_fbank_kernel), timed alone on its own stream position ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        frames = fe.num_frames_array(lens)
+        alg_bytes = 2.0 * float(lens.sum()) + 4.0 * 80 * float(frames.sum())       # int16 in, fp32 out
+        out = torch.empty((int(frames.sum()), 80), device=dev)
+        for i in range(3):
+            fe.fbank(dev_pool[i % POOL], offs, lens, layout='ragged', out=out)
+        torch.cuda.synchronize()
+        durs = []
+        for i in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fe.fbank(dev_pool[i % POOL], offs, lens, layout='ragged', out=out)
+            b.record()
+            torch.cuda.synchronize()
+            durs.append(a.elapsed_time(b))
+        dur_ms = float(np.mean(durs))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'fbank_traffic.json'))).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'kernel': 'oe_fbank_kernel<int16, mel80> (+ oe_tile_desc_kernel)',
+                'launch_ms': dur_ms, 'alg_bytes_per_launch': alg_bytes,
+                'peak_source': 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',
+                'note': 'co-limited by FP32 issue rate (about 12 k lane-ops/frame), see DESIGN.md'}
+        if world == 1:
+            v, cores, cms, impl = cpu_reference_throughput(lens, speeds, 3, 1)
+            cpu = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+                   'sample': '3 x one 256-utterance batch (%.0f audio-s each); oracle collate port calling %s, torchaudio.functional.speed, '
+                             'numpy norm/spec_aug on %d processes x 1 thread' % (audio_s, impl, cores)}
+
+    if rank == 0:
+        h2d = int(host_pool[0].numel() * 2)
+        line = {
+            'metric': 'fbank_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'audio_s_per_step_per_gpu': audio_s,
+                       'l2': 'inputs cycle through %d distinct batches (%.0f MB int16 per GPU) > 126 MB L2' %
+                             (POOL, POOL * h2d / 1e6),
+                       'parallelism': 'utterance sharding, dp%d; one 161 x f64 NCCL all-reduce closes the timed region'
+                                      % world if world > 1 else 'single GPU'},
+            'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': BATCH * 4 + 161 * 8, 'ms_per_step': ms_e2e / args.steps,
+                    'api': 'openeat_b200.dataset.audio_collate_func.collate_packed (pinned int16 -> GPU features; '
+                           'frame counts + CMVN stats read back)'},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', init_method='env://', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

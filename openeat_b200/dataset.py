@@ -1,0 +1,297 @@
+"""Drop-in for the front-end part of ``openeat/dataset/dataset.py``: ``_extract_feature`` and
+``audio_collate_func`` with the reference's signatures, output structure, sort order, Python-``random``
+call order and drop-on-error convention -- the numeric work is ONE fused launch
+sequence per batch on the GPU instead of a per-utterance CPU loop.
+
+Differences a caller can observe (all deliberate):
+  * tensors come back on the GPU by default (``output_device='cpu'`` restores the reference's CPU
+    tensors); ``features`` are the same zero-padded (B, Tmax, F) fp32 tensor either way;
+  * wav decoding is built in for 16-bit PCM WAV (stdlib ``wave``; the reference needs libsox);
+    an item's second field may also be an in-memory int16 / fp32 array or ``(array, sample_rate)``;
+  * speed perturb uses the torchaudio sinc resampler semantics (libsox is not reproducible here);
+  * optional extras the reference applies later on the device can be fused in:
+    ``global_cmvn=(mean, istd)`` (GlobalCMVN, encoder.py:221-222) and ``cmvn_stats`` accumulation.
+"""
+import logging
+import random
+import wave
+
+import numpy as np
+import torch
+
+from .audio_processor import _speed_generator
+from .feature_processor import plan_spec_augmentation, plan_spec_substitute
+from .frontend import aligned_offsets, default_frontend, pack_waveforms, speed_ratio
+
+IGNORE_ID = -1  # openeat/utils/common.py:24
+
+
+def read_wav(path, start=None, end=None):
+    """dataset.py:62-72 for 16-bit PCM WAV: returns (int16 samples of channel 0, sample_rate);
+    ``start`` / ``end`` are seconds (segmented wav.scp entries ``path,start,end``)."""
+    with wave.open(path, 'rb') as w:
+        sr = w.getframerate()
+        if w.getsampwidth() != 2:
+            raise ValueError('%s: only 16-bit PCM wav is supported' % path)
+        nch = w.getnchannels()
+        if start is not None:
+            s = int(float(start) * sr)
+            e = int(float(end) * sr)
+            w.setpos(min(s, w.getnframes()))
+            raw = w.readframes(max(0, e - s))
+        else:
+            raw = w.readframes(w.getnframes())
+    pcm = np.frombuffer(raw, dtype='<i2')
+    if nch > 1:
+        pcm = pcm.reshape(-1, nch)[:, 0]
+    return pcm, sr
+
+
+def _load_item(x):
+    """(samples, sample_rate) for one batch item ``(key, path_or_array, tokenid, speed)``."""
+    wav = x[1]
+    if isinstance(wav, str):
+        value = wav.strip().split(",")
+        # 1 for general wav.scp, 3 for segmented wav.scp (dataset.py:56-58)
+        assert len(value) == 1 or len(value) == 3
+        if len(value) == 3:
+            return read_wav(value[0], value[1], value[2])
+        return read_wav(value[0])
+    if isinstance(wav, tuple):
+        return np.asarray(wav[0]), int(wav[1])
+    return np.asarray(wav), 16000
+
+
+class _Plan(object):
+    """Host-side description of one batch after all random draws, before any GPU work.  ``src[i]`` is the
+    position, in the packed input buffer, of the utterance that ends up i-th after the length sort."""
+    __slots__ = ('keys', 'labels', 'src', 'ratios', 'frames', 'sample_rate')
+
+
+def _plan_batch(keys_in, labels_in, nsamples, sample_rates, speeds_in, conf, target_rate=16000, loaded=None):
+    """The host half of _extract_feature (dataset.py:47-118) for utterances that are already in memory:
+    decide speeds with the reference's RNG call order, compute frame counts, drop failures (printing
+    the reference's message), sort by length descending.  ``loaded[i]`` False marks an utterance whose
+    load failed before the reference would have drawn any random number."""
+    speed_perturb_rate = conf.get('speed_perturb_rate', 0.5)
+    speeds = conf.get('speeds', None)
+    fe = default_frontend(conf['mel_bins'], target_rate)
+    keys, labels, src, ratios, lengths = [], [], [], [], []
+    for i in range(len(keys_in)):
+        if loaded is not None and not loaded[i]:
+            continue
+        try:
+            sample_rate = int(sample_rates[i])
+            chain = []
+            resample_rate = conf.get('resample_rate', sample_rate)
+            n = int(nsamples[i])
+            if resample_rate != sample_rate:                     # dataset.py:77-84
+                g = int(np.gcd(int(sample_rate), int(resample_rate)))
+                chain.append((int(sample_rate) // g, int(resample_rate) // g))
+                n = fe.resample_out_len(n, *chain[-1])
+                sample_rate = resample_rate
+            speed = speeds_in[i]
+            if random.random() < speed_perturb_rate:             # dataset.py:88-89 (drawn for every utterance)
+                speed = _speed_generator(speeds)
+            if speed != 1.0:                                     # dataset.py:90-91
+                chain.append(speed_ratio(speed, sample_rate))
+                n = fe.resample_out_len(n, *chain[-1])
+            if sample_rate != target_rate:
+                raise ValueError('sample rate %d is not supported by this front-end build (needs %d; '
+                                 'set resample_rate)' % (sample_rate, target_rate))
+            if conf['wav_dither'] != 0.0:
+                raise ValueError('wav_dither is stochastic (torch.randn inside kaldi.fbank) and is not '
+                                 'built; use 0.0')
+            m = fe.num_frames(n)
+            # kaldi.py:142 asserts 2 <= window_size <= len(waveform); the reference prints it and drops
+            assert m > 0, 'choose a window size 400 that is [2, %d]' % n
+            keys.append(keys_in[i])
+            labels.append(np.array(labels_in[i]))
+            src.append(i)
+            ratios.append(chain)
+            lengths.append(m)
+        except (Exception) as e:                                 # dataset.py:108-111
+            print(e)
+            logging.warning('read utterance {} error'.format(keys_in[i]))
+    order = np.argsort(lengths)[::-1] if lengths else []          # dataset.py:114
+    p = _Plan()
+    p.keys = [keys[i] for i in order]
+    p.labels = [labels[i] for i in order]
+    p.src = np.array([src[i] for i in order], dtype=np.int64)
+    p.ratios = [ratios[i] for i in order]
+    p.frames = np.array([lengths[i] for i in order], dtype=np.int32)
+    p.sample_rate = target_rate
+    return p
+
+
+def _load_batch(batch):
+    """Decodes every item; a failing item is reported like the reference does and marked not loaded."""
+    waves, rates, loaded = [], [], []
+    for x in batch:
+        try:
+            pcm, sr = _load_item(x)
+            waves.append(pcm)
+            rates.append(sr)
+            loaded.append(True)
+        except (Exception) as e:                                 # dataset.py:108-111
+            print(e)
+            logging.warning('read utterance {} error'.format(x[0]))
+            waves.append(np.zeros(0, np.int16))
+            rates.append(16000)
+            loaded.append(False)
+    return waves, rates, loaded
+
+
+def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused):
+    """The device half: [resample chain] -> fused fbank of every planned utterance into one tensor.
+    ``dev_wav`` is the packed device buffer (int16 or fp32) the plan's ``src`` indices refer to."""
+    fe = default_frontend(mel_bins, plan.sample_rate)
+    B = len(plan.src)
+    F = mel_bins
+    if B == 0:
+        return None, fe
+    tmax = int(plan.frames.max())
+    if out_layout == 'padded':
+        out = torch.empty((B, tmax, F), dtype=torch.float32, device=fe.device)
+        rows = np.arange(B, dtype=np.int64) * tmax
+        nrows = np.full(B, tmax, dtype=np.int32)
+    else:
+        out = torch.empty((int(plan.frames.sum()), F), dtype=torch.float32, device=fe.device)
+        rows = np.concatenate([[0], np.cumsum(plan.frames[:-1].astype(np.int64))]).astype(np.int64)
+        nrows = plan.frames.copy()
+    offs = np.asarray(offs, dtype=np.int64)
+    lens = np.asarray(lens, dtype=np.int32)
+    direct = np.array([i for i in range(B) if not plan.ratios[i]], dtype=np.int64)
+    resamp = np.array([i for i in range(B) if plan.ratios[i]], dtype=np.int64)
+
+    def call(wav, o, l, idx):
+        kw = dict(fused)
+        for k in ('tmask', 'fmask'):
+            if kw.get(k) is not None:
+                kw[k] = np.ascontiguousarray(np.asarray(kw[k])[idx])
+        if kw.get('frame_maps') is not None:
+            kw['frame_maps'] = [kw['frame_maps'][i] for i in idx]
+        fe.fbank(wav, o, l, layout='custom', out=out.view(-1, F), out_rows=rows[idx], out_nrows=nrows[idx], **kw)
+
+    if len(direct):
+        call(dev_wav, offs[plan.src[direct]], lens[plan.src[direct]], direct)
+    if len(resamp):
+        cur, cur_offs, cur_lens = dev_wav, offs[plan.src[resamp]], lens[plan.src[resamp]]
+        depth = max(len(plan.ratios[i]) for i in resamp)
+        for d in range(depth):                                   # resample_rate stage, then speed stage
+            stage = [plan.ratios[i][d] if d < len(plan.ratios[i]) else None for i in resamp]
+            cur, cur_offs, cur_lens = fe.resample(cur, cur_offs, cur_lens, stage)
+        call(cur, cur_offs, cur_lens, resamp)
+    return out, fe
+
+
+def _pack_loaded(waves):
+    any_f32 = any(np.asarray(w).dtype.kind == 'f' for w in waves)
+    return pack_waveforms(waves, dtype=np.float32 if any_f32 else np.int16)
+
+
+def _extract_feature(batch, feature_extraction_conf):
+    """openeat/dataset/dataset.py:39-118.  Returns (sorted_keys, sorted_feats, sorted_labels) with
+    ``sorted_feats`` a list of (T_i, mel_bins) float32 numpy arrays, longest first."""
+    waves, rates, loaded = _load_batch(batch)
+    plan = _plan_batch([x[0] for x in batch], [x[2] for x in batch], [len(w) for w in waves], rates,
+                       [x[3] for x in batch], feature_extraction_conf, loaded=loaded)
+    out = None
+    if len(plan.src):
+        buf, offs, lens = _pack_loaded(waves)
+        fe = default_frontend(feature_extraction_conf['mel_bins'])
+        out, _ = _run_plan(plan, feature_extraction_conf['mel_bins'], buf.to(fe.device, non_blocking=True), offs, lens,
+                           out_layout='ragged')
+    feats = []
+    if out is not None:
+        host = out.cpu().numpy()
+        r = 0
+        for m in plan.frames:
+            feats.append(host[r:r + m])
+            r += int(m)
+    return plan.keys, feats, plan.labels
+
+
+class audio_collate_func(object):
+    """Collate function for AudioDataset -- openeat/dataset/dataset.py:155-239, ``data_type='wav'``.
+
+    Extra keyword-only options (not in the reference): ``output_device`` ('cuda' default, or 'cpu'),
+    ``global_cmvn=(mean, istd)`` fp32 tensors to fuse GlobalCMVN (applied to padding too, exactly like
+    the encoder does on the padded batch), ``cmvn_stats`` a float64 [2F+1] device tensor to accumulate
+    raw-feature statistics into.
+    """
+
+    def __init__(self, feature_dither=0.0, spec_aug=False, spec_aug_conf=None, spec_sub=False,
+                 spec_sub_conf=None, data_type="kaldi", feature_extraction_conf=None, normalization=True,
+                 *, output_device='cuda', global_cmvn=None, cmvn_stats=None):
+        self.feature_dither = feature_dither
+        self.spec_sub = spec_sub
+        self.spec_aug = spec_aug
+        self.spec_sub_conf = spec_sub_conf
+        self.spec_aug_conf = spec_aug_conf
+        self.data_type = data_type
+        self.feature_extraction_conf = feature_extraction_conf
+        self.normalization = normalization
+        self.output_device = output_device
+        self.global_cmvn = global_cmvn
+        self.cmvn_stats = cmvn_stats
+        print('normalize feature', self.normalization)              # dataset.py:183
+        if data_type != 'wav':
+            raise NotImplementedError("openeat_b200.audio_collate_func accelerates data_type='wav'; Kaldi-ark "
+                                      "features (dataset.py:120-152) are a 'next' row (SURVEY 8f.4)")
+        if feature_dither != 0.0:
+            raise NotImplementedError('feature_dither is stochastic (np.random per cell) and is not built; '
+                                      'every shipped recipe sets 0.0')
+
+    def __call__(self, batch):
+        if len(batch) == 1:                                          # dataset.py:186-187
+            batch = batch[0]
+        waves, rates, loaded = _load_batch(batch)
+        buf, offs, lens = _pack_loaded(waves)
+        return self.collate_packed(buf, offs, lens, [x[0] for x in batch], [x[2] for x in batch],
+                                   [x[3] for x in batch], sample_rates=rates, loaded=loaded)
+
+    def collate_packed(self, wav, offsets, lens, keys, labels, speeds=None, sample_rates=None, loaded=None):
+        """Same result as ``__call__`` for a batch that is already decoded and packed: ``wav`` is one int16
+        (or fp32, int16 scale) tensor -- pinned host memory (copied asynchronously) or already on the
+        device -- holding utterance i at ``offsets[i]`` (multiples of 8 samples) with ``lens[i]`` samples.
+        This is the entry point a native data loader hands its PCM to."""
+        conf = self.feature_extraction_conf
+        B_in = len(keys)
+        speeds = [1.0] * B_in if speeds is None else speeds
+        sample_rates = [16000] * B_in if sample_rates is None else sample_rates
+        plan = _plan_batch(keys, labels, lens, sample_rates, speeds, conf, loaded=loaded)
+        F = conf['mel_bins']
+        frames = plan.frames
+        fused = {'normalization': bool(self.normalization)}
+        if self.spec_sub:                                            # dataset.py:204-205, sorted order
+            fused['frame_maps'] = [plan_spec_substitute(int(t), **self.spec_sub_conf) for t in frames]
+        if self.spec_aug:                                            # dataset.py:208-209, sorted order
+            plans = [plan_spec_augmentation(int(t), F, **self.spec_aug_conf) for t in frames]
+            if len(plans) and len(plans[0][0]):
+                fused['tmask'] = np.array([p[0] for p in plans], dtype=np.int32)
+            if len(plans) and len(plans[0][1]):
+                fused['fmask'] = np.array([p[1] for p in plans], dtype=np.int32)
+        if self.global_cmvn is not None:
+            fused['cmvn'] = self.global_cmvn
+            fused['cmvn_on_padding'] = True
+        if self.cmvn_stats is not None:
+            fused['stats'] = self.cmvn_stats
+        features = None
+        if len(plan.src):
+            fe = default_frontend(F, plan.sample_rate)
+            dev_wav = wav if wav.is_cuda else wav.to(fe.device, non_blocking=True)
+            features, _ = _run_plan(plan, F, dev_wav, offsets, lens, **fused)
+        dev = torch.device(self.output_device)
+        features_length = torch.from_numpy(np.array(frames, dtype=np.int32))
+        ys = plan.labels
+        if features is None:                                         # dataset.py:219-220
+            features = torch.Tensor([])
+            targets = torch.Tensor([])
+        else:
+            targets = torch.nn.utils.rnn.pad_sequence([torch.from_numpy(np.asarray(y)).int() for y in ys],
+                                                      True, IGNORE_ID)
+        targets_length = torch.from_numpy(np.array([y.shape[0] for y in ys], dtype=np.int32))
+        inputs = {'features': features.to(dev), 'features_length': features_length.to(dev),
+                  'targets': targets.to(dev), 'targets_length': targets_length.to(dev)}
+        return plan.keys, inputs

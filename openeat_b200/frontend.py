@@ -123,6 +123,7 @@ class Frontend(object):
         self.torch_tables = torch_tables
         self._resamplers = {}
         self._ws = {}
+        self.launches = 0     # kernels launched through this handle (bench.py reports it as gpu_launches)
 
     def __del__(self):
         h = getattr(self, 'handle', None)
@@ -197,6 +198,7 @@ class Frontend(object):
         check(self.lib.oe_resample_workspace_bytes(self.handle, ctypes.byref(rb), ctypes.byref(need)))
         s, sp = self._stream(stream)
         ws = self._workspace(('rs', s.cuda_stream), need.value)
+        self.launches += 1 if B and int(olens.max()) > 0 else 0
         check(self.lib.oe_resample(self.handle, ctypes.byref(rb), ctypes.c_void_p(wav.data_ptr()),
                                    ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
                                    ws.numel(), sp))
@@ -204,7 +206,7 @@ class Frontend(object):
 
     # ------------------------------------------------------------------ fbank (+ fused chain)
     def fbank(self, wav, offsets, lens, *, layout='padded', out=None, max_rows=None, out_rows=None,
-              normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
+              out_nrows=None, normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
               cmvn_on_padding=False, stats=None, stream=None, features_in=False, want_out=True):
         """Runs one ragged batch.
 
@@ -212,7 +214,9 @@ class Frontend(object):
                   (rows, mel_bins) fp32 feature matrix.
         offsets   [B] sample (row) offsets, lens [B] samples (rows).
         layout    'padded' -> (B, Tmax, F) zero padded like pad_sequence (dataset.py:217-218);
-                  'ragged' -> (sum T_b, F).
+                  'ragged' -> (sum T_b, F);
+                  'custom' -> caller gives out (rows, F), out_rows [B] and optionally out_nrows [B]
+                  (used to let several calls fill one padded tensor).
         tmask / fmask   int32 [B, n, 2] half-open ranges (spec_aug plan) or None.
         frame_maps      list of int32 index maps (spec_sub plan) or None.
         cmvn      (mean, istd) fp32 device tensors, istd may be None (norm_var=False).
@@ -254,8 +258,16 @@ class Frontend(object):
                 out_rows = np.ascontiguousarray(out_rows, dtype=np.int64)
             if out is None:
                 out = torch.empty((int(frames.sum()), F), dtype=torch.float32, device=self.device)
+        elif layout == 'custom':
+            if out is None or out_rows is None:
+                raise FrontendError("layout='custom' needs out and out_rows")
+            out_rows = np.ascontiguousarray(out_rows, dtype=np.int64)
+            if out_nrows is not None:
+                nrows = np.ascontiguousarray(out_nrows, dtype=np.int32)
         else:
             raise ValueError(layout)
+        self.launches += self._count_launches(B, int(frames.sum()) if B else 0, features_in, normalization,
+                                              frame_maps is not None, stats is not None, out is not None)
         tm = fm = None
         n_t = n_f = 0
         if tmask is not None and np.size(tmask):
@@ -294,12 +306,29 @@ class Frontend(object):
                                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
         return out, out_frames
 
+    @staticmethod
+    def _count_launches(B, total_frames, features_in, norm, has_map, has_stats, has_out):
+        """Mirror of the launch sequence in oe_fbank_batch (csrc/oe_frontend.cu)."""
+        if B == 0 or total_frames == 0:
+            return 0
+        two_phase = features_in or norm or has_map
+        n = 1                                             # oe_tile_desc_kernel
+        if features_in:
+            n += 1 if (norm or has_stats) else 0          # oe_feat_tile_stats_kernel
+        else:
+            n += 1                                        # oe_fbank_kernel
+        n += 1 if norm else 0                             # oe_utt_stats_kernel
+        n += 2 if has_stats else 0                        # oe_global_stats_{partial,final}_kernel
+        n += 1 if (two_phase and has_out) else 0          # oe_finalize_kernel
+        return n
+
     def cmvn_apply(self, x, mean, istd=None, out=None, stream=None):
         """GlobalCMVN.forward on a contiguous fp32 device tensor (..., F)."""
         x = x.contiguous()
         if out is None:
             out = torch.empty_like(x)
         _, sp = self._stream(stream)
+        self.launches += 1 if x.numel() else 0
         check(self.lib.oe_cmvn_apply(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                      x.numel() // x.shape[-1], x.shape[-1], ctypes.c_void_p(mean.data_ptr()),
                                      ctypes.c_void_p(istd.data_ptr()) if istd is not None else None, sp))

@@ -45,6 +45,23 @@ def default_fbank_fn():
         return fn, 'oracle.fbank.fbank (numpy)'
 
 
+def default_speed_fn():
+    """Speed perturb for the timed CPU baseline: ``torchaudio.functional.speed`` (conv1d-based, the
+    substitute oracle itself) when torchaudio is importable, else the numpy restatement."""
+    try:
+        import torch
+        import torchaudio.functional as TF
+
+        def fn(waveform, sample_rate, speed):
+            if speed == 1.0:
+                return waveform
+            y, _ = TF.speed(torch.from_numpy(np.ascontiguousarray(waveform, dtype=np.float32))[None], sample_rate, speed)
+            return y[0].numpy()
+        return fn
+    except Exception:  # pragma: no cover
+        return ospeed.speed_perturb
+
+
 def read_wav(path, start=None, end=None):
     """16-bit PCM mono/multi-channel -> (float32 int16-scale samples of channel 0, sample_rate).
     Mirrors dataset.py:62-75 (``start``/``end`` in seconds -> frame_offset/num_frames)."""
@@ -65,10 +82,12 @@ def read_wav(path, start=None, end=None):
     return pcm.astype(np.float32), sr
 
 
-def extract_feature(batch, conf, fbank_fn=None, rng=random):
+def extract_feature(batch, conf, fbank_fn=None, rng=random, speed_fn=None):
     """dataset.py:39-118."""
     if fbank_fn is None:
         fbank_fn = default_fbank_fn()[0]
+    if speed_fn is None:
+        speed_fn = ospeed.speed_perturb
     speed_perturb_rate = conf.get('speed_perturb_rate', 0.5)
     speeds = conf.get('speeds', None)
     keys, feats, lengths, labels = [], [], [], []
@@ -93,7 +112,7 @@ def extract_feature(batch, conf, fbank_fn=None, rng=random):
             if rng.random() < speed_perturb_rate:
                 speed = ospeed.speed_generator(speeds, rng)
             if speed != 1.0:
-                waveform = ospeed.speed_perturb(waveform, sample_rate, speed)
+                waveform = speed_fn(waveform, sample_rate, speed)
             mat = fbank_fn(waveform, conf['mel_bins'], conf['wav_dither'], sample_rate)
             feats.append(mat)
             keys.append(x[0])
@@ -120,7 +139,7 @@ class AudioCollate(object):
 
     def __init__(self, feature_dither=0.0, spec_aug=False, spec_aug_conf=None, spec_sub=False,
                  spec_sub_conf=None, data_type='wav', feature_extraction_conf=None, normalization=True,
-                 fbank_fn=None, rng=random):
+                 fbank_fn=None, rng=random, speed_fn=None):
         assert data_type == 'wav'
         assert feature_dither == 0.0, 'feature dither is stochastic: no parity claim (SURVEY 8a a6)'
         self.spec_aug, self.spec_aug_conf = spec_aug, spec_aug_conf or {}
@@ -128,12 +147,13 @@ class AudioCollate(object):
         self.conf = feature_extraction_conf
         self.normalization = normalization
         self.fbank_fn = fbank_fn
+        self.speed_fn = speed_fn
         self.rng = rng
 
     def __call__(self, batch):
         if len(batch) == 1:
             batch = batch[0]
-        keys, xs, ys = extract_feature(batch, self.conf, self.fbank_fn, self.rng)
+        keys, xs, ys = extract_feature(batch, self.conf, self.fbank_fn, self.rng, self.speed_fn)
         if self.normalization:
             xs = [augment.normalization(x) for x in xs]
         if self.spec_sub:

@@ -1,0 +1,209 @@
+"""GPU tests of the reference-facing Python API (same names / arguments / error behaviour as OpenEAT's)
+against goldens produced by the reference's own functions (tests/golden, oracle/make_golden.py)."""
+import os
+import random
+import wave
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import collate as K          # noqa: E402
+from oracle import fbank as F            # noqa: E402
+from oracle import signals               # noqa: E402
+
+CONF = {'resample_rate': 16000, 'speed_perturb_rate': 0, 'speeds': [0.9, 1.1, 0.1], 'wav_dither': 0.0,
+        'mel_bins': 80}
+LENS = [16000, 9000, 5200, 12345, 300, 7777]
+VARIANTS = [('plain', dict(normalization=False)),
+            ('norm_aug', dict(normalization=True, spec_aug=True,
+                              spec_aug_conf=dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))),
+            ('sub_aug', dict(normalization=False, spec_sub=True, spec_sub_conf=dict(num_t_sub=3, max_t=30),
+                             spec_aug=True, spec_aug_conf=dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10)))]
+
+
+def write_wav(path, pcm, sr=16000):
+    with wave.open(str(path), 'wb') as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(np.asarray(pcm, dtype='<i2').tobytes())
+
+
+@pytest.fixture(scope='module')
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, 'collate.npz'))
+
+
+@pytest.fixture()
+def wav_batch(gold, tmp_path):
+    """The very batch the reference's audio_collate_func saw: wav files on disk, one < 400 samples,
+    plus a segmented entry ``path,start,end``."""
+    batch = []
+    for i in range(len(LENS)):
+        p = tmp_path / ('u%d.wav' % i)
+        write_wav(p, gold['pcm%d' % i])
+        batch.append(('utt%d' % i, str(p), [i + 1] * (i + 2), 1.0))
+    batch.append(('seg', str(tmp_path / 'u0.wav') + ',0.25,0.75', [9, 9], 1.0))
+    return batch
+
+
+@pytest.mark.parametrize('tag,kw', VARIANTS)
+def test_audio_collate_func_matches_reference_output(gold, wav_batch, tag, kw):
+    from openeat_b200.dataset import audio_collate_func
+    fn = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, **kw)
+    random.seed(4242)
+    keys, out = fn([wav_batch])                                   # DataLoader wraps the pre-built batch in a list
+    assert list(keys) == list(gold[tag + '_keys'])                # length-descending order, utt4 dropped
+    feats = out['features'].cpu().numpy()
+    ref = gold[tag + '_features']
+    assert out['features'].dtype == torch.float32 and out['features_length'].dtype == torch.int32
+    assert out['targets'].dtype == torch.int32 and out['targets_length'].dtype == torch.int32
+    assert np.array_equal(out['features_length'].cpu().numpy(), gold[tag + '_features_length'])
+    assert np.array_equal(out['targets'].cpu().numpy(), gold[tag + '_targets'])          # padded with -1
+    assert np.array_equal(out['targets_length'].cpu().numpy(), gold[tag + '_targets_length'])
+    assert feats.shape == ref.shape
+    assert np.array_equal(feats == 0, ref == 0)                   # SpecAug / SpecSub indices and padding bit-exact
+    assert np.abs(feats - ref).max() < 2e-3
+    # CPU tensors on request, like the reference's DataLoader workers return
+    fn_cpu = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, output_device='cpu', **kw)
+    random.seed(4242)
+    _, out_cpu = fn_cpu(wav_batch)                                # un-wrapped list form (dataset.py:186-187)
+    assert not out_cpu['features'].is_cuda and np.array_equal(out_cpu['features'].numpy(), feats)
+
+
+def test_extract_feature_signature_and_drop_convention(gold, wav_batch, capsys):
+    from openeat_b200.dataset import _extract_feature
+    keys, feats, labels = _extract_feature(wav_batch, CONF)
+    assert 'choose a window size 400 that is [2, 300]' in capsys.readouterr().out   # printed, not raised
+    assert keys == list(gold['plain_keys'])
+    assert [f.shape[0] for f in feats] == gold['plain_features_length'].tolist()
+    assert all(isinstance(f, np.ndarray) and f.dtype == np.float32 and f.shape[1] == 80 for f in feats)
+    for f, n in zip(feats, gold['plain_features_length']):
+        idx = keys.index(keys[[x.shape[0] for x in feats].index(f.shape[0])])
+        assert np.abs(f - gold['plain_features'][idx, :n]).max() < 1e-3
+    assert [len(l) for l in labels] == gold['plain_targets_length'].tolist()
+    assert _extract_feature([('bad', '/nonexistent.wav', [1], 1.0)], CONF) == ([], [], [])   # never raises
+    assert _extract_feature([], CONF) == ([], [], [])
+
+
+def test_empty_batch_like_reference(gold):
+    from openeat_b200.dataset import audio_collate_func
+    fn = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)
+    keys, out = fn([('short', gold['pcm4'], [1, 2], 1.0)])        # only a 300-sample utterance: dropped
+    assert keys == [] and out['features'].numel() == 0 and out['features_length'].numel() == 0
+
+
+def test_online_speed_perturb_in_collate(gold):
+    """speed_perturb_rate=1 -> the reference's generator always yields 0.9 (appendix A.1); offline speeds
+    arrive as item[3].  Checked against the CPU port with the substitute resampler oracle."""
+    from openeat_b200.dataset import audio_collate_func
+    conf = dict(CONF, speed_perturb_rate=1.0)
+    batch = [('u%d' % i, gold['pcm%d' % i], [1, 2, 3], 1.0) for i in (0, 1, 2, 3)]
+    random.seed(7)
+    keys, out = audio_collate_func(data_type='wav', feature_extraction_conf=conf, normalization=False)(batch)
+    obatch = [(k, (gold['pcm%d' % i].astype(np.float32), 16000), l, s) for (k, _, l, s), i in zip(batch, (0, 1, 2, 3))]
+    random.seed(7)
+    okeys, oout = K.AudioCollate(feature_extraction_conf=conf, normalization=False)(obatch)
+    assert keys == okeys
+    assert np.array_equal(out['features_length'].cpu().numpy(), oout['features_length'])
+    assert out['features_length'].tolist() == [F.num_frames(int(np.ceil(10 * n / 9))) for n in (16000, 12345, 9000, 5200)]
+    assert np.abs(out['features'].cpu().numpy() - oout['features']).max() < 2e-3
+    # offline speeds (dataset-level speed list) through item[3], online rate 0
+    batch2 = [('a', gold['pcm0'], [1], 1.1), ('b', gold['pcm1'], [2], 1.0), ('c', gold['pcm3'], [3], 0.9)]
+    keys2, out2 = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)(batch2)
+    obatch2 = [(k, (w.astype(np.float32), 16000), l, s) for k, w, l, s in batch2]
+    okeys2, oout2 = K.AudioCollate(feature_extraction_conf=CONF, normalization=False)(obatch2)
+    assert keys2 == okeys2 and np.abs(out2['features'].cpu().numpy() - oout2['features']).max() < 2e-3
+
+
+def test_resample_rate_path(gold):
+    """An 8 kHz file with resample_rate 16000 goes through the same sinc kernel as
+    torchaudio.transforms.Resample (dataset.py:77-84)."""
+    from openeat_b200.dataset import audio_collate_func
+    x8 = signals.make('speech', 6000, 77)
+    batch = [('k8', (x8, 8000), [1], 1.0), ('k16', (gold['pcm1'], 16000), [2], 1.0)]
+    keys, out = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)(batch)
+    okeys, oout = K.AudioCollate(feature_extraction_conf=CONF, normalization=False)(
+        [(k, (w[0].astype(np.float32), w[1]), l, s) for k, w, l, s in batch])
+    assert keys == okeys and np.abs(out['features'].cpu().numpy() - oout['features']).max() < 2e-3
+
+
+def test_fused_global_cmvn_and_stats(gold, golden_dir):
+    from openeat_b200.cmvn import GlobalCMVN, load_cmvn
+    from openeat_b200.dataset import audio_collate_func
+    mean, istd = load_cmvn(os.path.join(golden_dir, 'cmvn_stats.json'), True)
+    mean_t, istd_t = torch.from_numpy(mean).float().cuda(), torch.from_numpy(istd).float().cuda()
+    batch = [('u%d' % i, gold['pcm%d' % i], [1], 1.0) for i in (0, 1, 2, 3, 5)]
+    plain = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)
+    stats = torch.zeros(161, dtype=torch.float64, device='cuda')
+    fused = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False,
+                               global_cmvn=(mean_t, istd_t), cmvn_stats=stats)
+    _, a = plain(batch)
+    _, b = fused(batch)
+    ref = GlobalCMVN(mean_t, istd_t)(a['features'])                # what the encoder does to the padded batch
+    assert torch.equal(ref, b['features'])
+    assert stats[160].item() == int(a['features_length'].sum())
+
+
+def test_speed_processors(golden_dir):
+    from openeat_b200.audio_processor import _speed_generator, _speed_perturb
+    g = np.load(os.path.join(golden_dir, 'speed.npz'))
+    a = np.load(os.path.join(golden_dir, 'augment.npz'))
+    random.seed(5)
+    draws = [_speed_generator([0.9, 1.1, 0.1]) for _ in range(8)] + [_speed_generator(None)] + [_speed_generator([1.05])]
+    assert np.array_equal(np.array(draws), a['speed_draws'])
+    random.seed(6)
+    assert np.array_equal(np.array([_speed_generator([0.9, 1.1, 0]) for _ in range(8)]), a['speed_draws_uniform'])
+    w = torch.from_numpy(g['x'])[None]
+    assert _speed_perturb(w, 16000, 1.0) is w                      # audio_processor.py:31
+    for s, tag in [(0.9, '090'), (1.1, '110')]:
+        y = _speed_perturb(w, 16000, s)
+        assert y.shape == (1, g['y' + tag].shape[0]) and not y.is_cuda
+        assert np.abs(y[0].numpy() - g['y' + tag]).max() < 0.05
+        assert _speed_perturb(w.cuda(), 16000, s).is_cuda
+
+
+@pytest.mark.parametrize('i', range(5))
+def test_feature_processors_bit_exact(golden_dir, i):
+    from openeat_b200.feature_processor import _normalization, _spec_augmentation, _spec_substitute
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    x = g['x%d' % i]
+    x0 = x.copy()
+    random.seed(1000 + i)
+    assert np.array_equal(_spec_augmentation(x, num_t_mask=3, num_f_mask=2, max_t=50, max_f=10), g['aug%d' % i])
+    random.seed(2000 + i)
+    assert np.array_equal(_spec_substitute(x, max_t=30, num_t_sub=3), g['sub%d' % i])
+    random.seed(3000 + i)
+    y = _spec_augmentation(_spec_substitute(x, max_t=30, num_t_sub=3), num_t_mask=3, num_f_mask=2, max_t=50, max_f=10)
+    assert np.array_equal(y, g['subaug%d' % i])
+    assert np.array_equal(x, x0)                                   # input untouched, new array returned
+    if x.shape[0] > 1:
+        assert np.abs(_normalization(x) - g['norm%d' % i]).max() < 1e-5
+
+
+def test_global_cmvn_module(golden_dir):
+    from openeat_b200.cmvn import GlobalCMVN, load_cmvn
+    g = np.load(os.path.join(golden_dir, 'cmvn.npz'))
+    mean, istd = load_cmvn(os.path.join(golden_dir, 'cmvn_stats.json'), True)
+    m = GlobalCMVN(torch.from_numpy(mean).float(), torch.from_numpy(istd).float()).cuda()
+    assert sorted(m.state_dict()) == ['istd', 'mean']              # checkpoint compatibility
+    assert np.array_equal(m(torch.from_numpy(g['x']).cuda()).cpu().numpy(), g['y'])
+    m2 = GlobalCMVN(torch.from_numpy(mean).float(), torch.from_numpy(istd).float(), norm_var=False).cuda()
+    assert np.array_equal(m2(torch.from_numpy(g['x']).cuda()).cpu().numpy(), g['y_novar'])
+    with pytest.raises(RuntimeError):
+        m(torch.from_numpy(g['x']))                                # CPU tensor: no fallback
+
+
+def test_compute_cmvn_stats_roundtrip(gold, tmp_path, tables):
+    from openeat_b200.cmvn import compute_cmvn_stats, load_cmvn
+    waves = [gold['pcm%d' % i] for i in (0, 1, 2, 3, 4, 5)]
+    path = str(tmp_path / 'global_cmvn.json')
+    s, q, n = compute_cmvn_stats([waves[:3], waves[3:]], out_json=path)
+    feats = np.concatenate([F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1]) for w in waves if len(w) >= 400])
+    assert n == feats.shape[0]
+    mean, istd = load_cmvn(path, True)                             # the reference-format consumer reads it back
+    np.testing.assert_allclose(mean, feats.astype(np.float64).mean(0), rtol=1e-4)
+    np.testing.assert_allclose(istd, 1.0 / feats.astype(np.float64).std(0), rtol=1e-4)

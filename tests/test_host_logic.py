@@ -1,0 +1,119 @@
+"""CPU tests of the host-side logic: RNG plans, sharding, CMVN file formats, the world_size-2 gloo path."""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import augment as A
+
+
+def test_plans_follow_the_reference_rng_order():
+    from openeat_b200.feature_processor import plan_spec_augmentation, plan_spec_substitute
+    for seed, T in [(1, 498), (2, 48), (3, 1), (4, 7)]:
+        random.seed(seed)
+        subs = A.plan_spec_substitute(T, max_t=30, num_t_sub=3)
+        ref_aug = A.plan_spec_augmentation(T, 80, 3, 2, 50, 10)
+        tail = random.random()
+        random.seed(seed)
+        idx = plan_spec_substitute(T, max_t=30, num_t_sub=3)
+        aug = plan_spec_augmentation(T, 80, 3, 2, 50, 10)
+        assert np.array_equal(idx, A.substitute_index_map(T, subs)) and aug == ref_aug
+        assert random.random() == tail                              # same number of RNG words consumed
+
+
+def test_speed_generator_is_pure_host_logic(golden_dir):
+    from openeat_b200.audio_processor import _speed_generator
+    a = np.load(os.path.join(golden_dir, 'augment.npz'))
+    random.seed(5)
+    draws = [_speed_generator([0.9, 1.1, 0.1]) for _ in range(8)] + [_speed_generator(None)] + [_speed_generator([1.05])]
+    assert np.array_equal(np.array(draws), a['speed_draws'])
+    with pytest.raises(AssertionError):
+        _speed_generator([1.1, 0.9, 0.1])
+
+
+def test_cmvn_file_formats(golden_dir, tmp_path):
+    from openeat_b200.cmvn import load_cmvn, write_json_cmvn
+    g = np.load(os.path.join(golden_dir, 'cmvn.npz'))
+    mean, istd = load_cmvn(os.path.join(golden_dir, 'cmvn_stats.json'), True)
+    assert np.array_equal(mean, g['mean_json']) and np.array_equal(istd, g['istd_json'])
+    mean, istd = load_cmvn(os.path.join(golden_dir, 'cmvn_stats.kaldi.txt'), False)
+    assert np.array_equal(mean, g['mean_kaldi']) and np.array_equal(istd, g['istd_kaldi'])
+    p = str(tmp_path / 'c.json')
+    write_json_cmvn(p, g['sum'], g['sumsq'], int(g['count']))
+    mean2, istd2 = load_cmvn(p, True)
+    assert np.array_equal(mean2, g['mean_json']) and np.array_equal(istd2, g['istd_json'])
+    (tmp_path / 'bin').write_text('\0B junk')
+    with pytest.raises(ValueError):
+        load_cmvn(str(tmp_path / 'bin'), False)
+
+
+def test_sharding_and_batching():
+    from openeat_b200.sharding import dynamic_batches, shard_by_length, static_batches
+    rng = np.random.default_rng(1004)
+    lens = np.round(rng.uniform(1, 35, 2000) * 16000).astype(np.int64)
+    for ws in (1, 2, 4, 8):
+        shards = shard_by_length(lens, ws)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(2000))
+        loads = np.array([lens[s].sum() for s in shards])
+        assert loads.max() - loads.min() <= lens.max()              # balanced to within one utterance
+        assert all(np.array_equal(a, b) for a, b in zip(shards, shard_by_length(lens, ws)))   # deterministic
+    frames = (1 + (lens - 400) // 160).tolist()
+    batches = dynamic_batches(frames, 10000)
+    assert sorted(i for b in batches for i in b) == list(range(2000))
+    assert all(sum(frames[i] for i in b) <= 10000 or len(b) == 1 for b in batches)
+    assert static_batches(5, 2) == [[0, 1], [2, 3], [4]]
+
+
+WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from openeat_b200.cmvn import all_reduce_stats, write_json_cmvn, load_cmvn
+from openeat_b200.sharding import shard_by_length
+from oracle import fbank as F, signals, cmvn as C
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', init_method='env://')
+lens = [8000, 4000, 12000, 6000, 9000, 5000, 700]
+shard = shard_by_length(lens, world)[rank]
+feats = [F.fbank(signals.make('speech', lens[i], 500 + i).astype(np.float32)) for i in shard]
+s, q, n = C.compute_cmvn_stats(feats)                 # the local (per-GPU) part, stood in for by the oracle on CPU
+stats = torch.from_numpy(np.concatenate([s, q, [float(n)]]))
+all_reduce_stats(stats)                               # the path's one collective
+if rank == 0:
+    st = stats.numpy()
+    write_json_cmvn(sys.argv[2], st[:80], st[80:160], int(round(st[160])))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_stats_allreduce_gloo(tmp_path):
+    """N>1 host path on CPU: shard by length, local stats, ONE all-reduce of 161 doubles, rank 0 writes the
+    JSON the reference's load_cmvn reads; result equals the single-process statistics."""
+    from oracle import cmvn as C
+    from oracle import fbank as F
+    from oracle import signals
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    out = str(tmp_path / 'cmvn.json')
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), root, out], env=env))
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    lens = [8000, 4000, 12000, 6000, 9000, 5000, 700]
+    feats = [F.fbank(signals.make('speech', n, 500 + i).astype(np.float32)) for i, n in enumerate(lens)]
+    s, q, n = C.compute_cmvn_stats(feats)
+    import json
+    st = json.load(open(out))
+    assert st['frame_num'] == n
+    np.testing.assert_allclose(st['mean_stat'], s, rtol=1e-12)
+    np.testing.assert_allclose(st['var_stat'], q, rtol=1e-12)
+    mean, istd = C.load_cmvn(out, True)
+    assert np.isfinite(mean).all() and np.isfinite(istd).all()
