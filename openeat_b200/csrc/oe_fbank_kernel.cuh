@@ -43,6 +43,7 @@ struct FbankParams {
     const float* cmvn_istd;
     int cmvn_on_pad;
     float* tile_stats;              // [total_tiles][3][2][F]: per row-group column sum and sum of squared deviations
+    double* cta_stats;              // [gridDim.x][3][2][F] or null: this CTA's running sum / sum of squares (fp64)
     const DevTables* tab;
     float mel_w[512];               // standard-structure fast path: weights (x 1/4) in mel80::kOff order;
                                     // lives in the kernel-parameter constant bank -> FFMA constant operands
@@ -73,11 +74,12 @@ constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
 constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
 constexpr int kSmMask = kSmTwU + 9 * kRowE * 8;            // uchar rowmask[32], colmask[128]
 constexpr int kSmDesc = kSmMask + 32 + kMaxMel;            // TileDesc[2]
-constexpr int kSmStd = kSmDesc + 2 * 48;                   // end of the standard-mel layout
+constexpr int kSmAcc = kSmDesc + 2 * 48;                   // double acc[3][2][128]: CMVN-statistics accumulators
+constexpr int kSmStd = kSmAcc + 3 * 2 * kMaxMel * 8;       // end of the standard-mel layout
 constexpr int kSmMelIdx = kSmStd;                          // generic mel only: int start/len/off [3][128], group_begin[9] (+pad)
 constexpr int kSmMelW = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // generic mel only: float mel_w[nnz]
 static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0 &&
-              kSmDesc % 16 == 0, "align");
+              kSmDesc % 16 == 0 && kSmAcc % 16 == 0, "align");
 constexpr int kRowS = 34;           // float2 per frame of the self-conjugate-row scratch (32 + 2 pad = 272 B), in the p area
 static_assert(kSmRaw + 673 * 32 <= kSmTwA, "raw prefetch buffer must fit behind the power tile");
 static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
@@ -179,6 +181,9 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     const int rowO = F + 1;
 
     TileDesc* const sDesc = reinterpret_cast<TileDesc*>(smem + kSmDesc);
+    double* const sAcc = reinterpret_cast<double*>(smem + kSmAcc);
+    if (P.cta_stats != nullptr)
+        for (int i = tid; i < 3 * 2 * kMaxMel; i += kThreads) sAcc[i] = 0.0;
 
     // ---- first tile: descriptor, then its waveform starts moving before anything else ----
     int tile = blockIdx.x;
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                 }
             }
             __syncthreads();                                       // (5) output tile complete
-            if (P.tile_stats != nullptr) {
+            if (P.tile_stats != nullptr || P.cta_stats != nullptr) {
                 for (int idx = tid; idx < 3 * F; idx += kThreads) {
                     const int rg = idx / F, f = idx - rg * F;
                     const int n = stats_rows(nvalid, rg);
@@ -474,10 +479,16 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                             const float d = col[r * rowO] - mean;
                             m2 = fmaf(d, d, m2);
                         }
+                        if (P.cta_stats != nullptr) {          // sum x^2 = M2 + n mean^2, accumulated in fp64, fixed order
+                            sAcc[(rg * 2 + 0) * kMaxMel + f] += (double)s;
+                            sAcc[(rg * 2 + 1) * kMaxMel + f] += (double)m2 + (double)s * (double)mean;
+                        }
                     }
-                    float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * F;
-                    st[f] = s;
-                    st[F + f] = m2;
+                    if (P.tile_stats != nullptr) {
+                        float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * F;
+                        st[f] = s;
+                        st[F + f] = m2;
+                    }
                 }
             }
         } else {
@@ -531,6 +542,14 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
         }
     }
     cp_async_wait_all();
+    if (P.cta_stats != nullptr) {      // each accumulator is owned by one thread: no barrier needed
+        for (int idx = tid; idx < 3 * F; idx += kThreads) {
+            const int rg = idx / F, f = idx - rg * F;
+            double* const dst = P.cta_stats + ((int64_t)blockIdx.x * 3 + rg) * 2 * F;
+            dst[f] = sAcc[(rg * 2 + 0) * kMaxMel + f];
+            dst[F + f] = sAcc[(rg * 2 + 1) * kMaxMel + f];
+        }
+    }
 }
 
 }  // namespace oe

@@ -113,85 +113,85 @@ struct UttStatsParams {
 
 // feature_processor.py:5-8: mean and population std over the frames of one utterance, merged from the
 // per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2].
-__global__ void oe_utt_stats_kernel(const UttStatsParams P) {
-    const int b = blockIdx.x, f = threadIdx.x;
-    if (f >= P.F) return;
+// block = (F columns) x (kUttSlices slices of the partial list), combined through shared memory.
+constexpr int kUttSlices = 8;
+__global__ void __launch_bounds__(kMaxMel * kUttSlices) oe_utt_stats_kernel(const UttStatsParams P) {
+    __shared__ double sh[kUttSlices][kMaxMel];
+    const int b = blockIdx.x, f = threadIdx.x, y = threadIdx.y;
     const int nfr = P.n_frames[b];
     const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
+    const int np = 3 * ntiles;
     const float* base = P.tile_stats + (int64_t)P.tile_prefix[b] * 3 * 2 * P.F;
+    double acc = 0.0;
+    if (f < P.F) {
+#pragma unroll 4
+        for (int i = y; i < np; i += kUttSlices) acc += (double)base[(int64_t)i * 2 * P.F + f];
+    }
+    sh[y][f] = acc;
+    __syncthreads();
     double S = 0.0;
-    for (int i = 0; i < 3 * ntiles; ++i) S += (double)base[(int64_t)i * 2 * P.F + f];
-    const double mean = S / (double)nfr;
-    double m2 = 0.0;
-    for (int i = 0; i < ntiles; ++i) {
-        const int nvalid = min(kTileFrames, nfr - i * kTileFrames);
 #pragma unroll
-        for (int rg = 0; rg < 3; ++rg) {
-            const int rows = stats_rows(nvalid, rg);
-            const float* st = base + (int64_t)(3 * i + rg) * 2 * P.F;
+    for (int j = 0; j < kUttSlices; ++j) S += sh[j][f];
+    const double mean = S / (double)nfr;
+    __syncthreads();
+    acc = 0.0;
+    if (f < P.F) {
+#pragma unroll 4
+        for (int i = y; i < np; i += kUttSlices) {
+            const int nvalid = min(kTileFrames, nfr - (i / 3) * kTileFrames);
+            const int rows = stats_rows(nvalid, i % 3);
+            const float* st = base + (int64_t)i * 2 * P.F;
             const float inv = rows > 0 ? 1.0f / (float)rows : 0.f;     // rows <= 11: one fp32 rounding on a partial mean
             const double d = (double)(st[f] * inv) - mean;
-            m2 += (double)st[P.F + f] + (double)rows * d * d;
+            acc += (double)st[P.F + f] + (double)rows * d * d;
         }
     }
-    P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
-    P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / (double)nfr);
+    sh[y][f] = acc;
+    __syncthreads();
+    if (y == 0 && f < P.F) {
+        double m2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < kUttSlices; ++j) m2 += sh[j][f];
+        P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
+        P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / (double)nfr);
+    }
 }
 
 struct GlobalStatsParams {
-    const float* tile_stats;
-    const TileDesc* tiles;
-    double* partial;     // [kStatBlocks][2F]
-    double* stats;       // [2F+1] accumulated in place
+    const double* partial;   // [n_partials][2F]: sum, sum of squares written by the producer CTAs
+    double* stats;           // [2F+1] accumulated in place
     double count;
-    int total_tiles;
+    int n_partials;
     int F;
 };
-constexpr int kStatBlocks = 64;
 
-// compute_cmvn_stats, stage 1: block g sums a contiguous range of tiles in a fixed order (fp64).
-__global__ void oe_global_stats_partial_kernel(const GlobalStatsParams P) {
-    const int f = threadIdx.x, g = blockIdx.x;
-    if (f >= P.F) return;
-    const int per = (P.total_tiles + kStatBlocks - 1) / kStatBlocks;
-    const int t_lo = g * per, t_hi = min(P.total_tiles, t_lo + per);
-    double s = 0.0, q = 0.0;
-    for (int t = t_lo; t < t_hi; ++t) {
-        const int nvalid = P.tiles[t].nvalid;
+// compute_cmvn_stats: += sum, sum of squares and frame count into the caller's accumulator.  The producers'
+// partials are combined in index order (the tile -> CTA assignment is static), so the result is bitwise
+// reproducible run to run.
+__global__ void __launch_bounds__(256) oe_global_stats_final_kernel(const GlobalStatsParams P) {
+    __shared__ double sh[256];
+    const int f = blockIdx.x, j = threadIdx.x;               // one block per statistic (2F sums + the count)
+    if (f == 2 * P.F) {
+        if (j == 0) P.stats[2 * P.F] += P.count;
+        return;
+    }
+    double s = 0.0;
+    for (int g = j; g < P.n_partials; g += 256) s += P.partial[(int64_t)g * 2 * P.F + f];
+    sh[j] = s;
+    __syncthreads();
 #pragma unroll
-        for (int rg = 0; rg < 3; ++rg) {
-            const int rows = stats_rows(nvalid, rg);
-            if (rows == 0) continue;
-            const float* st = P.tile_stats + ((int64_t)t * 3 + rg) * 2 * P.F;
-            const double sb = (double)st[f];
-            s += sb;
-            q += (double)st[P.F + f] + sb * sb / (double)rows;
-        }
+    for (int w = 128; w >= 1; w >>= 1) {                      // fixed-shape tree: same order every run
+        if (j < w) sh[j] += sh[j + w];
+        __syncthreads();
     }
-    P.partial[(int64_t)g * 2 * P.F + f] = s;
-    P.partial[(int64_t)g * 2 * P.F + P.F + f] = q;
-}
-
-// stage 2: += sum, sum of squares and frame count into the caller's accumulator.
-__global__ void oe_global_stats_final_kernel(const GlobalStatsParams P) {
-    const int f = threadIdx.x;
-    if (f < P.F) {
-        double s = 0.0, q = 0.0;
-        for (int g = 0; g < kStatBlocks; ++g) {
-            s += P.partial[(int64_t)g * 2 * P.F + f];
-            q += P.partial[(int64_t)g * 2 * P.F + P.F + f];
-        }
-        P.stats[f] += s;
-        P.stats[P.F + f] += q;
-    } else if (f == P.F) {
-        P.stats[2 * P.F] += P.count;
-    }
+    if (j == 0) P.stats[f] += sh[0];
 }
 
 struct FeatStatsParams {
     const float* feats;          // ragged rows, pitch F
     const TileDesc* tiles;
     float* tile_stats;
+    double* cta_stats;           // [gridDim.x][3][2][F] or null
     int F, total_tiles;
 };
 
@@ -199,9 +199,11 @@ struct FeatStatsParams {
 // features (data_type != 'wav', dataset.py:190-191, or the numpy-level processor mirrors).
 __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
     const int f = threadIdx.x;
+    double as[3] = {0.0, 0.0, 0.0}, aq[3] = {0.0, 0.0, 0.0};
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileDesc d = P.tiles[tile];
         if (f >= P.F || d.nvalid <= 0) continue;
+#pragma unroll
         for (int rg = 0; rg < 3; ++rg) {
             const int n = stats_rows(d.nvalid, rg);
             const float* src = P.feats + (d.wav_start + 11 * rg) * P.F + f;   // feats mode: wav_start counts rows
@@ -213,10 +215,20 @@ __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
                     const float dd = src[(int64_t)r * P.F] - mean;
                     m2 = fmaf(dd, dd, m2);
                 }
+                as[rg] += (double)s;
+                aq[rg] += (double)m2 + (double)s * (double)mean;
             }
             float* const st = P.tile_stats + ((int64_t)tile * 3 + rg) * 2 * P.F;
             st[f] = s;
             st[P.F + f] = m2;
+        }
+    }
+    if (P.cta_stats != nullptr && f < P.F) {
+#pragma unroll
+        for (int rg = 0; rg < 3; ++rg) {
+            double* const dst = P.cta_stats + ((int64_t)blockIdx.x * 3 + rg) * 2 * P.F;
+            dst[f] = as[rg];
+            dst[P.F + f] = aq[rg];
         }
     }
 }
@@ -344,12 +356,14 @@ struct ResampleParams {
 };
 
 // torchaudio functional.py:1401-1432: y[m*new + p] = sum_q k[p][q] * xpad[m*orig + q], xpad = x shifted by width.
+// Generic table-driven kernel (any ratio); `skip_fast` leaves utterances to the specialised kernel below.
 template <bool kF32>
-__global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P) {
+__global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P, int fast_a, int fast_b) {
     const int b = blockIdx.y;
     const int n_out = P.out_len[b];
     const int n_in = P.in_len[b];
     const int tid_ = P.table_id[b];
+    if (tid_ >= 0 && (tid_ == fast_a || tid_ == fast_b)) return;
     float* const out = P.out + P.out_off[b];
     const int64_t ioff = P.in_off[b];
     const int stride = gridDim.x * blockDim.x;
@@ -376,6 +390,67 @@ __global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P
     }
 }
 
+// ---- specialised polyphase kernel for the speed-perturb ratios (9:10 and 11:10, width 7) ----
+// hann-windowed sinc taps vanish where the window argument is clamped (functional.py:1370-1381):
+// tap (p, q) is non-zero only if |(-p/new + (q - width)/orig) * 0.99 min(orig, new)| < 6.
+OE_CX bool rs_tap_nonzero(int orig, int neu, int width, int p, int q) {
+    const double base = (orig < neu ? orig : neu) * 0.99;
+    const double t = (-(double)p / neu + (double)(q - width) / orig) * base;
+    return t < 6.0 && t > -6.0;
+}
+
+struct RsFastParams {
+    ResampleParams r;
+    int table_id;
+    float coef[10 * 25];            // [new][taps] in the kernel-parameter constant bank
+};
+
+constexpr int kRsM = 256;           // polyphase blocks (of `new` outputs) per CTA, one per thread
+
+template <bool kF32, int ORIG, int NEW, int WIDTH>
+__global__ void __launch_bounds__(kRsM) oe_resample_fast_kernel(const RsFastParams P) {
+    constexpr int TAPS = 2 * WIDTH + ORIG;
+    constexpr int XIN = kRsM * ORIG + 2 * WIDTH;
+    __shared__ float sx[XIN + 8];
+    __shared__ float sy[kRsM * NEW];
+    const int b = blockIdx.y;
+    if (P.r.table_id[b] != P.table_id) return;
+    const int n_out = P.r.out_len[b];
+    const int m0 = blockIdx.x * kRsM;
+    if (m0 * NEW >= n_out) return;
+    const int n_in = P.r.in_len[b];
+    const int64_t ioff = P.r.in_off[b];
+    const int tid = threadIdx.x;
+    const int x_base = m0 * ORIG - WIDTH;                       // first input sample this CTA needs
+    for (int i = tid; i < XIN; i += kRsM) {
+        const int xi = x_base + i;
+        float v = 0.f;
+        if (xi >= 0 && xi < n_in)
+            v = kF32 ? __ldg(reinterpret_cast<const float*>(P.r.in) + ioff + xi)
+                     : (float)__ldg(reinterpret_cast<const int16_t*>(P.r.in) + ioff + xi);
+        sx[i] = v;
+    }
+    __syncthreads();
+    {
+        float x[TAPS];
+#pragma unroll
+        for (int q = 0; q < TAPS; ++q) x[q] = sx[tid * ORIG + q];
+        static_for<0, NEW>([&](auto pp) {
+            constexpr int p = decltype(pp)::value;
+            float acc = 0.f;
+            static_for<0, TAPS>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                if constexpr (rs_tap_nonzero(ORIG, NEW, WIDTH, p, q)) acc = fmaf(P.coef[p * TAPS + q], x[q], acc);
+            });
+            sy[tid * NEW + p] = acc;
+        });
+    }
+    __syncthreads();
+    float* const out = P.r.out + P.r.out_off[b] + (int64_t)m0 * NEW;
+    const int n_here = min(kRsM * NEW, n_out - m0 * NEW);
+    for (int i = tid; i < n_here; i += kRsM) out[i] = sy[i];
+}
+
 }  // namespace oe
 
 // ==========================================================================================
@@ -389,6 +464,7 @@ struct oe_frontend {
     std::vector<float> window, mel;
     std::vector<oe::RsTable> rs;
     std::vector<float> rs_coefs;
+    int rs_fast_9_10, rs_fast_11_10;   // table ids served by oe_resample_fast_kernel, or -1
     oe::RsTable* d_rs;
     float* d_rs_coefs;
     size_t fbank_smem;
@@ -478,7 +554,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     if (pitch < F) return fail(OE_ERR_INVALID, "out_pitch smaller than num_mel_bins");
     M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr;
     M.feats = feats;
-    M.need_stats = bt->norm_mode != OE_NORM_NONE || bt->d_stats != nullptr;
+    M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
     M.total_frames = M.total_rows = M.total_map = 0;
     M.max_rows = 0;
     int64_t tiles = 0;
@@ -520,7 +596,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 3 * 2 * F : 0);
     M.utt_mean = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
     M.utt_std = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
-    M.stat_partial = take(bt->d_stats ? 8 * (size_t)oe::kStatBlocks * 2 * F : 0);
+    M.stat_partial = take(bt->d_stats ? 8 * (size_t)(fe->sm_count * 8) * 3 * 2 * F : 0);
     M.total = o;
     return OE_OK;
 }
@@ -569,6 +645,7 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->d_tab = nullptr;
     fe->d_rs = nullptr;
     fe->d_rs_coefs = nullptr;
+    fe->rs_fast_9_10 = fe->rs_fast_11_10 = -1;
     const int nb = cfg->num_mel_bins, nf = cfg->fft_size / 2;
     if (window) fe->window.assign(window, window + cfg->frame_length); else default_window(cfg->frame_length, fe->window);
     if (mel) fe->mel.assign(mel, mel + (size_t)nb * nf); else default_mel(*cfg, fe->mel);
@@ -780,20 +857,27 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
         OE_CUDA(cudaGetLastError());
     }
+    int n_stat_partials = 0;
     if (M.feats) {
-        if (M.need_stats && M.total_tiles > 0) {
+        if ((M.need_stats || bt->d_stats) && M.total_tiles > 0) {
             oe::FeatStatsParams S;
             S.feats = reinterpret_cast<const float*>(d_wav);
             S.tiles = P.tiles;
             S.tile_stats = P.tile_stats;
+            S.cta_stats = bt->d_stats ? reinterpret_cast<double*>(ws + M.stat_partial) : nullptr;
             S.F = F;
             S.total_tiles = M.total_tiles;
+            n_stat_partials = 3 * std::min(M.total_tiles, fe->sm_count * 8);
             oe::oe_feat_tile_stats_kernel<<<std::min(M.total_tiles, fe->sm_count * 8), oe::kMaxMel, 0, stream>>>(S);
             OE_CUDA(cudaGetLastError());
         }
     } else if (M.total_tiles > 0) {
         const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
         const bool f32 = bt->wav_dtype == OE_WAV_F32;
+        if (bt->d_stats) {
+            P.cta_stats = reinterpret_cast<double*>(ws + M.stat_partial);
+            n_stat_partials = 3 * grid;
+        }
         if (fe->std_mel) {
             if (f32) oe::oe_fbank_kernel<true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
             else oe::oe_fbank_kernel<false, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
@@ -811,20 +895,17 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
         U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
         U.F = F;
-        oe::oe_utt_stats_kernel<<<B, oe::kMaxMel, 0, stream>>>(U);
+        oe::oe_utt_stats_kernel<<<B, dim3(oe::kMaxMel, oe::kUttSlices), 0, stream>>>(U);
         OE_CUDA(cudaGetLastError());
     }
-    if (bt->d_stats && M.total_tiles > 0) {
+    if (bt->d_stats && n_stat_partials > 0) {
         oe::GlobalStatsParams G;
-        G.tile_stats = P.tile_stats;
-        G.tiles = P.tiles;
-        G.partial = reinterpret_cast<double*>(ws + M.stat_partial);
+        G.partial = reinterpret_cast<const double*>(ws + M.stat_partial);
         G.stats = bt->d_stats;
         G.count = (double)M.total_frames;
-        G.total_tiles = M.total_tiles;
+        G.n_partials = n_stat_partials;
         G.F = F;
-        oe::oe_global_stats_partial_kernel<<<oe::kStatBlocks, oe::kMaxMel, 0, stream>>>(G);
-        oe::oe_global_stats_final_kernel<<<1, oe::kMaxMel + 32, 0, stream>>>(G);
+        oe::oe_global_stats_final_kernel<<<2 * F + 1, 256, 0, stream>>>(G);
         OE_CUDA(cudaGetLastError());
     }
     if (M.two_phase && d_out && M.total_rows > 0) {
@@ -918,6 +999,14 @@ int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* ke
             fe->rs_coefs.push_back(v);
         }
     fe->rs.push_back(t);
+    if (width == 7 && neu == 10 && (orig == 9 || orig == 11)) {
+        // the specialised kernel skips taps the hann-sinc formula makes zero: only valid if this table has them zero
+        bool ok = true;
+        for (int p = 0; p < neu && ok; ++p)
+            for (int q = 0; q < ntaps && ok; ++q)
+                if (!oe::rs_tap_nonzero(orig, neu, width, p, q) && std::fabs(fe->rs_coefs[t.coef_off + p * ntaps + q]) > 1e-12f) ok = false;
+        if (ok) (orig == 9 ? fe->rs_fast_9_10 : fe->rs_fast_11_10) = (int)fe->rs.size() - 1;
+    }
     OE_CUDA(cudaSetDevice(fe->device));
     OE_CUDA(cudaMemcpy(fe->d_rs, fe->rs.data(), sizeof(oe::RsTable) * fe->rs.size(), cudaMemcpyHostToDevice));
     OE_CUDA(cudaMemcpy(fe->d_rs_coefs, fe->rs_coefs.data(), sizeof(float) * fe->rs_coefs.size(), cudaMemcpyHostToDevice));
@@ -978,11 +1067,36 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
     P.out_len = reinterpret_cast<const int32_t*>(ws + 2 * a8 + 2 * a4);
     P.tables = fe->d_rs;
     P.coefs = fe->d_rs_coefs;
-    dim3 grid((unsigned)std::min((max_out + 1023) / 1024, 1024), (unsigned)B);
-    if (bt->wav_dtype == OE_WAV_F32)
-        oe::oe_resample_kernel<true><<<grid, 256, 0, stream>>>(P);
-    else
-        oe::oe_resample_kernel<false><<<grid, 256, 0, stream>>>(P);
+    const bool f32 = bt->wav_dtype == OE_WAV_F32;
+    bool need_generic = false, need_9 = false, need_11 = false;
+    for (int b = 0; b < B; ++b) {
+        if (out_len[b] == 0) continue;
+        if (tab[b] >= 0 && tab[b] == fe->rs_fast_9_10) need_9 = true;
+        else if (tab[b] >= 0 && tab[b] == fe->rs_fast_11_10) need_11 = true;
+        else need_generic = true;
+    }
+    if (need_generic) {
+        dim3 grid((unsigned)std::min((max_out + 1023) / 1024, 1024), (unsigned)B);
+        if (f32) oe::oe_resample_kernel<true><<<grid, 256, 0, stream>>>(P, fe->rs_fast_9_10, fe->rs_fast_11_10);
+        else oe::oe_resample_kernel<false><<<grid, 256, 0, stream>>>(P, fe->rs_fast_9_10, fe->rs_fast_11_10);
+    }
+    for (int which = 0; which < 2; ++which) {
+        if (!(which == 0 ? need_9 : need_11)) continue;
+        const int id = which == 0 ? fe->rs_fast_9_10 : fe->rs_fast_11_10;
+        oe::RsFastParams Q;
+        Q.r = P;
+        Q.table_id = id;
+        memset(Q.coef, 0, sizeof(Q.coef));
+        memcpy(Q.coef, fe->rs_coefs.data() + fe->rs[id].coef_off, sizeof(float) * fe->rs[id].neu * fe->rs[id].taps);
+        dim3 grid((unsigned)((max_out + oe::kRsM * 10 - 1) / (oe::kRsM * 10)), (unsigned)B);
+        if (which == 0) {
+            if (f32) oe::oe_resample_fast_kernel<true, 9, 10, 7><<<grid, oe::kRsM, 0, stream>>>(Q);
+            else oe::oe_resample_fast_kernel<false, 9, 10, 7><<<grid, oe::kRsM, 0, stream>>>(Q);
+        } else {
+            if (f32) oe::oe_resample_fast_kernel<true, 11, 10, 7><<<grid, oe::kRsM, 0, stream>>>(Q);
+            else oe::oe_resample_fast_kernel<false, 11, 10, 7><<<grid, oe::kRsM, 0, stream>>>(Q);
+        }
+    }
     OE_CUDA(cudaGetLastError());
     return OE_OK;
 }

