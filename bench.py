@@ -180,7 +180,7 @@ def run_ours(args, rank, world, local_rank):
 
     from openeat_b200.cmvn import all_reduce_stats
     from openeat_b200.dataset import _plan_batch, _run_plan, audio_collate_func
-    from openeat_b200.feature_processor import plan_spec_augmentation
+    from openeat_b200 import planner
     from openeat_b200.frontend import default_frontend
 
     torch.cuda.set_device(local_rank)
@@ -202,8 +202,8 @@ def run_ours(args, rank, world, local_rank):
     plans = []
     for _ in range(POOL):
         plan = _plan_batch(keys, labels, lens, [16000] * BATCH, speeds, CONF)
-        aug = [plan_spec_augmentation(int(t), 80, **AUG) for t in plan.frames]
-        plans.append((plan, np.array([a[0] for a in aug], np.int32), np.array([a[1] for a in aug], np.int32)))
+        _, tm, fm = planner.plan_augment(plan.frames, 80, None, AUG)
+        plans.append((plan, tm, fm))
 
     def step_resident(i):
         plan, tm, fm = plans[i % POOL]

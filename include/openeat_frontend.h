@@ -141,6 +141,29 @@ int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* 
 int oe_resample(oe_frontend* fe, const oe_resample_batch* batch, const void* d_in, float* d_out,
                 void* d_workspace, size_t workspace_bytes, oe_stream stream);
 
+/* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
+ * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).
+ * These helpers continue that very generator natively: `mt_state` is `random.getstate()[1]` (624 state
+ * words + position, 625 uint32), advanced in place exactly as CPython's random.random() /
+ * _randbelow_with_getrandbits() would, so the indices equal the reference's for the same seed and the
+ * caller can `random.setstate` the result back.
+ *
+ * oe_plan_speeds: per utterance, in input order (dataset.py:87-89):
+ *     speed = item_speeds[i]; if random.random() < perturb_rate: speed = _speed_generator(speeds)
+ *   with _speed_generator of audio_processor.py:5-18 (`speeds_cfg` = [start, end, step] or [fixed];
+ *   n_speeds_cfg == 0 means None -> [0.9, 1.1, 0.1]).  active[i] == 0 skips the utterance (failed load:
+ *   the reference raised before drawing).
+ * oe_plan_augment: for all utterances in the given (length-sorted) order first every _spec_substitute
+ *   draw (feature_processor.py:57-63, composed into frame_map), then every _spec_augmentation draw
+ *   (:31-41) -> half-open, clipped ranges.  Pass do_sub / do_aug = 0 to skip either. */
+int oe_plan_speeds(uint32_t* mt_state, int32_t n, double perturb_rate, const double* speeds_cfg,
+                   int32_t n_speeds_cfg, const double* item_speeds, const uint8_t* active,
+                   double* out_speeds);
+int oe_plan_augment(uint32_t* mt_state, int32_t n, const int32_t* frames, int32_t num_freq,
+                    int32_t do_sub, int32_t sub_max_t, int32_t sub_num_t_sub,
+                    int32_t do_aug, int32_t num_t_mask, int32_t num_f_mask, int32_t max_t, int32_t max_f,
+                    int32_t* frame_map, int32_t* tmask, int32_t* fmask);
+
 #ifdef __cplusplus
 }
 #endif

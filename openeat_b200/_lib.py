@@ -21,6 +21,9 @@ OE_NORM_NONE, OE_NORM_PER_UTT = 0, 1
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
 
 
 class OeConfig(ctypes.Structure):
@@ -73,6 +76,11 @@ SYMBOLS = {
                                                    ctypes.POINTER(ctypes.c_size_t)]),
     'oe_resample': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeResampleBatch), ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    'oe_plan_speeds': (ctypes.c_int, [c_u32p, ctypes.c_int32, ctypes.c_double, c_f64p, ctypes.c_int32, c_f64p, c_u8p,
+                                      c_f64p]),
+    'oe_plan_augment': (ctypes.c_int, [c_u32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_int32, c_i32p, c_i32p, c_i32p]),
 }
 
 _lib = None

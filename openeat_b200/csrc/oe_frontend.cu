@@ -1101,4 +1101,138 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
     return OE_OK;
 }
 
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Host-side planning: Python-`random`-compatible Mersenne Twister (CPython Modules/_randommodule.c
+// semantics: genrand_uint32, random() = (a>>5, b>>6) 53-bit, getrandbits(k<=32) = genrand >> (32-k),
+// Random._randbelow_with_getrandbits).
+namespace {
+
+struct PyMT {
+    uint32_t* mt;     // 624 words
+    uint32_t* pos;    // index
+    uint32_t next() {
+        constexpr int N = 624, M = 397;
+        constexpr uint32_t MATRIX_A = 0x9908b0dfU, UPPER = 0x80000000U, LOWER = 0x7fffffffU;
+        if (*pos >= (uint32_t)N) {
+            int kk;
+            uint32_t y;
+            for (kk = 0; kk < N - M; kk++) {
+                y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+                mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1U) ? MATRIX_A : 0U);
+            }
+            for (; kk < N - 1; kk++) {
+                y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+                mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1U) ? MATRIX_A : 0U);
+            }
+            y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+            mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1U) ? MATRIX_A : 0U);
+            *pos = 0;
+        }
+        uint32_t y = mt[(*pos)++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680U;
+        y ^= (y << 15) & 0xefc60000U;
+        y ^= (y >> 18);
+        return y;
+    }
+    double random() {
+        const uint32_t a = next() >> 5, b = next() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    uint32_t randbelow(uint32_t n) {            // n >= 1
+        int k = 0;
+        for (uint32_t v = n; v; v >>= 1) ++k;   // n.bit_length()
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+    int32_t randint(int32_t a, int32_t b) { return a + (int32_t)randbelow((uint32_t)(b - a + 1)); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int oe_plan_speeds(uint32_t* mt_state, int32_t n, double perturb_rate, const double* speeds_cfg,
+                   int32_t n_speeds_cfg, const double* item_speeds, const uint8_t* active, double* out_speeds) {
+    if (!mt_state || n < 0 || (n > 0 && (!item_speeds || !out_speeds))) return fail(OE_ERR_INVALID, "null pointer");
+    double cfg[3] = {0.9, 1.1, 0.1};            // audio_processor.py:6-7
+    int ncfg = 3;
+    if (n_speeds_cfg > 0) {
+        if (!speeds_cfg || (n_speeds_cfg != 1 && n_speeds_cfg < 3)) return fail(OE_ERR_INVALID, "speeds must be [fixed] or [start, end, step]");
+        ncfg = n_speeds_cfg;
+        for (int i = 0; i < ncfg && i < 3; ++i) cfg[i] = speeds_cfg[i];
+    }
+    if (ncfg > 1 && !(cfg[1] > cfg[0])) return fail(OE_ERR_INVALID, "speeds is wrong !");   // audio_processor.py:10
+    PyMT g{mt_state, mt_state + 624};
+    for (int i = 0; i < n; ++i) {
+        out_speeds[i] = item_speeds[i];
+        if (active && !active[i]) continue;
+        if (g.random() < perturb_rate) {         // dataset.py:88
+            if (ncfg > 1) {
+                if (cfg[2] != 0.0) {             // randrange(int(s0/step), int(s0/step)+1) * step
+                    const long long lo = (long long)(cfg[0] / cfg[2]);
+                    out_speeds[i] = (double)(lo + (long long)g.randbelow(1)) * cfg[2];
+                } else {
+                    out_speeds[i] = cfg[0] + g.random() * (cfg[1] - cfg[0]);
+                }
+            } else {
+                out_speeds[i] = cfg[0];
+            }
+        }
+    }
+    return OE_OK;
+}
+
+int oe_plan_augment(uint32_t* mt_state, int32_t n, const int32_t* frames, int32_t num_freq,
+                    int32_t do_sub, int32_t sub_max_t, int32_t sub_num, int32_t do_aug, int32_t n_t,
+                    int32_t n_f, int32_t max_t, int32_t max_f, int32_t* frame_map, int32_t* tmask, int32_t* fmask) {
+    if (!mt_state || n < 0 || (n > 0 && !frames)) return fail(OE_ERR_INVALID, "null pointer");
+    if (do_sub && (!frame_map || sub_max_t < 1 || sub_num < 0)) return fail(OE_ERR_INVALID, "bad spec_sub arguments");
+    if (do_aug && ((n_t > 0 && (!tmask || max_t < 1)) || (n_f > 0 && (!fmask || max_f < 1)) || num_freq < 1 || n_t < 0 || n_f < 0))
+        return fail(OE_ERR_INVALID, "bad spec_aug arguments");
+    for (int i = 0; i < n; ++i)
+        if (frames[i] < 1) return fail(OE_ERR_INVALID, "frames[%d] must be >= 1", i);
+    PyMT g{mt_state, mt_state + 624};
+    if (do_sub) {                                // feature_processor.py:55-64, all utterances first (dataset.py:204-205)
+        std::vector<int32_t> tmp;
+        int64_t off = 0;
+        for (int i = 0; i < n; ++i) {
+            const int T = frames[i];
+            int32_t* idx = frame_map + off;
+            for (int t = 0; t < T; ++t) idx[t] = t;
+            for (int j = 0; j < sub_num; ++j) {
+                const int start = g.randint(0, T - 1);
+                const int length = g.randint(1, sub_max_t);
+                const int end = std::min(T, start + length);
+                const int pos = g.randint(0, start);
+                tmp.assign(idx + start - pos, idx + end - pos);      // numpy reads the source before writing
+                std::copy(tmp.begin(), tmp.end(), idx + start);
+            }
+            off += T;
+        }
+    }
+    if (do_aug) {                                // feature_processor.py:31-41 (dataset.py:208-209)
+        for (int i = 0; i < n; ++i) {
+            const int T = frames[i];
+            for (int j = 0; j < n_t; ++j) {
+                const int start = g.randint(0, T - 1);
+                const int length = g.randint(1, max_t);
+                tmask[((int64_t)i * n_t + j) * 2] = start;
+                tmask[((int64_t)i * n_t + j) * 2 + 1] = std::min(T, start + length);
+            }
+            for (int j = 0; j < n_f; ++j) {
+                const int start = g.randint(0, num_freq - 1);
+                const int length = g.randint(1, max_f);
+                fmask[((int64_t)i * n_f + j) * 2] = start;
+                fmask[((int64_t)i * n_f + j) * 2 + 1] = std::min(num_freq, start + length);
+            }
+        }
+    }
+    return OE_OK;
+}
+
 }  // extern "C"

@@ -19,9 +19,8 @@ import wave
 import numpy as np
 import torch
 
-from .audio_processor import _speed_generator
-from .feature_processor import plan_spec_augmentation, plan_spec_substitute
-from .frontend import aligned_offsets, default_frontend, pack_waveforms, speed_ratio
+from . import planner
+from .frontend import default_frontend, pack_waveforms, speed_ratio
 
 IGNORE_ID = -1  # openeat/utils/common.py:24
 
@@ -64,62 +63,65 @@ def _load_item(x):
 
 class _Plan(object):
     """Host-side description of one batch after all random draws, before any GPU work.  ``src[i]`` is the
-    position, in the packed input buffer, of the utterance that ends up i-th after the length sort."""
-    __slots__ = ('keys', 'labels', 'src', 'ratios', 'frames', 'sample_rate')
+    position, in the packed input buffer, of the utterance that ends up i-th after the length sort;
+    ``stage1`` / ``stage2`` are the (orig, new) resampling ratios of the resample_rate and speed stages
+    (0, 0 = none)."""
+    __slots__ = ('keys', 'labels', 'src', 'stage1', 'stage2', 'frames', 'sample_rate')
+
+
+def _ceil_ratio(n, orig, new):
+    """torchaudio functional.py:1427: ceil(new * n / orig), vectorised."""
+    return (new * n + orig - 1) // orig
 
 
 def _plan_batch(keys_in, labels_in, nsamples, sample_rates, speeds_in, conf, target_rate=16000, loaded=None):
     """The host half of _extract_feature (dataset.py:47-118) for utterances that are already in memory:
-    decide speeds with the reference's RNG call order, compute frame counts, drop failures (printing
-    the reference's message), sort by length descending.  ``loaded[i]`` False marks an utterance whose
-    load failed before the reference would have drawn any random number."""
-    speed_perturb_rate = conf.get('speed_perturb_rate', 0.5)
-    speeds = conf.get('speeds', None)
+    decide speeds with the reference's RNG call order (natively, openeat_b200.planner), compute frame
+    counts, drop failures (printing the reference's message), sort by length descending.  ``loaded[i]``
+    False marks an utterance whose load failed before the reference would have drawn any random number."""
+    B = len(keys_in)
+    n = np.asarray(nsamples, dtype=np.int64).reshape(B)
+    sr = np.asarray(sample_rates, dtype=np.int64).reshape(B)
+    active = np.ones(B, dtype=bool) if loaded is None else np.asarray(loaded, dtype=bool)
     fe = default_frontend(conf['mel_bins'], target_rate)
-    keys, labels, src, ratios, lengths = [], [], [], [], []
-    for i in range(len(keys_in)):
-        if loaded is not None and not loaded[i]:
-            continue
-        try:
-            sample_rate = int(sample_rates[i])
-            chain = []
-            resample_rate = conf.get('resample_rate', sample_rate)
-            n = int(nsamples[i])
-            if resample_rate != sample_rate:                     # dataset.py:77-84
-                g = int(np.gcd(int(sample_rate), int(resample_rate)))
-                chain.append((int(sample_rate) // g, int(resample_rate) // g))
-                n = fe.resample_out_len(n, *chain[-1])
-                sample_rate = resample_rate
-            speed = speeds_in[i]
-            if random.random() < speed_perturb_rate:             # dataset.py:88-89 (drawn for every utterance)
-                speed = _speed_generator(speeds)
-            if speed != 1.0:                                     # dataset.py:90-91
-                chain.append(speed_ratio(speed, sample_rate))
-                n = fe.resample_out_len(n, *chain[-1])
-            if sample_rate != target_rate:
-                raise ValueError('sample rate %d is not supported by this front-end build (needs %d; '
-                                 'set resample_rate)' % (sample_rate, target_rate))
-            if conf['wav_dither'] != 0.0:
-                raise ValueError('wav_dither is stochastic (torch.randn inside kaldi.fbank) and is not '
-                                 'built; use 0.0')
-            m = fe.num_frames(n)
-            # kaldi.py:142 asserts 2 <= window_size <= len(waveform); the reference prints it and drops
-            assert m > 0, 'choose a window size 400 that is [2, %d]' % n
-            keys.append(keys_in[i])
-            labels.append(np.array(labels_in[i]))
-            src.append(i)
-            ratios.append(chain)
-            lengths.append(m)
-        except (Exception) as e:                                 # dataset.py:108-111
-            print(e)
-            logging.warning('read utterance {} error'.format(keys_in[i]))
-    order = np.argsort(lengths)[::-1] if lengths else []          # dataset.py:114
+    speed = planner.plan_speeds(conf.get('speed_perturb_rate', 0.5), conf.get('speeds', None),
+                                np.asarray(speeds_in, dtype=np.float64).reshape(B), active)   # dataset.py:87-89
+    stage1 = np.zeros((B, 2), dtype=np.int64)
+    stage2 = np.zeros((B, 2), dtype=np.int64)
+    rr = sr.copy() if 'resample_rate' not in conf else np.full(B, int(conf['resample_rate']), dtype=np.int64)
+    for s in np.unique(sr[active & (rr != sr)]):                  # dataset.py:77-84
+        sel = active & (sr == s) & (rr != sr)
+        r = int(rr[sel][0])
+        g = int(np.gcd(int(s), r))
+        stage1[sel] = (int(s) // g, r // g)
+        n[sel] = _ceil_ratio(n[sel], int(s) // g, r // g)
+    for v in np.unique(speed[active & (speed != 1.0)]):           # dataset.py:90-91
+        sel = active & (speed == v)
+        for r in np.unique(rr[sel]):
+            sel2 = sel & (rr == r)
+            ratio = speed_ratio(float(v), int(r))
+            stage2[sel2] = ratio
+            n[sel2] = _ceil_ratio(n[sel2], ratio[0], ratio[1])
+    frames = fe.num_frames_array(n)
+    bad = active & ((rr != target_rate) | (frames == 0) | (conf['wav_dither'] != 0.0))
+    for i in np.nonzero(bad)[0]:                                  # dataset.py:108-111: print, warn, drop
+        if rr[i] != target_rate:
+            print('sample rate %d is not supported by this front-end build (needs %d; set resample_rate)' % (rr[i], target_rate))
+        elif conf['wav_dither'] != 0.0:
+            print('wav_dither is stochastic (torch.randn inside kaldi.fbank) and is not built; use 0.0')
+        else:   # kaldi.py:142 asserts 2 <= window_size <= len(waveform); the reference prints it and drops
+            print('choose a window size 400 that is [2, %d]' % n[i])
+        logging.warning('read utterance {} error'.format(keys_in[i]))
+    keep = np.nonzero(active & ~bad)[0]
+    order = np.argsort(frames[keep])[::-1] if len(keep) else np.zeros(0, dtype=np.int64)   # dataset.py:114
+    src = keep[order]
     p = _Plan()
-    p.keys = [keys[i] for i in order]
-    p.labels = [labels[i] for i in order]
-    p.src = np.array([src[i] for i in order], dtype=np.int64)
-    p.ratios = [ratios[i] for i in order]
-    p.frames = np.array([lengths[i] for i in order], dtype=np.int32)
+    p.keys = [keys_in[i] for i in src]
+    p.labels = [labels_in[i] for i in src]
+    p.src = src
+    p.stage1 = stage1[src]
+    p.stage2 = stage2[src]
+    p.frames = frames[src].astype(np.int32)
     p.sample_rate = target_rate
     return p
 
@@ -161,26 +163,27 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
         nrows = plan.frames.copy()
     offs = np.asarray(offs, dtype=np.int64)
     lens = np.asarray(lens, dtype=np.int32)
-    direct = np.array([i for i in range(B) if not plan.ratios[i]], dtype=np.int64)
-    resamp = np.array([i for i in range(B) if plan.ratios[i]], dtype=np.int64)
+    needs = (plan.stage1[:, 0] != 0) | (plan.stage2[:, 0] != 0)
+    direct = np.nonzero(~needs)[0]
+    resamp = np.nonzero(needs)[0]
 
     def call(wav, o, l, idx):
         kw = dict(fused)
         for k in ('tmask', 'fmask'):
             if kw.get(k) is not None:
-                kw[k] = np.ascontiguousarray(np.asarray(kw[k])[idx])
-        if kw.get('frame_maps') is not None:
-            kw['frame_maps'] = [kw['frame_maps'][i] for i in idx]
+                kw[k] = np.ascontiguousarray(kw[k][idx])
+        if kw.get('frame_map') is not None:                      # concatenated map -> this subset's rows
+            fm, starts = kw.pop('frame_map'), kw.pop('frame_map_starts')
+            kw['frame_maps'] = [fm[starts[i]:starts[i] + plan.frames[i]] for i in idx]
         fe.fbank(wav, o, l, layout='custom', out=out.view(-1, F), out_rows=rows[idx], out_nrows=nrows[idx], **kw)
 
     if len(direct):
         call(dev_wav, offs[plan.src[direct]], lens[plan.src[direct]], direct)
     if len(resamp):
         cur, cur_offs, cur_lens = dev_wav, offs[plan.src[resamp]], lens[plan.src[resamp]]
-        depth = max(len(plan.ratios[i]) for i in resamp)
-        for d in range(depth):                                   # resample_rate stage, then speed stage
-            stage = [plan.ratios[i][d] if d < len(plan.ratios[i]) else None for i in resamp]
-            cur, cur_offs, cur_lens = fe.resample(cur, cur_offs, cur_lens, stage)
+        for stage in (plan.stage1[resamp], plan.stage2[resamp]):     # resample_rate stage, then speed stage
+            if (stage[:, 0] != 0).any():
+                cur, cur_offs, cur_lens = fe.resample(cur, cur_offs, cur_lens, stage)
         call(cur, cur_offs, cur_lens, resamp)
     return out, fe
 
@@ -194,7 +197,7 @@ def _extract_feature(batch, feature_extraction_conf):
     """openeat/dataset/dataset.py:39-118.  Returns (sorted_keys, sorted_feats, sorted_labels) with
     ``sorted_feats`` a list of (T_i, mel_bins) float32 numpy arrays, longest first."""
     waves, rates, loaded = _load_batch(batch)
-    plan = _plan_batch([x[0] for x in batch], [x[2] for x in batch], [len(w) for w in waves], rates,
+    plan = _plan_batch([x[0] for x in batch], [np.array(x[2]) for x in batch], [len(w) for w in waves], rates,
                        [x[3] for x in batch], feature_extraction_conf, loaded=loaded)
     out = None
     if len(plan.src):
@@ -258,20 +261,24 @@ class audio_collate_func(object):
         This is the entry point a native data loader hands its PCM to."""
         conf = self.feature_extraction_conf
         B_in = len(keys)
+        if B_in and not wav.is_cuda:             # start the H2D copy first: it overlaps the host-side planning
+            wav = wav.to(default_frontend(conf['mel_bins']).device, non_blocking=True)
         speeds = [1.0] * B_in if speeds is None else speeds
         sample_rates = [16000] * B_in if sample_rates is None else sample_rates
         plan = _plan_batch(keys, labels, lens, sample_rates, speeds, conf, loaded=loaded)
         F = conf['mel_bins']
         frames = plan.frames
         fused = {'normalization': bool(self.normalization)}
-        if self.spec_sub:                                            # dataset.py:204-205, sorted order
-            fused['frame_maps'] = [plan_spec_substitute(int(t), **self.spec_sub_conf) for t in frames]
-        if self.spec_aug:                                            # dataset.py:208-209, sorted order
-            plans = [plan_spec_augmentation(int(t), F, **self.spec_aug_conf) for t in frames]
-            if len(plans) and len(plans[0][0]):
-                fused['tmask'] = np.array([p[0] for p in plans], dtype=np.int32)
-            if len(plans) and len(plans[0][1]):
-                fused['fmask'] = np.array([p[1] for p in plans], dtype=np.int32)
+        # dataset.py:204-209: every spec_sub draw, then every spec_aug draw, in length-sorted order
+        fmap, tmask, fmask = planner.plan_augment(frames, F, self.spec_sub_conf if self.spec_sub else None,
+                                                  self.spec_aug_conf if self.spec_aug else None)
+        if fmap is not None:
+            fused['frame_map'] = fmap
+            fused['frame_map_starts'] = np.concatenate([[0], np.cumsum(frames[:-1].astype(np.int64))]) if len(frames) else []
+        if tmask is not None:
+            fused['tmask'] = tmask
+        if fmask is not None:
+            fused['fmask'] = fmask
         if self.global_cmvn is not None:
             fused['cmvn'] = self.global_cmvn
             fused['cmvn_on_padding'] = True
@@ -279,19 +286,21 @@ class audio_collate_func(object):
             fused['stats'] = self.cmvn_stats
         features = None
         if len(plan.src):
-            fe = default_frontend(F, plan.sample_rate)
-            dev_wav = wav if wav.is_cuda else wav.to(fe.device, non_blocking=True)
-            features, _ = _run_plan(plan, F, dev_wav, offsets, lens, **fused)
+            features, _ = _run_plan(plan, F, wav, offsets, lens, **fused)
         dev = torch.device(self.output_device)
         features_length = torch.from_numpy(np.array(frames, dtype=np.int32))
         ys = plan.labels
+        tlen = np.array([len(y) for y in ys], dtype=np.int32)
         if features is None:                                         # dataset.py:219-220
             features = torch.Tensor([])
             targets = torch.Tensor([])
-        else:
-            targets = torch.nn.utils.rnn.pad_sequence([torch.from_numpy(np.asarray(y)).int() for y in ys],
-                                                      True, IGNORE_ID)
-        targets_length = torch.from_numpy(np.array([y.shape[0] for y in ys], dtype=np.int32))
+        else:                                                        # pad_sequence(..., True, IGNORE_ID), dataset.py:225-226
+            tpad = np.full((len(ys), int(tlen.max()) if len(ys) else 0), IGNORE_ID, dtype=np.int32)
+            if tpad.size:
+                tpad[np.arange(tpad.shape[1])[None, :] < tlen[:, None]] = np.concatenate(
+                    [np.asarray(y, dtype=np.int32).reshape(-1) for y in ys])
+            targets = torch.from_numpy(tpad)
+        targets_length = torch.from_numpy(tlen)
         inputs = {'features': features.to(dev), 'features_length': features_length.to(dev),
                   'targets': targets.to(dev), 'targets_length': targets_length.to(dev)}
         return plan.keys, inputs

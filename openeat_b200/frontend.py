@@ -182,9 +182,20 @@ class Frontend(object):
         B = len(lens)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         lens = np.ascontiguousarray(lens, dtype=np.int32)
-        ids = np.array([-1 if r is None else self.resampler_id(*r) for r in ratios], dtype=np.int32)
-        olens = np.array([n if r is None else self.resample_out_len(n, *r) for n, r in zip(lens, ratios)],
-                         dtype=np.int32)
+        if isinstance(ratios, np.ndarray):                       # [B, 2] int array, (0, 0) = plain copy
+            ids = np.full(B, -1, dtype=np.int32)
+            olens = lens.astype(np.int64)
+            key = ratios[:, 0] * 65536 + ratios[:, 1]
+            for k in np.unique(key[key != 0]):
+                o, n = int(k) >> 16, int(k) & 65535
+                sel = key == k
+                ids[sel] = self.resampler_id(o, n)
+                olens[sel] = (n * olens[sel] + o - 1) // o
+            olens = olens.astype(np.int32)
+        else:
+            ids = np.array([-1 if r is None else self.resampler_id(*r) for r in ratios], dtype=np.int32)
+            olens = np.array([n if r is None else self.resample_out_len(n, *r) for n, r in zip(lens, ratios)],
+                             dtype=np.int32)
         if out_offsets is None:
             out_offsets, total = aligned_offsets(olens)
         else:

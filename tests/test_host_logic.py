@@ -24,6 +24,44 @@ def test_plans_follow_the_reference_rng_order():
         assert random.random() == tail                              # same number of RNG words consumed
 
 
+def test_native_planner_continues_python_random():
+    """oe_plan_speeds / oe_plan_augment (C, Mersenne Twister) == the reference's Python loops for the same
+    random.seed, and they leave Python's generator in the same state."""
+    from openeat_b200 import planner
+    from oracle import speed as S
+    for seed, rate, cfg in [(0, 0.5, None), (1, 1.0, [0.9, 1.1, 0.1]), (2, 0.7, [0.9, 1.1, 0]), (3, 0.3, [1.05]), (4, 0.0, None)]:
+        frames = np.array([498, 48, 7, 1, 298, 1000, 33, 2], np.int32)
+        item = np.array([1.0, 0.9, 1.1, 1.0, 1.0, 1.0, 0.9, 1.0])
+        active = np.array([1, 1, 0, 1, 1, 1, 1, 1], bool)
+        random.seed(seed)
+        ref_speed = []
+        for i in range(8):
+            s = item[i]
+            if active[i] and random.random() < rate:
+                s = S.speed_generator(cfg)
+            ref_speed.append(s)
+        subs = [A.plan_spec_substitute(int(t), max_t=30, num_t_sub=3) for t in frames]
+        ref_map = np.concatenate([A.substitute_index_map(int(t), s) for t, s in zip(frames, subs)])
+        ref_aug = [A.plan_spec_augmentation(int(t), 80, 3, 2, 50, 10) for t in frames]
+        tail = random.random()
+        random.seed(seed)
+        speed = planner.plan_speeds(rate, cfg, item, active)
+        fmap, tm, fm = planner.plan_augment(frames, 80, dict(max_t=30, num_t_sub=3),
+                                            dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))
+        assert speed.tolist() == ref_speed
+        assert np.array_equal(fmap, ref_map)
+        assert tm.tolist() == [[list(r) for r in p[0]] for p in ref_aug]
+        assert fm.tolist() == [[list(r) for r in p[1]] for p in ref_aug]
+        assert random.random() == tail
+    # defaults of feature_processor.py when a conf omits keys; aug only; sub only
+    random.seed(9)
+    ref = A.plan_spec_augmentation(100, 80)
+    random.seed(9)
+    _, tm, fm = planner.plan_augment([100], 80, None, {})
+    assert tm[0].tolist() == [list(r) for r in ref[0]] and fm[0].tolist() == [list(r) for r in ref[1]]
+    assert planner.plan_augment([5, 6], 80, None, None) == (None, None, None)
+
+
 def test_speed_generator_is_pure_host_logic(golden_dir):
     from openeat_b200.audio_processor import _speed_generator
     a = np.load(os.path.join(golden_dir, 'augment.npz'))

@@ -1,0 +1,61 @@
+"""Developer tool: where does the HOST time of one bench step go (cProfile over the resident and e2e steps)."""
+import cProfile
+import os
+import pstats
+import random
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from openeat_b200 import planner
+from openeat_b200.dataset import _plan_batch, _run_plan, audio_collate_func
+from openeat_b200.frontend import default_frontend
+
+dev = torch.device('cuda', 0)
+fe = default_frontend(80, 16000, dev)
+lens, speeds = bench.workload(0)
+host_pool, offs = bench.synth_pool_host(lens, 0, 2)
+dev_pool = [h.to(dev) for h in host_pool]
+keys = ['u%d' % i for i in range(bench.BATCH)]
+labels = [[1, 2, 3]] * bench.BATCH
+mean = torch.linspace(8.0, 12.0, 80, device=dev)
+istd = torch.linspace(0.4, 0.6, 80, device=dev)
+stats = torch.zeros(161, dtype=torch.float64, device=dev)
+random.seed(1)
+plan = _plan_batch(keys, labels, lens, [16000] * bench.BATCH, speeds, bench.CONF)
+_, tm, fm = planner.plan_augment(plan.frames, 80, None, bench.AUG)
+collate = audio_collate_func(data_type='wav', feature_extraction_conf=bench.CONF, normalization=True, spec_aug=True,
+                             spec_aug_conf=bench.AUG, global_cmvn=(mean, istd), cmvn_stats=stats)
+
+
+def resident(n):
+    for i in range(n):
+        _run_plan(plan, 80, dev_pool[i % 2], offs, lens, normalization=True, tmask=tm, fmask=fm, cmvn=(mean, istd),
+                  cmvn_on_padding=True, stats=stats)
+
+
+def e2e(n):
+    for i in range(n):
+        _, out = collate.collate_packed(host_pool[i % 2], offs, lens, keys, labels, speeds)
+        out['features_length'].cpu(), stats.cpu()
+
+
+for name, fn in (('resident', resident), ('e2e', e2e)):
+    fn(5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fn(50)
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    print('%s: host enqueue %.3f ms/step, with GPU drain %.3f ms/step' % (name, t_host / 50 * 1e3, t_all / 50 * 1e3))
+    pr = cProfile.Profile()
+    pr.enable()
+    fn(50)
+    pr.disable()
+    torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
