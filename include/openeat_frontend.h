@@ -86,6 +86,10 @@ typedef struct {
                                     frame count of the RAW log-mel frames (compute_cmvn_stats; the
                                     reference only ships the consumer, openeat/utils/cmvn.py:30-35) */
     int32_t* out_frames;         /* [B] out, or NULL: frames per utterance, 1+(N-400)//160 (kaldi.py:67) */
+    const int32_t* resample_ids; /* [B] or NULL: fused speed perturb (_speed_perturb, audio_processor.py:19-35) --
+                                    table id from oe_add_resampler (9:10 or 11:10, i.e. speed 0.9 / 1.1) or -1.
+                                    The utterance is resampled while it is staged: no intermediate waveform;
+                                    wav_lens stay INPUT lengths, frames follow ceil(new*N/orig).  int16 input only */
 } oe_batch;
 
 /* One ragged resampling batch (speed perturb).  Replaces _speed_perturb

@@ -21,13 +21,22 @@ struct __align__(16) TileDesc {
     int t0;                 // first frame of the tile
     int nvalid;             // real frames in the tile (<= 0: padding-only tile)
     int rows_here;          // rows to write (real + padding)
-    long long wav_start;    // element index of sample 160*t0 in the waveform buffer
-    int wav_remain;         // samples from there to the end of the utterance
-    int pad0;
+    long long wav_utt;      // element index of the utterance's sample 0 in the waveform buffer
+    int in_first;           // utterance-relative index of the first staged input sample (multiple of 8, may be < 0)
+    int in_len;             // utterance length in input samples
     long long out_start;    // first output row of the tile
-    long long pad1;
+    int rs;                 // fused speed perturb: 0 none, 1 = 9:10 (speed 0.9), 2 = 11:10 (speed 1.1)
+    int pad;
 };
 static_assert(sizeof(TileDesc) == 48, "TileDesc is three 16-byte cp.async pieces");
+
+// Fused speed perturb (polyphase, NEW = 10 outputs per ORIG inputs, width 7).  A tile needs resampled samples
+// [160 t0 - 10, 160 t0 + 5380) = 539 polyphase blocks starting at block 16 t0 - 1.
+constexpr int kRsBlocks = 539;
+__host__ __device__ __forceinline__ int rs_orig(int rs) { return rs == 1 ? 9 : 11; }
+__host__ __device__ __forceinline__ int rs_first_input(int rs, int t0) { return (16 * t0 - 1) * rs_orig(rs) - 7; }
+constexpr int kRsMaxIn = kRsBlocks * 11 + 14 + 8;          // staged input samples incl. alignment slack (5951)
+constexpr int kRsPieces = (kRsMaxIn + 7) / 8;              // 16-byte int16 pieces (744)
 
 struct FbankParams {
     const void* wav;
@@ -47,6 +56,7 @@ struct FbankParams {
     const DevTables* tab;
     float mel_w[512];               // standard-structure fast path: weights (x 1/4) in mel80::kOff order;
                                     // lives in the kernel-parameter constant bank -> FFMA constant operands
+    float rs_coef[2][256];          // fused speed perturb: sinc taps [new = 10][taps] for 9:10 and 11:10
 };
 
 // rows of a 32-frame tile covered by statistics row-group rg (0..2): [11 rg, min(nvalid, 11 rg + 11))
@@ -75,13 +85,16 @@ constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
 constexpr int kSmMask = kSmTwU + 9 * kRowE * 8;            // uchar rowmask[32], colmask[128]
 constexpr int kSmDesc = kSmMask + 32 + kMaxMel;            // TileDesc[2]
 constexpr int kSmAcc = kSmDesc + 2 * 48;                   // double acc[3][2][128]: CMVN-statistics accumulators
-constexpr int kSmStd = kSmAcc + 3 * 2 * kMaxMel * 8;       // end of the standard-mel layout
+constexpr int kSmEdge = kSmAcc + 3 * 2 * kMaxMel * 8;      // float edge[32]: fused-resampler block edges
+constexpr int kSmStd = kSmEdge + 32 * 4;                   // end of the standard-mel layout
 constexpr int kSmMelIdx = kSmStd;                          // generic mel only: int start/len/off [3][128], group_begin[9] (+pad)
 constexpr int kSmMelW = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // generic mel only: float mel_w[nnz]
 static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0 &&
               kSmDesc % 16 == 0 && kSmAcc % 16 == 0, "align");
 constexpr int kRowS = 34;           // float2 per frame of the self-conjugate-row scratch (32 + 2 pad = 272 B), in the p area
 static_assert(kSmRaw + 673 * 32 <= kSmTwA, "raw prefetch buffer must fit behind the power tile");
+static_assert(kRsPieces * 16 <= 673 * 32, "resampler input must fit the raw prefetch buffer");
+static_assert(kRsMaxIn * 4 <= kBins * kRowP * 4, "fp32 resampler input must fit in front of the raw buffer");
 static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -94,30 +107,55 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Asynchronously stages the raw samples [s_base - 8, s_base + 5376) of one utterance into shared memory,
 // zero-filling everything outside [0, wlen) (cp.async src-size form), so the waveform's HBM latency
 // overlaps the previous tile's FFT.  Chunk j of the buffer holds samples s_base - 8 + 8 j.
-// `start` = element index of the tile's first sample, `remain` = samples left in the utterance from there,
-// `utt_start` = the tile begins the utterance (nothing before it may be read).
+// Piece q holds utterance samples in_first + (8 | 4) q ...; pieces are 8-sample aligned, so none straddles 0.
 template <bool kF32>
-__device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, long long start, int remain,
-                                              bool utt_start, int tid) {
+__device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, const TileDesc* d, int tid) {
+    const int in_first = d->in_first, in_len = d->in_len;
     if (kF32) {
-        const float* w = reinterpret_cast<const float*>(wav) + start;
+        const float* w = reinterpret_cast<const float*>(wav) + d->wav_utt;
         for (int q = tid; q < 673 * 2; q += kThreads) {
-            const int s = 4 * q - 8;                       // relative to the tile's first sample
-            int valid = remain - s;
+            const int s = in_first + 4 * q;
+            int valid = in_len - s;
             valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-            if (s < 0 && utt_start) valid = 0;
+            if (s < 0) valid = 0;
             cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 4 * valid);
         }
     } else {
-        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + start;
-        for (int q = tid; q < 673; q += kThreads) {
-            const int s = 8 * q - 8;
-            int valid = remain - s;
+        const int16_t* w = reinterpret_cast<const int16_t*>(wav) + d->wav_utt;
+        const int pieces = d->rs ? kRsPieces : 673;
+        for (int q = tid; q < pieces; q += kThreads) {
+            const int s = in_first + 8 * q;
+            int valid = in_len - s;
             valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
-            if (s < 0 && utt_start) valid = 0;
+            if (s < 0) valid = 0;
             cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 2 * valid);
         }
     }
+}
+
+// One polyphase block (10 outputs) of the fused speed perturb; taps the hann window zeroes are pruned at
+// compile time (same predicate as oe_resample_fast_kernel), coefficients are kernel-parameter constants.
+OE_CX bool rs_tap_nonzero(int orig, int neu, int width, int p, int q) {
+    const double base = (orig < neu ? orig : neu) * 0.99;
+    const double t = (-(double)p / neu + (double)(q - width) / orig) * base;
+    return t < 6.0 && t > -6.0;
+}
+
+template <int ORIG>
+__device__ __forceinline__ void rs_block(const float* __restrict__ xin, const float (&coef)[256], float (&y)[10]) {
+    constexpr int TAPS = 14 + ORIG;
+    float x[TAPS];
+#pragma unroll
+    for (int q = 0; q < TAPS; ++q) x[q] = xin[q];
+    static_for<0, 10>([&](auto pp) {
+        constexpr int p = decltype(pp)::value;
+        float acc = 0.f;
+        static_for<0, TAPS>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            if constexpr (rs_tap_nonzero(ORIG, 10, 7, p, q)) acc = fmaf(coef[p * TAPS + q], x[q], acc);
+        });
+        y[p] = acc;
+    });
 }
 
 __device__ __forceinline__ void prefetch_desc(TileDesc* dst, const TileDesc* src, int tid) {
@@ -193,8 +231,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        const TileDesc d = sDesc[0];
-        if (d.nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, d.wav_start, d.wav_remain, d.t0 == 0, tid);
+        if (sDesc[0].nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, sDesc, tid);
         cp_async_commit();
     }
     // ---- one-time table staging ----
@@ -251,13 +288,52 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
             }
         }
         if (nvalid > 0) {
+            // ---- [fused speed perturb: raw -> fp32 -> polyphase sinc -> resampled tile in sp] ----
+            const int rs = kF32 ? 0 : dp->rs;
+            float* const sEdge = reinterpret_cast<float*>(smem + kSmEdge);
+            if (rs != 0) {
+                float* const xin = sPw;                               // fp32 input window, front of the (idle) E area
+                const int16_t* const r16 = reinterpret_cast<const int16_t*>(sRaw);
+                for (int i = tid; i < kRsPieces * 2; i += kThreads) {       // 4 samples per thread-iteration
+                    const int2 v = *reinterpret_cast<const int2*>(r16 + 4 * i);
+                    float4 f;
+                    f.x = (float)(int16_t)(v.x & 0xffff); f.y = (float)(v.x >> 16);
+                    f.z = (float)(int16_t)(v.y & 0xffff); f.w = (float)(v.y >> 16);
+                    *reinterpret_cast<float4*>(xin + 4 * i) = f;
+                }
+                __syncthreads();
+                const int orig = rs_orig(rs);
+                const int shift = rs_first_input(rs, t0) - dp->in_first;   // 0..7
+                for (int mi = tid; mi < kRsBlocks; mi += kThreads) {       // block mi -> tile samples 10 mi - 10 .. 10 mi - 1
+                    float y[10];
+                    if (rs == 1) rs_block<9>(xin + shift + mi * 9, P.rs_coef[0], y);
+                    else rs_block<11>(xin + shift + mi * 11, P.rs_coef[1], y);
+                    if (mi == 0) {
+                        sEdge[0] = y[9];                                   // sample just before the tile
+                    } else {
+                        float2* const dst = reinterpret_cast<float2*>(sp + 10 * mi - 10);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            if (10 * mi - 10 + 2 * j < 5376) dst[j] = make_float2(y[2 * j], y[2 * j + 1]);
+                    }
+                }
+                __syncthreads();
+                if (tid >= 1 && tid < 21) sEdge[tid] = sp[256 * tid - 1];  // block edges, read before the in-place pass
+                __syncthreads();
+            }
             // ---- convert: p[j] = x[j] - preemph * x[j-1] (kaldi.py:193-198), 8-sample block sums ----
             {
                 const bool utt_start = t0 == 0;
                 for (int blk = warp; blk < 21; blk += 8) {
                     const int i0 = blk * 256 + 4 * lane, i1 = i0 + 128;
                     float xa[4], xb[4], edge;
-                    if (kF32) {
+                    if (rs != 0) {                                         // resampled tile, in place in sp
+                        const float4 a = *reinterpret_cast<const float4*>(sp + i0);
+                        const float4 c = *reinterpret_cast<const float4*>(sp + i1);
+                        xa[0] = a.x; xa[1] = a.y; xa[2] = a.z; xa[3] = a.w;
+                        xb[0] = c.x; xb[1] = c.y; xb[2] = c.z; xb[3] = c.w;
+                        edge = sEdge[blk];
+                    } else if (kF32) {
                         const float* r = reinterpret_cast<const float*>(sRaw) + 8;
                         const float4 a = *reinterpret_cast<const float4*>(r + i0);
                         const float4 c = *reinterpret_cast<const float4*>(r + i1);
@@ -287,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                     pb.y = fmaf(-preemph, xb[0], xb[1]);
                     pb.z = fmaf(-preemph, xb[1], xb[2]);
                     pb.w = fmaf(-preemph, xb[2], xb[3]);
+                    __syncwarp();                                          // in-place variant: all lanes have read
                     *reinterpret_cast<float4*>(sp + i0) = pa;
                     *reinterpret_cast<float4*>(sp + i1) = pb;
                     float sa = (xa[0] + xa[1]) + (xa[2] + xa[3]);
@@ -372,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
             __syncthreads();           // (3) exchange buffer is dead -> power tile + next tile's raw samples
             if (next < P.total_tiles) {
                 const TileDesc* const dn = sDesc + (slot ^ 1);
-                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn->wav_start, dn->wav_remain, dn->t0 == 0, tid);
+                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
             }
             cp_async_commit();
             fft_dif<16>(ar, ai);
@@ -496,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
             __syncthreads();
             if (next < P.total_tiles) {
                 const TileDesc* const dn = sDesc + (slot ^ 1);
-                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn->wav_start, dn->wav_remain, dn->t0 == 0, tid);
+                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
             }
             cp_async_commit();
         }

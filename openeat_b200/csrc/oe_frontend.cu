@@ -77,9 +77,10 @@ struct TileDescParams {
     const int32_t* n_frames;
     const int32_t* n_rows;
     const int64_t* out_row;
+    const int32_t* rs_mode;      // [B] fused speed perturb: 0 none, 1 = 9:10, 2 = 11:10
     TileDesc* tiles;
     int B, total_tiles;
-    int shift;                   // samples per frame step (160), or 1 when the input already is features
+    int feats;                   // the input already is features: offsets / lengths count rows
 };
 
 // Expands the per-utterance metadata into one self-contained descriptor per 32-frame tile.
@@ -93,11 +94,14 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
     d.t0 = t0;
     d.nvalid = min(kTileFrames, P.n_frames[b] - t0);
     d.rows_here = min(kTileFrames, P.n_rows[b] - t0);
-    d.wav_start = P.wav_off[b] + (long long)t0 * P.shift;
-    d.wav_remain = P.wav_len[b] - t0 * P.shift;
-    d.pad0 = 0;
+    d.wav_utt = P.wav_off[b];
+    d.in_len = P.wav_len[b];
+    d.rs = P.feats ? 0 : P.rs_mode[b];
+    if (P.feats) d.in_first = t0;
+    else if (d.rs == 0) d.in_first = t0 * kShift - 8;
+    else d.in_first = rs_first_input(d.rs, t0) & ~7;          // floor to a multiple of 8 (also for negatives)
     d.out_start = P.out_row[b] + t0;
-    d.pad1 = 0;
+    d.pad = 0;
     P.tiles[tile] = d;
 }
 
@@ -206,7 +210,7 @@ __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
 #pragma unroll
         for (int rg = 0; rg < 3; ++rg) {
             const int n = stats_rows(d.nvalid, rg);
-            const float* src = P.feats + (d.wav_start + 11 * rg) * P.F + f;   // feats mode: wav_start counts rows
+            const float* src = P.feats + (d.wav_utt + d.t0 + 11 * rg) * P.F + f;   // feats mode: offsets count rows
             float s = 0.f, m2 = 0.f;
             if (n > 0) {
                 for (int r = 0; r < n; ++r) s += src[(int64_t)r * P.F];
@@ -393,12 +397,6 @@ __global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P
 // ---- specialised polyphase kernel for the speed-perturb ratios (9:10 and 11:10, width 7) ----
 // hann-windowed sinc taps vanish where the window argument is clamped (functional.py:1370-1381):
 // tap (p, q) is non-zero only if |(-p/new + (q - width)/orig) * 0.99 min(orig, new)| < 6.
-OE_CX bool rs_tap_nonzero(int orig, int neu, int width, int p, int q) {
-    const double base = (orig < neu ? orig : neu) * 0.99;
-    const double t = (-(double)p / neu + (double)(q - width) / orig) * base;
-    return t < 6.0 && t > -6.0;
-}
-
 struct RsFastParams {
     ResampleParams r;
     int table_id;
@@ -529,7 +527,7 @@ void default_mel(const oe_config& c, std::vector<float>& m) {
 
 struct Meta {               // device-side metadata block layout (byte offsets into the workspace)
     size_t wav_off, out_row, frame_prefix, row_prefix, map_off;          // int64 arrays
-    size_t wav_len, n_frames, n_rows, tile_prefix, tmask, fmask, fmap, tiles;   // int32 arrays
+    size_t wav_len, n_frames, n_rows, tile_prefix, rs_mode, tmask, fmask, fmap, tiles;   // int32 arrays
     size_t meta_bytes;
     size_t raw, tile_stats, utt_mean, utt_std, stat_partial, total;
     int max_rows;
@@ -563,7 +561,16 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
         if (bt->wav_lens[b] < 0) return fail(OE_ERR_INVALID, "negative wav_len at %d", b);
         if (bt->wav_offsets[b] < 0 || (!feats && (bt->wav_offsets[b] & 7)))
             return fail(OE_ERR_INVALID, "wav_offsets[%d] must be a non-negative multiple of 8 samples", b);
-        const int nfr = feats ? bt->wav_lens[b] : oe_num_frames(fe, bt->wav_lens[b]);
+        int64_t eff_len = bt->wav_lens[b];
+        if (bt->resample_ids && bt->resample_ids[b] >= 0) {
+            const int id = bt->resample_ids[b];
+            if (feats || bt->wav_dtype != OE_WAV_I16) return fail(OE_ERR_UNSUPPORTED, "fused speed perturb takes int16 PCM input");
+            if (id != fe->rs_fast_9_10 && id != fe->rs_fast_11_10)
+                return fail(OE_ERR_UNSUPPORTED, "resample_ids[%d]=%d: only the 9:10 and 11:10 (width 7) tables can be fused; "
+                                                "use oe_resample for other ratios", b, id);
+            eff_len = oe_resample_out_len(eff_len, fe->rs[id].orig, fe->rs[id].neu);
+        }
+        const int nfr = feats ? bt->wav_lens[b] : oe_num_frames(fe, eff_len);
         const int nrows = bt->out_nrows ? bt->out_nrows[b] : nfr;
         if (nrows < nfr) return fail(OE_ERR_INVALID, "out_nrows[%d]=%d < frames %d", b, nrows, nfr);
         if (frames_out) (*frames_out)[b] = nfr;
@@ -587,6 +594,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.n_frames = take(4 * (size_t)B);
     M.n_rows = take(4 * (size_t)B);
     M.tile_prefix = take(4 * (size_t)(B + 1));
+    M.rs_mode = take(4 * (size_t)B);
     M.tmask = take(8 * (size_t)B * bt->n_tmask);
     M.fmask = take(8 * (size_t)B * bt->n_fmask);
     M.fmap = take(4 * (size_t)M.total_map);
@@ -793,6 +801,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         i32(M.n_frames)[b] = nfr;
         i32(M.n_rows)[b] = M.two_phase ? nfr : nrows;
         i32(M.tile_prefix)[b] = tp;
+        i32(M.rs_mode)[b] = (bt->resample_ids && bt->resample_ids[b] >= 0) ? (bt->resample_ids[b] == fe->rs_fast_9_10 ? 1 : 2) : 0;
         fp += nfr;
         rp += nrows;
         tp += ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
@@ -823,6 +832,10 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     const int32_t* d_tile_prefix = reinterpret_cast<const int32_t*>(ws + M.tile_prefix);
     P.total_tiles = M.total_tiles;
     if (fe->std_mel) memcpy(P.mel_w, fe->mel_w_std, sizeof(P.mel_w));
+    for (int which = 0; which < 2; ++which) {
+        const int id = which == 0 ? fe->rs_fast_9_10 : fe->rs_fast_11_10;
+        if (id >= 0) memcpy(P.rs_coef[which], fe->rs_coefs.data() + fe->rs[id].coef_off, sizeof(float) * fe->rs[id].neu * fe->rs[id].taps);
+    }
     P.tab = fe->d_tab;
     P.tile_stats = M.need_stats ? reinterpret_cast<float*>(ws + M.tile_stats) : nullptr;
     const int64_t* d_tile_out_row;
@@ -850,10 +863,11 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         T.n_frames = d_n_frames;
         T.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
         T.out_row = d_tile_out_row;
+        T.rs_mode = reinterpret_cast<const int32_t*>(ws + M.rs_mode);
         T.tiles = reinterpret_cast<oe::TileDesc*>(ws + M.tiles);
         T.B = B;
         T.total_tiles = M.total_tiles;
-        T.shift = M.feats ? 1 : oe::kShift;
+        T.feats = M.feats ? 1 : 0;
         oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
         OE_CUDA(cudaGetLastError());
     }

@@ -164,6 +164,17 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
     offs = np.asarray(offs, dtype=np.int64)
     lens = np.asarray(lens, dtype=np.int32)
     needs = (plan.stage1[:, 0] != 0) | (plan.stage2[:, 0] != 0)
+    # speed 0.9 / 1.1 on int16 PCM: resampled inside the fbank kernel's staging -> the whole batch is ONE call
+    fusable = (dev_wav.dtype == torch.int16 and not (plan.stage1[:, 0] != 0).any() and
+               np.isin(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1], (0, 9 * 65536 + 10, 11 * 65536 + 10)).all())
+    if fusable and needs.any():
+        kw = dict(fused)
+        if kw.get('frame_map') is not None:
+            fm, starts = kw.pop('frame_map'), kw.pop('frame_map_starts')
+            kw['frame_maps'] = [fm[starts[i]:starts[i] + plan.frames[i]] for i in range(B)]
+        fe.fbank(dev_wav, offs[plan.src], lens[plan.src], layout='custom', out=out.view(-1, F), out_rows=rows,
+                 out_nrows=nrows, speed_ratios=plan.stage2, **kw)
+        return out, fe
     direct = np.nonzero(~needs)[0]
     resamp = np.nonzero(needs)[0]
 

@@ -218,7 +218,8 @@ class Frontend(object):
     # ------------------------------------------------------------------ fbank (+ fused chain)
     def fbank(self, wav, offsets, lens, *, layout='padded', out=None, max_rows=None, out_rows=None,
               out_nrows=None, normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
-              cmvn_on_padding=False, stats=None, stream=None, features_in=False, want_out=True):
+              cmvn_on_padding=False, stats=None, stream=None, features_in=False, want_out=True,
+              speed_ratios=None):
         """Runs one ragged batch.
 
         wav       packed device tensor: int16 PCM, fp32 on the int16 scale, or (features_in) a
@@ -232,6 +233,8 @@ class Frontend(object):
         frame_maps      list of int32 index maps (spec_sub plan) or None.
         cmvn      (mean, istd) fp32 device tensors, istd may be None (norm_var=False).
         stats     float64 device tensor [2F+1] accumulating sum / sumsq / count of raw frames.
+        speed_ratios  int [B, 2] (orig, new) per utterance, (0, 0) = none: speed perturb FUSED into the
+                  fbank kernel's staging (int16 input; 9:10 and 11:10 only, i.e. speeds 0.9 / 1.1).
         Returns (out tensor or None, frames int32 ndarray).
         """
         B = len(lens)
@@ -245,7 +248,17 @@ class Frontend(object):
             dtype = OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16
             if wav.dtype not in (torch.float32, torch.int16):
                 raise FrontendError('waveform must be int16 or float32, got %s' % wav.dtype)
-            frames = self.num_frames_array(lens)
+            eff = lens.astype(np.int64)
+            if speed_ratios is not None:
+                speed_ratios = np.asarray(speed_ratios, dtype=np.int64).reshape(B, 2)
+                rs_ids = np.full(B, -1, dtype=np.int32)
+                key = speed_ratios[:, 0] * 65536 + speed_ratios[:, 1]
+                for k in np.unique(key[key != 0]):
+                    o, n = int(k) >> 16, int(k) & 65535
+                    sel = key == k
+                    rs_ids[sel] = self.resampler_id(o, n)
+                    eff[sel] = (n * eff[sel] + o - 1) // o
+            frames = self.num_frames_array(eff)
         nrows = None
         if not want_out:
             out = None
@@ -302,12 +315,13 @@ class Frontend(object):
             mean_p = ctypes.c_void_p(mean.data_ptr())
             istd_p = ctypes.c_void_p(istd.data_ptr()) if istd is not None else None
         out_frames = np.zeros(B, dtype=np.int32)
+        rs_p = _ptr(rs_ids, c_i32p) if (speed_ratios is not None and not features_in) else None
         bt = OeBatch(B, dtype, _ptr(offsets, c_i64p), _ptr(lens, c_i32p), _ptr(out_rows, c_i64p),
                      _ptr(nrows, c_i32p), 0, OE_NORM_PER_UTT if normalization else OE_NORM_NONE, n_t, n_f,
                      _ptr(tm, c_i32p), _ptr(fm, c_i32p), _ptr(fmap, c_i32p), _ptr(fmap_off, c_i64p),
                      mean_p, istd_p, 1 if cmvn_on_padding else 0,
                      ctypes.c_void_p(stats.data_ptr()) if stats is not None else None,
-                     _ptr(out_frames, c_i32p))
+                     _ptr(out_frames, c_i32p), rs_p)
         need = ctypes.c_size_t()
         check(self.lib.oe_fbank_workspace_bytes(self.handle, ctypes.byref(bt), ctypes.byref(need)))
         s, sp = self._stream(stream)

@@ -228,6 +228,34 @@ def test_speed_perturb_resampler(fe, golden_dir):
     assert np.abs(y.cpu().numpy() - g['fb090']).max() < 2e-3
 
 
+def test_fused_speed_perturb_equals_separate_resampler(fe, golden_dir):
+    """Speed perturb fused into the fbank kernel's staging (no intermediate waveform) == oe_resample followed
+    by fbank on its fp32 output -- same taps, same summation order, so bit for bit -- across tile
+    boundaries, utterance ends and utterances the perturbation pushes below / above one window."""
+    from openeat_b200.frontend import pack_waveforms
+    lens = [16000, 9000, 50000, 5200, 7777, 400, 450, 5121 * 9 // 10, 361]
+    waves = [signals.make('speech' if i % 2 else 'white', n, 600 + i) for i, n in enumerate(lens)]
+    ratios = np.array([[9, 10], [11, 10], [9, 10], [0, 0], [11, 10], [9, 10], [11, 10], [9, 10], [9, 10]])
+    buf, offs, ln = pack_waveforms(waves)
+    dev = buf.cuda()
+    fused, frames = fe.fbank(dev, offs, ln, layout='padded', speed_ratios=ratios)
+    r, ro, rl = fe.resample(dev, offs, ln, ratios)
+    sep, frames2 = fe.fbank(r, ro, rl, layout='padded')
+    torch.cuda.synchronize()
+    assert frames.tolist() == frames2.tolist()
+    assert frames.tolist() == [F.num_frames(-(-n * b // a) if a else n) for n, (a, b) in zip(lens, ratios.tolist())]
+    assert torch.equal(fused, sep)
+    # and against torchaudio.functional.speed -> kaldi.fbank (golden)
+    g = np.load(os.path.join(golden_dir, 'speed.npz'))
+    b16, o16, l16 = pack_waveforms([g['x'].astype(np.int16)] * 2)
+    y, _ = fe.fbank(b16.cuda(), o16, l16, layout='padded', speed_ratios=np.array([[9, 10], [11, 10]]))
+    y = y.cpu().numpy()
+    assert np.abs(y[0, :g['fb090'].shape[0]] - g['fb090']).max() < 2e-3
+    assert np.abs(y[1, :g['fb110'].shape[0]] - g['fb110']).max() < 2e-3
+    with pytest.raises(Exception):
+        fe.fbank(dev, offs, ln, layout='padded', speed_ratios=np.array([[1, 2]] * len(lens)))   # not fusable: says so
+
+
 def test_global_cmvn_apply(fe, golden_dir):
     g = np.load(os.path.join(golden_dir, 'cmvn.npz'))
     mean = torch.from_numpy(g['mean_json']).float().cuda()
