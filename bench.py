@@ -213,11 +213,25 @@ def run_ours(args, rank, world, local_rank):
     collate = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=True, spec_aug=True,
                                  spec_aug_conf=AUG, global_cmvn=(mean, istd), cmvn_stats=stats)
 
+    from openeat_b200.dataset import PrefetchingCollator
+
+    def host_batches():
+        i = 0
+        while True:
+            yield (host_pool[i % POOL], offs, lens, keys, labels, speeds)
+            i += 1
+
+    pipe = PrefetchingCollator(collate, host_batches())
+    d2h = {'n': torch.empty(BATCH, dtype=torch.int32).pin_memory(),
+           's': torch.empty(161, dtype=torch.float64).pin_memory()}
+
     def step_e2e(i):
-        """Public API from pinned host memory: H2D of the PCM, all kernels, D2H of the step's result
-        (frame counts + the running CMVN statistics; the features stay on the GPU for the model)."""
-        _, out = collate.collate_packed(host_pool[i % POOL], offs, lens, keys, labels, speeds)
-        return out['features_length'].cpu(), stats.cpu()
+        """Public API from pinned host memory: H2D of this step's PCM (PrefetchingCollator: on a side stream,
+        one batch ahead), all kernels, and a D2H read of the step's result (frame counts + the running CMVN
+        statistics; the features stay on the GPU for the model)."""
+        _, out = next(pipe)
+        d2h['n'].copy_(out['features_length'], non_blocking=True)
+        d2h['s'].copy_(stats, non_blocking=True)
 
     def timed(fn, steps, warmup, with_allreduce):
         for i in range(warmup):
@@ -241,16 +255,31 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), fe.launches - l0
 
+    def timed_repeated(fn, with_allreduce, min_seconds):
+        """Times EXACTLY args.steps steps (barrier + sync on both sides); the K-step region is repeated until
+        `min_seconds` have passed so that nvidia-smi (100 ms period) sees the clocks under this very load; the
+        median repeat is reported."""
+        runs, launches, t0 = [], 0, time.perf_counter()
+        while True:
+            ms, launches = timed(fn, args.steps, warmup if not runs else 0, with_allreduce)
+            runs.append(ms)
+            go = torch.tensor([1.0 if time.perf_counter() - t0 < min_seconds and len(runs) < 400 else 0.0], device=dev)
+            if world > 1:
+                dist.broadcast(go, 0)
+            if go.item() == 0.0:
+                break
+        return float(np.median(runs)), launches, len(runs)
+
     warmup = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total, launches = timed(step_resident, args.steps, warmup, world > 1)
+    ms_total, launches, reps = timed_repeated(step_resident, world > 1, 1.5)
     clocks = sampler.stop() if rank == 0 else None
     value = world * audio_s * args.steps / (ms_total * 1e-3)
     stats.zero_()
     random.seed(99 + rank)
-    ms_e2e, _ = timed(step_e2e, args.steps, warmup, world > 1)
+    ms_e2e, _, _ = timed_repeated(step_e2e, world > 1, 0.5)
     e2e_value = world * audio_s * args.steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel (oe_fbank_kernel), timed alone on its own stream position ----
@@ -305,12 +334,15 @@ def run_ours(args, rank, world, local_rank):
             'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'audio_s_per_step_per_gpu': audio_s,
                        'l2': 'inputs cycle through %d distinct batches (%.0f MB int16 per GPU) > 126 MB L2' %
                              (POOL, POOL * h2d / 1e6),
+                       'timing': 'median of %d back-to-back repeats of the %d-step timed region (each bracketed by '
+                                 'barrier + synchronize; repeats only lengthen the window nvidia-smi samples)' % (reps, args.steps),
                        'parallelism': 'utterance sharding, dp%d; one 161 x f64 NCCL all-reduce closes the timed region'
                                       % world if world > 1 else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': BATCH * 4 + 161 * 8, 'ms_per_step': ms_e2e / args.steps,
-                    'api': 'openeat_b200.dataset.audio_collate_func.collate_packed (pinned int16 -> GPU features; '
-                           'frame counts + CMVN stats read back)'},
+                    'api': 'openeat_b200.dataset.PrefetchingCollator over audio_collate_func.collate_packed (pinned int16 '
+                           '-> GPU features; H2D of batch i+1 overlaps batch i; frame counts + CMVN stats read back '
+                           'every step)'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
         }
         if cpu is not None:

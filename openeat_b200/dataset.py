@@ -315,3 +315,49 @@ class audio_collate_func(object):
         inputs = {'features': features.to(dev), 'features_length': features_length.to(dev),
                   'targets': targets.to(dev), 'targets_length': targets_length.to(dev)}
         return plan.keys, inputs
+
+
+class PrefetchingCollator(object):
+    """Pipelines ``audio_collate_func.collate_packed`` over an iterator of packed host batches: the pinned
+    PCM of batch i+1 crosses PCIe on a side stream while batch i runs its kernels, so the steady-state cost
+    per batch is max(H2D copy, kernels, host planning) instead of their sum.  Yields exactly what
+    ``collate_packed`` returns, in order (what torch's DataLoader prefetching does for the reference's
+    CPU workers, done here for the one resource the GPU front-end is bound by: the H2D copy).
+
+    ``batches`` yields tuples ``(pinned_wav, offsets, lens, keys, labels, speeds)``.
+    """
+
+    def __init__(self, collate, batches):
+        self.collate = collate
+        self.batches = iter(batches)
+        fe = default_frontend(collate.feature_extraction_conf['mel_bins'])
+        self.device = fe.device
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._stage()
+
+    def _stage(self):
+        try:
+            item = next(self.batches)
+        except StopIteration:
+            self._next = None
+            return
+        wav = item[0]
+        with torch.cuda.stream(self.copy_stream):
+            dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
+        self._next = (dev, ev) + tuple(item[1:])
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        dev, ev, offs, lens, keys, labels, speeds = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
+        dev.record_stream(cur)
+        self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
+        return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds)

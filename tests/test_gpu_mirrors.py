@@ -157,6 +157,30 @@ def test_fused_global_cmvn_and_stats(gold, golden_dir):
     assert stats[160].item() == int(a['features_length'].sum())
 
 
+def test_prefetching_collator_equals_direct_calls(gold):
+    """H2D of batch i+1 overlapped with batch i on a side stream must not change any result."""
+    from openeat_b200.dataset import PrefetchingCollator, audio_collate_func
+    from openeat_b200.frontend import pack_waveforms
+    conf = dict(CONF, speed_perturb_rate=0.5)
+    kw = dict(data_type='wav', feature_extraction_conf=conf, normalization=True, spec_aug=True,
+              spec_aug_conf=dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))
+    batches = []
+    for r in range(4):
+        ids = [(i + r) % 6 for i in range(5)]
+        buf, offs, lens = pack_waveforms([gold['pcm%d' % i] for i in ids])
+        batches.append((buf, offs, lens, ['u%d' % i for i in ids], [[i + 1] * 3 for i in ids], [1.0, 0.9, 1.1, 1.0, 1.0]))
+    fn = audio_collate_func(**kw)
+    random.seed(31)
+    direct = [fn.collate_packed(*b) for b in batches]
+    random.seed(31)
+    piped = list(PrefetchingCollator(audio_collate_func(**kw), batches))
+    assert len(piped) == 4
+    for (k1, o1), (k2, o2) in zip(direct, piped):
+        assert k1 == k2
+        for name in o1:
+            assert torch.equal(o1[name], o2[name]), name
+
+
 def test_speed_processors(golden_dir):
     from openeat_b200.audio_processor import _speed_generator, _speed_perturb
     g = np.load(os.path.join(golden_dir, 'speed.npz'))
