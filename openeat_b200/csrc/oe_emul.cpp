@@ -1,81 +1,55 @@
-// Host-side emulation of the per-frame math of the fbank kernel (stage A -> twiddle ->
-// exchange -> stage B -> untangle), running the very same templates from oe_fft.h that the
-// sm_100a kernel instantiates.  Built with g++ into liboe_emul.so for tests/test_host_emul.py;
-// it is test tooling and is never loaded by the product path.
+// Host-side emulation of the per-frame math of the fbank kernel (stage A -> twiddle -> exchange ->
+// stage B -> row exchange -> untangle), running the very same templates from oe_fft.h that the sm_100a
+// kernel instantiates -- with the packed two-frame type V2 emulated as a pair of floats.  Built with g++
+// into liboe_emul.so for tests/test_host_emul.py; it is test tooling and is never loaded by the product path.
 #include <cmath>
 
 #include "oe_fft.h"
 
-namespace {
-struct Cf {
-    float re, im;
-};
-}  // namespace
-
 extern "C" {
 
-// h: one windowed frame (400 samples; the kernel builds it from shared memory).
-// pw: 257 power-spectrum bins |X[k]|^2.
-void oe_emul_frame(const float* h, float* pw) {
-    Cf E[16][16];                                  // exchange buffer: [k1][tau]
+// ha, hb: two windowed frames (400 samples each; the kernel builds them from shared memory).
+// pa, pb: 256 power-spectrum bins |X[k]|^2, k = 0..255, per frame.
+void oe_emul_frame_pair(const float* ha, const float* hb, float* pa, float* pb) {
+    static oe::V2 Er[16][16], Ei[16][16];          // first exchange: [k1][tau]
+    static oe::V2 Zr[16][16], Zi[16][16];          // second exchange: [k1][k2]
     for (int tau = 0; tau < 16; ++tau) {           // ---- stage A ----
-        float zr[16], zi[16];
+        oe::V2 zr[16], zi[16];
         for (int n1 = 0; n1 < 16; ++n1) {
             const int j = 2 * (16 * n1 + tau);
-            zr[n1] = (j < 400) ? h[j] : 0.0f;
-            zi[n1] = (j + 1 < 400) ? h[j + 1] : 0.0f;
+            zr[n1] = oe::v2_make(j < 400 ? ha[j] : 0.f, j < 400 ? hb[j] : 0.f);
+            zi[n1] = oe::v2_make(j + 1 < 400 ? ha[j + 1] : 0.f, j + 1 < 400 ? hb[j + 1] : 0.f);
         }
-        oe::fft_dif<16, 13>(zr, zi);
+        oe::fft_dif<16, 13, oe::V2>(zr, zi);
         for (int pos = 0; pos < 16; ++pos) {
             const int k1 = oe::bitrev<16>(pos);
-            const double ang = -2.0 * oe::kPi * (double)(tau * k1) / 256.0;
-            const float c = (float)std::cos(ang), s = (float)std::sin(ang);
-            E[k1][tau].re = zr[pos] * c - zi[pos] * s;
-            E[k1][tau].im = zr[pos] * s + zi[pos] * c;
+            const double ang = 2.0 * oe::kPi * (double)((tau * k1) % 256) / 256.0;
+            const oe::V2 c = oe::vbcast((float)std::cos(ang)), s = oe::vbcast((float)-std::sin(ang));
+            Er[k1][tau] = oe::vsub(oe::vmul(zr[pos], c), oe::vmul(zi[pos], s));
+            Ei[k1][tau] = oe::vfma(zr[pos], s, oe::vmul(zi[pos], c));
         }
     }
-    for (int u = 0; u < 8; ++u) {                  // ---- stage B ----
-        const int ra = oe::stage_b_row_a(u), rb = oe::stage_b_row_b(u);
-        float ar[16], ai[16], br[16], bi[16];
+    for (int k1 = 0; k1 < 16; ++k1) {              // ---- stage B: one row per lane ----
+        oe::V2 ar[16], ai[16];
         for (int n2 = 0; n2 < 16; ++n2) {
-            ar[n2] = E[ra][n2].re;
-            ai[n2] = E[ra][n2].im;
-            br[n2] = E[rb][n2].re;
-            bi[n2] = E[rb][n2].im;
+            ar[n2] = Er[k1][n2];
+            ai[n2] = Ei[k1][n2];
         }
-        oe::fft_dif<16>(ar, ai);
-        oe::fft_dif<16>(br, bi);
-        auto tw = [](int k, float& c, float& s) {
-            c = (float)std::cos(2.0 * oe::kPi * k / 512.0);
-            s = (float)std::sin(2.0 * oe::kPi * k / 512.0);
-        };
-        float c, s, pk, pnk;
-        if (u != 0) {
-            for (int k2 = 0; k2 < 16; ++k2) {      // P = Z[u + 16 k2], Q = Z[(16-u) + 16 (15-k2)]
-                const int p = oe::bitrev<16>(k2), q = oe::bitrev<16>(15 - k2);
-                const int k = u + 16 * k2;
-                tw(k, c, s);
-                oe::untangle_power(ar[p], ai[p], br[q], bi[q], c, s, pk, pnk);
-                pw[k] = 0.25f * pk;
-                pw[256 - k] = 0.25f * pnk;
-            }
-        } else {
-            for (int k2 = 0; k2 <= 8; ++k2) {      // row 0: P = Z[16 k2], Q = Z[16 ((16-k2) mod 16)]
-                const int p = oe::bitrev<16>(k2), q = oe::bitrev<16>((16 - k2) & 15);
-                const int k = 16 * k2;
-                tw(k, c, s);
-                oe::untangle_power(ar[p], ai[p], ar[q], ai[q], c, s, pk, pnk);
-                pw[k] = 0.25f * pk;
-                pw[256 - k] = 0.25f * pnk;
-            }
-            for (int k2 = 0; k2 < 8; ++k2) {       // row 8: P = Z[8 + 16 k2], Q = Z[8 + 16 (15-k2)]
-                const int p = oe::bitrev<16>(k2), q = oe::bitrev<16>(15 - k2);
-                const int k = 8 + 16 * k2;
-                tw(k, c, s);
-                oe::untangle_power(br[p], bi[p], br[q], bi[q], c, s, pk, pnk);
-                pw[k] = 0.25f * pk;
-                pw[256 - k] = 0.25f * pnk;
-            }
+        oe::fft_dif<16, 16, oe::V2>(ar, ai);
+        for (int pos = 0; pos < 16; ++pos) {
+            Zr[k1][oe::bitrev<16>(pos)] = ar[pos];
+            Zi[k1][oe::bitrev<16>(pos)] = ai[pos];
+        }
+    }
+    for (int k1 = 0; k1 < 16; ++k1) {              // ---- untangle: partner row, one output per (k1, k2) ----
+        const int pr = oe::partner_row(k1);
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const int k = k1 + 16 * k2, q2 = oe::partner_k2(k1, k2);
+            const oe::V2 c = oe::vbcast((float)std::cos(2.0 * oe::kPi * k / 512.0));
+            const oe::V2 s = oe::vbcast((float)std::sin(2.0 * oe::kPi * k / 512.0));
+            const oe::V2 p = oe::untangle_power(Zr[k1][k2], Zi[k1][k2], Zr[pr][q2], Zi[pr][q2], c, s);
+            pa[k] = 0.25f * oe::v2_lo(p);
+            pb[k] = 0.25f * oe::v2_hi(p);
         }
     }
 }

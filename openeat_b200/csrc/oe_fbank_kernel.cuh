@@ -51,6 +51,7 @@ struct FbankParams {
     const float* cmvn_mean;
     const float* cmvn_istd;
     int cmvn_on_pad;
+    int out_vec;                    // rows are dense (pitch == F) and `out` is 16-byte aligned: float4 stores allowed
     float* tile_stats;              // [total_tiles][3][2][F]: per row-group column sum and sum of squared deviations
     double* cta_stats;              // [gridDim.x][3][2][F] or null: this CTA's running sum / sum of squares (fp64)
     const DevTables* tab;
@@ -76,26 +77,30 @@ __device__ __forceinline__ int find_utt(const int32_t* __restrict__ prefix, int 
 
 // ------------------------------------------------------------------------------------------
 // shared memory map (bytes)
+constexpr int kGroupX = 4096;                              // exchange bytes per 16-thread group: 2 planes x 16 rows x 128 B
+constexpr int kRowP = 34;                                  // floats per power-spectrum row: 32 frames + 2 pad (conflict-free STS.64)
 constexpr int kSmP = 0;                                    // float p[5376]      | out tile (32 x (F+1))
 constexpr int kSmS8 = kSmP + 5376 * 4;                     // float s8[672]
-constexpr int kSmE = kSmS8 + kChunks * 4;                  // float2 E[16][2][16][18] | float P[256][36] + raw prefetch
-constexpr int kSmRaw = kSmE + kBins * kRowP * 4;           // next tile's raw samples: 673 chunks of 8 (i16: 16 B, f32: 32 B)
-constexpr int kSmTwA = kSmE + 16 * 2 * 16 * kRowE * 8;     // float2 twA[16][18]
-constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[9][18]
-constexpr int kSmMask = kSmTwU + 9 * kRowE * 8;            // uchar rowmask[32], colmask[128]
+constexpr int kSmE = kSmS8 + kChunks * 4;                  // exchange buffers [16 groups][4096 B] | power tile [256][34]
+constexpr int kSmRawF32 = kSmE + kBins * kRowP * 4;        // fp32 input: next tile's raw samples share the exchange area (behind the power tile)
+constexpr int kSmRaw = kSmE + 16 * kGroupX;                // int16 input: dedicated prefetch buffer (745 pieces of 16 B)
+constexpr int kSmTwA = kSmRaw + 11936;                     // float2 twA[16][18]
+constexpr int kSmTwU = kSmTwA + 16 * kRowE * 8;            // float2 twU[16][18]
+constexpr int kSmMask = kSmTwU + 16 * kRowE * 8;           // uchar rowmask[32], colmask[128]
 constexpr int kSmDesc = kSmMask + 32 + kMaxMel;            // TileDesc[2]
 constexpr int kSmAcc = kSmDesc + 2 * 48;                   // double acc[3][2][128]: CMVN-statistics accumulators
 constexpr int kSmEdge = kSmAcc + 3 * 2 * kMaxMel * 8;      // float edge[32]: fused-resampler block edges
 constexpr int kSmStd = kSmEdge + 32 * 4;                   // end of the standard-mel layout
 constexpr int kSmMelIdx = kSmStd;                          // generic mel only: int start/len/off [3][128], group_begin[9] (+pad)
 constexpr int kSmMelW = kSmMelIdx + (3 * kMaxMel + 12) * 4;  // generic mel only: float mel_w[nnz]
-static_assert(kSmE % 16 == 0 && kSmRaw % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0 &&
+static_assert(kSmE % 16 == 0, "exchange rows hold 16-byte chunks");
+static_assert(kSmRaw % 16 == 0 && kSmRawF32 % 16 == 0 && kSmTwA % 16 == 0 && kSmTwU % 16 == 0 && kSmMelW % 16 == 0 &&
               kSmDesc % 16 == 0 && kSmAcc % 16 == 0, "align");
-constexpr int kRowS = 34;           // float2 per frame of the self-conjugate-row scratch (32 + 2 pad = 272 B), in the p area
-static_assert(kSmRaw + 673 * 32 <= kSmTwA, "raw prefetch buffer must fit behind the power tile");
-static_assert(kRsPieces * 16 <= 673 * 32, "resampler input must fit the raw prefetch buffer");
-static_assert(kRsMaxIn * 4 <= kBins * kRowP * 4, "fp32 resampler input must fit in front of the raw buffer");
+static_assert(kSmRawF32 + 673 * 32 <= kSmRaw, "fp32 raw prefetch must fit behind the power tile");
+static_assert(kRsPieces * 16 <= 11936 && 673 * 16 <= 11936, "int16 raw prefetch buffer too small");
+static_assert(kRsMaxIn * 4 <= 16 * kGroupX, "fp32 resampler input must fit the exchange area");
 static_assert(32 * (kMaxMel + 1) * 4 <= 5376 * 4, "out tile must fit in the staging area");
+static_assert(kSmStd + 1024 <= 116224, "two CTAs per SM");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -199,9 +204,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     extern __shared__ __align__(16) unsigned char smem[];
     float* const sp = reinterpret_cast<float*>(smem + kSmP);
     float* const s8 = reinterpret_cast<float*>(smem + kSmS8);
-    float2* const sE = reinterpret_cast<float2*>(smem + kSmE);
     float* const sPw = reinterpret_cast<float*>(smem + kSmE);
-    unsigned char* const sRaw = smem + kSmRaw;
+    unsigned char* const sRaw = smem + (kF32 ? kSmRawF32 : kSmRaw);
     float2* const sTwA = reinterpret_cast<float2*>(smem + kSmTwA);
     float2* const sTwU = reinterpret_cast<float2*>(smem + kSmTwU);
     unsigned char* const sRowMask = smem + kSmMask;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     }
     // ---- one-time table staging ----
     for (int i = tid; i < 16 * kRowE; i += kThreads) sTwA[i] = tab->twA[i];
-    for (int i = tid; i < 9 * kRowE; i += kThreads) sTwU[i] = tab->twU[i];
+    for (int i = tid; i < 16 * kRowE; i += kThreads) sTwU[i] = tab->twU[i];
     if (!kStdMel) {
         for (int i = tid; i < kMaxMel; i += kThreads) {
             sMelStart[i] = tab->mel_start[i];
@@ -376,11 +380,19 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                     }
                 }
             }
+            if (!kF32) cp_async_wait_all();    // next tile's descriptor has landed (this thread's pieces; (2) publishes them)
             __syncthreads();                                       // (2)
-
-            // ---- stage A: frame means (kaldi.py:183-186), then 16-point FFTs of z[16 n1 + tau] ----
-            float zr[2][16], zi[2][16];
+            if (!kF32) {               // int16: the raw buffer has been consumed -> next tile's samples start moving now
+                if (next < P.total_tiles) {
+                    const TileDesc* const dn = sDesc + (slot ^ 1);
+                    if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
+                }
+                cp_async_commit();
+            }
+            // ---- stage A: frame means (kaldi.py:183-186), one packed 16-point FFT of z[16 n1 + tau] for 2 frames ----
+            unsigned char* const gx = smem + kSmE + grp * kGroupX;   // this group's exchange area: re plane, im plane (+2048)
             {
+                V2 zr[16], zi[16];
                 const float* q0 = s8 + 20 * (2 * grp) + tau;
                 float m0 = (q0[0] + q0[16]) + q0[32], m1 = (q0[20] + q0[36]) + q0[52];
                 if (tau < 2) {
@@ -398,123 +410,109 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                 for (int n1 = 0; n1 < 13; ++n1) {
                     const float2 v0 = *reinterpret_cast<const float2*>(base + 32 * n1);
                     const float2 v1 = *reinterpret_cast<const float2*>(base + kShift + 32 * n1);
-                    zr[0][n1] = (v0.x - c0) * wv0[n1];
-                    zi[0][n1] = (v0.y - c0) * wv1[n1];
-                    zr[1][n1] = (v1.x - c1) * wv0[n1];
-                    zi[1][n1] = (v1.y - c1) * wv1[n1];
+                    zr[n1] = v2_make((v0.x - c0) * wv0[n1], (v1.x - c1) * wv0[n1]);
+                    zi[n1] = v2_make((v0.y - c0) * wv1[n1], (v1.y - c1) * wv1[n1]);
                 }
 #pragma unroll
-                for (int n1 = 13; n1 < 16; ++n1) {
-                    zr[0][n1] = zi[0][n1] = zr[1][n1] = zi[1][n1] = 0.f;
-                }
-            }
-            fft_dif<16, 13>(zr[0], zi[0]);
-            fft_dif<16, 13>(zr[1], zi[1]);
-            {
-                float2* const e0 = sE + ((grp * 2 + 0) * 16) * kRowE + tau;
-                float2* const e1 = sE + ((grp * 2 + 1) * 16) * kRowE + tau;
+                for (int n1 = 13; n1 < 16; ++n1) zr[n1] = zi[n1] = vbcast(0.f);
+                fft_dif<16, 13, V2>(zr, zi);
+                // twiddle by W256^(tau k1) and store row k1: cell tau of 8 B (frame pair), 16-byte chunks
+                // XOR-swizzled by k1 & 7 so that the row reads (LDS.128, one row per lane) are conflict-free
+                unsigned off8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) off8[j] = (unsigned)((((tau >> 1) ^ j) << 4) + ((tau & 1) << 3));
                 const float4* const tw4 = reinterpret_cast<const float4*>(sTwA + tau * kRowE);
                 static_for<0, 8>([&](auto ii) {
                     constexpr int i = decltype(ii)::value;
-                    const float4 t = tw4[i];                       // k1 = 2i: (t.x, t.y), 2i+1: (t.z, t.w)
+                    const float4 t = tw4[i];                       // k1 = 2i: (t.x, t.y), 2i+1: (t.z, t.w); (cos, -sin)
                     constexpr int p0 = bitrev<16>(2 * i), p1 = bitrev<16>(2 * i + 1);
-                    if constexpr (i == 0) {
-                        e0[0] = make_float2(zr[0][p0], zi[0][p0]);
-                        e1[0] = make_float2(zr[1][p0], zi[1][p0]);
-                    } else {
-                        e0[(2 * i) * kRowE] = make_float2(zr[0][p0] * t.x - zi[0][p0] * t.y, zr[0][p0] * t.y + zi[0][p0] * t.x);
-                        e1[(2 * i) * kRowE] = make_float2(zr[1][p0] * t.x - zi[1][p0] * t.y, zr[1][p0] * t.y + zi[1][p0] * t.x);
+                    V2 r0 = zr[p0], i0 = zi[p0];
+                    if constexpr (i != 0) {
+                        const V2 c = vbcast(t.x), sn = vbcast(t.y);
+                        r0 = vfma(zi[p0], vbcast(-t.y), vmul(zr[p0], c));
+                        i0 = vfma(zr[p0], sn, vmul(zi[p0], c));
                     }
-                    e0[(2 * i + 1) * kRowE] = make_float2(zr[0][p1] * t.z - zi[0][p1] * t.w, zr[0][p1] * t.w + zi[0][p1] * t.z);
-                    e1[(2 * i + 1) * kRowE] = make_float2(zr[1][p1] * t.z - zi[1][p1] * t.w, zr[1][p1] * t.w + zi[1][p1] * t.z);
+                    const V2 c1v = vbcast(t.z), s1v = vbcast(t.w);
+                    const V2 r1 = vfma(zi[p1], vbcast(-t.w), vmul(zr[p1], c1v));
+                    const V2 i1 = vfma(zr[p1], s1v, vmul(zi[p1], c1v));
+                    unsigned char* const d0 = gx + (2 * i) * 128 + off8[(2 * i) & 7];
+                    unsigned char* const d1 = gx + (2 * i + 1) * 128 + off8[(2 * i + 1) & 7];
+                    *reinterpret_cast<V2*>(d0) = r0;
+                    *reinterpret_cast<V2*>(d0 + 2048) = i0;
+                    *reinterpret_cast<V2*>(d1) = r1;
+                    *reinterpret_cast<V2*>(d1 + 2048) = i1;
                 });
             }
             __syncwarp();
 
-            // ---- stage B: lane (fsel, u) transforms rows u and 16-u (0 and 8 for u == 0) ----
-            const int fsel = tau >> 3, u = tau & 7;
-            float ar[16], ai[16], br[16], bi[16];
+            // ---- stage B: lane k1 = tau transforms row k1 of both frames; rows exchanged; untangle ----
+            V2 pk[16];
             {
-                const int ra = stage_b_row_a(u), rb = stage_b_row_b(u);
-                const float4* const pa = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + ra) * kRowE);
-                const float4* const pb = reinterpret_cast<const float4*>(sE + ((grp * 2 + fsel) * 16 + rb) * kRowE);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 va = pa[i], vb = pb[i];
-                    ar[2 * i] = va.x; ai[2 * i] = va.y; ar[2 * i + 1] = va.z; ai[2 * i + 1] = va.w;
-                    br[2 * i] = vb.x; bi[2 * i] = vb.y; br[2 * i + 1] = vb.z; bi[2 * i + 1] = vb.w;
-                }
-            }
-            cp_async_wait_all();       // next tile's descriptor has landed (this thread's pieces)
-            __syncthreads();           // (3) exchange buffer is dead -> power tile + next tile's raw samples
-            if (next < P.total_tiles) {
-                const TileDesc* const dn = sDesc + (slot ^ 1);
-                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
-            }
-            cp_async_commit();
-            fft_dif<16>(ar, ai);
-            fft_dif<16>(br, bi);
-            {
-                // Lanes u = 1..7 own the conjugate row pair (u, 16-u).  Lane u = 0 owns the two self-conjugate
-                // rows 0 and 8: it runs the same code (results discarded) and hands its rows to the frame's 8
-                // lanes through a small scratch, two conjugate pairs per lane -> no divergent second path.
-                float* const pcol = sPw + (2 * grp + fsel);
-                float2* const sc = reinterpret_cast<float2*>(sp) + (2 * grp + fsel) * kRowS;
-                if (u == 0) {
-                    float4* const sc4 = reinterpret_cast<float4*>(sc);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        sc4[i] = make_float4(ar[2 * i], ai[2 * i], ar[2 * i + 1], ai[2 * i + 1]);      // position j: Z[16 * bitrev(j)]
-                        sc4[8 + i] = make_float4(br[2 * i], bi[2 * i], br[2 * i + 1], bi[2 * i + 1]);  // position j: Z[8 + 16 * bitrev(j)]
-                    }
-                }
-                const bool own = u != 0;
-                const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + u * kRowE);
-                static_for<0, 8>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    const float4 t = tw4[i];
-                    {
-                        constexpr int k2 = 2 * i;
-                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                        float pk, pnk;
-                        untangle_power(ar[p], ai[p], br[q], bi[q], t.x, t.y, pk, pnk);
-                        const int k = u + 16 * k2;
-                        if (own) {
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                    }
-                    {
-                        constexpr int k2 = 2 * i + 1;
-                        constexpr int p = bitrev<16>(k2), q = bitrev<16>(15 - k2);
-                        float pk, pnk;
-                        untangle_power(ar[p], ai[p], br[q], bi[q], t.z, t.w, pk, pnk);
-                        const int k = u + 16 * k2;
-                        if (own) {
-                            pcol[k * kRowP] = pk;
-                            pcol[(256 - k) * kRowP] = pnk;
-                        }
-                    }
-                });
-                __syncwarp();
+                V2 ar[16], ai[16];
                 {
-                    // row 8: P = Z[8 + 16 u], Q = Z[8 + 16 (15 - u)]  -> bins 8 + 16 u and 248 - 16 u
-                    const int ru = __brev((unsigned)u) >> 28, rq = __brev((unsigned)(15 - u)) >> 28;
-                    const float2 p8 = sc[16 + ru], q8 = sc[16 + rq];
-                    const float2 t8 = sTwU[8 * kRowE + u];
-                    float pk, pnk;
-                    untangle_power(p8.x, p8.y, q8.x, q8.y, t8.x, t8.y, pk, pnk);
-                    pcol[(8 + 16 * u) * kRowP] = pk;
-                    pcol[(248 - 16 * u) * kRowP] = pnk;
-                    // row 0: P = Z[16 (u+1)], Q = Z[16 (15 - u)]      -> bins 16 (u+1) and 256 - 16 (u+1)
-                    // (bin 0 and bin 256 carry no mel weight for any low_freq >= 0 and are never formed)
-                    const int r1 = __brev((unsigned)((u + 1) & 15)) >> 28;
-                    const float2 p0 = sc[r1], q0 = sc[rq];
-                    const float2 t0w = sTwU[u + 1];
-                    untangle_power(p0.x, p0.y, q0.x, q0.y, t0w.x, t0w.y, pk, pnk);
-                    pcol[(16 * (u + 1)) * kRowP] = pk;
-                    if (u != 7) pcol[(240 - 16 * u) * kRowP] = pnk;
+                    const unsigned char* const row = gx + tau * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 vr = *reinterpret_cast<const uint4*>(row + ((c ^ (tau & 7)) << 4));
+                        const uint4 vi = *reinterpret_cast<const uint4*>(row + 2048 + ((c ^ (tau & 7)) << 4));
+                        ar[2 * c] = v2_make(__uint_as_float(vr.x), __uint_as_float(vr.y));
+                        ar[2 * c + 1] = v2_make(__uint_as_float(vr.z), __uint_as_float(vr.w));
+                        ai[2 * c] = v2_make(__uint_as_float(vi.x), __uint_as_float(vi.y));
+                        ai[2 * c + 1] = v2_make(__uint_as_float(vi.z), __uint_as_float(vi.w));
+                    }
                 }
+                __syncwarp();                                      // every lane has its row: the area is reused for Z
+                fft_dif<16, 16, V2>(ar, ai);                       // position p holds Z[tau + 16 bitrev(p)]
+                // Z[k1][k2] -> slot (k2 + k1) mod 16 of row k1 (8 B cells, additive swizzle: conflict-free both ways)
+                {
+                    unsigned char* const wrow = gx + tau * 128;
+                    const unsigned wk = (unsigned)tau << 3;
+                    static_for<0, 16>([&](auto pp) {
+                        constexpr int pos = decltype(pp)::value;
+                        constexpr int k2 = bitrev<16>(pos);
+                        unsigned char* const d = wrow + (((k2 << 3) + wk) & 120);
+                        *reinterpret_cast<V2*>(d) = ar[pos];
+                        *reinterpret_cast<V2*>(d + 2048) = ai[pos];
+                    });
+                }
+                __syncwarp();
+                // conjugate partner Z[256 - k]: row (16 - k1) mod 16, index 15 - k2 (k1 >= 1) or (16 - k2) mod 16 (k1 == 0)
+                {
+                    const int prow = (16 - tau) & 15;
+                    const unsigned char* const rrow = gx + prow * 128;
+                    const unsigned rk = (unsigned)((15 + (tau == 0 ? 1 : 0) + prow) << 3);     // slot = (K - k2) mod 16
+                    const float4* const tw4 = reinterpret_cast<const float4*>(sTwU + tau * kRowE);
+                    static_for<0, 8>([&](auto ii) {
+                        constexpr int i = decltype(ii)::value;
+                        const float4 t = tw4[i];                   // k = tau + 16 k2: k2 = 2i -> (t.x, t.y), 2i+1 -> (t.z, t.w)
+                        {
+                            constexpr int k2 = 2 * i, pos = bitrev<16>(k2);
+                            const unsigned char* const q = rrow + ((rk - (k2 << 3)) & 120);
+                            const V2 qr = *reinterpret_cast<const V2*>(q), qi = *reinterpret_cast<const V2*>(q + 2048);
+                            pk[k2] = untangle_power<V2>(ar[pos], ai[pos], qr, qi, vbcast(t.x), vbcast(t.y));
+                        }
+                        {
+                            constexpr int k2 = 2 * i + 1, pos = bitrev<16>(k2);
+                            const unsigned char* const q = rrow + ((rk - (k2 << 3)) & 120);
+                            const V2 qr = *reinterpret_cast<const V2*>(q), qi = *reinterpret_cast<const V2*>(q + 2048);
+                            pk[k2] = untangle_power<V2>(ar[pos], ai[pos], qr, qi, vbcast(t.z), vbcast(t.w));
+                        }
+                    });
+                }
+            }
+            if (kF32) cp_async_wait_all();   // fp32 input: the next descriptor is needed right after (3)
+            __syncthreads();           // (3) every group is done with its exchange area -> power tile [+ fp32 raw prefetch]
+            if (kF32) {
+                if (next < P.total_tiles) {
+                    const TileDesc* const dn = sDesc + (slot ^ 1);
+                    if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
+                }
+                cp_async_commit();
+            }
+            {
+                float* const prow = sPw + tau * kRowP + 2 * grp;   // bin k = tau + 16 k2, columns (2 grp, 2 grp + 1)
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) *reinterpret_cast<V2*>(prow + 16 * k2 * kRowP) = pk[k2];
             }
             __syncthreads();                                       // (4) power tile complete
 
@@ -583,7 +581,19 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
             const bool has_cmvn = P.cmvn_mean != nullptr;
             const int pitch = (int)P.pitch;
             float* const dst0 = P.out + out_start * P.pitch;
-            if (!fused && !has_cmvn) {
+            if (kStdMel && P.out_vec && !fused && !has_cmvn) {
+                // the tile is one contiguous run of rows_here * 80 floats: flat float4 stores
+                constexpr int kQ = mel80::kBins / 4;                  // float4 per row
+                const int nq = rows_here * kQ;
+                float4* const dst4 = reinterpret_cast<float4*>(dst0);
+                for (int c = tid; c < nq; c += kThreads) {
+                    const int r = c / kQ, col = (c - r * kQ) * 4;
+                    const float* const src = sp + r * rowO + col;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nvalid) v = make_float4(src[0], src[1], src[2], src[3]);
+                    dst4[c] = v;
+                }
+            } else if (!fused && !has_cmvn) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = warp + 8 * i;

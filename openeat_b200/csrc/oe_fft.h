@@ -4,17 +4,19 @@
 // One real 512-point frame (kaldi.py:616 rfft of the zero-padded 400-sample frame h) is computed
 // as a 256-point complex FFT of z[n] = h[2n] + i h[2n+1] followed by the real-FFT untangle.  The
 // 256-point FFT is split Cooley-Tukey style as 256 = 16 x 16.  A group of 16 threads owns TWO
-// frames:
-//   stage A  thread tau holds z[16*n1 + tau], n1 = 0..15, of both frames and runs a 16-point DIF
-//            FFT per frame in registers (n1 >= 13 are zero padding: 16*13 >= 200),
+// frames, carried as the two halves of Blackwell's packed f32x2 registers (`V2`): every FADD2 /
+// FMUL2 / FFMA2 serves both frames, halving the issue slots of the transform.
+//   stage A  thread tau holds z[16*n1 + tau], n1 = 0..15, of both frames and runs one packed
+//            16-point DIF FFT in registers (n1 >= 13 are zero padding: 16*13 >= 200),
 //   twiddle  Y_tau[k1] *= W256^(tau*k1),
-//   exchange through shared memory (half-warp local),
-//   stage B  thread t = 8*f + u runs, for frame f, two 16-point FFTs over tau for the rows
-//            k1 in {u, 16 - u} ({0, 8} for u = 0), giving Z[k1 + 16*k2],
-//   untangle X[k] = E + W512^k O and X[256-k] = conj(E - W512^k O) from Z[k] and Z[256-k], which
-//            by construction live in the same thread; only |X|^2 is formed.
+//   exchange through shared memory (half-warp local, XOR-swizzled),
+//   stage B  lane k1 runs one packed 16-point FFT over tau for row k1, giving Z[k1 + 16*k2],
+//   exchange of the rows (half-warp local): lane k1 fetches Z[256-k] from the conjugate row
+//            (16 - k1) mod 16 -- rows 0 and 8 are their own partners, no special case,
+//   untangle X[k] = E + W512^k O from Z[k] and Z[256-k]; only |X[k]|^2 is formed, k = 0..255.
 // All loops are unrolled at compile time with constant indices so every array stays in
-// registers and every twiddle is an immediate.
+// registers and every twiddle is an immediate.  The same templates run on the host with plain
+// floats (T = float) or an emulated pair (T = V2) for the CPU tests.
 #pragma once
 #include <type_traits>
 
@@ -35,6 +37,73 @@ OE_HD void static_for(F&& f) {
         static_for<I + 1, N>(f);
     }
 }
+
+// ---- packed pair of fp32 (two frames side by side) ----
+struct V2 {
+#if defined(__CUDA_ARCH__)
+    unsigned long long v;     // one aligned 64-bit register pair: lo = frame 0, hi = frame 1
+#else
+    float lo, hi;
+#endif
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ V2 v2_make(float lo, float hi) {
+    V2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float v2_lo(V2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return lo;
+}
+__device__ __forceinline__ float v2_hi(V2 a) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    return hi;
+}
+__device__ __forceinline__ V2 vadd(V2 a, V2 b) {
+    V2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ V2 vsub(V2 a, V2 b) {
+    V2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ V2 vmul(V2 a, V2 b) {
+    V2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ V2 vfma(V2 a, V2 b, V2 c) {     // a * b + c
+    V2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+#else
+inline V2 v2_make(float lo, float hi) { return V2{lo, hi}; }
+inline float v2_lo(V2 a) { return a.lo; }
+inline float v2_hi(V2 a) { return a.hi; }
+inline V2 vadd(V2 a, V2 b) { return V2{a.lo + b.lo, a.hi + b.hi}; }
+inline V2 vsub(V2 a, V2 b) { return V2{a.lo - b.lo, a.hi - b.hi}; }
+inline V2 vmul(V2 a, V2 b) { return V2{a.lo * b.lo, a.hi * b.hi}; }
+inline V2 vfma(V2 a, V2 b, V2 c) { return V2{a.lo * b.lo + c.lo, a.hi * b.hi + c.hi}; }
+#endif
+OE_HD V2 vbcast(float s) { return v2_make(s, s); }
+OE_HD V2 vneg(V2 a) { return vsub(vbcast(0.f), a); }
+
+// scalar overloads so the FFT templates also instantiate with T = float
+OE_HD float vadd(float a, float b) { return a + b; }
+OE_HD float vsub(float a, float b) { return a - b; }
+OE_HD float vmul(float a, float b) { return a * b; }
+OE_HD float vfma(float a, float b, float c) { return a * b + c; }
+OE_HD float vneg(float a) { return -a; }
+template <class T> OE_HD T vconst(float s);
+template <> OE_HD float vconst<float>(float s) { return s; }
+template <> OE_HD V2 vconst<V2>(float s) { return vbcast(s); }
 
 // ---- compile-time trigonometry (double Taylor series after octant reduction) ----
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -89,81 +158,79 @@ OE_CX int bitrev(int i) {
 
 // One radix-2 decimation-in-frequency butterfly with twiddle W_M^J = exp(-2*pi*i*J/M):
 //   a' = a + b,  b' = (a - b) * W.   B_ZERO: b is known to be zero (pruned padding).
-template <int J, int M, bool B_ZERO>
-OE_HD void dif_butterfly(float& ar, float& ai, float& br, float& bi) {
-    float dr, di;
+template <int J, int M, bool B_ZERO, class T>
+OE_HD void dif_butterfly(T& ar, T& ai, T& br, T& bi) {
+    T dr, di;
     if constexpr (B_ZERO) {
         dr = ar;
         di = ai;
     } else {
-        const float ur = ar, ui = ai;
-        ar = ur + br;
-        ai = ui + bi;
-        dr = ur - br;
-        di = ui - bi;
+        const T ur = ar, ui = ai;
+        ar = vadd(ur, br);
+        ai = vadd(ui, bi);
+        dr = vsub(ur, br);
+        di = vsub(ui, bi);
     }
     if constexpr (J == 0) {
         br = dr;
         bi = di;
     } else if constexpr (4 * J == M) {            // W = -i
         br = di;
-        bi = -dr;
+        bi = vneg(dr);
     } else if constexpr (8 * J == M) {            // W = (1 - i)/sqrt2
-        constexpr float r = 0.70710678118654752440f;
-        br = (dr + di) * r;
-        bi = (di - dr) * r;
+        const T r = vconst<T>(0.70710678118654752440f);
+        br = vmul(vadd(dr, di), r);
+        bi = vmul(vsub(di, dr), r);
     } else if constexpr (8 * J == 3 * M) {        // W = (-1 - i)/sqrt2
-        constexpr float r = 0.70710678118654752440f;
-        br = (di - dr) * r;
-        bi = -(dr + di) * r;
+        const T r = vconst<T>(0.70710678118654752440f);
+        br = vmul(vsub(di, dr), r);
+        bi = vmul(vadd(dr, di), vconst<T>(-0.70710678118654752440f));
     } else {
         constexpr float c = static_cast<float>(cos2pi(J, M));
         constexpr float s = static_cast<float>(sin2pi(J, M));
-        br = dr * c + di * s;                     // (dr + i di)(c - i s)
-        bi = di * c - dr * s;
+        br = vfma(dr, vconst<T>(c), vmul(di, vconst<T>(s)));     // (dr + i di)(c - i s)
+        bi = vfma(di, vconst<T>(c), vmul(dr, vconst<T>(-s)));
     }
 }
 
-template <int N, int HALF, int ZERO_FROM>
+template <int N, int HALF, int ZERO_FROM, class T>
 struct DifStage {
-    static OE_HD void run(float (&re)[N], float (&im)[N]) {
+    static OE_HD void run(T (&re)[N], T (&im)[N]) {
         static_for<0, N / (2 * HALF)>([&](auto blk) {
             static_for<0, HALF>([&](auto jj) {
                 constexpr int j = decltype(jj)::value;
                 constexpr int a = decltype(blk)::value * 2 * HALF + j;
                 constexpr int b = a + HALF;
-                dif_butterfly<j, 2 * HALF, (b >= ZERO_FROM)>(re[a], im[a], re[b], im[b]);
+                dif_butterfly<j, 2 * HALF, (b >= ZERO_FROM), T>(re[a], im[a], re[b], im[b]);
             });
         });
-        if constexpr (HALF > 1) DifStage<N, HALF / 2, N>::run(re, im);   // later stages: no zeros
+        if constexpr (HALF > 1) DifStage<N, HALF / 2, N, T>::run(re, im);   // later stages: no zeros
     }
 };
 
 // In-place N-point DIF FFT (forward, e^{-i...}).  Afterwards position i holds X[bitrev<N>(i)].
 // Inputs at positions >= ZERO_FROM (only meaningful for ZERO_FROM > N/2) must be zero and are
 // never read by the first stage.
-template <int N, int ZERO_FROM = N>
-OE_HD void fft_dif(float (&re)[N], float (&im)[N]) {
+template <int N, int ZERO_FROM = N, class T = float>
+OE_HD void fft_dif(T (&re)[N], T (&im)[N]) {
     static_assert(ZERO_FROM > N / 2, "pruning only covers the upper half");
-    DifStage<N, N / 2, ZERO_FROM>::run(re, im);
+    DifStage<N, N / 2, ZERO_FROM, T>::run(re, im);
 }
 
-// Rows of the 16 x 16 decomposition owned by stage-B lane u (0..7) of a frame.
-OE_HD int stage_b_row_a(int u) { return u; }
-OE_HD int stage_b_row_b(int u) { return u == 0 ? 8 : 16 - u; }
+// Conjugate partner of Z[k1 + 16 k2] in the 16 x 16 layout: Z[256 - k] sits in row (16 - k1) mod 16 at
+// index 15 - k2 (k1 >= 1) or (16 - k2) mod 16 (k1 == 0: k = 16 k2, 256 - k = 16 (16 - k2)).
+OE_HD int partner_row(int k1) { return (16 - k1) & 15; }
+OE_HD int partner_k2(int k1, int k2) { return k1 == 0 ? ((16 - k2) & 15) : 15 - k2; }
 
-// Real-FFT untangle of one conjugate pair.  P = Z[k], Q = Z[256-k], (c, s) = (cos, sin)(2*pi*k/512).
-// Returns 4*|X[k]|^2 and 4*|X[256-k]|^2 (the 1/4 is folded into the mel weights).
-OE_HD void untangle_power(float pr, float pi, float qr, float qi, float c, float s,
-                          float& pk, float& pnk) {
-    const float er = pr + qr, ei = pi - qi;      // 2E = P + conj(Q)
-    const float orr = pi + qi, oi = qr - pr;     // 2O = (P - conj(Q)) / i
-    const float tr = c * orr + s * oi;           // T = (c - i s) * 2O
-    const float ti = c * oi - s * orr;
-    const float ar = er + tr, ai = ei + ti;      // 2X[k]
-    const float br = er - tr, bi = ei - ti;      // 2 conj(X[256-k])
-    pk = ar * ar + ai * ai;
-    pnk = br * br + bi * bi;
+// Real-FFT untangle, one output: P = Z[k], Q = Z[256-k], (c, s) = (cos, sin)(2*pi*k/512).
+// Returns 4*|X[k]|^2 (the 1/4 is folded into the mel weights).
+template <class T>
+OE_HD T untangle_power(T pr, T pi, T qr, T qi, T c, T s) {
+    const T er = vadd(pr, qr), ei = vsub(pi, qi);      // 2E = P + conj(Q)
+    const T orr = vadd(pi, qi), oi = vsub(qr, pr);     // 2O = (P - conj(Q)) / i
+    const T ar = vfma(s, oi, vfma(c, orr, er));        // 2X = 2E + (c - i s) * 2O
+    const T ai = vsub(vfma(c, oi, ei), vmul(s, orr));
+    return vfma(ar, ar, vmul(ai, ai));
 }
 
 }  // namespace oe

@@ -44,13 +44,12 @@ constexpr int kChunks = 672;        // 8-sample chunks staged per tile (5376 sam
 constexpr int kMaxMel = 128;
 constexpr int kMaxNnz = 2048;
 constexpr int kRowE = 18;           // complex per exchange row: 16 + 2 pad -> 144 B (conflict-free LDS.128)
-constexpr int kRowP = 36;           // floats per power-spectrum row: 32 frames + 4 pad
 constexpr int kRowO = 81;           // floats per output-tile row (80 + 1 pad); generic: F + 1
 
 struct DevTables {
     float window[kFft];             // zero beyond frame_length
     float2 twA[16 * kRowE];         // W256^(tau*k1) = (cos, -sin)
-    float2 twU[9 * kRowE];          // (cos, sin)(2 pi k / 512), k = u + 16*k2; row 8 = u 8
+    float2 twU[16 * kRowE];         // (cos, sin)(2 pi k / 512), k = k1 + 16*k2, row k1
     int mel_start[kMaxMel];
     int mel_len[kMaxMel];
     int mel_off[kMaxMel];
@@ -675,7 +674,7 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
             const double a = 2.0 * oe::kPi * (double)((tau * k1) % 256) / 256.0;
             h.twA[tau * oe::kRowE + k1] = make_float2((float)std::cos(a), (float)-std::sin(a));
         }
-    for (int u = 0; u < 9; ++u)
+    for (int u = 0; u < 16; ++u)
         for (int k2 = 0; k2 < 16; ++k2) {
             const double a = 2.0 * oe::kPi * (double)(u + 16 * k2) / 512.0;
             h.twU[u * oe::kRowE + k2] = make_float2((float)std::cos(a), (float)std::sin(a));
@@ -855,6 +854,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         P.cmvn_istd = bt->d_cmvn_istd;
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
+    P.out_vec = (P.pitch == F && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
     if (M.total_tiles > 0) {
         oe::TileDescParams T;
         T.tile_prefix = d_tile_prefix;

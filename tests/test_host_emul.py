@@ -1,5 +1,5 @@
-"""The in-register FFT templates of the CUDA kernel (csrc/oe_fft.h), compiled for the host and
-driven through the same 16-thread decomposition, against numpy (CPU, no GPU needed)."""
+"""The in-register FFT templates of the CUDA kernel (csrc/oe_fft.h), compiled for the host and driven through
+the same 16-thread / two-frame (packed f32x2, emulated as a float pair) decomposition, against numpy (CPU)."""
 import ctypes
 
 import numpy as np
@@ -15,32 +15,50 @@ def emul():
     _lib.build()
     lib = ctypes.CDLL(_lib.EMUL_PATH)
     P = ctypes.POINTER(ctypes.c_float)
-    lib.oe_emul_frame.argtypes = [P, P]
+    lib.oe_emul_frame_pair.argtypes = [P, P, P, P]
 
-    def power(h):
-        h = np.ascontiguousarray(h, dtype=np.float32)
-        pw = np.zeros(257, np.float32)
-        lib.oe_emul_frame(h.ctypes.data_as(P), pw.ctypes.data_as(P))
-        return pw
+    def power(ha, hb):
+        ha = np.ascontiguousarray(ha, dtype=np.float32)
+        hb = np.ascontiguousarray(hb, dtype=np.float32)
+        pa, pb = np.zeros(256, np.float32), np.zeros(256, np.float32)
+        lib.oe_emul_frame_pair(ha.ctypes.data_as(P), hb.ctypes.data_as(P), pa.ctypes.data_as(P), pb.ctypes.data_as(P))
+        return pa, pb
     return power
+
+
+def ref_power(h):
+    return (np.abs(np.fft.rfft(h.astype(np.float64), 512)) ** 2)[:256]
 
 
 @pytest.mark.parametrize('kind', signals.CLASSES)
 def test_frame_power_spectrum(emul, kind, tables):
     x = signals.make(kind, 400 + 160 * 5, 3).astype(np.float32)
     h = F.windowed_frames(x, np.float32, window=tables[0])[:, :400]
-    for row in h:
-        ref = np.abs(np.fft.rfft(row.astype(np.float64), 512)) ** 2
-        got = emul(row)
-        scale = max(ref.max(), 1e-30)
-        assert np.abs(got - ref).max() <= 2e-6 * scale
+    for a, b in zip(h[0::2], h[1::2]):
+        for got, row in zip(emul(a, b), (a, b)):
+            ref = ref_power(row)
+            assert np.abs(got - ref).max() <= 2e-6 * max(ref.max(), 1e-30)
+
+
+def test_the_two_packed_frames_do_not_interact(emul):
+    """A loud and a -100 dB frame side by side: each must be as accurate as on its own (the two frames are the
+    two halves of an f32x2 register, never mixed -- unlike packing them as real/imaginary parts)."""
+    rng = np.random.default_rng(5)
+    loud = (rng.normal(0, 20000, 400) * np.hanning(400)).astype(np.float32)
+    quiet = (rng.normal(0, 0.2, 400) * np.hanning(400)).astype(np.float32)
+    pa, pb = emul(loud, quiet)
+    qa, qb = emul(quiet, loud)
+    assert np.array_equal(pa, qb) and np.array_equal(pb, qa)
+    ref = ref_power(quiet)
+    assert np.abs(pb - ref).max() <= 2e-6 * ref.max()
 
 
 def test_impulse_and_tone_bins(emul):
     h = np.zeros(400, np.float32)
     h[3] = 1.0
-    assert np.allclose(emul(h), 1.0, atol=1e-6)                 # flat spectrum
+    pa, pb = emul(h, 2 * h)
+    assert np.allclose(pa, 1.0, atol=1e-6) and np.allclose(pb, 4.0, atol=4e-6)      # flat spectra
     n = np.arange(400)
-    for k in (1, 8, 16, 37, 128, 200, 255):                      # every row class of the 16x16 split
-        pw = emul(np.cos(2 * np.pi * k * n / 512).astype(np.float32))
-        assert pw.argmax() == k
+    for k in (1, 8, 15, 16, 37, 128, 200, 255):                    # every row class of the 16 x 16 split
+        pa, pb = emul(np.cos(2 * np.pi * k * n / 512).astype(np.float32), h)
+        assert pa.argmax() == k
