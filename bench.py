@@ -236,6 +236,8 @@ def run_ours(args, rank, world, local_rank):
     def timed(fn, steps, warmup, with_allreduce):
         for i in range(warmup):
             fn(i)
+        if with_allreduce and warmup:
+            all_reduce_stats(stats)              # the collective is warmed up like everything else
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

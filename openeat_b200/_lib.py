@@ -12,7 +12,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libopeneat_frontend.so')
 EMUL_PATH = os.path.join(CSRC, 'liboe_emul.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '--shared', '-Xcompiler', '-fPIC', '-diag-suppress', '177']
+              '--shared', '-Xcompiler', '-fPIC', '-diag-suppress', '177,550']
 
 OE_OK = 0
 OE_WAV_I16, OE_WAV_F32, OE_FEATS_F32 = 0, 1, 2

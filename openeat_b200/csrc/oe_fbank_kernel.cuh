@@ -199,7 +199,9 @@ __device__ __forceinline__ void mel_group_std(const float* __restrict__ pcol, co
     });
 }
 
-template <bool kF32, bool kStdMel>
+// kRs: the batch contains utterances with fused speed perturb (int16 input only); compiled out otherwise to keep
+// the hot loop small (the kernel is instruction-cache sensitive).
+template <bool kF32, bool kStdMel, bool kRs>
 __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* const sp = reinterpret_cast<float*>(smem + kSmP);
@@ -293,9 +295,9 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
         }
         if (nvalid > 0) {
             // ---- [fused speed perturb: raw -> fp32 -> polyphase sinc -> resampled tile in sp] ----
-            const int rs = kF32 ? 0 : dp->rs;
+            const int rs = (kF32 || !kRs) ? 0 : dp->rs;
             float* const sEdge = reinterpret_cast<float*>(smem + kSmEdge);
-            if (rs != 0) {
+            if (kRs && rs != 0) {
                 float* const xin = sPw;                               // fp32 input window, front of the (idle) E area
                 const int16_t* const r16 = reinterpret_cast<const int16_t*>(sRaw);
                 for (int i = tid; i < kRsPieces * 2; i += kThreads) {       // 4 samples per thread-iteration
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
                 for (int blk = warp; blk < 21; blk += 8) {
                     const int i0 = blk * 256 + 4 * lane, i1 = i0 + 128;
                     float xa[4], xb[4], edge;
-                    if (rs != 0) {                                         // resampled tile, in place in sp
+                    if (kRs && rs != 0) {                                  // resampled tile, in place in sp
                         const float4 a = *reinterpret_cast<const float4*>(sp + i0);
                         const float4 c = *reinterpret_cast<const float4*>(sp + i1);
                         xa[0] = a.x; xa[1] = a.y; xa[2] = a.z; xa[3] = a.w;

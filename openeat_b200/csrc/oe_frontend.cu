@@ -258,71 +258,77 @@ struct FinalizeParams {
 };
 
 // dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
-// grid = (utterances, 32-row chunks); 8 threads per row; VEC = float4 path (F, pitch, bases 16-byte friendly).
+// grid = (utterances, row chunks).  VEC = 4: thread = (float4 column chunk, row lane); the per-column
+// constants (mean, 1/std, CMVN, frequency mask) live in registers for the whole chunk of rows.
+constexpr int kFinRows = 128;       // rows per block
 template <int VEC>
 __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P) {
-    __shared__ float sMean[kMaxMel], sStd[kMaxMel], sCm[kMaxMel], sCi[kMaxMel];
-    __shared__ unsigned char sCol[kMaxMel];
     const int b = blockIdx.x;
-    const int r0 = blockIdx.y * 32;
+    const int r0 = blockIdx.y * kFinRows;
     const int nrows = (int)(P.row_prefix[b + 1] - P.row_prefix[b]);
     if (r0 >= nrows) return;
-    const int tid = threadIdx.x;
     const int F = P.F;
-    if (tid < F) {
-        sMean[tid] = P.utt_mean ? P.utt_mean[(int64_t)b * F + tid] : 0.f;
-        sStd[tid] = P.utt_std ? P.utt_std[(int64_t)b * F + tid] : 1.f;
-        sCm[tid] = P.cmvn_mean ? P.cmvn_mean[tid] : 0.f;
-        sCi[tid] = P.cmvn_istd ? P.cmvn_istd[tid] : 1.f;
+    const int ncol = (F + VEC - 1) / VEC;                 // column chunks per row
+    const int lanes = 256 / ncol;                         // row lanes per block
+    const int cc = threadIdx.x % ncol, rl = threadIdx.x / ncol;
+    if (rl >= lanes) return;
+    const int c = cc * VEC;
+    const int nfr = P.n_frames[b];
+    const bool norm = P.utt_mean != nullptr, has_cm = P.cmvn_mean != nullptr, has_ci = P.cmvn_istd != nullptr;
+    float mean[VEC], rstd[VEC], cm[VEC], ci[VEC];
+    bool cmask[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int f = c + e < F ? c + e : F - 1;
+        mean[e] = norm ? P.utt_mean[(int64_t)b * F + f] : 0.f;
+        rstd[e] = norm ? 1.0f / P.utt_std[(int64_t)b * F + f] : 1.f;      // 0 variance: 1/0 = inf, 0 * inf = NaN like x/0
+        cm[e] = has_cm ? P.cmvn_mean[f] : 0.f;
+        ci[e] = has_ci ? P.cmvn_istd[f] : 1.f;
         bool m = false;
         for (int j = 0; j < P.n_fmask; ++j) {
             const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
-            m |= (tid >= r[0]) & (tid < r[1]);
+            m |= (f >= r[0]) & (f < r[1]);
         }
-        sCol[tid] = m;
+        cmask[e] = m;
     }
-    __syncthreads();
-    const int t = r0 + (tid >> 3), t8 = tid & 7;
-    if (t >= nrows) return;
-    const int nfr = P.n_frames[b];
-    const bool real = t < nfr;
-    bool rmask = false;
-    const float* src = P.raw;
-    if (real) {
-        for (int j = 0; j < P.n_tmask; ++j) {
-            const int32_t* r = P.tmask + ((int64_t)b * P.n_tmask + j) * 2;
-            rmask |= (t >= r[0]) & (t < r[1]);
-        }
-        const int ts = P.frame_map ? P.frame_map[P.map_off[b] + t] : t;
-        src = P.raw + (P.frame_prefix[b] + ts) * F;
-    }
-    float* const dst = P.out + (P.out_row[b] + t) * P.pitch;
-    const bool norm = P.utt_mean != nullptr;
-    const bool cm = P.cmvn_mean != nullptr && (real || P.cmvn_on_pad);
-    const bool ci = P.cmvn_istd != nullptr;
-    for (int c = t8 * VEC; c < F; c += 8 * VEC) {
+    const int64_t raw0 = P.frame_prefix[b];
+    const int64_t out0 = P.out_row[b];
+    const int32_t* const fmap = P.frame_map ? P.frame_map + P.map_off[b] : nullptr;
+    const int32_t* const tm = P.tmask + (int64_t)b * P.n_tmask * 2;
+    const int r_end = min(nrows, r0 + kFinRows);
+    for (int t = r0 + rl; t < r_end; t += lanes) {
+        const bool real = t < nfr;
         float v[VEC];
-        if (VEC == 4) {
-            const float4 x = real ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[0] = x.x; v[1 % VEC] = x.y; v[2 % VEC] = x.z; v[3 % VEC] = x.w;
-        } else {
-            v[0] = real ? src[c] : 0.f;
-        }
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            float y = v[e];
-            if (real) {
-                if (norm) y = (y - sMean[c + e]) / sStd[c + e];
-                if (rmask || sCol[c + e]) y = 0.f;
+        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+        if (real) {
+            bool rmask = false;
+            for (int j = 0; j < P.n_tmask; ++j) rmask |= (t >= tm[2 * j]) & (t < tm[2 * j + 1]);
+            const int ts = fmap ? fmap[t] : t;
+            const float* const src = P.raw + (raw0 + ts) * F + c;
+            if (VEC == 4) {
+                const float4 x = *reinterpret_cast<const float4*>(src);
+                v[0] = x.x; v[1 % VEC] = x.y; v[2 % VEC] = x.z; v[3 % VEC] = x.w;
+            } else {
+                v[0] = src[0];
             }
-            if (cm) {
-                y = y - sCm[c + e];
-                if (ci) y = y * sCi[c + e];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                float y = norm ? (v[e] - mean[e]) * rstd[e] : v[e];
+                if (rmask || cmask[e]) y = 0.f;
+                v[e] = y;
             }
-            v[e] = y;
         }
-        if (VEC == 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-        else dst[c] = v[0];
+        if (has_cm && (real || P.cmvn_on_pad)) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                v[e] = v[e] - cm[e];
+                if (has_ci) v[e] = v[e] * ci[e];
+            }
+        }
+        float* const dst = P.out + (out0 + t) * P.pitch + c;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        else dst[0] = v[0];
     }
 }
 
@@ -724,10 +730,13 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     memset(fe->mel_w_std, 0, sizeof(fe->mel_w_std));
     if (fe->std_mel) memcpy(fe->mel_w_std, h.mel_w, sizeof(float) * nnz);
     fe->fbank_smem = fe->std_mel ? align_up((size_t)oe::kSmStd, 16) : align_up((size_t)oe::kSmMelW + 4 * (size_t)nnz, 16);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->fbank_smem);
+    const int smem_i = (int)fe->fbank_smem;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
     if (e != cudaSuccess) {
         if (fe->d_tab) cudaFree(fe->d_tab);
         if (fe->d_rs) cudaFree(fe->d_rs);
@@ -892,12 +901,16 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             P.cta_stats = reinterpret_cast<double*>(ws + M.stat_partial);
             n_stat_partials = 3 * grid;
         }
+        bool any_rs = false;
+        for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
         if (fe->std_mel) {
-            if (f32) oe::oe_fbank_kernel<true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else oe::oe_fbank_kernel<false, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            if (f32) oe::oe_fbank_kernel<true, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else if (any_rs) oe::oe_fbank_kernel<false, true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else oe::oe_fbank_kernel<false, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
         } else {
-            if (f32) oe::oe_fbank_kernel<true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else oe::oe_fbank_kernel<false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            if (f32) oe::oe_fbank_kernel<true, false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else if (any_rs) oe::oe_fbank_kernel<false, false, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            else oe::oe_fbank_kernel<false, false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
         }
         OE_CUDA(cudaGetLastError());
     }
@@ -950,7 +963,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         Z.F = F;
         const bool vec = (F % 4 == 0) && (pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(Z.raw) & 15) &&
                          !(reinterpret_cast<uintptr_t>(d_out) & 15);
-        dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + 31) / 32));
+        dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + oe::kFinRows - 1) / oe::kFinRows));
         if (vec) oe::oe_finalize_kernel<4><<<zgrid, 256, 0, stream>>>(Z);
         else oe::oe_finalize_kernel<1><<<zgrid, 256, 0, stream>>>(Z);
         OE_CUDA(cudaGetLastError());
