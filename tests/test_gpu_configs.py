@@ -1,0 +1,145 @@
+"""BASELINE.json configs at (or near) their full shapes, checked through size-independent properties
+(BASELINE.md section 4): streaming windows == whole stream, statistics are linear over shards, spec_sub is a
+pure row gather, masks / padding are exact, results are bitwise reproducible."""
+import random
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import fbank as F          # noqa: E402
+from oracle import signals             # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def fe():
+    from openeat_b200.frontend import Frontend
+    return Frontend(mel_bins=80, sample_rate=16000)
+
+
+def device_noise(total, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return (torch.randn(total, generator=g, device='cuda') * 3000.0).round_().clamp_(-32768, 32767).to(torch.int16)
+
+
+def test_config5_twenty_minute_stream_in_16_frame_windows(fe):
+    """20-minute stream = 119 998 frames = 7 500 windows of 16 frames (2 800 samples, 240 overlap) run as ONE
+    ragged batch, with global CMVN: bitwise equal to the whole-stream features (frames are independent)."""
+    n = 160 * 16 * 7500 + 240
+    x = device_noise(n, 1006)
+    mean = torch.linspace(8.0, 12.0, 80, device='cuda')
+    istd = torch.linspace(0.4, 0.6, 80, device='cuda')
+    whole, fr = fe.fbank(x, np.array([0]), np.array([n]), layout='ragged', cmvn=(mean, istd))
+    assert fr[0] == 119998 + 2                    # 7 500 * 16 frames (+2: the stream length is a multiple of the hop here)
+    offs = np.arange(7500, dtype=np.int64) * 2560
+    lens = np.full(7500, 2800, dtype=np.int32)
+    parts, frames = fe.fbank(x, offs, lens, layout='ragged', cmvn=(mean, istd))
+    assert (frames == 16).all()
+    assert torch.equal(parts, whole)
+    # CPU oracle on a slice in the middle of the stream
+    lo = 160 * 16 * 3000
+    ref = F.fbank(x[lo:lo + 2800].cpu().numpy().astype(np.float32))
+    ref = (ref - mean.cpu().numpy()) * istd.cpu().numpy()
+    assert np.abs(parts[16 * 3000:16 * 3001].cpu().numpy() - ref).max() < 1e-3
+
+
+def test_config3_librispeech_shape_sharded_stats_are_linear(fe):
+    """Variable 1-35 s utterances, length-sorted dynamic batches (dataset.py:337-352), sharded over 8 'ranks':
+    per-rank CMVN statistics add up (bitwise in the count, 1e-12 relative in the sums) to the single-rank pass,
+    whatever the batching -- the property the one all-reduce of the path relies on."""
+    from openeat_b200.frontend import aligned_offsets
+    from openeat_b200.sharding import dynamic_batches, shard_by_length
+    lens = signals.lengths_uniform(400, 1.0, 35.0, 1004).astype(np.int32)        # ~2 h of audio
+    offs, total = aligned_offsets(lens)
+    x = device_noise(total, 1004)
+    frames = fe.num_frames_array(lens)
+
+    def stats_of(index_lists):
+        st = torch.zeros(161, dtype=torch.float64, device='cuda')
+        for idx in index_lists:
+            idx = np.asarray(idx)
+            fe.fbank(x, offs[idx], lens[idx], layout='ragged', stats=st, want_out=False)
+        return st.cpu().numpy()
+
+    everything = stats_of([np.arange(400)])
+    batched = stats_of(dynamic_batches(frames.tolist(), 10000))
+    shards = shard_by_length(lens, 8)
+    per_rank = [stats_of([[int(s[i]) for i in b] for b in dynamic_batches(frames[s].tolist(), 10000)]) for s in shards]
+    summed = np.sum(per_rank, axis=0)
+    assert everything[160] == batched[160] == summed[160] == frames.sum()
+    np.testing.assert_allclose(batched[:160], everything[:160], rtol=1e-11)
+    np.testing.assert_allclose(summed[:160], everything[:160], rtol=1e-11)
+    loads = [int(lens[s].sum()) for s in shards]
+    assert max(loads) - min(loads) <= int(lens.max())
+    # mean / variance are sane numbers for Gaussian noise through the mel bank
+    mean = everything[:80] / everything[160]
+    var = everything[80:160] / everything[160] - mean ** 2
+    assert np.all(var > 0) and np.all(np.isfinite(mean))
+
+
+def test_config4_short_utterances_with_spec_sub_is_a_row_gather(fe):
+    """ASRU shape: 256 utterances of 0.5-3 s, spec_sub (3, 30): the substituted batch is exactly the raw batch
+    gathered through the composed index map (bitwise), and spec_aug zeros exactly the planned cells."""
+    from openeat_b200 import planner
+    from openeat_b200.frontend import aligned_offsets
+    lens = signals.lengths_uniform(256, 0.5, 3.0, 1005).astype(np.int32)
+    offs, total = aligned_offsets(lens)
+    x = device_noise(total, 1005)
+    frames = fe.num_frames_array(lens)
+    raw, _ = fe.fbank(x, offs, lens, layout='padded')
+    random.seed(1005)
+    fmap, tm, fm = planner.plan_augment(frames, 80, dict(num_t_sub=3, max_t=30),
+                                        dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))
+    starts = np.concatenate([[0], np.cumsum(frames[:-1].astype(np.int64))])
+    maps = [fmap[s:s + t] for s, t in zip(starts, frames)]
+    sub, _ = fe.fbank(x, offs, lens, layout='padded', frame_maps=maps)
+    both, _ = fe.fbank(x, offs, lens, layout='padded', frame_maps=maps, tmask=tm, fmask=fm)
+    raw, sub, both = raw.cpu().numpy(), sub.cpu().numpy(), both.cpu().numpy()
+    for b in (0, 1, 17, 100, 255):
+        t = int(frames[b])
+        assert np.array_equal(sub[b, :t], raw[b, :t][maps[b]])
+        expect = sub[b, :t].copy()
+        for s, e in tm[b]:
+            expect[s:e] = 0
+        for s, e in fm[b]:
+            expect[:, s:e] = 0
+        assert np.array_equal(both[b, :t], expect)
+        assert np.all(both[b, t:] == 0)
+
+
+def test_config2_full_batch_properties(fe):
+    """Batch 256 of 2-10 s with fused speed perturb + normalisation + spec_aug + CMVN: bitwise reproducible,
+    padding exactly (0 - mean) * istd, masked cells likewise, every utterance normalised (mean 0, var 1)."""
+    from openeat_b200 import planner
+    from openeat_b200.frontend import aligned_offsets
+    lens = signals.lengths_uniform(256, 2.0, 10.0, 1002).astype(np.int32)
+    offs, total = aligned_offsets(lens)
+    x = device_noise(total, 1002)
+    rs = np.random.default_rng(1003).integers(0, 3, 256)
+    ratios = np.array([[(9, 10), (0, 0), (11, 10)][i] for i in rs])
+    eff = np.where(ratios[:, 0] > 0, -(-lens.astype(np.int64) * ratios[:, 1] // np.maximum(ratios[:, 0], 1)), lens)
+    frames = fe.num_frames_array(eff)
+    random.seed(7)
+    _, tm, fm = planner.plan_augment(frames, 80, None, dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))
+    mean = torch.linspace(8.0, 12.0, 80, device='cuda')
+    istd = torch.linspace(0.4, 0.6, 80, device='cuda')
+    kw = dict(layout='padded', normalization=True, tmask=tm, fmask=fm, cmvn=(mean, istd), cmvn_on_padding=True,
+              speed_ratios=ratios)
+    a, fr = fe.fbank(x, offs, lens, **kw)
+    b, _ = fe.fbank(x, offs, lens, **kw)
+    assert fr.tolist() == frames.tolist()
+    assert torch.equal(a, b)
+    plain, _ = fe.fbank(x, offs, lens, layout='padded', normalization=True, speed_ratios=ratios)
+    a, plain = a.cpu().numpy(), plain.cpu().numpy()
+    zero_after = ((np.float32(0) - mean.cpu().numpy()) * istd.cpu().numpy()).astype(np.float32)
+    for i in (0, 3, 128, 255):
+        t = int(frames[i])
+        assert np.array_equal(a[i, t:], np.broadcast_to(zero_after, a[i, t:].shape))
+        for s, e in tm[i]:
+            assert np.array_equal(a[i, s:e], np.broadcast_to(zero_after, a[i, s:e].shape))
+        for s, e in fm[i]:
+            assert np.array_equal(a[i, :t, s:e], np.broadcast_to(zero_after[s:e], a[i, :t, s:e].shape))
+        np.testing.assert_allclose(plain[i, :t].mean(0), 0.0, atol=2e-4)
+        np.testing.assert_allclose(plain[i, :t].std(0), 1.0, atol=2e-4)
