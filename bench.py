@@ -192,6 +192,11 @@ def run_ours(args, rank, world, local_rank):
     keys = ['utt%d' % i for i in range(BATCH)]
     labels = [[1, 2, 3]] * BATCH
     audio_s = float(lens.sum()) / 16000.0
+    job_audio_s = audio_s                    # audio seconds per step over ALL ranks (each rank has its own lengths)
+    if world > 1:
+        t = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        job_audio_s = float(t.item())
     # synthetic global CMVN (any finite vectors exercise the same arithmetic)
     mean = torch.linspace(8.0, 12.0, 80, device=dev)
     istd = torch.linspace(0.4, 0.6, 80, device=dev)
@@ -278,11 +283,11 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     ms_total, launches, reps = timed_repeated(step_resident, world > 1, 1.5)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * audio_s * args.steps / (ms_total * 1e-3)
+    value = job_audio_s * args.steps / (ms_total * 1e-3)
     stats.zero_()
     random.seed(99 + rank)
     ms_e2e, _, _ = timed_repeated(step_e2e, world > 1, 0.5)
-    e2e_value = world * audio_s * args.steps / (ms_e2e * 1e-3)
+    e2e_value = job_audio_s * args.steps / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel (oe_fbank_kernel), timed alone on its own stream position ----
     roof = None
@@ -333,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
             'metric': 'fbank_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'audio_s_per_step_per_gpu': audio_s,
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'audio_s_per_step_per_gpu': job_audio_s / world,
                        'l2': 'inputs cycle through %d distinct batches (%.0f MB int16 per GPU) > 126 MB L2' %
                              (POOL, POOL * h2d / 1e6),
                        'timing': 'median of %d back-to-back repeats of the %d-step timed region (each bracketed by '

@@ -317,6 +317,101 @@ class audio_collate_func(object):
         return plan.keys, inputs
 
 
+def _default_tokenizer(text):
+    """Character / word tokens the way openeat/dataset/text_processor.py:2-22 splits WITHOUT a BPE model:
+    every CJK character is a token, every other run of text one token.  Text normalisation and BPE are not
+    part of the front-end path: pass the recipe's own callable as ``tokenizer`` for
+    identical token ids."""
+    import re
+    pattern = re.compile(r'([\u4e00-\u9fff])')
+    tokens = []
+    for ch_or_w in [w for w in pattern.split(text.upper()) if len(w.strip()) > 0]:
+        tokens.append(ch_or_w)
+    return tokens
+
+
+class AudioDataset(torch.utils.data.Dataset):
+    """openeat/dataset/dataset.py:241-376 for ``data_type='wav'``: parses ``format.data`` (one utterance per
+    line, tab-separated ``key:value`` fields ``utt feat feat_shape text`` [+ ``token tokenid token_shape``]),
+    applies the length filters, the offline speed list, the optional sort and the static / dynamic / shuffle
+    batching -- each item is a PRE-BUILT batch ``[(key, path, tokenid, speed), ...]`` for
+    ``audio_collate_func`` -- including the reference's quirks (``num_frames *= speed``
+    accumulates over the speed list and only affects sorting / batching; the 'dynamic' loop leaves an empty
+    first batch when the first utterance alone exceeds ``max_frames_in_batch``).
+
+    ``tokenizer``: callable text -> list of tokens applied to the ``text`` field of 4-field lines (default:
+    the reference's CJK / non-CJK split without BPE or punctuation stripping)."""
+
+    def __init__(self, data_file, char_dict, bpe_model=None, max_length=10240, min_length=0, token_max_length=200,
+                 token_min_length=0, batch_type='static', batch_size=1, max_frames_in_batch=0, sort=False,
+                 speed_perturb=False, speeds=[0.9, 1.1, 0.1], data_type="kaldi", tokenizer=None):
+        import codecs
+        assert batch_type in ['static', 'dynamic', 'shuffle']
+        if data_type != 'wav':
+            raise NotImplementedError("openeat_b200.AudioDataset covers data_type='wav' (Kaldi-ark features: SURVEY 8f.4)")
+        if bpe_model is not None and tokenizer is None:
+            raise NotImplementedError('pass tokenizer= (e.g. a sentencepiece-backed callable); BPE is outside the front-end path')
+        tokenizer = tokenizer or _default_tokenizer
+        self.batch_size = 1 if batch_type in ['static', 'dynamic'] else batch_size       # dataset.py:295
+        self.char_dict = char_dict
+        self.vocab_size = len(char_dict)
+        if speed_perturb:
+            speed_list = [float(s) for s in np.arange(speeds[0], speeds[1], speeds[2])]   # dataset.py:298-301
+        else:
+            speed_list = [1.0]
+        data = []
+        with codecs.open(data_file, 'r', encoding='utf-8') as f:
+            for line in f:
+                arr = line.strip().split('\t')
+                if len(arr) != 4 and len(arr) != 7:
+                    continue
+                key = arr[0].split(':')[1]
+                if len(arr) == 4:
+                    text = arr[3].split(':')[1]
+                    tokens = tokenizer(text)
+                    tokenid = [char_dict[w] if w in char_dict else char_dict['<unk>'] for w in tokens]
+                else:
+                    tokenid = arr[5].split(':')[1]                 # dataset.py:318-319 keeps the string
+                path = ':'.join(arr[1].split(':')[1:])
+                num_frames = int(float(arr[2].split(':')[1]) * 1000 / 10)                # dataset.py:324
+                length = num_frames
+                token_length = len(tokenid)
+                if min_length < length < max_length and token_min_length < token_length < token_max_length:
+                    for speed in speed_list:
+                        num_frames *= speed                        # dataset.py:334-336 (accumulates)
+                        data.append((key, path, num_frames, tokenid, speed))
+        if sort:
+            data = sorted(data, key=lambda x: x[2])
+        num_data = len(data)
+        if batch_type == 'dynamic':                                # dataset.py:341-352
+            assert (max_frames_in_batch > 0)
+            self.data = [[]]
+            num_frames_in_batch = 0
+            for i in range(num_data):
+                length = data[i][2]
+                num_frames_in_batch += length
+                if num_frames_in_batch > max_frames_in_batch:
+                    self.data.append([])
+                    num_frames_in_batch = length
+                self.data[-1].append((data[i][0], data[i][1], data[i][3], data[i][4]))
+        elif batch_type == 'static':                               # dataset.py:355-364
+            self.data = []
+            cur = 0
+            while cur < num_data:
+                end = min(cur + batch_size, num_data)
+                self.data.append([(data[i][0], data[i][1], data[i][3], data[i][4]) for i in range(cur, end)])
+                cur = end
+        else:                                                      # dataset.py:365-368
+            self.data = [[data[i][0], data[i][1], data[i][3], data[i][4]] for i in range(num_data)]
+        print(len(self.data))                                      # dataset.py:370
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+
 class PrefetchingCollator(object):
     """Pipelines ``audio_collate_func.collate_packed`` over an iterator of packed host batches: the pinned
     PCM of batch i+1 crosses PCIe on a side stream while batch i runs its kernels, so the steady-state cost

@@ -164,6 +164,37 @@ def main():
         sp['fb' + tag] = tfbank(sp['y' + tag], torch.float32)
     np.savez_compressed(os.path.join(OUT, 'speed.npz'), **sp)
 
+    # 7. the reference's AudioDataset (list parsing + batching) on a synthetic format.data
+    import zhon.hanzi                                # shim module: give it a punctuation set so the regex compiles
+    zhon.hanzi.punctuation = '\u3002\uff0c'
+    rng = np.random.default_rng(88)
+    words = ['HELLO', 'WORLD', '\u4f60', '\u597d', 'OKAY', '\u7684', 'A', 'B']
+    char_dict = {w: i for i, w in enumerate(['<blank>', '<unk>'] + words + ['<sos/eos>'])}
+    lines = []
+    for i in range(40):
+        secs = float(np.round(rng.uniform(0.05, 21.0), 2))
+        nw = int(rng.integers(1, 6))
+        text = ' '.join(words[j] for j in rng.integers(0, len(words), nw))
+        lines.append('utt:u%03d\tfeat:/data/wav/u%03d.wav\tfeat_shape:%s\ttext:%s' % (i, i, secs, text))
+    lines.insert(5, 'utt:seg0\tfeat:/data/wav/long.wav,1.5,4.25\tfeat_shape:2.75\ttext:HELLO \u4f60')
+    lines.insert(9, 'malformed line without tabs')
+    list_path = os.path.join(OUT, 'format.data')
+    with open(list_path, 'w', encoding='utf-8') as f:
+        f.write('\n'.join(lines) + '\n')
+    with open(os.path.join(OUT, 'format.dict.json'), 'w', encoding='utf-8') as f:
+        json.dump(char_dict, f, ensure_ascii=False)
+    ds_gold = {}
+    for tag, kw in [('static', dict(batch_type='static', batch_size=4, sort=True, max_length=2000, min_length=10)),
+                    ('dynamic', dict(batch_type='dynamic', max_frames_in_batch=3000, sort=True, max_length=2000, min_length=10)),
+                    ('dynamic_unsorted_speed', dict(batch_type='dynamic', max_frames_in_batch=1500, sort=False,
+                                                    speed_perturb=True, max_length=2000, min_length=10)),
+                    ('shuffle', dict(batch_type='shuffle', batch_size=8, sort=False))]:
+        ds = ref_ds.AudioDataset(list_path, char_dict, None, data_type='wav', **kw)
+        ds_gold[tag] = [[[x[0], x[1], list(x[2]), float(x[3])] for x in (b if tag != 'shuffle' else [b])] for b in ds.data]
+        ds_gold[tag + '_batch_size'] = ds.batch_size
+    with open(os.path.join(OUT, 'audio_dataset.json'), 'w', encoding='utf-8') as f:
+        json.dump(ds_gold, f, ensure_ascii=False)
+
     with open(os.path.join(OUT, 'manifest.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(OUT)))

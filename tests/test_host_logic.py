@@ -155,3 +155,27 @@ def test_world_size_2_stats_allreduce_gloo(tmp_path):
     np.testing.assert_allclose(st['var_stat'], q, rtol=1e-12)
     mean, istd = C.load_cmvn(out, True)
     assert np.isfinite(mean).all() and np.isfinite(istd).all()
+
+
+def test_audio_dataset_matches_reference_batches(golden_dir):
+    """List parsing + length filter + offline speed list + sort + static / dynamic / shuffle batching against the
+    batches the reference's own AudioDataset built from the same format.data (tests/golden/audio_dataset.json)."""
+    import json
+    from openeat_b200.dataset import AudioDataset
+    gold = json.load(open(os.path.join(golden_dir, 'audio_dataset.json'), encoding='utf-8'))
+    char_dict = json.load(open(os.path.join(golden_dir, 'format.dict.json'), encoding='utf-8'))
+    path = os.path.join(golden_dir, 'format.data')
+    cases = [('static', dict(batch_type='static', batch_size=4, sort=True, max_length=2000, min_length=10)),
+             ('dynamic', dict(batch_type='dynamic', max_frames_in_batch=3000, sort=True, max_length=2000, min_length=10)),
+             ('dynamic_unsorted_speed', dict(batch_type='dynamic', max_frames_in_batch=1500, sort=False,
+                                             speed_perturb=True, max_length=2000, min_length=10)),
+             ('shuffle', dict(batch_type='shuffle', batch_size=8, sort=False))]
+    for tag, kw in cases:
+        ds = AudioDataset(path, char_dict, None, data_type='wav', **kw)
+        got = [[[x[0], x[1], list(x[2]), float(x[3])] for x in (b if tag != 'shuffle' else [b])] for b in ds.data]
+        assert got == gold[tag], tag
+        assert ds.batch_size == gold[tag + '_batch_size'] and len(ds) == len(gold[tag])
+    ds = AudioDataset(path, char_dict, None, data_type='wav', batch_type='static', batch_size=4)
+    assert any(',1.5,4.25' in item[1] for b in ds.data for item in b)        # segmented entries survive as path,start,end
+    with pytest.raises(NotImplementedError):
+        AudioDataset(path, char_dict, None, data_type='kaldi')
