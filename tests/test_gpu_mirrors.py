@@ -240,3 +240,49 @@ def test_compute_cmvn_stats_roundtrip(gold, tmp_path, tables):
     mean, istd = load_cmvn(path, True)                             # the reference-format consumer reads it back
     np.testing.assert_allclose(mean, feats.astype(np.float64).mean(0), rtol=1e-4)
     np.testing.assert_allclose(istd, 1.0 / feats.astype(np.float64).std(0), rtol=1e-4)
+
+
+def test_wenet_style_processor_chain(gold, tmp_path, tables):
+    """speed_perturb -> compute_fbank -> utt_normalize -> spec_sub -> spec_aug -> global_cmvn -> batch -> padding over
+    sample dicts, against the CPU oracle with the same random draws."""
+    from openeat_b200 import processor as P
+    from oracle import augment as A, cmvn as C, speed as S
+    lens = [16000, 9000, 5200, 12345, 300, 7777]
+    lines = []
+    for i in range(len(lens)):
+        p = tmp_path / ('p%d.wav' % i)
+        write_wav(p, gold['pcm%d' % i])
+        lines.append('{"key": "k%d", "wav": "%s", "txt": "x"}' % (i, p))
+    lines.append('utt:seg\tfeat:%s,0.25,0.75\tfeat_shape:0.5\ttext:x' % (tmp_path / 'p0.wav'))
+    lines.append('{"key": "missing", "wav": "/nonexistent.wav", "txt": ""}')
+    samples = list(P.parse_raw(lines))
+    assert [s['key'] for s in samples] == ['k0', 'k1', 'k2', 'k3', 'k4', 'k5', 'seg']
+    mean = torch.linspace(8.0, 12.0, 80)
+    istd = torch.linspace(0.4, 0.6, 80)
+    random.seed(77)
+    chain = P.padding(P.batch(P.global_cmvn(P.spec_aug(P.spec_sub(P.utt_normalize(P.compute_fbank(
+        P.speed_perturb(iter(samples)), num_mel_bins=80, batch_size=4)), max_t=30, num_t_sub=3),
+        num_t_mask=3, num_f_mask=2, max_t=50, max_f=10), mean, istd), batch_size=16))
+    keys, feats, labels, flen, llen = next(chain)
+    # the oracle replays the lazy generators' draw order in one pass: compute_fbank pulls a group of 4 samples
+    # through speed_perturb (4 speed draws), then every surviving sample of the group gets its spec_sub and
+    # spec_aug draws as it travels down the chain, then the next group is pulled
+    random.seed(77)
+    out = {}
+    for g in (samples[:4], samples[4:]):
+        pert = [S.speed_perturb(smp['wav'].astype(np.float32), 16000, random.choice([0.9, 1.0, 1.1])) for smp in g]
+        for smp, w in zip(g, pert):
+            if len(w) < 400:
+                continue
+            x = A.normalization(F.fbank(np.asarray(w, np.float32), window=tables[0], mel=tables[1]))
+            x = A.spec_substitute(x, max_t=30, num_t_sub=3)
+            x = A.spec_augmentation(x, 3, 2, 50, 10)
+            out[smp['key']] = C.global_cmvn(x, mean.numpy(), istd.numpy())
+    assert 'k4' not in out and set(keys) == set(out)
+    assert flen.tolist() == sorted(flen.tolist(), reverse=True)
+    feats = feats.cpu().numpy()
+    for i, k in enumerate(keys):
+        t = int(flen[i])
+        assert out[k].shape[0] == t
+        assert np.abs(feats[i, :t] - out[k]).max() < 3e-3
+        assert np.all(feats[i, t:] == 0)
