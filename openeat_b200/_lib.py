@@ -93,7 +93,8 @@ class FrontendError(RuntimeError):
 def build(force=False, verbose=False):
     """nvcc -> csrc/libopeneat_frontend.so (sm_100a), g++ -> csrc/liboe_emul.so (test tooling)."""
     src = os.path.join(CSRC, 'oe_frontend.cu')
-    deps = [src, os.path.join(CSRC, 'oe_fft.h'),
+    deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
+            os.path.join(CSRC, 'oe_fbank2_kernel.cuh'), os.path.join(CSRC, 'oe_mel80.h'),
             os.path.join(os.path.dirname(CSRC), '..', 'include', 'openeat_frontend.h')]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         cmd = ['nvcc'] + NVCC_FLAGS + ['-o', LIB_PATH, src]

@@ -217,6 +217,122 @@ OE_HD void fft_dif(T (&re)[N], T (&im)[N]) {
     DifStage<N, N / 2, ZERO_FROM, T>::run(re, im);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second-generation blocks (oe_fbank2_kernel): radix-4 16-point FFT and the pair untangle.
+//
+// fft16_r4: two radix-4 DIF passes.  Pass 1 combines positions (j, j+4, j+8, j+12) and leaves output m
+// at position j + 4m, times W16^(j m); pass 2 is a 4-point DFT over positions 4m .. 4m+3.  Afterwards
+// position p holds X[r4pos(p)] (base-4 digit reversal, an involution).  The W16^4 = -i twiddle is folded
+// into the adds of pass 2, so the transform has no negations: 128 add/sub + 32 twiddle operations
+// (16 fewer add/sub with PRUNE13: inputs 13..15 are zero and never read).
+OE_CX int r4pos(int k) { return 4 * (k & 3) + (k >> 2); }
+
+// 4-point forward DFT in place: a <- out0, b <- out1, c <- out2, d <- out3.
+// D_ZERO: d is zero (never read).  C_ROT: the c slot holds c0 and stands for -i * c0.
+template <bool D_ZERO, bool C_ROT, class T>
+OE_HD void bfly4(T& ar, T& ai, T& br, T& bi, T& cr, T& ci, T& dr, T& di) {
+    T t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i;
+    if constexpr (C_ROT) {                     // c = (ci, -cr)
+        t0r = vadd(ar, ci);
+        t0i = vsub(ai, cr);
+        t1r = vsub(ar, ci);
+        t1i = vadd(ai, cr);
+    } else {
+        t0r = vadd(ar, cr);
+        t0i = vadd(ai, ci);
+        t1r = vsub(ar, cr);
+        t1i = vsub(ai, ci);
+    }
+    if constexpr (D_ZERO) {
+        t2r = br;
+        t2i = bi;
+        t3r = br;
+        t3i = bi;
+    } else {
+        t2r = vadd(br, dr);
+        t2i = vadd(bi, di);
+        t3r = vsub(br, dr);
+        t3i = vsub(bi, di);
+    }
+    ar = vadd(t0r, t2r);
+    ai = vadd(t0i, t2i);
+    cr = vsub(t0r, t2r);
+    ci = vsub(t0i, t2i);
+    br = vadd(t1r, t3i);                       // out1 = t1 - i t3
+    bi = vsub(t1i, t3r);
+    dr = vsub(t1r, t3i);                       // out3 = t1 + i t3
+    di = vadd(t1i, t3r);
+}
+
+// (r + i im) *= W16^E = exp(-2 pi i E / 16), E in {1, 2, 3, 6, 9}
+template <int E, class T>
+OE_HD void mul_w16(T& r, T& i) {
+    if constexpr (E == 2) {
+        const T h = vconst<T>(0.70710678118654752440f);
+        const T a = vadd(r, i), b = vsub(i, r);
+        r = vmul(a, h);
+        i = vmul(b, h);
+    } else if constexpr (E == 6) {
+        const T a = vsub(i, r), b = vadd(r, i);
+        r = vmul(a, vconst<T>(0.70710678118654752440f));
+        i = vmul(b, vconst<T>(-0.70710678118654752440f));
+    } else {
+        constexpr float c = static_cast<float>(cos2pi(E, 16));
+        constexpr float s = static_cast<float>(sin2pi(E, 16));
+        const T nr = vfma(r, vconst<T>(c), vmul(i, vconst<T>(s)));     // (r + i im)(c - i s)
+        const T ni = vfma(i, vconst<T>(c), vmul(r, vconst<T>(-s)));
+        r = nr;
+        i = ni;
+    }
+}
+
+template <bool PRUNE13, class T>
+OE_HD void fft16_r4(T (&re)[16], T (&im)[16]) {
+    bfly4<false, false, T>(re[0], im[0], re[4], im[4], re[8], im[8], re[12], im[12]);
+    bfly4<PRUNE13, false, T>(re[1], im[1], re[5], im[5], re[9], im[9], re[13], im[13]);
+    bfly4<PRUNE13, false, T>(re[2], im[2], re[6], im[6], re[10], im[10], re[14], im[14]);
+    bfly4<PRUNE13, false, T>(re[3], im[3], re[7], im[7], re[11], im[11], re[15], im[15]);
+    mul_w16<1, T>(re[5], im[5]);               // position j + 4m carries W16^(j m); (j, m) = (2, 2) is folded below
+    mul_w16<2, T>(re[9], im[9]);
+    mul_w16<3, T>(re[13], im[13]);
+    mul_w16<2, T>(re[6], im[6]);
+    mul_w16<6, T>(re[14], im[14]);
+    mul_w16<3, T>(re[7], im[7]);
+    mul_w16<6, T>(re[11], im[11]);
+    mul_w16<9, T>(re[15], im[15]);
+    bfly4<false, false, T>(re[0], im[0], re[1], im[1], re[2], im[2], re[3], im[3]);
+    bfly4<false, false, T>(re[4], im[4], re[5], im[5], re[6], im[6], re[7], im[7]);
+    bfly4<false, true, T>(re[8], im[8], re[9], im[9], re[10], im[10], re[11], im[11]);
+    bfly4<false, false, T>(re[12], im[12], re[13], im[13], re[14], im[14], re[15], im[15]);
+}
+
+// (r + i im) *= (c - i s) with a per-lane scalar twiddle shared by both packed frames.  Scalar FMUL/FFMA on
+// the register halves: same FMA-pipe time as two packed operations and no broadcast moves.
+OE_HD void cmul_lane(V2& r, V2& i, float c, float s) {
+    const float rl = v2_lo(r), rh = v2_hi(r), il = v2_lo(i), ih = v2_hi(i);
+    r = v2_make(rl * c + il * s, rh * c + ih * s);
+    i = v2_make(il * c - rl * s, ih * c - rh * s);
+}
+OE_HD void cmul_lane(float& r, float& i, float c, float s) {
+    const float nr = r * c + i * s, ni = i * c - r * s;
+    r = nr;
+    i = ni;
+}
+
+// Real-FFT untangle of the pair (k, 256 - k): P = Z[k], Q = Z[256 - k], (c, s) = (cos, sin)(2 pi k / 512).
+// 2 X[k] = E + W O and 2 conj(X[256 - k]) = E - W O with E = P + conj(Q), O = (P - conj(Q)) / i share E, O and
+// W O.  Returns 4 |X[k]|^2 in pk and 4 |X[256 - k]|^2 in pq (the 1/4 is folded into the mel weights).
+template <class T>
+OE_HD void untangle_pair(T pr, T pi, T qr, T qi, float c, float s, T& pk, T& pq) {
+    const T er = vadd(pr, qr), ei = vsub(pi, qi);
+    T orr = vadd(pi, qi), oi = vsub(qr, pr);
+    cmul_lane(orr, oi, c, s);                                  // W O
+    const T ar = vadd(er, orr), ai = vadd(ei, oi);
+    const T br = vsub(er, orr), bi = vsub(ei, oi);
+    pk = vfma(ar, ar, vmul(ai, ai));
+    pq = vfma(br, br, vmul(bi, bi));
+}
+
 // Conjugate partner of Z[k1 + 16 k2] in the 16 x 16 layout: Z[256 - k] sits in row (16 - k1) mod 16 at
 // index 15 - k2 (k1 >= 1) or (16 - k2) mod 16 (k1 == 0: k = 16 k2, 256 - k = 16 (16 - k2)).
 OE_HD int partner_row(int k1) { return (16 - k1) & 15; }

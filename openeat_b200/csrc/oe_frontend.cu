@@ -25,6 +25,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -65,6 +66,7 @@ struct DevTables {
 
 #include "oe_mel80.h"
 #include "oe_fbank_kernel.cuh"
+#include "oe_fbank2_kernel.cuh"
 
 namespace oe {
 
@@ -472,6 +474,7 @@ struct oe_frontend {
     float* d_rs_coefs;
     size_t fbank_smem;
     bool std_mel;                  // the mel matrix has the baked mel80 structure -> fast kernel
+    bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     float mel_w_std[512];
 };
 
@@ -737,6 +740,13 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::oe_fbank_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<false, false>::End);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<false, true>::End);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<true, false>::End);
+    {   // developer switch for A/B timing: OE_FBANK_V1=1 keeps the first-generation kernel on the standard mel layout
+        const char* v1 = getenv("OE_FBANK_V1");
+        fe->force_v1 = v1 && v1[0] == '1';
+    }
     if (e != cudaSuccess) {
         if (fe->d_tab) cudaFree(fe->d_tab);
         if (fe->d_rs) cudaFree(fe->d_rs);
@@ -903,7 +913,11 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         }
         bool any_rs = false;
         for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
-        if (fe->std_mel) {
+        if (fe->std_mel && !fe->force_v1) {
+            if (f32) oe::k2::oe_fbank2_kernel<true, false><<<grid, oe::kThreads, oe::k2::Smem<true, false>::End, stream>>>(P);
+            else if (any_rs) oe::k2::oe_fbank2_kernel<false, true><<<grid, oe::kThreads, oe::k2::Smem<false, true>::End, stream>>>(P);
+            else oe::k2::oe_fbank2_kernel<false, false><<<grid, oe::kThreads, oe::k2::Smem<false, false>::End, stream>>>(P);
+        } else if (fe->std_mel) {
             if (f32) oe::oe_fbank_kernel<true, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
             else if (any_rs) oe::oe_fbank_kernel<false, true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
             else oe::oe_fbank_kernel<false, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
