@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     unsigned char* const xw = gx + tau * 8;                               // stage A stores: + k1 * kXRow (+ kXPlane)
     const unsigned char* const xr = gx + tau * kXRow;                     // stage B row loads: + 16 c (+ kXPlane)
     unsigned char* const pubw = gx + tau * kPubRow;                       // publish: + (k2 - 8) * 8 (+ kPubPlane)
-    const unsigned char* const pubr = gx + ((16 - tau) & 15) * kPubRow + (tau == 0 ? 8 : 0);   // partner: + (7 - k2) * 8
+    const unsigned char* const pubr = gx + ((16 - tau) & 15) * kPubRow;                     // partner: + (7 - k2) * 8
     unsigned char* const pwA = gx + kPwBase + slice_off(grp) + tau * 8;           // bin k1 + 16 k2: + 128 k2
     unsigned char* const pwB = gx + kPwBase + slice_off(grp) + (256 - tau) * 8;   // bin 256 - k:  - 128 k2
 
@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
             __syncwarp();
             // ---- stage B: lane k1 = tau transforms row k1 of both frames ----
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = cc < 4 ? 2 * cc : 2 * cc - 7;        // chunks 0 2 4 6 (butterflies j = 0, 1 of the first pass) first
                 const ulonglong2 vr = *reinterpret_cast<const ulonglong2*>(xr + 16 * c);
                 const ulonglong2 vi = *reinterpret_cast<const ulonglong2*>(xr + kXPlane + 16 * c);
                 zr[2 * c] = v2_from_bits(vr.x);
@@ -322,33 +323,32 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                 sts_v2(pubw + (k2 - 8) * 8 + kPubPlane, zi[pos]);
             });
             __syncwarp();
-            // ---- pair untangle: P = Z[k1 + 16 k2], Q = Z[256 - k] = row (16 - k1) mod 16, index 15 - k2 (row 0:
-            // 16 - k2, expressed as the one-cell offset in pubr; its k2 = 0 pair only feeds the weightless bins 0 / 256) ----
+            // ---- pair untangle: P = Z[k1 + 16 k2], Q = Z[256 - k] = row (16 - k1) mod 16, index 15 - k2.  Row 0 is its own
+            // partner with index 16 - k2: lane 0 takes Q from its own registers (any shared-memory placement of its row
+            // collides with exactly one other lane of the half-warp; measured: +9 wavefronts per frame) and its k2 = 0
+            // pair only feeds the weightless bins 0 / 256 ----
             {
                 const float4* const tu4 = reinterpret_cast<const float4*>(smem + S::TwU + tau * 80);
+                const bool lane0 = tau == 0;
                 static_for<0, 4>([&](auto ii) {
                     constexpr int i = decltype(ii)::value;
                     const float4 t = tu4[i];                       // k2 = 2i: (t.x, t.y), 2i + 1: (t.z, t.w)
-                    {
-                        constexpr int k2 = 2 * i, pos = r4pos(k2);
-                        const V2 qr = lds_v2(pubr + (7 - k2) * 8), qi = lds_v2(pubr + (7 - k2) * 8 + kPubPlane);
+                    static_for<0, 2>([&](auto jj) {
+                        constexpr int k2 = 2 * i + decltype(jj)::value, pos = r4pos(k2), own = r4pos((16 - k2) & 15);
+                        V2 qr = zr[own], qi = zi[own];
+                        if (!lane0) {
+                            qr = lds_v2(pubr + (7 - k2) * 8);
+                            qi = lds_v2(pubr + (7 - k2) * 8 + kPubPlane);
+                        }
                         V2 pk, pq;
-                        untangle_pair<V2>(zr[pos], zi[pos], qr, qi, t.x, t.y, pk, pq);
+                        untangle_pair<V2>(zr[pos], zi[pos], qr, qi, (k2 & 1) ? t.z : t.x, (k2 & 1) ? t.w : t.y, pk, pq);
                         sts_v2(pwA + 128 * k2, pk);
                         sts_v2(pwB - 128 * k2, pq);
-                    }
-                    {
-                        constexpr int k2 = 2 * i + 1, pos = r4pos(k2);
-                        const V2 qr = lds_v2(pubr + (7 - k2) * 8), qi = lds_v2(pubr + (7 - k2) * 8 + kPubPlane);
-                        V2 pk, pq;
-                        untangle_pair<V2>(zr[pos], zi[pos], qr, qi, t.z, t.w, pk, pq);
-                        sts_v2(pwA + 128 * k2, pk);
-                        sts_v2(pwB - 128 * k2, pq);
-                    }
+                    });
                 });
                 constexpr int p8 = r4pos(8);                       // bin 128: X[128] = conj(Z[128]) (row 0, k2 = 8)
                 const V2 z2 = vfma(zr[p8], zr[p8], vmul(zi[p8], zi[p8]));
-                if (tau == 0) sts_v2(pwA + 128 * 8, vmul(z2, vbcast(4.f)));
+                if (lane0) sts_v2(pwA + 128 * 8, vmul(z2, vbcast(4.f)));
             }
             cp_async_wait_all();       // next tile's descriptor has landed (this thread's pieces; (4) publishes them)
             __syncthreads();           // (4) power slices complete; the raw buffer has been consumed
@@ -417,16 +417,23 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
             const int pitch = (int)P.pitch;
             float* const dst0 = P.out + out_start * P.pitch;
             if (P.out_vec && !fused && !has_cmvn) {
-                // the tile is one contiguous run of rows_here * 80 floats: flat float4 stores
-                constexpr int kQ = F / 4;                             // float4 per row
-                const int nq = rows_here * kQ;
+                // dense rows: float4 stores.  A warp step covers 4 rows x 8 float4: lane = (row & 3, float4 & 7), so the four
+                // scalar reads per lane hit banks 4 (q + rg) + {0, 17, 2, 19}[row & 3] + i: all 32 distinct (rows are 81 floats
+                // apart), and every row gets one 128-byte store segment.
+                constexpr int kQ = F / 4;                             // 20 float4 per row: q blocks of 8, 8, 4
+                const int rl = lane & 3, ql = lane >> 2;
                 float4* const dst4 = reinterpret_cast<float4*>(dst0);
-                for (int c = tid; c < nq; c += kThreads) {
-                    const int r = c / kQ, col = (c - r * kQ) * 4;
-                    const float* const src = sTile + r * rowO + col;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nvalid) v = make_float4(src[0], src[1], src[2], src[3]);
-                    dst4[c] = v;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int it = warp + 8 * i;                      // 24 steps = 8 row groups x 3 q blocks
+                    const int rg = it / 3, qb = it - 3 * rg;
+                    const int r = 4 * rg + rl, q = 8 * qb + ql;
+                    if (q < kQ && r < rows_here) {
+                        const float* const src = sTile + r * rowO + 4 * q;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < nvalid) v = make_float4(src[0], src[1], src[2], src[3]);
+                        dst4[r * kQ + q] = v;
+                    }
                 }
             } else {
 #pragma unroll
