@@ -9,7 +9,7 @@ import os
 import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
-LIB_PATH = os.path.join(CSRC, 'libopeneat_frontend.so')
+LIB_PATH = os.environ.get('OE_LIB_PATH') or os.path.join(CSRC, 'libopeneat_frontend.so')   # OE_LIB_PATH: developer A/B builds
 EMUL_PATH = os.path.join(CSRC, 'liboe_emul.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--shared', '-Xcompiler', '-fPIC', '-diag-suppress', '177,550']

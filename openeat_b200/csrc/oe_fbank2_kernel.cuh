@@ -121,17 +121,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     if (P.cta_stats != nullptr)
         for (int i = tid; i < 3 * 2 * F; i += kThreads) sAcc[i] = 0.0;
 
-    // ---- first tile: descriptor, then its waveform starts moving before anything else ----
     int tile = blockIdx.x;
     int slot = 0;
-    if (tile < P.total_tiles) {
-        prefetch_desc(sDesc, P.tiles + tile, tid);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-        if (sDesc[0].nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, sDesc, tid);
-        cp_async_commit();
-    }
     // ---- one-time table staging: twiddles as (cos, +sin) ----
     {
         float2* const twA = reinterpret_cast<float2*>(smem + S::TwA);
@@ -151,6 +142,17 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     for (int n1 = 0; n1 < 13; ++n1) {
         wv0[n1] = tab->window[32 * n1 + 2 * tau];
         wv1[n1] = tab->window[32 * n1 + 2 * tau + 1];
+    }
+    // ---- everything above only read launch constants: with a programmatic dependent launch it overlaps the tail of
+    // the descriptor kernel; the tile descriptors are touched from here on ----
+    grid_dep_wait();
+    if (tile < P.total_tiles) {                // first tile: descriptor, then its waveform
+        prefetch_desc(sDesc, P.tiles + tile, tid);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        if (sDesc[0].nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, sDesc, tid);
+        cp_async_commit();
     }
     const float preemph = tab->preemph;
     const float dc_scale = (1.0f - preemph) * (1.0f / (float)kWin);
@@ -364,7 +366,11 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                 const int fr = 4 * (gl >> 1) + (gl & 1) + 2 * h;
                 const float* const pcol = reinterpret_cast<const float*>(smem + S::X + gl * kXGroup + kPwBase + slice_off(gl) + 4 * h);
                 float* const orow = sTile + fr * rowO;
+#ifdef OE_EXP_MEL_SAME
+                switch (0) {
+#else
                 switch (warp) {
+#endif
                     case 0: mel_group2<0>(pcol, P, orow, log_floor); break;
                     case 1: mel_group2<1>(pcol, P, orow, log_floor); break;
                     case 2: mel_group2<2>(pcol, P, orow, log_floor); break;
@@ -383,10 +389,15 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                     float s = 0.f, m2 = 0.f;
                     if (n > 0) {
                         const float* col = sTile + (11 * rg) * rowO + f;
-                        for (int r = 0; r < n; ++r) s += col[r * rowO];
+                        float x[11];
+#pragma unroll
+                        for (int r = 0; r < 11; ++r) x[r] = r < n ? col[r * rowO] : 0.f;
+#pragma unroll
+                        for (int r = 0; r < 11; ++r) s += x[r];            // + 0.f beyond n: exact
                         const float mean = s / (float)n;
-                        for (int r = 0; r < n; ++r) {
-                            const float d = col[r * rowO] - mean;
+#pragma unroll
+                        for (int r = 0; r < 11; ++r) {
+                            const float d = r < n ? x[r] - mean : 0.f;
                             m2 = fmaf(d, d, m2);
                         }
                         if (P.cta_stats != nullptr) {          // sum x^2 = M2 + n mean^2, accumulated in fp64, fixed order

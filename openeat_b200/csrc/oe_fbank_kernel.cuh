@@ -128,6 +128,11 @@ __device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wa
     } else {
         const int16_t* w = reinterpret_cast<const int16_t*>(wav) + d->wav_utt;
         const int pieces = d->rs ? kRsPieces : 673;
+        if (in_first >= 0 && in_first + 8 * pieces <= in_len) {       // interior tile: every piece is whole
+            const int16_t* const src = w + in_first;
+            for (int q = tid; q < pieces; q += kThreads) cp_async16(raw + 16 * q, src + 8 * q, 16);
+            return;
+        }
         for (int q = tid; q < pieces; q += kThreads) {
             const int s = in_first + 8 * q;
             int valid = in_len - s;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank_kernel(const FbankParams
     if (P.cta_stats != nullptr)
         for (int i = tid; i < 3 * 2 * kMaxMel; i += kThreads) sAcc[i] = 0.0;
 
+    grid_dep_wait();
     // ---- first tile: descriptor, then its waveform starts moving before anything else ----
     int tile = blockIdx.x;
     int slot = 0;

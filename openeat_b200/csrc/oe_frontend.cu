@@ -47,6 +47,10 @@ constexpr int kMaxNnz = 2048;
 constexpr int kRowE = 18;           // complex per exchange row: 16 + 2 pad -> 144 B (conflict-free LDS.128)
 constexpr int kRowO = 81;           // floats per output-tile row (80 + 1 pad); generic: F + 1
 
+// Programmatic dependent launch: blocks until the preceding grid in the stream has completed and its writes are
+// visible (returns immediately when the kernel was launched without the attribute).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct DevTables {
     float window[kFft];             // zero beyond frame_length
     float2 twA[16 * kRowE];         // W256^(tau*k1) = (cos, -sin)
@@ -85,10 +89,19 @@ struct TileDescParams {
 };
 
 // Expands the per-utterance metadata into one self-contained descriptor per 32-frame tile.
+constexpr int kDescSmemUtts = 4096;
 __global__ void oe_tile_desc_kernel(const TileDescParams P) {
+    // the binary search runs on a shared-memory copy of the prefix array (one coalesced read instead of
+    // log2(B) dependent global loads per thread)
+    __shared__ int32_t sh_prefix[kDescSmemUtts + 1];
+    const bool staged = P.B <= kDescSmemUtts;
+    if (staged) {
+        for (int i = threadIdx.x; i <= P.B; i += blockDim.x) sh_prefix[i] = P.tile_prefix[i];
+        __syncthreads();
+    }
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= P.total_tiles) return;
-    const int b = find_utt(P.tile_prefix, P.B, tile);
+    const int b = staged ? find_utt(sh_prefix, P.B, tile) : find_utt(P.tile_prefix, P.B, tile);
     const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
     TileDesc d;
     d.b = b;
@@ -108,30 +121,83 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
 
 // ------------------------------------------------------------------------------------------
 struct UttStatsParams {
-    const float* tile_stats;
+    const float* tile_stats;     // null: no per-utterance statistics wanted (global role only)
     const int32_t* tile_prefix;
     const int32_t* n_frames;
     float* utt_mean;     // [B][F]
     float* utt_std;      // [B][F]
     int F;
+    int B;
+    // compute_cmvn_stats role of the blocks behind the B utterance blocks (gridDim.x = B + global_blocks)
+    const double* partial;   // [n_partials][2F]: sum, sum of squares written by the producer CTAs
+    double* stats;           // [2F+1] accumulated in place
+    double count;
+    int n_partials;
 };
 
-// feature_processor.py:5-8: mean and population std over the frames of one utterance, merged from the
-// per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2].
-// block = (F columns) x (kUttSlices slices of the partial list), combined through shared memory.
-constexpr int kUttSlices = 8;
-__global__ void __launch_bounds__(kMaxMel * kUttSlices) oe_utt_stats_kernel(const UttStatsParams P) {
+constexpr int kUttSlices = 4;
+constexpr int kUttMaxPart = 24;          // partial sums per slice held in registers: covers 32 tiles = 1 024 frames per utterance
+constexpr int kGlobStats = 8;            // statistics per global-role block
+
+// rows and 1 / rows of partial i = 3 tile + rg of an utterance with nfr frames (rows <= 11: one fp32 rounding on a partial mean)
+__device__ __forceinline__ void part_rows(int nfr, int tile, int rg, int& rows, float& inv) {
+    rows = stats_rows(min(kTileFrames, nfr - tile * kTileFrames), rg);
+    inv = rows > 0 ? __frcp_rn((float)rows) : 0.f;
+}
+
+// Block role 1 (blockIdx.x < B), feature_processor.py:5-8: mean and population std over the frames of one utterance,
+// merged from the per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2]
+// (two passes over the partials: robust for constant features, where a one-pass difference of sums would cancel).
+// block = (F columns) x (kUttSlices slices of the partial list), combined through shared memory; the partial sums stay
+// in registers between the passes.  Slice y owns partials i = y + 4 u: row group i % 3 and tile i / 3 follow from
+// (y + u) % 3 and (y + 4 u) / 3 without divisions in the loop.  <= 64 registers: three 320-thread blocks per SM.
+// Block role 2 (blockIdx.x >= B), compute_cmvn_stats: += sum, sum of squares and frame count into the caller's
+// accumulator.  The producers' partials are combined in a fixed order (strided sums per lane, then in lane order;
+// the tile -> CTA assignment is static), so the result is bitwise reproducible run to run.
+__global__ void __launch_bounds__(kMaxMel * kUttSlices, 2) oe_utt_stats_kernel(const UttStatsParams P) {
     __shared__ double sh[kUttSlices][kMaxMel];
-    const int b = blockIdx.x, f = threadIdx.x, y = threadIdx.y;
+    const int f = threadIdx.x, y = threadIdx.y;
+    grid_dep_wait();
+    if ((int)blockIdx.x >= P.B) {
+        const int nthr = blockDim.x * kUttSlices, lanes = nthr / kGlobStats;   // lanes per statistic
+        const int t = y * blockDim.x + f, slot = t / lanes, l = t - slot * lanes;
+        const int stat = ((int)blockIdx.x - P.B) * kGlobStats + slot;
+        double* const flat = &sh[0][0];
+        double s = 0.0;
+        if (slot < kGlobStats && stat < 2 * P.F) {
+            const double* __restrict__ src = P.partial + stat;
+#pragma unroll 8
+            for (int g = l; g < P.n_partials; g += lanes) s += src[(int64_t)g * 2 * P.F];
+        }
+        flat[t] = s;
+        __syncthreads();
+        if (l == 0 && slot < kGlobStats) {
+            if (stat < 2 * P.F) {
+                double tot = 0.0;
+                for (int j = 0; j < lanes; ++j) tot += flat[t + j];
+                P.stats[stat] += tot;
+            } else if (stat == 2 * P.F) {
+                P.stats[2 * P.F] += P.count;
+            }
+        }
+        return;
+    }
+    const int b = blockIdx.x;
     const int nfr = P.n_frames[b];
     const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
     const int np = 3 * ntiles;
-    const float* base = P.tile_stats + (int64_t)P.tile_prefix[b] * 3 * 2 * P.F;
+    const int F2 = 2 * P.F;
+    const float* __restrict__ base = P.tile_stats + (int64_t)P.tile_prefix[b] * 3 * F2 + f;
+    float ps[kUttMaxPart];
     double acc = 0.0;
-    if (f < P.F) {
-#pragma unroll 4
-        for (int i = y; i < np; i += kUttSlices) acc += (double)base[(int64_t)i * 2 * P.F + f];
+#pragma unroll
+    for (int u = 0; u < kUttMaxPart; ++u) {
+        const int i = y + u * kUttSlices;
+        ps[u] = i < np ? base[(int64_t)i * F2] : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < kUttMaxPart; ++u) acc += (double)ps[u];
+    for (int i = y + kUttMaxPart * kUttSlices; i < np; i += kUttSlices) acc += (double)base[(int64_t)i * F2];
     sh[y][f] = acc;
     __syncthreads();
     double S = 0.0;
@@ -140,56 +206,36 @@ __global__ void __launch_bounds__(kMaxMel * kUttSlices) oe_utt_stats_kernel(cons
     const double mean = S / (double)nfr;
     __syncthreads();
     acc = 0.0;
-    if (f < P.F) {
-#pragma unroll 4
-        for (int i = y; i < np; i += kUttSlices) {
-            const int nvalid = min(kTileFrames, nfr - (i / 3) * kTileFrames);
-            const int rows = stats_rows(nvalid, i % 3);
-            const float* st = base + (int64_t)i * 2 * P.F;
-            const float inv = rows > 0 ? 1.0f / (float)rows : 0.f;     // rows <= 11: one fp32 rounding on a partial mean
-            const double d = (double)(st[f] * inv) - mean;
-            acc += (double)st[P.F + f] + (double)rows * d * d;
+    const int y3 = y % 3, yq = y / 3;
+#pragma unroll
+    for (int u = 0; u < kUttMaxPart; ++u) {
+        const int i = y + u * kUttSlices;                         // i % 3 = (y + u) % 3, i / 3 = u + (y + u) / 3
+        if (i < np) {
+            const int c3 = (y3 + u % 3) % 3;                      // u is a compile-time constant
+            const int tile = u + (u / 3) + yq + ((y3 + u % 3) >= 3 ? 1 : 0);
+            int rows;
+            float inv;
+            part_rows(nfr, tile, c3, rows, inv);
+            const double d = (double)(ps[u] * inv) - mean;
+            acc += (double)base[(int64_t)i * F2 + P.F] + (double)rows * d * d;
         }
+    }
+    for (int i = y + kUttMaxPart * kUttSlices; i < np; i += kUttSlices) {
+        int rows;
+        float inv;
+        part_rows(nfr, i / 3, i % 3, rows, inv);
+        const double d = (double)(base[(int64_t)i * F2] * inv) - mean;
+        acc += (double)base[(int64_t)i * F2 + P.F] + (double)rows * d * d;
     }
     sh[y][f] = acc;
     __syncthreads();
-    if (y == 0 && f < P.F) {
+    if (y == 0) {
         double m2 = 0.0;
 #pragma unroll
         for (int j = 0; j < kUttSlices; ++j) m2 += sh[j][f];
         P.utt_mean[(int64_t)b * P.F + f] = (float)mean;
         P.utt_std[(int64_t)b * P.F + f] = (float)sqrt(m2 / (double)nfr);
     }
-}
-
-struct GlobalStatsParams {
-    const double* partial;   // [n_partials][2F]: sum, sum of squares written by the producer CTAs
-    double* stats;           // [2F+1] accumulated in place
-    double count;
-    int n_partials;
-    int F;
-};
-
-// compute_cmvn_stats: += sum, sum of squares and frame count into the caller's accumulator.  The producers'
-// partials are combined in index order (the tile -> CTA assignment is static), so the result is bitwise
-// reproducible run to run.
-__global__ void __launch_bounds__(256) oe_global_stats_final_kernel(const GlobalStatsParams P) {
-    __shared__ double sh[256];
-    const int f = blockIdx.x, j = threadIdx.x;               // one block per statistic (2F sums + the count)
-    if (f == 2 * P.F) {
-        if (j == 0) P.stats[2 * P.F] += P.count;
-        return;
-    }
-    double s = 0.0;
-    for (int g = j; g < P.n_partials; g += 256) s += P.partial[(int64_t)g * 2 * P.F + f];
-    sh[j] = s;
-    __syncthreads();
-#pragma unroll
-    for (int w = 128; w >= 1; w >>= 1) {                      // fixed-shape tree: same order every run
-        if (j < w) sh[j] += sh[j + w];
-        __syncthreads();
-    }
-    if (j == 0) P.stats[f] += sh[0];
 }
 
 struct FeatStatsParams {
@@ -203,6 +249,7 @@ struct FeatStatsParams {
 // Same per-tile column statistics as the fbank kernel's epilogue, for batches that arrive as
 // features (data_type != 'wav', dataset.py:190-191, or the numpy-level processor mirrors).
 __global__ void oe_feat_tile_stats_kernel(const FeatStatsParams P) {
+    grid_dep_wait();
     const int f = threadIdx.x;
     double as[3] = {0.0, 0.0, 0.0}, aq[3] = {0.0, 0.0, 0.0};
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -261,10 +308,14 @@ struct FinalizeParams {
 
 // dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
 // grid = (utterances, row chunks).  VEC = 4: thread = (float4 column chunk, row lane); the per-column
-// constants (mean, 1/std, CMVN, frequency mask) live in registers for the whole chunk of rows.
+// constants (mean, 1/std, CMVN, frequency mask) live in registers for the whole chunk of rows.  One row per thread
+// in flight is deliberate: the raw rows are L2 hits, the kernel is bound by the HBM writes, and a 4-row unrolled
+// variant (64 registers) measured 9 us slower in the warm pipeline (tools/ab_step.py) although ncu's cold-cache
+// replay showed it faster.
 constexpr int kFinRows = 128;       // rows per block
 template <int VEC>
 __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P) {
+    grid_dep_wait();
     const int b = blockIdx.x;
     const int r0 = blockIdx.y * kFinRows;
     const int nrows = (int)(P.row_prefix[b + 1] - P.row_prefix[b]);
@@ -481,6 +532,27 @@ struct oe_frontend {
 namespace {
 
 thread_local char g_err[512] = "";
+
+// Launch with programmatic stream serialization (PDL): the grid may be scheduled while its predecessor in the stream
+// drains; every kernel launched this way executes grid_dep_wait() before it touches anything a predecessor wrote
+// (and every kernel of the chain does so, which keeps the ordering transitive).  OE_NO_PDL=1 disables it.
+template <class Params>
+cudaError_t launch_dep(void (*kern)(const Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params& prm) {
+    static const bool no_pdl = [] { const char* e = getenv("OE_NO_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, prm);
+}
+
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -901,7 +973,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             S.F = F;
             S.total_tiles = M.total_tiles;
             n_stat_partials = 3 * std::min(M.total_tiles, fe->sm_count * 8);
-            oe::oe_feat_tile_stats_kernel<<<std::min(M.total_tiles, fe->sm_count * 8), oe::kMaxMel, 0, stream>>>(S);
+            OE_CUDA(launch_dep(oe::oe_feat_tile_stats_kernel, dim3(std::min(M.total_tiles, fe->sm_count * 8)), dim3(oe::kMaxMel), 0, stream, S));
             OE_CUDA(cudaGetLastError());
         }
     } else if (M.total_tiles > 0) {
@@ -914,40 +986,44 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         bool any_rs = false;
         for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
         if (fe->std_mel && !fe->force_v1) {
-            if (f32) oe::k2::oe_fbank2_kernel<true, false><<<grid, oe::kThreads, oe::k2::Smem<true, false>::End, stream>>>(P);
-            else if (any_rs) oe::k2::oe_fbank2_kernel<false, true><<<grid, oe::kThreads, oe::k2::Smem<false, true>::End, stream>>>(P);
-            else oe::k2::oe_fbank2_kernel<false, false><<<grid, oe::kThreads, oe::k2::Smem<false, false>::End, stream>>>(P);
+            if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
+            else if (any_rs) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, true>::End, stream, P));
+            else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
         } else if (fe->std_mel) {
-            if (f32) oe::oe_fbank_kernel<true, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else if (any_rs) oe::oe_fbank_kernel<false, true, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else oe::oe_fbank_kernel<false, true, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            if (f32) OE_CUDA(launch_dep(oe::oe_fbank_kernel<true, true, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
+            else if (any_rs) OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, true, true>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
+            else OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, true, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
         } else {
-            if (f32) oe::oe_fbank_kernel<true, false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else if (any_rs) oe::oe_fbank_kernel<false, false, true><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
-            else oe::oe_fbank_kernel<false, false, false><<<grid, oe::kThreads, fe->fbank_smem, stream>>>(P);
+            if (f32) OE_CUDA(launch_dep(oe::oe_fbank_kernel<true, false, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
+            else if (any_rs) OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
+            else OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, false, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
         }
         OE_CUDA(cudaGetLastError());
     }
-    if (bt->norm_mode != OE_NORM_NONE) {
-        oe::UttStatsParams U;
-        U.tile_stats = P.tile_stats;
-        U.tile_prefix = d_tile_prefix;
-        U.n_frames = d_n_frames;
-        U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
-        U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
-        U.F = F;
-        oe::oe_utt_stats_kernel<<<B, dim3(oe::kMaxMel, oe::kUttSlices), 0, stream>>>(U);
-        OE_CUDA(cudaGetLastError());
-    }
-    if (bt->d_stats && n_stat_partials > 0) {
-        oe::GlobalStatsParams G;
-        G.partial = reinterpret_cast<const double*>(ws + M.stat_partial);
-        G.stats = bt->d_stats;
-        G.count = (double)M.total_frames;
-        G.n_partials = n_stat_partials;
-        G.F = F;
-        oe::oe_global_stats_final_kernel<<<2 * F + 1, 256, 0, stream>>>(G);
-        OE_CUDA(cudaGetLastError());
+    {
+        const bool want_utt = bt->norm_mode != OE_NORM_NONE;
+        const bool want_glob = bt->d_stats && n_stat_partials > 0;
+        if (want_utt || want_glob) {
+            oe::UttStatsParams U;
+            memset(&U, 0, sizeof(U));
+            U.tile_stats = P.tile_stats;
+            U.tile_prefix = d_tile_prefix;
+            U.n_frames = d_n_frames;
+            U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
+            U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
+            U.F = F;
+            U.B = want_utt ? B : 0;
+            int glob_blocks = 0;
+            if (want_glob) {
+                U.partial = reinterpret_cast<const double*>(ws + M.stat_partial);
+                U.stats = bt->d_stats;
+                U.count = (double)M.total_frames;
+                U.n_partials = n_stat_partials;
+                glob_blocks = (2 * F + 1 + oe::kGlobStats - 1) / oe::kGlobStats;
+            }
+            OE_CUDA(launch_dep(oe::oe_utt_stats_kernel, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));   // blockDim.x = F <= kMaxMel
+            OE_CUDA(cudaGetLastError());
+        }
     }
     if (M.two_phase && d_out && M.total_rows > 0) {
         oe::FinalizeParams Z;
@@ -978,8 +1054,8 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         const bool vec = (F % 4 == 0) && (pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(Z.raw) & 15) &&
                          !(reinterpret_cast<uintptr_t>(d_out) & 15);
         dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + oe::kFinRows - 1) / oe::kFinRows));
-        if (vec) oe::oe_finalize_kernel<4><<<zgrid, 256, 0, stream>>>(Z);
-        else oe::oe_finalize_kernel<1><<<zgrid, 256, 0, stream>>>(Z);
+        if (vec) OE_CUDA(launch_dep(oe::oe_finalize_kernel<4>, zgrid, dim3(256), 0, stream, Z));
+        else OE_CUDA(launch_dep(oe::oe_finalize_kernel<1>, zgrid, dim3(256), 0, stream, Z));
         OE_CUDA(cudaGetLastError());
     }
     return OE_OK;

@@ -34,6 +34,15 @@ __global__ void k(float* out, int iters, float s) {
         } else if (MODE == 3) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) p[i] = fadd2(p[i], ss);
+        } else if (MODE == 5) {   // packed mul
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(p[i]) : "l"(p[i]), "l"(ss));
+        } else if (MODE == 6) {   // 8 packed adds + 8 scalar FMUL
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = fadd2(p[i], ss); a[i] = a[i] * s; }
+        } else if (MODE == 7) {   // 8 packed adds + 8 integer LOP3/IADD (ALU pipe)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = fadd2(p[i], ss); a[i] = __int_as_float((__float_as_int(a[i]) ^ it) + i); }
         } else if (MODE == 4) {   // mixed: 8 scalar FFMA + 4 packed per iteration (same flops as mode 0)
 #pragma unroll
             for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], s, 0.5f);
@@ -48,8 +57,8 @@ __global__ void k(float* out, int iters, float s) {
 }
 
 template <int MODE>
-void run(const char* name, float* d, double flops_per_iter_thread) {
-    const int iters = 4096, blocks = 148 * 8, threads = 256;
+void run(const char* name, float* d, double flops_per_iter_thread, int per_sm = 8) {
+    const int iters = 4096, blocks = 148 * per_sm, threads = 256;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -72,6 +81,17 @@ int main() {
     run<2>("scalar FADD x16", d, 16);
     run<3>("add.rn.f32x2 x8", d, 16);
     run<4>("8 FFMA + 4 FFMA2", d, 32);
+    run<5>("mul.rn.f32x2 x8", d, 16);
+    run<6>("8 FADD2 + 8 FMUL", d, 24);
+    run<7>("8 FADD2 + 8x(LOP3+IADD)", d, 16);
+    printf("-- 2 CTAs (16 warps) per SM --\n");
+    run<0>("scalar FFMA x16", d, 32, 2);
+    run<1>("fma.rn.f32x2 x8", d, 32, 2);
+    run<2>("scalar FADD x16", d, 16, 2);
+    run<3>("add.rn.f32x2 x8", d, 16, 2);
+    run<5>("mul.rn.f32x2 x8", d, 16, 2);
+    run<6>("8 FADD2 + 8 FMUL", d, 24, 2);
+    run<7>("8 FADD2 + 8x(LOP3+IADD)", d, 16, 2);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
