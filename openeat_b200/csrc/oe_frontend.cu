@@ -135,26 +135,26 @@ struct UttStatsParams {
     int n_partials;
 };
 
-constexpr int kUttSlices = 4;
-constexpr int kUttMaxPart = 24;          // partial sums per slice held in registers: covers 32 tiles = 1 024 frames per utterance
+constexpr int kUttSlices = 8;
+constexpr int kUttMaxPart = 12;          // partial sums per slice held in registers: covers 32 tiles = 1 024 frames per utterance
 constexpr int kGlobStats = 8;            // statistics per global-role block
 
-// rows and 1 / rows of partial i = 3 tile + rg of an utterance with nfr frames (rows <= 11: one fp32 rounding on a partial mean)
-__device__ __forceinline__ void part_rows(int nfr, int tile, int rg, int& rows, float& inv) {
-    rows = stats_rows(min(kTileFrames, nfr - tile * kTileFrames), rg);
-    inv = rows > 0 ? __frcp_rn((float)rows) : 0.f;
-}
+// 1 / rows for rows = 0..11, correctly rounded (rows <= 11: one fp32 rounding on a partial mean)
+__constant__ float kInvRows[12] = {0.f, 1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.f / 5.f, 1.f / 6.f,
+                                   1.f / 7.f, 1.f / 8.f, 1.f / 9.f, 1.f / 10.f, 1.f / 11.f};
 
 // Block role 1 (blockIdx.x < B), feature_processor.py:5-8: mean and population std over the frames of one utterance,
 // merged from the per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2]
 // (two passes over the partials: robust for constant features, where a one-pass difference of sums would cancel).
 // block = (F columns) x (kUttSlices slices of the partial list), combined through shared memory; the partial sums stay
-// in registers between the passes.  Slice y owns partials i = y + 4 u: row group i % 3 and tile i / 3 follow from
-// (y + u) % 3 and (y + 4 u) / 3 without divisions in the loop.  <= 64 registers: three 320-thread blocks per SM.
+// in registers between the passes; loads use clamped 32-bit indices (no branches).  The kernel is a latency chain
+// (five dependent round trips plus an fp64 division and a square root), so it is sized for one wave: F <= 80 runs
+// 640-thread blocks at <= 51 registers, two per SM.
 // Block role 2 (blockIdx.x >= B), compute_cmvn_stats: += sum, sum of squares and frame count into the caller's
 // accumulator.  The producers' partials are combined in a fixed order (strided sums per lane, then in lane order;
 // the tile -> CTA assignment is static), so the result is bitwise reproducible run to run.
-__global__ void __launch_bounds__(kMaxMel * kUttSlices, 2) oe_utt_stats_kernel(const UttStatsParams P) {
+template <int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) oe_utt_stats_kernel(const UttStatsParams P) {
     __shared__ double sh[kUttSlices][kMaxMel];
     const int f = threadIdx.x, y = threadIdx.y;
     grid_dep_wait();
@@ -184,8 +184,11 @@ __global__ void __launch_bounds__(kMaxMel * kUttSlices, 2) oe_utt_stats_kernel(c
     }
     const int b = blockIdx.x;
     const int nfr = P.n_frames[b];
-    const int ntiles = (nfr + kTileFrames - 1) / kTileFrames;
-    const int np = 3 * ntiles;
+    const int np = 3 * ((nfr + kTileFrames - 1) / kTileFrames);
+    if (np == 0) {                                                  // dropped utterance (no frames): nothing reads these
+        if (y == 0) P.utt_mean[(int64_t)b * P.F + f] = P.utt_std[(int64_t)b * P.F + f] = 0.f;
+        return;
+    }
     const int F2 = 2 * P.F;
     const float* __restrict__ base = P.tile_stats + (int64_t)P.tile_prefix[b] * 3 * F2 + f;
     float ps[kUttMaxPart];
@@ -193,11 +196,12 @@ __global__ void __launch_bounds__(kMaxMel * kUttSlices, 2) oe_utt_stats_kernel(c
 #pragma unroll
     for (int u = 0; u < kUttMaxPart; ++u) {
         const int i = y + u * kUttSlices;
-        ps[u] = i < np ? base[(int64_t)i * F2] : 0.f;
+        const float v = base[min(i, np - 1) * F2];
+        ps[u] = i < np ? v : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < kUttMaxPart; ++u) acc += (double)ps[u];
-    for (int i = y + kUttMaxPart * kUttSlices; i < np; i += kUttSlices) acc += (double)base[(int64_t)i * F2];
+    for (int i = y + kUttMaxPart * kUttSlices; i < np; i += kUttSlices) acc += (double)base[i * F2];
     sh[y][f] = acc;
     __syncthreads();
     double S = 0.0;
@@ -206,26 +210,21 @@ __global__ void __launch_bounds__(kMaxMel * kUttSlices, 2) oe_utt_stats_kernel(c
     const double mean = S / (double)nfr;
     __syncthreads();
     acc = 0.0;
-    const int y3 = y % 3, yq = y / 3;
+    const float* __restrict__ base2 = base + P.F;
 #pragma unroll
     for (int u = 0; u < kUttMaxPart; ++u) {
-        const int i = y + u * kUttSlices;                         // i % 3 = (y + u) % 3, i / 3 = u + (y + u) / 3
-        if (i < np) {
-            const int c3 = (y3 + u % 3) % 3;                      // u is a compile-time constant
-            const int tile = u + (u / 3) + yq + ((y3 + u % 3) >= 3 ? 1 : 0);
-            int rows;
-            float inv;
-            part_rows(nfr, tile, c3, rows, inv);
-            const double d = (double)(ps[u] * inv) - mean;
-            acc += (double)base[(int64_t)i * F2 + P.F] + (double)rows * d * d;
-        }
+        const int i = y + u * kUttSlices;
+        const float m2p = base2[min(i, np - 1) * F2];
+        const int tile = i / 3, rg = i - 3 * tile;
+        const int rows = i < np ? stats_rows(min(kTileFrames, nfr - tile * kTileFrames), rg) : 0;
+        const double d = (double)(ps[u] * kInvRows[rows]) - mean;
+        acc += rows > 0 ? (double)m2p + (double)rows * d * d : 0.0;
     }
     for (int i = y + kUttMaxPart * kUttSlices; i < np; i += kUttSlices) {
-        int rows;
-        float inv;
-        part_rows(nfr, i / 3, i % 3, rows, inv);
-        const double d = (double)(base[(int64_t)i * F2] * inv) - mean;
-        acc += (double)base[(int64_t)i * F2 + P.F] + (double)rows * d * d;
+        const int tile = i / 3, rg = i - 3 * tile;
+        const int rows = stats_rows(min(kTileFrames, nfr - tile * kTileFrames), rg);
+        const double d = (double)(base[i * F2] * kInvRows[rows]) - mean;
+        acc += rows > 0 ? (double)base2[i * F2] + (double)rows * d * d : 0.0;
     }
     sh[y][f] = acc;
     __syncthreads();
@@ -962,6 +961,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
         OE_CUDA(cudaGetLastError());
     }
+    static const int skip = [] { const char* e = getenv("OE_DEV_SKIP"); return e ? atoi(e) : 0; }();   // developer timing only: 2 fbank, 4 stats, 8 finalize
     int n_stat_partials = 0;
     if (M.feats) {
         if ((M.need_stats || bt->d_stats) && M.total_tiles > 0) {
@@ -976,7 +976,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             OE_CUDA(launch_dep(oe::oe_feat_tile_stats_kernel, dim3(std::min(M.total_tiles, fe->sm_count * 8)), dim3(oe::kMaxMel), 0, stream, S));
             OE_CUDA(cudaGetLastError());
         }
-    } else if (M.total_tiles > 0) {
+    } else if (M.total_tiles > 0 && !(skip & 2)) {
         const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
         const bool f32 = bt->wav_dtype == OE_WAV_F32;
         if (bt->d_stats) {
@@ -1003,7 +1003,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     {
         const bool want_utt = bt->norm_mode != OE_NORM_NONE;
         const bool want_glob = bt->d_stats && n_stat_partials > 0;
-        if (want_utt || want_glob) {
+        if ((want_utt || want_glob) && !(skip & 4)) {
             oe::UttStatsParams U;
             memset(&U, 0, sizeof(U));
             U.tile_stats = P.tile_stats;
@@ -1012,20 +1012,21 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
             U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
             U.F = F;
-            U.B = want_utt ? B : 0;
+            U.B = (want_utt && !(skip & 16)) ? B : 0;
             int glob_blocks = 0;
-            if (want_glob) {
+            if (want_glob && !(skip & 32)) {
                 U.partial = reinterpret_cast<const double*>(ws + M.stat_partial);
                 U.stats = bt->d_stats;
                 U.count = (double)M.total_frames;
                 U.n_partials = n_stat_partials;
                 glob_blocks = (2 * F + 1 + oe::kGlobStats - 1) / oe::kGlobStats;
             }
-            OE_CUDA(launch_dep(oe::oe_utt_stats_kernel, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));   // blockDim.x = F <= kMaxMel
+            if (F <= 80) OE_CUDA(launch_dep(oe::oe_utt_stats_kernel<640, 2>, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));
+            else OE_CUDA(launch_dep(oe::oe_utt_stats_kernel<oe::kMaxMel * oe::kUttSlices, 1>, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));
             OE_CUDA(cudaGetLastError());
         }
     }
-    if (M.two_phase && d_out && M.total_rows > 0) {
+    if (M.two_phase && d_out && M.total_rows > 0 && !(skip & 8)) {
         oe::FinalizeParams Z;
         memset(&Z, 0, sizeof(Z));
         Z.raw = M.feats ? reinterpret_cast<const float*>(d_wav) : reinterpret_cast<const float*>(ws + M.raw);

@@ -62,6 +62,21 @@ def med(fn, n=20, reps=int(os.environ.get('AB_REPS', '40'))):
     return float(np.median(r)), float(np.min(r))
 
 
+def step_nonorm(i):          # single pass: fused speed perturb + masks + CMVN straight into the padded tensor
+    plan, tm, fm = plans[i % bench.POOL]
+    _run_plan(plan, 80, dev_pool[i % bench.POOL], offs, lens, normalization=False, tmask=tm, fmask=fm,
+              cmvn=(mean, istd), cmvn_on_padding=True, stats=None)
+
+
+def step_nostats(i):
+    plan, tm, fm = plans[i % bench.POOL]
+    _run_plan(plan, 80, dev_pool[i % bench.POOL], offs, lens, normalization=True, tmask=tm, fmask=fm,
+              cmvn=(mean, istd), cmvn_on_padding=True, stats=None)
+
+
+if os.environ.get('AB_PARTS'):
+    print('single-pass (rs + masks + cmvn, padded out) %.1f us | two-phase without global stats %.1f us' % (
+        med(step_nonorm)[0], med(step_nostats)[0]))
 s_med, s_min = med(step)
 f_med, f_min = med(fbank_only)
 print('%-40s step %.1f us (min %.1f)   fbank-only %.1f us (min %.1f)' % (
