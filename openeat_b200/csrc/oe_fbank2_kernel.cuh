@@ -428,12 +428,11 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
             const int pitch = (int)P.pitch;
             float* const dst0 = P.out + out_start * P.pitch;
             if (P.out_vec && !fused && !has_cmvn) {
-                // dense rows: float4 stores.  A warp step covers 4 rows x 8 float4: lane = (row & 3, float4 & 7), so the four
-                // scalar reads per lane hit banks 4 (q + rg) + {0, 17, 2, 19}[row & 3] + i: all 32 distinct (rows are 81 floats
-                // apart), and every row gets one 128-byte store segment.
+                // float4 stores (pitch and base 16-byte aligned).  A warp step covers 4 rows x 8 float4: lane = (row & 3,
+                // float4 & 7), so the four scalar reads per lane hit banks 4 (q + rg) + {0, 17, 2, 19}[row & 3] + i: all 32
+                // distinct (tile rows are 81 floats apart), and every row gets one 128-byte store segment.
                 constexpr int kQ = F / 4;                             // 20 float4 per row: q blocks of 8, 8, 4
                 const int rl = lane & 3, ql = lane >> 2;
-                float4* const dst4 = reinterpret_cast<float4*>(dst0);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int it = warp + 8 * i;                      // 24 steps = 8 row groups x 3 q blocks
@@ -443,7 +442,41 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                         const float* const src = sTile + r * rowO + 4 * q;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (r < nvalid) v = make_float4(src[0], src[1], src[2], src[3]);
-                        dst4[r * kQ + q] = v;
+                        *reinterpret_cast<float4*>(dst0 + (int64_t)r * pitch + 4 * q) = v;
+                    }
+                }
+            } else if (P.out_vec) {
+                // the same lane mapping with [mask] -> [CMVN] applied (kept apart from the plain path above: merging them
+                // cost 4 % on the plain path through register allocation of the whole kernel)
+                constexpr int kQ = F / 4;                             // 20 float4 per row: q blocks of 8, 8, 4
+                const int rl = lane & 3, ql = lane >> 2;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int it = warp + 8 * i;                      // 24 steps = 8 row groups x 3 q blocks
+                    const int rg = it / 3, qb = it - 3 * rg;
+                    const int r = 4 * rg + rl, q = 8 * qb + ql;
+                    if (q < kQ && r < rows_here) {
+                        const bool real = r < nvalid;
+                        const float* const src = sTile + r * rowO + 4 * q;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (real) v = make_float4(src[0], src[1], src[2], src[3]);
+                        if (fused && real) {
+                            const uchar4 cm = *reinterpret_cast<const uchar4*>(sColMask + 4 * q);
+                            const bool rm = sRowMask[r] != 0;
+                            if (rm || cm.x) v.x = 0.f;
+                            if (rm || cm.y) v.y = 0.f;
+                            if (rm || cm.z) v.z = 0.f;
+                            if (rm || cm.w) v.w = 0.f;
+                        }
+                        if (has_cmvn && (real || P.cmvn_on_pad)) {
+                            const float* const m = P.cmvn_mean + 4 * q;
+                            v = make_float4(v.x - __ldg(m), v.y - __ldg(m + 1), v.z - __ldg(m + 2), v.w - __ldg(m + 3));
+                            if (P.cmvn_istd != nullptr) {
+                                const float* const sd = P.cmvn_istd + 4 * q;
+                                v = make_float4(v.x * __ldg(sd), v.y * __ldg(sd + 1), v.z * __ldg(sd + 2), v.w * __ldg(sd + 3));
+                            }
+                        }
+                        *reinterpret_cast<float4*>(dst0 + (int64_t)r * pitch + 4 * q) = v;
                     }
                 }
             } else {

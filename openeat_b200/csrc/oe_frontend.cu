@@ -384,6 +384,56 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
     }
 }
 
+// Padding rows of the single-pass layout: the fbank kernel writes whole 32-frame tiles (real frames plus the padding
+// rows that share the last tile); rows [32 ceil(frames / 32), out_nrows) of every utterance are filled here with
+// 0 or (0 - mean) * istd (dataset.py:214-218 pad_sequence, then GlobalCMVN on the padded tensor).  Reads only the
+// launch metadata, so under a programmatic dependent launch it runs in the shadow of the fbank kernel's tail.
+struct PadFillParams {
+    const int32_t* n_frames;
+    const int32_t* n_rows;
+    const int64_t* out_row;
+    float* out;
+    int64_t pitch;
+    const float* cmvn_mean;      // null: zeros
+    const float* cmvn_istd;
+    int F;
+};
+constexpr int kPadRows = 128;        // rows per block
+__global__ void __launch_bounds__(256) oe_pad_fill_kernel(const PadFillParams P) {
+    const int b = blockIdx.x;
+    const int first = (P.n_frames[b] + kTileFrames - 1) / kTileFrames * kTileFrames + blockIdx.y * kPadRows;
+    const int last = min(P.n_rows[b], first + kPadRows);
+    if (first >= last) return;
+    float* const dst = P.out + (P.out_row[b] + first) * P.pitch;
+    const int F = P.F;
+    if (P.pitch == F && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) {      // dense rows: one flat float4 run
+        const int q = F / 4, n4 = (last - first) * q;
+        for (int i = threadIdx.x; i < n4; i += 256) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.cmvn_mean != nullptr) {
+                const int c = (i % q) * 4;
+                const float* const m = P.cmvn_mean + c;            // caller buffers: no alignment assumed
+                v = make_float4(0.f - m[0], 0.f - m[1], 0.f - m[2], 0.f - m[3]);
+                if (P.cmvn_istd != nullptr) {
+                    const float* const s = P.cmvn_istd + c;
+                    v = make_float4(v.x * s[0], v.y * s[1], v.z * s[2], v.w * s[3]);
+                }
+            }
+            reinterpret_cast<float4*>(dst)[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < (last - first) * F; i += 256) {
+            const int r = i / F, f = i - r * F;
+            float v = 0.f;
+            if (P.cmvn_mean != nullptr) {
+                v = 0.f - P.cmvn_mean[f];
+                if (P.cmvn_istd != nullptr) v = v * P.cmvn_istd[f];
+            }
+            dst[(int64_t)r * P.pitch + f] = v;
+        }
+    }
+}
+
 // openeat/modules/cmvn.py:43-46
 __global__ void __launch_bounds__(256) oe_cmvn_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                       int64_t n, int dim, const float* __restrict__ mean,
@@ -611,6 +661,7 @@ struct Meta {               // device-side metadata block layout (byte offsets i
     size_t raw, tile_stats, utt_mean, utt_std, stat_partial, total;
     int max_rows;
     int64_t total_frames, total_rows, total_map;
+    int64_t pad_rows;           // output rows behind the last 32-frame tile of each utterance
     int total_tiles;
     bool two_phase, need_stats, feats;
 };
@@ -633,6 +684,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
     M.total_frames = M.total_rows = M.total_map = 0;
+    M.pad_rows = 0;
     M.max_rows = 0;
     int64_t tiles = 0;
     if (frames_out) frames_out->resize(B);
@@ -656,8 +708,8 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
         M.total_frames += nfr;
         M.total_rows += nrows;
         M.max_rows = std::max(M.max_rows, nrows);
-        const int cover = M.two_phase ? nfr : nrows;
-        tiles += (cover + oe::kTileFrames - 1) / oe::kTileFrames;
+        tiles += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;      // padding rows behind the last tile: oe_pad_fill_kernel
+        M.pad_rows += std::max(0, nrows - (nfr + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
         if (bt->frame_map) M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
     }
     if (tiles > INT32_MAX) return fail(OE_ERR_INVALID, "batch too large");
@@ -893,7 +945,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         i32(M.rs_mode)[b] = (bt->resample_ids && bt->resample_ids[b] >= 0) ? (bt->resample_ids[b] == fe->rs_fast_9_10 ? 1 : 2) : 0;
         fp += nfr;
         rp += nrows;
-        tp += ((M.two_phase ? nfr : nrows) + oe::kTileFrames - 1) / oe::kTileFrames;
+        tp += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;
     }
     i64(M.frame_prefix)[B] = fp;
     i64(M.row_prefix)[B] = rp;
@@ -944,7 +996,8 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         P.cmvn_istd = bt->d_cmvn_istd;
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
-    P.out_vec = (P.pitch == F && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
+    // float4 row stores: gen-1 kernel needs dense rows (pitch == F), gen-2 any 16-byte aligned pitch
+    P.out_vec = (((fe->std_mel && !fe->force_v1) ? P.pitch % 4 == 0 : P.pitch == F) && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
     if (M.total_tiles > 0) {
         oe::TileDescParams T;
         T.tile_prefix = d_tile_prefix;
@@ -999,6 +1052,23 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             else OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, false, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
         }
         OE_CUDA(cudaGetLastError());
+    }
+    if (!M.two_phase && d_out && M.pad_rows > 0) {
+        int max_pad = 0;
+        for (int b = 0; b < B; ++b) {
+            const int nrows = bt->out_nrows ? bt->out_nrows[b] : frames[b];
+            max_pad = std::max(max_pad, nrows - (frames[b] + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
+        }
+        oe::PadFillParams Q;
+        Q.n_frames = d_n_frames;
+        Q.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
+        Q.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        Q.out = d_out;
+        Q.pitch = pitch;
+        Q.cmvn_mean = (bt->d_cmvn_mean && bt->cmvn_on_padding) ? bt->d_cmvn_mean : nullptr;
+        Q.cmvn_istd = bt->d_cmvn_istd;
+        Q.F = F;
+        OE_CUDA(launch_dep(oe::oe_pad_fill_kernel, dim3(B, (max_pad + oe::kPadRows - 1) / oe::kPadRows), dim3(256), 0, stream, Q));
     }
     {
         const bool want_utt = bt->norm_mode != OE_NORM_NONE;
