@@ -132,6 +132,10 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* batch, const void* d_wav, fl
                    void* d_workspace, size_t workspace_bytes, oe_stream stream);
 
 /* GlobalCMVN.forward (openeat/modules/cmvn.py:43-46): y = (x - mean) [* istd], rows x dim fp32. */
+/* Number of kernels this handle has launched so far (oe_fbank_batch and oe_resample; every launch site of the
+ * library counts itself).  bench.py reports the difference over its timed region as `gpu_launches`. */
+int64_t oe_frontend_launch_count(const oe_frontend* fe);
+
 int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
                   const float* d_istd, oe_stream stream);
 

@@ -61,6 +61,7 @@ SYMBOLS = {
     'oe_frontend_create': (ctypes.c_int, [ctypes.POINTER(OeConfig), c_f32p, c_f32p, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_void_p)]),
     'oe_frontend_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'oe_frontend_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
     'oe_frontend_get_tables': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p]),
     'oe_num_frames': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int64]),
     'oe_fbank_workspace_bytes': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeBatch),

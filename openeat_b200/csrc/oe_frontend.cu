@@ -575,6 +575,7 @@ struct oe_frontend {
     size_t fbank_smem;
     bool std_mel;                  // the mel matrix has the baked mel80 structure -> fast kernel
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
+    long long launches;            // kernels launched through this handle
     float mel_w_std[512];
 };
 
@@ -782,6 +783,7 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->cfg = *cfg;
     fe->device = device;
     fe->d_tab = nullptr;
+    fe->launches = 0;
     fe->d_rs = nullptr;
     fe->d_rs_coefs = nullptr;
     fe->rs_fast_9_10 = fe->rs_fast_11_10 = -1;
@@ -890,6 +892,8 @@ int oe_frontend_destroy(oe_frontend* fe) {
     delete fe;
     return OE_OK;
 }
+
+int64_t oe_frontend_launch_count(const oe_frontend* fe) { return fe ? fe->launches : 0; }
 
 int oe_frontend_get_tables(const oe_frontend* fe, float* window, float* mel) {
     if (!fe) return fail(OE_ERR_INVALID, "null frontend");
@@ -1012,6 +1016,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         T.total_tiles = M.total_tiles;
         T.feats = M.feats ? 1 : 0;
         oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
+        ++fe->launches;
         OE_CUDA(cudaGetLastError());
     }
     static const int skip = [] { const char* e = getenv("OE_DEV_SKIP"); return e ? atoi(e) : 0; }();   // developer timing only: 2 fbank, 4 stats, 8 finalize
@@ -1026,6 +1031,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             S.F = F;
             S.total_tiles = M.total_tiles;
             n_stat_partials = 3 * std::min(M.total_tiles, fe->sm_count * 8);
+            ++fe->launches;
             OE_CUDA(launch_dep(oe::oe_feat_tile_stats_kernel, dim3(std::min(M.total_tiles, fe->sm_count * 8)), dim3(oe::kMaxMel), 0, stream, S));
             OE_CUDA(cudaGetLastError());
         }
@@ -1038,6 +1044,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         }
         bool any_rs = false;
         for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
+        ++fe->launches;
         if (fe->std_mel && !fe->force_v1) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else if (any_rs) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, true>::End, stream, P));
@@ -1068,6 +1075,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         Q.cmvn_mean = (bt->d_cmvn_mean && bt->cmvn_on_padding) ? bt->d_cmvn_mean : nullptr;
         Q.cmvn_istd = bt->d_cmvn_istd;
         Q.F = F;
+        ++fe->launches;
         OE_CUDA(launch_dep(oe::oe_pad_fill_kernel, dim3(B, (max_pad + oe::kPadRows - 1) / oe::kPadRows), dim3(256), 0, stream, Q));
     }
     {
@@ -1091,6 +1099,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
                 U.n_partials = n_stat_partials;
                 glob_blocks = (2 * F + 1 + oe::kGlobStats - 1) / oe::kGlobStats;
             }
+            ++fe->launches;
             if (F <= 80) OE_CUDA(launch_dep(oe::oe_utt_stats_kernel<640, 2>, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));
             else OE_CUDA(launch_dep(oe::oe_utt_stats_kernel<oe::kMaxMel * oe::kUttSlices, 1>, dim3(U.B + glob_blocks), dim3(F, oe::kUttSlices), 0, stream, U));
             OE_CUDA(cudaGetLastError());
@@ -1125,6 +1134,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         const bool vec = (F % 4 == 0) && (pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(Z.raw) & 15) &&
                          !(reinterpret_cast<uintptr_t>(d_out) & 15);
         dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + oe::kFinRows - 1) / oe::kFinRows));
+        ++fe->launches;
         if (vec) OE_CUDA(launch_dep(oe::oe_finalize_kernel<4>, zgrid, dim3(256), 0, stream, Z));
         else OE_CUDA(launch_dep(oe::oe_finalize_kernel<1>, zgrid, dim3(256), 0, stream, Z));
         OE_CUDA(cudaGetLastError());
@@ -1264,6 +1274,7 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
         else need_generic = true;
     }
     if (need_generic) {
+        ++fe->launches;
         dim3 grid((unsigned)std::min((max_out + 1023) / 1024, 1024), (unsigned)B);
         if (f32) oe::oe_resample_kernel<true><<<grid, 256, 0, stream>>>(P, fe->rs_fast_9_10, fe->rs_fast_11_10);
         else oe::oe_resample_kernel<false><<<grid, 256, 0, stream>>>(P, fe->rs_fast_9_10, fe->rs_fast_11_10);
@@ -1271,6 +1282,7 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
     for (int which = 0; which < 2; ++which) {
         if (!(which == 0 ? need_9 : need_11)) continue;
         const int id = which == 0 ? fe->rs_fast_9_10 : fe->rs_fast_11_10;
+        ++fe->launches;
         oe::RsFastParams Q;
         Q.r = P;
         Q.table_id = id;

@@ -123,7 +123,7 @@ class Frontend(object):
         self.torch_tables = torch_tables
         self._resamplers = {}
         self._ws = {}
-        self.launches = 0     # kernels launched through this handle (bench.py reports it as gpu_launches)
+        self._extra_launches = 0     # oe_cmvn_apply takes no handle: counted here
 
     def __del__(self):
         h = getattr(self, 'handle', None)
@@ -209,7 +209,6 @@ class Frontend(object):
         check(self.lib.oe_resample_workspace_bytes(self.handle, ctypes.byref(rb), ctypes.byref(need)))
         s, sp = self._stream(stream)
         ws = self._workspace(('rs', s.cuda_stream), need.value)
-        self.launches += 1 if B and int(olens.max()) > 0 else 0
         check(self.lib.oe_resample(self.handle, ctypes.byref(rb), ctypes.c_void_p(wav.data_ptr()),
                                    ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
                                    ws.numel(), sp))
@@ -290,8 +289,6 @@ class Frontend(object):
                 nrows = np.ascontiguousarray(out_nrows, dtype=np.int32)
         else:
             raise ValueError(layout)
-        self.launches += self._count_launches(B, int(frames.sum()) if B else 0, features_in, normalization,
-                                              frame_maps is not None, stats is not None, out is not None)
         tm = fm = None
         n_t = n_f = 0
         if tmask is not None and np.size(tmask):
@@ -331,21 +328,11 @@ class Frontend(object):
                                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
         return out, out_frames
 
-    @staticmethod
-    def _count_launches(B, total_frames, features_in, norm, has_map, has_stats, has_out):
-        """Mirror of the launch sequence in oe_fbank_batch (csrc/oe_frontend.cu)."""
-        if B == 0 or total_frames == 0:
-            return 0
-        two_phase = features_in or norm or has_map
-        n = 1                                             # oe_tile_desc_kernel
-        if features_in:
-            n += 1 if (norm or has_stats) else 0          # oe_feat_tile_stats_kernel
-        else:
-            n += 1                                        # oe_fbank_kernel
-        n += 1 if norm else 0                             # oe_utt_stats_kernel
-        n += 1 if has_stats else 0                        # oe_global_stats_final_kernel
-        n += 1 if (two_phase and has_out) else 0          # oe_finalize_kernel
-        return n
+    @property
+    def launches(self):
+        """Kernels launched through this handle, counted by the library at every launch site
+        (bench.py reports the difference over its timed region as gpu_launches)."""
+        return int(self.lib.oe_frontend_launch_count(self.handle)) + self._extra_launches
 
     def cmvn_apply(self, x, mean, istd=None, out=None, stream=None):
         """GlobalCMVN.forward on a contiguous fp32 device tensor (..., F)."""
@@ -353,7 +340,7 @@ class Frontend(object):
         if out is None:
             out = torch.empty_like(x)
         _, sp = self._stream(stream)
-        self.launches += 1 if x.numel() else 0
+        self._extra_launches += 1 if x.numel() else 0
         check(self.lib.oe_cmvn_apply(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                      x.numel() // x.shape[-1], x.shape[-1], ctypes.c_void_p(mean.data_ptr()),
                                      ctypes.c_void_p(istd.data_ptr()) if istd is not None else None, sp))
