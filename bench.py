@@ -362,8 +362,11 @@ def run_ours(args, rank, world, local_rank):
 def main():
     # stdout carries exactly ONE JSON line: anything the mirrored reference code prints (e.g. dataset.py:183's
     # 'normalize feature ...') goes to stderr
+    # (and so does anything native code writes to fd 1, e.g. NCCL's version banner under NCCL_DEBUG=VERSION)
     global JSON_OUT
-    JSON_OUT = sys.stdout
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)

@@ -224,7 +224,7 @@ OE_HD void fft_dif(T (&re)[N], T (&im)[N]) {
 // at position j + 4m, times W16^(j m); pass 2 is a 4-point DFT over positions 4m .. 4m+3.  Afterwards
 // position p holds X[r4pos(p)] (base-4 digit reversal, an involution).  The W16^4 = -i twiddle is folded
 // into the adds of pass 2, so the transform has no negations: 128 add/sub + 32 twiddle operations
-// (16 fewer add/sub with PRUNE13: inputs 13..15 are zero and never read).
+// (12 fewer add/sub with PRUNE13: inputs 13..15 are zero and never read).
 OE_CX int r4pos(int k) { return 4 * (k & 3) + (k >> 2); }
 
 // 4-point forward DFT in place: a <- out0, b <- out1, c <- out2, d <- out3.
