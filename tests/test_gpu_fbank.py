@@ -277,3 +277,68 @@ def test_errors_are_reported_not_fatal(fe):
     from openeat_b200.frontend import Frontend
     with pytest.raises(FrontendError):
         Frontend(mel_bins=80, sample_rate=8000)                         # unsupported framing says so
+
+
+def test_generation_1_and_2_kernels_agree(tables, monkeypatch):
+    """The second-generation fbank kernel (radix-4 stages, pair untangle, per-group power slices) against the
+    first-generation one (OE_FBANK_V1=1 at handle creation) and the oracle, int16 and fp32 input, with a fused
+    speed perturb in the batch: both within 1e-3 of the oracle, and within 3e-4 of each other."""
+    from openeat_b200.frontend import Frontend
+    fe2 = Frontend(mel_bins=80, sample_rate=16000)
+    monkeypatch.setenv('OE_FBANK_V1', '1')
+    fe1 = Frontend(mel_bins=80, sample_rate=16000)
+    monkeypatch.delenv('OE_FBANK_V1')
+    lens = [400, 559, 5200, 16000, 33333, 80000]
+    waves = [signals.make(('white', 'speech', 'lsb')[i % 3], n, 40 + i) for i, n in enumerate(lens)]
+    for dtype in (np.int16, np.float32):
+        y1, f1 = run_raw(fe1, waves, dtype=dtype, layout='padded')
+        y2, f2 = run_raw(fe2, waves, dtype=dtype, layout='padded')
+        assert f1.tolist() == f2.tolist()
+        assert np.abs(y1 - y2).max() <= 3e-4
+        for i, w in enumerate(waves):
+            ref = F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1])
+            assert np.abs(y2[i, :f2[i]] - ref).max() <= 1e-3 and np.abs(y1[i, :f1[i]] - ref).max() <= 1e-3
+    ratios = np.array([[0, 0], [9, 10], [11, 10], [0, 0], [9, 10], [11, 10]], np.int32)
+    y1, f1 = run_raw(fe1, waves, layout='padded', speed_ratios=ratios)
+    y2, f2 = run_raw(fe2, waves, layout='padded', speed_ratios=ratios)
+    # speed 0.9 leaves the top mel bins with filter leakage only (ill-conditioned): the two roundings may differ more there
+    assert f1.tolist() == f2.tolist() and np.abs(y1 - y2).max() <= 1e-3
+
+
+def test_single_pass_padding_rows_and_launch_count(fe, tables):
+    """Padded single-pass layout: the fbank kernel writes whole 32-frame tiles, oe_pad_fill_kernel the rows behind
+    them.  Frame counts around the tile size (0 = dropped utterance, 1, 31, 32, 33, 64, 65) and a tensor much
+    longer than every utterance; the library's own launch counter sees descriptor + fbank + fill."""
+    frames = [0, 1, 31, 32, 33, 64, 65]
+    lens = [300] + [400 + 160 * (m - 1) for m in frames[1:]]
+    waves = [signals.make('white', n, 70 + i) for i, n in enumerate(lens)]
+    rng = np.random.default_rng(3)
+    mean, istd = rng.normal(10, 1, 80).astype(np.float32), rng.uniform(0.3, 0.7, 80).astype(np.float32)
+    mean_d, istd_d = torch.from_numpy(mean).cuda(), torch.from_numpy(istd).cuda()
+    from openeat_b200.frontend import pack_waveforms
+    buf, offs, ln = pack_waveforms(waves)
+    dev = buf.cuda()
+    tmax = 200
+    out = torch.full((len(waves), tmax, 80), float('nan'), device='cuda')
+    rows = np.arange(len(waves), dtype=np.int64) * tmax
+    nrows = np.full(len(waves), tmax, np.int32)
+    for on_pad in (False, True):
+        out.fill_(float('nan'))
+        n0 = fe.launches
+        _, got_frames = fe.fbank(dev, offs, ln, layout='custom', out=out.view(-1, 80), out_rows=rows, out_nrows=nrows,
+                                 cmvn=(mean_d, istd_d), cmvn_on_padding=on_pad)
+        assert fe.launches - n0 == 3
+        torch.cuda.synchronize()
+        y = out.cpu().numpy()
+        assert got_frames.tolist() == frames and np.isfinite(y).all()
+        pad_val = C.global_cmvn(np.zeros(80), mean, istd) if on_pad else np.zeros(80, np.float32)
+        for i, w in enumerate(waves):
+            if frames[i]:
+                ref = C.global_cmvn(F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1]), mean, istd)
+                assert np.abs(y[i, :frames[i]] - ref).max() <= 1e-3 * float(istd.max())
+            assert np.array_equal(y[i, frames[i]:], np.broadcast_to(pad_val, (tmax - frames[i], 80)))
+    # two-phase chain of the benchmark configuration: descriptors, fbank, statistics (per-utterance + global), finalize
+    stats = torch.zeros(161, dtype=torch.float64, device='cuda')
+    n0 = fe.launches
+    fe.fbank(dev, offs, ln, layout='padded', normalization=True, stats=stats)
+    assert fe.launches - n0 == 4
