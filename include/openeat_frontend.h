@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OE_ABI_VERSION 1
+#define OE_ABI_VERSION 2    /* 2: oe_batch gained feature_dither / dither_seed (appended) */
 
 enum { OE_OK = 0, OE_ERR_INVALID = 1, OE_ERR_UNSUPPORTED = 2, OE_ERR_CUDA = 3, OE_ERR_WORKSPACE = 4 };
 /* OE_WAV_I16: PCM int16.  OE_WAV_F32: fp32 on the int16 scale (dataset.py:75).
@@ -90,6 +90,12 @@ typedef struct {
                                     table id from oe_add_resampler (9:10 or 11:10, i.e. speed 0.9 / 1.1) or -1.
                                     The utterance is resampled while it is staged: no intermediate waveform;
                                     wav_lens stay INPUT lengths, frames follow ceil(new*N/orig).  int16 input only */
+    float feature_dither;        /* a of dataset.py:199-201: x + (U[0,1) - 0.5) * a on the (normalised) features, before
+                                    spec_sub / spec_aug; 0 = off.  The caller draws a = random.uniform(0, feature_dither)
+                                    on the host (same `random` call as the reference); the per-cell uniforms come from
+                                    Philox-4x32-10 keyed by dither_seed instead of numpy's global generator, so there is
+                                    no value parity for this option */
+    uint64_t dither_seed;        /* Philox key; vary it per batch */
 } oe_batch;
 
 /* One ragged resampling batch (speed perturb).  Replaces _speed_perturb

@@ -303,7 +303,22 @@ struct FinalizeParams {
     const float* cmvn_istd;
     int cmvn_on_pad;
     int F;
+    float dither_a;              // feature dither amplitude (dataset.py:199-201), 0 = off
+    unsigned long long dither_seed;
 };
+
+// Philox-4x32-10 (Salmon et al., SC'11): counter-based generator, four 32-bit words per (counter, key).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
 
 // dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
 // grid = (utterances, row chunks).  VEC = 4: thread = (float4 column chunk, row lane); the per-column
@@ -312,7 +327,9 @@ struct FinalizeParams {
 // variant (64 registers) measured 9 us slower in the warm pipeline (tools/ab_step.py) although ncu's cold-cache
 // replay showed it faster.
 constexpr int kFinRows = 128;       // rows per block
-template <int VEC>
+// DITHER is a template flag: the Philox code would otherwise raise the register count (40 -> 63) and cost the
+// plain path a third of its occupancy.
+template <int VEC, bool DITHER>
 __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P) {
     grid_dep_wait();
     const int b = blockIdx.x;
@@ -364,9 +381,19 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
             } else {
                 v[0] = src[0];
             }
+            float du[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) du[e] = 0.f;
+            if (DITHER) {                  // keyed by the SOURCE frame: substituted rows carry their noise along
+                const uint4 r = philox4x32_10(make_uint4((unsigned)(c / VEC), (unsigned)ts, (unsigned)b, 0u),
+                                              make_uint2((unsigned)P.dither_seed, (unsigned)(P.dither_seed >> 32)));
+                const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) du[e] = ((float)(w[e] >> 8) * (1.0f / 16777216.0f) - 0.5f) * P.dither_a;
+            }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                float y = norm ? (v[e] - mean[e]) * rstd[e] : v[e];
+                float y = (norm ? (v[e] - mean[e]) * rstd[e] : v[e]) + du[e];
                 if (rmask || cmask[e]) y = 0.f;
                 v[e] = y;
             }
@@ -681,7 +708,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     const int B = bt->batch, F = fe->cfg.num_mel_bins;
     const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
     if (pitch < F) return fail(OE_ERR_INVALID, "out_pitch smaller than num_mel_bins");
-    M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr;
+    M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr || bt->feature_dither != 0.f;
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
     M.total_frames = M.total_rows = M.total_map = 0;
@@ -1130,13 +1157,18 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         Z.cmvn_mean = bt->d_cmvn_mean;
         Z.cmvn_istd = bt->d_cmvn_istd;
         Z.cmvn_on_pad = bt->cmvn_on_padding;
+        Z.dither_a = bt->feature_dither;
+        Z.dither_seed = bt->dither_seed;
         Z.F = F;
         const bool vec = (F % 4 == 0) && (pitch % 4 == 0) && !(reinterpret_cast<uintptr_t>(Z.raw) & 15) &&
                          !(reinterpret_cast<uintptr_t>(d_out) & 15);
         dim3 zgrid((unsigned)B, (unsigned)((M.max_rows + oe::kFinRows - 1) / oe::kFinRows));
         ++fe->launches;
-        if (vec) OE_CUDA(launch_dep(oe::oe_finalize_kernel<4>, zgrid, dim3(256), 0, stream, Z));
-        else OE_CUDA(launch_dep(oe::oe_finalize_kernel<1>, zgrid, dim3(256), 0, stream, Z));
+        const bool dith = Z.dither_a != 0.f;
+        if (vec) OE_CUDA(dith ? launch_dep(oe::oe_finalize_kernel<4, true>, zgrid, dim3(256), 0, stream, Z)
+                              : launch_dep(oe::oe_finalize_kernel<4, false>, zgrid, dim3(256), 0, stream, Z));
+        else OE_CUDA(dith ? launch_dep(oe::oe_finalize_kernel<1, true>, zgrid, dim3(256), 0, stream, Z)
+                          : launch_dep(oe::oe_finalize_kernel<1, false>, zgrid, dim3(256), 0, stream, Z));
         OE_CUDA(cudaGetLastError());
     }
     return OE_OK;

@@ -8,18 +8,22 @@ Differences a caller can observe (all deliberate):
     tensors); ``features`` are the same zero-padded (B, Tmax, F) fp32 tensor either way;
   * wav decoding is built in for 16-bit PCM WAV (stdlib ``wave``; the reference needs libsox);
     an item's second field may also be an in-memory int16 / fp32 array or ``(array, sample_rate)``;
+  * ``data_type != 'wav'`` reads binary Kaldi archives with the built-in ``openeat_b200.kaldi_io.read_mat``
+    (the reference imports the third-party ``kaldi_io``); ``feature_dither`` draws its amplitude with the
+    reference's ``random.uniform`` call and the per-cell uniforms with Philox on the GPU (no value parity);
   * speed perturb uses the torchaudio sinc resampler semantics (libsox is not reproducible here);
   * optional extras the reference applies later on the device can be fused in:
     ``global_cmvn=(mean, istd)`` (GlobalCMVN, encoder.py:221-222) and ``cmvn_stats`` accumulation.
 """
 import logging
+import os
 import random
 import wave
 
 import numpy as np
 import torch
 
-from . import planner
+from . import kaldi_io, planner
 from .frontend import default_frontend, pack_waveforms, speed_ratio
 
 IGNORE_ID = -1  # openeat/utils/common.py:24
@@ -226,6 +230,30 @@ def _extract_feature(batch, feature_extraction_conf):
     return plan.keys, feats, plan.labels
 
 
+def _load_feature(batch):
+    """Load acoustic features from Kaldi archives -- openeat/dataset/dataset.py:120-152.
+    ``batch``: list of (key, 'file.ark:offset', tokenids, ...).  Returns (keys, feats, labels) sorted by
+    length descending.  Two reference behaviours are kept on purpose: an utterance that fails to load is
+    logged and dropped *after* its key was appended (dataset.py:136-146), and the label is appended twice
+    per utterance (dataset.py:141,143), so ``sorted_labels[j] = labels[order[j]]`` indexes a doubled list."""
+    keys, feats, lengths, labels = [], [], [], []
+    for x in batch:
+        try:
+            keys.append(x[0])
+            mat = kaldi_io.read_mat(x[1])
+            feats.append(mat)
+            lengths.append(mat.shape[0])
+            labels.append(np.array(x[2]))
+            labels.append(np.array(x[2]))
+        except Exception:
+            logging.warning('read utterance {} error'.format(x[0]))
+    order = np.argsort(lengths)[::-1]
+    sorted_keys = [keys[i] for i in order]
+    sorted_feats = [feats[i] for i in order]
+    sorted_labels = [labels[i] for i in order]
+    return sorted_keys, sorted_feats, sorted_labels
+
+
 class audio_collate_func(object):
     """Collate function for AudioDataset -- openeat/dataset/dataset.py:155-239, ``data_type='wav'``.
 
@@ -250,16 +278,18 @@ class audio_collate_func(object):
         self.global_cmvn = global_cmvn
         self.cmvn_stats = cmvn_stats
         print('normalize feature', self.normalization)              # dataset.py:183
-        if data_type != 'wav':
-            raise NotImplementedError("openeat_b200.audio_collate_func accelerates data_type='wav'; Kaldi-ark "
-                                      "features (dataset.py:120-152) are a 'next' row (SURVEY 8f.4)")
-        if feature_dither != 0.0:
-            raise NotImplementedError('feature_dither is stochastic (np.random per cell) and is not built; '
-                                      'every shipped recipe sets 0.0')
+        # feature_dither (dataset.py:199-201): `a` is drawn with the reference's random.uniform call; the per-cell
+        # uniforms come from Philox on the GPU (keyed by a per-object seed and a batch counter), not from numpy's
+        # global generator, which is left untouched -- the option is stochastic, there is no value parity
+        self._dither_seed = int.from_bytes(os.urandom(8), 'little')
+        self._dither_batches = 0
 
     def __call__(self, batch):
         if len(batch) == 1:                                          # dataset.py:186-187
             batch = batch[0]
+        if self.data_type != 'wav':                                  # dataset.py:190-191
+            keys, xs, ys = _load_feature(batch)
+            return self.collate_features(keys, xs, ys)
         waves, rates, loaded = _load_batch(batch)
         buf, offs, lens = _pack_loaded(waves)
         return self.collate_packed(buf, offs, lens, [x[0] for x in batch], [x[2] for x in batch],
@@ -280,6 +310,7 @@ class audio_collate_func(object):
         F = conf['mel_bins']
         frames = plan.frames
         fused = {'normalization': bool(self.normalization)}
+        self._dither_a = random.uniform(0, self.feature_dither) if self.feature_dither != 0.0 else 0.0   # dataset.py:200
         # dataset.py:204-209: every spec_sub draw, then every spec_aug draw, in length-sorted order
         fmap, tmask, fmask = planner.plan_augment(frames, F, self.spec_sub_conf if self.spec_sub else None,
                                                   self.spec_aug_conf if self.spec_aug else None)
@@ -295,12 +326,48 @@ class audio_collate_func(object):
             fused['cmvn_on_padding'] = True
         if self.cmvn_stats is not None:
             fused['stats'] = self.cmvn_stats
+        fused.update(self._draw_dither())
         features = None
         if len(plan.src):
             features, _ = _run_plan(plan, F, wav, offsets, lens, **fused)
+        return self._finish(plan.keys, features, frames, plan.labels)
+
+    def _draw_dither(self):
+        """dataset.py:199-201: one random.uniform per batch, placed between the speed draws (made while planning)
+        and the spec_sub / spec_aug draws -- callers invoke this BEFORE planner.plan_augment."""
+        if self.feature_dither == 0.0:
+            return {}
+        self._dither_batches += 1
+        return {'feature_dither': self._dither_a, 'dither_seed': self._dither_seed + self._dither_batches}
+
+    def collate_features(self, keys, xs, ys):
+        """The post-fbank chain for features that already exist (``data_type != 'wav'``, dataset.py:190-238):
+        ``xs`` is a list of (T_i, F) float arrays sorted by length as ``_load_feature`` returns them."""
+        F = int(xs[0].shape[1]) if len(xs) else (self.feature_extraction_conf or {}).get('mel_bins', 80)
+        frames = np.array([x.shape[0] for x in xs], dtype=np.int32)
+        self._dither_a = random.uniform(0, self.feature_dither) if self.feature_dither != 0.0 else 0.0
+        fmap, tmask, fmask = planner.plan_augment(frames, F, self.spec_sub_conf if self.spec_sub else None,
+                                                  self.spec_aug_conf if self.spec_aug else None)
+        features = None
+        if len(xs):
+            fe = default_frontend(F)
+            offs = np.concatenate([[0], np.cumsum(frames[:-1].astype(np.int64))]).astype(np.int64)
+            host = torch.from_numpy(np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float32) for x in xs])))
+            kw = dict(normalization=bool(self.normalization), tmask=tmask, fmask=fmask, features_in=True)
+            if fmap is not None:
+                kw['frame_maps'] = [fmap[offs[i]:offs[i] + frames[i]] for i in range(len(xs))]
+            if self.global_cmvn is not None:
+                kw['cmvn'] = self.global_cmvn
+                kw['cmvn_on_padding'] = True
+            if self.cmvn_stats is not None:
+                kw['stats'] = self.cmvn_stats
+            kw.update(self._draw_dither())
+            features, _ = fe.fbank(host.pin_memory().to(fe.device, non_blocking=True), offs, frames, layout='padded', **kw)
+        return self._finish(keys, features, frames, ys)
+
+    def _finish(self, keys, features, frames, ys):
         dev = torch.device(self.output_device)
         features_length = torch.from_numpy(np.array(frames, dtype=np.int32))
-        ys = plan.labels
         tlen = np.array([len(y) for y in ys], dtype=np.int32)
         if features is None:                                         # dataset.py:219-220
             features = torch.Tensor([])
@@ -314,7 +381,7 @@ class audio_collate_func(object):
         targets_length = torch.from_numpy(tlen)
         inputs = {'features': features.to(dev), 'features_length': features_length.to(dev),
                   'targets': targets.to(dev), 'targets_length': targets_length.to(dev)}
-        return plan.keys, inputs
+        return keys, inputs
 
 
 def _default_tokenizer(text):

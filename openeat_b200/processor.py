@@ -17,8 +17,11 @@ processor signatures.  Semantics follow OpenEAT's functions wherever both exist:
 Sample dicts use wenet's keys: ``key``, ``wav`` (1-D int16 / float array or (1, N) tensor on the int16 scale /
 [-1, 1) floats are NOT rescaled here), ``sample_rate``, ``label`` (token ids), ``feat`` ((T, F) CUDA tensor).
 """
+import io
 import json
 import random
+import tarfile
+import wave
 
 import numpy as np
 import torch
@@ -55,6 +58,44 @@ def parse_raw(lines):
         except Exception as e:
             print(e)
             print('read utterance {} error'.format(line[:60]))
+
+
+def tar_file_and_group(shards):
+    """wenet shard lists: every line of ``data.list`` (``data_type='shard'``) names one tar file whose members are
+    ``<key>.wav`` (16-bit PCM) and ``<key>.txt``, stored next to each other.  Yields the same sample dicts as
+    ``parse_raw``.  A member that cannot be decoded is skipped with a message (dataset.py:108-111 convention)."""
+    for shard in shards:
+        shard = shard.strip() if isinstance(shard, str) else shard
+        if not shard:
+            continue
+        with tarfile.open(shard, 'r:*') as tar:
+            cur, sample = None, {}
+            for member in tar:
+                if not member.isfile():
+                    continue
+                stem, _, ext = member.name.rpartition('.')
+                if cur is not None and stem != cur:
+                    if 'wav' in sample:
+                        yield dict(sample, key=cur, txt=sample.get('txt', ''))
+                    sample = {}
+                cur = stem
+                try:
+                    blob = tar.extractfile(member).read()
+                    if ext == 'txt':
+                        sample['txt'] = blob.decode('utf8').strip()
+                    elif ext == 'wav':
+                        with wave.open(io.BytesIO(blob)) as w:
+                            if w.getsampwidth() != 2:
+                                raise ValueError('only 16-bit PCM WAV members are supported')
+                            pcm = np.frombuffer(w.readframes(w.getnframes()), dtype='<i2')
+                            sample['wav'] = pcm.reshape(-1, w.getnchannels())[:, 0].copy()
+                            sample['sample_rate'] = w.getframerate()
+                except Exception as e:
+                    print(e)
+                    print('read utterance {} error'.format(member.name))
+                    sample.pop('wav', None)
+            if cur is not None and 'wav' in sample:
+                yield dict(sample, key=cur, txt=sample.get('txt', ''))
 
 
 def speed_perturb(data, speeds=None):

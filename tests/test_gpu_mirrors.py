@@ -286,3 +286,90 @@ def test_wenet_style_processor_chain(gold, tmp_path, tables):
         assert out[k].shape[0] == t
         assert np.abs(feats[i, :t] - out[k]).max() < 3e-3
         assert np.all(feats[i, t:] == 0)
+
+
+def test_kaldi_feature_path_matches_reference_chain(tmp_path, tables):
+    """data_type='kaldi' (dataset.py:120-152, 190-238): features read from a binary Kaldi archive, then
+    _normalization -> _spec_augmentation -> padding, against the reference's own functions (oracle mirrors of
+    feature_processor.py) on the same archive with the same `random` seed.  Includes the reference's doubled
+    label list (dataset.py:141,143)."""
+    import random
+    from openeat_b200 import kaldi_io
+    from openeat_b200.dataset import audio_collate_func, _load_feature
+    from oracle import augment as A
+    rng = np.random.default_rng(5)
+    T = [57, 120, 33, 240, 5]
+    mats = {'k%d' % i: rng.normal(3.0, 2.0, (t, 80)).astype(np.float32) for i, t in enumerate(T)}
+    scp = kaldi_io.write_mat_ark(str(tmp_path / 'f.ark'), mats.items())
+    batch = [(k, scp[k], [i + 1, i + 2], 1.0) for i, k in enumerate(mats)]
+    aug = dict(num_t_mask=2, num_f_mask=2, max_t=20, max_f=8)
+    coll = audio_collate_func(data_type='kaldi', spec_aug=True, spec_aug_conf=aug, normalization=True)
+    random.seed(11)
+    keys, out = coll(batch)
+    # the reference chain on the CPU
+    random.seed(11)
+    rkeys, xs, ys = _load_feature(batch)
+    assert keys == rkeys == [k for k, _ in sorted(mats.items(), key=lambda kv: -kv[1].shape[0])]
+    ref = [A.normalization(x) for x in xs]
+    ref = [A.spec_augmentation(x, **aug) for x in ref]
+    feats = out['features'].cpu().numpy()
+    assert out['features_length'].tolist() == [x.shape[0] for x in xs]
+    for i, r in enumerate(ref):
+        got = feats[i, :r.shape[0]]
+        assert np.array_equal(got == 0, r == 0)
+        assert np.abs(got - r).max() <= 2e-5
+        assert np.all(feats[i, r.shape[0]:] == 0)
+    # doubled labels: sorted_labels[j] = labels[order[j]] over [l0, l0, l1, l1, ...]
+    order = np.argsort([m.shape[0] for m in mats.values()])[::-1]
+    doubled = [lab for i in range(len(T)) for lab in ([i + 1, i + 2], [i + 1, i + 2])]
+    assert out['targets'].cpu().numpy()[:, :2].tolist() == [doubled[j] for j in order]
+
+
+def test_feature_dither_statistics_and_masks():
+    """feature_dither (dataset.py:199-201): x + (U[0,1) - 0.5) * a with a = random.uniform(0, fd) drawn like the
+    reference; stochastic, so only the distribution is checked: bounded by a/2, mean 0, variance a^2/12; masked
+    cells stay exactly 0; the `random` stream is consumed exactly as the reference does (speed gates, the dither
+    draw, then the mask draws); two batches get different noise."""
+    import random
+    from openeat_b200 import planner
+    from openeat_b200.dataset import audio_collate_func
+    from oracle import signals
+    lens = [48000, 32000, 16000]
+    frames = np.array([298, 198, 98], np.int32)
+    items = [('u%d' % i, signals.make('speech', n, 20 + i), [1], 1.0) for i, n in enumerate(lens)]
+    conf = {'mel_bins': 80, 'speed_perturb_rate': 0, 'speeds': [1.0], 'wav_dither': 0.0}
+    aug = dict(num_t_mask=1, num_f_mask=1, max_t=10, max_f=5)
+    kw = dict(data_type='wav', feature_extraction_conf=conf, normalization=True, spec_aug=True, spec_aug_conf=aug)
+    plain = audio_collate_func(**kw)
+    dith = audio_collate_func(feature_dither=0.5, **kw)
+    # what the reference does with `random` for this batch: 3 speed gates, the dither amplitude, then the masks
+    random.seed(3)
+    for _ in items:
+        random.random()
+    a = random.uniform(0, 0.5)
+    _, tm, fm = planner.plan_augment(frames, 80, None, aug)
+    expect_next = random.random()
+    random.seed(3)
+    _, o1 = dith(items)
+    assert random.random() == expect_next                      # same number of draws, same order
+    random.seed(3)
+    _, o2 = dith(items)
+    _, ob = plain(items)                                       # other masks (its stream has no dither draw)
+    y1, y2, yb = (o['features'].cpu().numpy() for o in (o1, o2, ob))
+    assert not np.array_equal(y1, y2)                          # a new Philox key per batch
+    noise = []
+    for i, t in enumerate(frames):
+        keep = np.ones((t, 80), bool)
+        for s_, e_ in tm[i]:
+            keep[s_:e_] = False
+        for s_, e_ in fm[i]:
+            keep[:, s_:e_] = False
+        assert np.all(y1[i, :t][~keep] == 0) and np.all(y2[i, :t][~keep] == 0)
+        both = keep & (yb[i, :t] != 0)
+        noise.append((y1[i, :t] - yb[i, :t])[both])
+        assert np.all(y1[i, t:] == 0)
+    noise = np.concatenate(noise)
+    assert noise.size > 20000
+    assert np.abs(noise).max() <= a / 2 + 1e-5
+    assert abs(noise.mean()) < 5 * a / np.sqrt(12 * noise.size) + 1e-6
+    assert abs(noise.var() - a * a / 12) < 0.05 * a * a / 12

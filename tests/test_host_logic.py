@@ -179,3 +179,57 @@ def test_audio_dataset_matches_reference_batches(golden_dir):
     assert any(',1.5,4.25' in item[1] for b in ds.data for item in b)        # segmented entries survive as path,start,end
     with pytest.raises(NotImplementedError):
         AudioDataset(path, char_dict, None, data_type='kaldi')
+
+
+def test_kaldi_io_roundtrip_and_rxspecifier(tmp_path):
+    """openeat_b200.kaldi_io: the binary matrix format kaldi_io.read_mat (dataset.py:138) reads -- archive written
+    here, read back by 'path:offset' (feats.scp form), by plain path (first entry) and as a generator; a double
+    matrix and a malformed header."""
+    import struct
+    from openeat_b200 import kaldi_io
+    rng = np.random.default_rng(0)
+    mats = {'utt%d' % i: rng.normal(size=(3 + 7 * i, 80)).astype(np.float32) for i in range(4)}
+    ark = str(tmp_path / 'feats.ark')
+    scp = kaldi_io.write_mat_ark(ark, mats.items())
+    for k, m in mats.items():
+        assert np.array_equal(kaldi_io.read_mat(scp[k]), m)
+    assert np.array_equal(kaldi_io.read_mat(ark), mats['utt0'])
+    assert [(k, v.shape) for k, v in kaldi_io.read_mat_ark(ark)] == [(k, m.shape) for k, m in mats.items()]
+    dm = str(tmp_path / 'd.ark')
+    with open(dm, 'wb') as fd:
+        fd.write(b'x \0BDM \4' + struct.pack('<i', 2) + b'\4' + struct.pack('<i', 3) + np.arange(6, dtype='<f8').tobytes())
+    assert np.array_equal(kaldi_io.read_mat(dm), np.arange(6.0).reshape(2, 3))
+    bad = str(tmp_path / 'bad.ark')
+    with open(bad, 'wb') as fd:
+        fd.write(b'x \0BCM ' + b'\0' * 32)
+    with pytest.raises(ValueError):
+        kaldi_io.read_mat(bad)
+
+
+def test_tar_shard_reader(tmp_path):
+    """processor.tar_file_and_group: wenet shard tars (<key>.wav + <key>.txt members) -> sample dicts; an entry whose
+    wav cannot be decoded is skipped, the rest of the shard survives."""
+    import io
+    import tarfile
+    import wave
+    from openeat_b200 import processor
+    rng = np.random.default_rng(1)
+    waves = {'a%d' % i: rng.integers(-3000, 3000, 1600 + 100 * i).astype(np.int16) for i in range(3)}
+    shard = str(tmp_path / 'shard_000.tar')
+    with tarfile.open(shard, 'w') as tar:
+        def add(name, blob):
+            ti = tarfile.TarInfo(name)
+            ti.size = len(blob)
+            tar.addfile(ti, io.BytesIO(blob))
+        for k, w in waves.items():
+            buf = io.BytesIO()
+            with wave.open(buf, 'wb') as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(w.tobytes())
+            add(k + '.txt', ('text of ' + k).encode())
+            add(k + '.wav', buf.getvalue())
+        add('broken.txt', b'x')
+        add('broken.wav', b'not a wav file')
+    got = list(processor.tar_file_and_group([shard]))
+    assert [s['key'] for s in got] == list(waves)
+    for s in got:
+        assert np.array_equal(s['wav'], waves[s['key']]) and s['sample_rate'] == 16000 and s['txt'] == 'text of ' + s['key']
