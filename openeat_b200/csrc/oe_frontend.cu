@@ -1046,7 +1046,6 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         ++fe->launches;
         OE_CUDA(cudaGetLastError());
     }
-    static const int skip = [] { const char* e = getenv("OE_DEV_SKIP"); return e ? atoi(e) : 0; }();   // developer timing only: 2 fbank, 4 stats, 8 finalize
     int n_stat_partials = 0;
     if (M.feats) {
         if ((M.need_stats || bt->d_stats) && M.total_tiles > 0) {
@@ -1062,7 +1061,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             OE_CUDA(launch_dep(oe::oe_feat_tile_stats_kernel, dim3(std::min(M.total_tiles, fe->sm_count * 8)), dim3(oe::kMaxMel), 0, stream, S));
             OE_CUDA(cudaGetLastError());
         }
-    } else if (M.total_tiles > 0 && !(skip & 2)) {
+    } else if (M.total_tiles > 0) {
         const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
         const bool f32 = bt->wav_dtype == OE_WAV_F32;
         if (bt->d_stats) {
@@ -1108,7 +1107,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     {
         const bool want_utt = bt->norm_mode != OE_NORM_NONE;
         const bool want_glob = bt->d_stats && n_stat_partials > 0;
-        if ((want_utt || want_glob) && !(skip & 4)) {
+        if (want_utt || want_glob) {
             oe::UttStatsParams U;
             memset(&U, 0, sizeof(U));
             U.tile_stats = P.tile_stats;
@@ -1117,9 +1116,9 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             U.utt_mean = reinterpret_cast<float*>(ws + M.utt_mean);
             U.utt_std = reinterpret_cast<float*>(ws + M.utt_std);
             U.F = F;
-            U.B = (want_utt && !(skip & 16)) ? B : 0;
+            U.B = want_utt ? B : 0;
             int glob_blocks = 0;
-            if (want_glob && !(skip & 32)) {
+            if (want_glob) {
                 U.partial = reinterpret_cast<const double*>(ws + M.stat_partial);
                 U.stats = bt->d_stats;
                 U.count = (double)M.total_frames;
@@ -1132,7 +1131,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             OE_CUDA(cudaGetLastError());
         }
     }
-    if (M.two_phase && d_out && M.total_rows > 0 && !(skip & 8)) {
+    if (M.two_phase && d_out && M.total_rows > 0) {
         oe::FinalizeParams Z;
         memset(&Z, 0, sizeof(Z));
         Z.raw = M.feats ? reinterpret_cast<const float*>(d_wav) : reinterpret_cast<const float*>(ws + M.raw);
