@@ -366,11 +366,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                 const int fr = 4 * (gl >> 1) + (gl & 1) + 2 * h;
                 const float* const pcol = reinterpret_cast<const float*>(smem + S::X + gl * kXGroup + kPwBase + slice_off(gl) + 4 * h);
                 float* const orow = sTile + fr * rowO;
-#ifdef OE_EXP_MEL_SAME
-                switch (0) {
-#else
                 switch (warp) {
-#endif
                     case 0: mel_group2<0>(pcol, P, orow, log_floor); break;
                     case 1: mel_group2<1>(pcol, P, orow, log_floor); break;
                     case 2: mel_group2<2>(pcol, P, orow, log_floor); break;

@@ -143,3 +143,41 @@ def test_config2_full_batch_properties(fe):
             assert np.array_equal(a[i, :t, s:e], np.broadcast_to(zero_after[s:e], a[i, :t, s:e].shape))
         np.testing.assert_allclose(plain[i, :t].mean(0), 0.0, atol=2e-4)
         np.testing.assert_allclose(plain[i, :t].std(0), 1.0, atol=2e-4)
+
+
+def test_multi_tile_ctas_equal_one_utterance_at_a_time():
+    """~1000 tiles on 296 persistent CTAs: every CTA walks several tiles, so every cross-tile shared-memory reuse of
+    the fbank kernels (raw buffer, exchange areas / power slices, output tile, descriptors, masks) is exercised.
+    Frames are independent of their batch, so the batched result must be BITWISE equal to running each utterance
+    alone (one tile per CTA, nothing reused) -- plain int16, fp32 input, and the fused speed-perturb + per-utterance
+    normalisation + masks + CMVN chain.  (compute-sanitizer's racecheck is not available on the GPU pool; this is
+    the race detector.)"""
+    from openeat_b200.frontend import Frontend, pack_waveforms
+    fe = Frontend(mel_bins=80, sample_rate=16000)
+    rng = np.random.default_rng(7)
+    B = 40
+    lens = rng.integers(5 * 16000, 10 * 16000, B)
+    waves = [rng.integers(-3000, 3000, n).astype(np.int16) for n in lens]
+    buf, offs, ln = pack_waveforms(waves)
+    dev = buf.cuda()
+    ratios = np.array([[(0, 0), (9, 10), (11, 10)][i % 3] for i in range(B)])
+    mean = torch.linspace(8.0, 12.0, 80, device='cuda')
+    istd = torch.linspace(0.4, 0.6, 80, device='cuda')
+    tm = np.array([[[3, 9], [40, 70]]] * B, np.int32)
+    fm = np.array([[[10, 14]]] * B, np.int32)
+    modes = [
+        (dev, dict()),
+        (dev.float(), dict()),
+        (dev, dict(tmask=tm, fmask=fm, cmvn=(mean, istd), cmvn_on_padding=False)),
+        (dev, dict(normalization=True, speed_ratios=ratios, tmask=tm, fmask=fm, cmvn=(mean, istd), cmvn_on_padding=False)),
+    ]
+    for rep in range(2):                                    # twice: a race need not show on the first run
+        for wav, kw in modes:
+            full, frames = fe.fbank(wav, offs, ln, layout='padded', **kw)
+            assert int(np.ceil(frames / 32).sum()) > 3 * 296
+            full = full.cpu().numpy()
+            for i in range(0, B, 3):                        # every third utterance alone
+                kw1 = {k: (v[i:i + 1] if k in ('tmask', 'fmask', 'speed_ratios') else v) for k, v in kw.items()}
+                one, f1 = fe.fbank(wav, offs[i:i + 1], ln[i:i + 1], layout='padded', **kw1)
+                assert f1[0] == frames[i]
+                assert np.array_equal(full[i, :frames[i]], one.cpu().numpy()[0]), (rep, i, sorted(kw))
