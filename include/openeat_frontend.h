@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OE_ABI_VERSION 2    /* 2: oe_batch gained feature_dither / dither_seed (appended) */
+#define OE_ABI_VERSION 2    /* 2: oe_batch gained feature_dither / dither_seed / wav_dither (appended) */
 
 enum { OE_OK = 0, OE_ERR_INVALID = 1, OE_ERR_UNSUPPORTED = 2, OE_ERR_CUDA = 3, OE_ERR_WORKSPACE = 4 };
 /* OE_WAV_I16: PCM int16.  OE_WAV_F32: fp32 on the int16 scale (dataset.py:75).
@@ -96,6 +96,10 @@ typedef struct {
                                     Philox-4x32-10 keyed by dither_seed instead of numpy's global generator, so there is
                                     no value parity for this option */
     uint64_t dither_seed;        /* Philox key; vary it per batch */
+    float wav_dither;            /* dither of kaldi.fbank (kaldi.py:179-181): every frame element gets + wav_dither * N(0,1)
+                                    before DC removal; 0 = off.  Normals from Philox-4x32-10 + Box-Muller keyed by
+                                    (dither_seed, utterance, frame, sample) instead of torch's global generator: no value
+                                    parity.  Not combinable with resample_ids (resample first) */
 } oe_batch;
 
 /* One ragged resampling batch (speed perturb).  Replaces _speed_perturb

@@ -45,7 +45,8 @@ class OeBatch(ctypes.Structure):
                 ('d_cmvn_mean', ctypes.c_void_p), ('d_cmvn_istd', ctypes.c_void_p),
                 ('cmvn_on_padding', ctypes.c_int32), ('d_stats', ctypes.c_void_p),
                 ('out_frames', c_i32p), ('resample_ids', c_i32p),
-                ('feature_dither', ctypes.c_float), ('dither_seed', ctypes.c_uint64)]
+                ('feature_dither', ctypes.c_float), ('dither_seed', ctypes.c_uint64),
+                ('wav_dither', ctypes.c_float)]
 
 
 class OeResampleBatch(ctypes.Structure):

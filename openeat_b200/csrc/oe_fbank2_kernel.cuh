@@ -101,7 +101,9 @@ __device__ __forceinline__ void mel_group2(const float* __restrict__ pcol, const
     });
 }
 
-template <bool kF32, bool kRs>
+// kDither: kaldi.fbank's dither (kaldi.py:179-181), one independent N(0,1) per frame element before DC removal; a
+// separate instantiation because the Philox + Box-Muller code roughly triples the front.
+template <bool kF32, bool kRs, bool kDither = false>
 __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParams P) {
     using S = Smem<kF32, kRs>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -235,8 +237,14 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                     float sa = 0.f, sb = 0.f, pa = 0.f, pb = 0.f;
 #pragma unroll
                     for (int n1 = 0; n1 < 13; ++n1) {
-                        const float2 a = *reinterpret_cast<const float2*>(tb + 32 * n1);
-                        const float2 c = *reinterpret_cast<const float2*>(tb + 2 * kShift + 32 * n1);
+                        float2 a = *reinterpret_cast<const float2*>(tb + 32 * n1);
+                        float2 c = *reinterpret_cast<const float2*>(tb + 2 * kShift + 32 * n1);
+                        if (kDither) {
+                            const float2 na = dither_normals(b, t0 + fA, 16 * n1 + tau, P.dither_seed);
+                            const float2 nc = dither_normals(b, t0 + fA + 2, 16 * n1 + tau, P.dither_seed);
+                            a.x = fmaf(P.wav_dither, na.x, a.x); a.y = fmaf(P.wav_dither, na.y, a.y);
+                            c.x = fmaf(P.wav_dither, nc.x, c.x); c.y = fmaf(P.wav_dither, nc.y, c.y);
+                        }
                         if (n1 < 12) {
                             sa += a.x + a.y;
                             sb += c.x + c.y;
@@ -261,8 +269,14 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
 #pragma unroll
                     for (int n1 = 0; n1 < 13; ++n1) {
                         const uint32_t wa = rw[16 * n1], wb = rw[kShift + 16 * n1];
-                        const float ea = (float)(int16_t)(wa & 0xffffu), oa = (float)((int32_t)wa >> 16);
-                        const float eb = (float)(int16_t)(wb & 0xffffu), ob = (float)((int32_t)wb >> 16);
+                        float ea = (float)(int16_t)(wa & 0xffffu), oa = (float)((int32_t)wa >> 16);
+                        float eb = (float)(int16_t)(wb & 0xffffu), ob = (float)((int32_t)wb >> 16);
+                        if (kDither) {
+                            const float2 na = dither_normals(b, t0 + fA, 16 * n1 + tau, P.dither_seed);
+                            const float2 nb = dither_normals(b, t0 + fA + 2, 16 * n1 + tau, P.dither_seed);
+                            ea = fmaf(P.wav_dither, na.x, ea); oa = fmaf(P.wav_dither, na.y, oa);
+                            eb = fmaf(P.wav_dither, nb.x, eb); ob = fmaf(P.wav_dither, nb.y, ob);
+                        }
                         const V2 xe = v2_make(ea, eb), xo = v2_make(oa, ob);
                         if (n1 < 12) acc = vadd(acc, vadd(xe, xo));
                         else acc = vfma(vadd(xe, xo), vbcast(m12), acc);

@@ -14,6 +14,31 @@
 
 namespace oe {
 
+// Philox-4x32-10 (Salmon et al., SC'11): counter-based generator, four 32-bit words per (counter, key).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Two independent N(0, 1) draws for frame element pair `idx` of frame `frame` of utterance `b` (wav dither):
+// Box-Muller on the first two Philox words.
+__device__ __forceinline__ float2 dither_normals(unsigned b, unsigned frame, unsigned idx, unsigned long long seed) {
+    const uint4 r = philox4x32_10(make_uint4(idx, frame, b, 0x57415644u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float u1 = (float)((r.x >> 8) + 1u) * (1.0f / 16777216.0f);      // (0, 1]
+    const float u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);             // [0, 1)
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
 // Everything one tile needs, self-contained (no dependent loads): built on the device by
 // oe_tile_desc_kernel and pulled into shared memory one tile ahead with cp.async.
 struct __align__(16) TileDesc {
@@ -52,6 +77,8 @@ struct FbankParams {
     const float* cmvn_istd;
     int cmvn_on_pad;
     int out_vec;                    // rows are dense (pitch == F) and `out` is 16-byte aligned: float4 stores allowed
+    float wav_dither;               // kaldi.fbank dither (gen-2 kernel, kDither instantiations), 0 = off
+    unsigned long long dither_seed;
     float* tile_stats;              // [total_tiles][3][2][F]: per row-group column sum and sum of squared deviations
     double* cta_stats;              // [gridDim.x][3][2][F] or null: this CTA's running sum / sum of squares (fp64)
     const DevTables* tab;

@@ -307,19 +307,6 @@ struct FinalizeParams {
     unsigned long long dither_seed;
 };
 
-// Philox-4x32-10 (Salmon et al., SC'11): counter-based generator, four 32-bit words per (counter, key).
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
 // dataset.py:195-218 on the device: normalise -> substitute -> mask -> pad, then GlobalCMVN.
 // grid = (utterances, row chunks).  VEC = 4: thread = (float4 column chunk, row lane); the per-column
 // constants (mean, 1/std, CMVN, frequency mask) live in registers for the whole chunk of rows.  One row per thread
@@ -708,6 +695,13 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     const int B = bt->batch, F = fe->cfg.num_mel_bins;
     const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
     if (pitch < F) return fail(OE_ERR_INVALID, "out_pitch smaller than num_mel_bins");
+    if (bt->wav_dither != 0.f) {                         // validated here, before anything is launched
+        if (feats) return fail(OE_ERR_INVALID, "wav_dither needs waveform input");
+        if (!fe->std_mel || fe->force_v1) return fail(OE_ERR_UNSUPPORTED, "wav_dither is built for the standard 80-bin kernel only");
+        for (int b = 0; bt->resample_ids && b < B; ++b)
+            if (bt->resample_ids[b] >= 0)
+                return fail(OE_ERR_UNSUPPORTED, "wav_dither cannot be combined with a fused speed perturb: resample first (oe_resample)");
+    }
     M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr || bt->feature_dither != 0.f;
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
@@ -895,6 +889,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<false, false>::End);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<false, true>::End);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<true, false>::End);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<false, false>::End);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(oe::k2::oe_fbank2_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, oe::k2::Smem<true, false>::End);
     {   // developer switch for A/B timing: OE_FBANK_V1=1 keeps the first-generation kernel on the standard mel layout
         const char* v1 = getenv("OE_FBANK_V1");
         fe->force_v1 = v1 && v1[0] == '1';
@@ -1071,7 +1067,12 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         bool any_rs = false;
         for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
         ++fe->launches;
-        if (fe->std_mel && !fe->force_v1) {
+        P.wav_dither = bt->wav_dither;
+        P.dither_seed = bt->dither_seed;
+        if (bt->wav_dither != 0.f) {
+            if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
+            else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
+        } else if (fe->std_mel && !fe->force_v1) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else if (any_rs) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, true>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));

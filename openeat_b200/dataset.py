@@ -70,7 +70,7 @@ class _Plan(object):
     position, in the packed input buffer, of the utterance that ends up i-th after the length sort;
     ``stage1`` / ``stage2`` are the (orig, new) resampling ratios of the resample_rate and speed stages
     (0, 0 = none)."""
-    __slots__ = ('keys', 'labels', 'src', 'stage1', 'stage2', 'frames', 'sample_rate')
+    __slots__ = ('keys', 'labels', 'src', 'stage1', 'stage2', 'frames', 'sample_rate', 'wav_dither')
 
 
 def _ceil_ratio(n, orig, new):
@@ -107,12 +107,10 @@ def _plan_batch(keys_in, labels_in, nsamples, sample_rates, speeds_in, conf, tar
             stage2[sel2] = ratio
             n[sel2] = _ceil_ratio(n[sel2], ratio[0], ratio[1])
     frames = fe.num_frames_array(n)
-    bad = active & ((rr != target_rate) | (frames == 0) | (conf['wav_dither'] != 0.0))
+    bad = active & ((rr != target_rate) | (frames == 0))
     for i in np.nonzero(bad)[0]:                                  # dataset.py:108-111: print, warn, drop
         if rr[i] != target_rate:
             print('sample rate %d is not supported by this front-end build (needs %d; set resample_rate)' % (rr[i], target_rate))
-        elif conf['wav_dither'] != 0.0:
-            print('wav_dither is stochastic (torch.randn inside kaldi.fbank) and is not built; use 0.0')
         else:   # kaldi.py:142 asserts 2 <= window_size <= len(waveform); the reference prints it and drops
             print('choose a window size 400 that is [2, %d]' % n[i])
         logging.warning('read utterance {} error'.format(keys_in[i]))
@@ -127,6 +125,7 @@ def _plan_batch(keys_in, labels_in, nsamples, sample_rates, speeds_in, conf, tar
     p.stage2 = stage2[src]
     p.frames = frames[src].astype(np.int32)
     p.sample_rate = target_rate
+    p.wav_dither = float(conf.get('wav_dither', 0.0) or 0.0)      # kaldi.fbank(dither=...), dataset.py:98
     return p
 
 
@@ -169,7 +168,10 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
     lens = np.asarray(lens, dtype=np.int32)
     needs = (plan.stage1[:, 0] != 0) | (plan.stage2[:, 0] != 0)
     # speed 0.9 / 1.1 on int16 PCM: resampled inside the fbank kernel's staging -> the whole batch is ONE call
-    fusable = (dev_wav.dtype == torch.int16 and not (plan.stage1[:, 0] != 0).any() and
+    if plan.wav_dither != 0.0:                               # Philox key per call; os.urandom: Python's `random` stream stays the reference's
+        fused = dict(fused, wav_dither=plan.wav_dither,
+                     dither_seed=fused.get('dither_seed') or int.from_bytes(os.urandom(8), 'little'))
+    fusable = (plan.wav_dither == 0.0 and dev_wav.dtype == torch.int16 and not (plan.stage1[:, 0] != 0).any() and
                np.isin(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1], (0, 9 * 65536 + 10, 11 * 65536 + 10)).all())
     if fusable and needs.any():
         kw = dict(fused)

@@ -218,7 +218,7 @@ class Frontend(object):
     def fbank(self, wav, offsets, lens, *, layout='padded', out=None, max_rows=None, out_rows=None,
               out_nrows=None, normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
               cmvn_on_padding=False, stats=None, stream=None, features_in=False, want_out=True,
-              speed_ratios=None, feature_dither=0.0, dither_seed=0):
+              speed_ratios=None, feature_dither=0.0, dither_seed=0, wav_dither=0.0):
         """Runs one ragged batch.
 
         wav       packed device tensor: int16 PCM, fp32 on the int16 scale, or (features_in) a
@@ -236,6 +236,8 @@ class Frontend(object):
                   fbank kernel's staging (int16 input; 9:10 and 11:10 only, i.e. speeds 0.9 / 1.1).
         feature_dither  amplitude a of dataset.py:199-201 (x + (U[0,1) - 0.5) * a after the normalisation, before
                   spec_sub / spec_aug), 0 = off; uniforms from Philox keyed by dither_seed (no value parity).
+        wav_dither      kaldi.fbank's dither (kaldi.py:179-181): + wav_dither * N(0,1) on every frame element, Philox +
+                  Box-Muller keyed by dither_seed (no value parity); not with speed_ratios (resample first).
         Returns (out tensor or None, frames int32 ndarray).
         """
         B = len(lens)
@@ -320,7 +322,7 @@ class Frontend(object):
                      _ptr(tm, c_i32p), _ptr(fm, c_i32p), _ptr(fmap, c_i32p), _ptr(fmap_off, c_i64p),
                      mean_p, istd_p, 1 if cmvn_on_padding else 0,
                      ctypes.c_void_p(stats.data_ptr()) if stats is not None else None,
-                     _ptr(out_frames, c_i32p), rs_p, float(feature_dither), int(dither_seed) & 0xFFFFFFFFFFFFFFFF)
+                     _ptr(out_frames, c_i32p), rs_p, float(feature_dither), int(dither_seed) & 0xFFFFFFFFFFFFFFFF, float(wav_dither))
         need = ctypes.c_size_t()
         check(self.lib.oe_fbank_workspace_bytes(self.handle, ctypes.byref(bt), ctypes.byref(need)))
         s, sp = self._stream(stream)

@@ -19,6 +19,7 @@ Sample dicts use wenet's keys: ``key``, ``wav`` (1-D int16 / float array or (1, 
 """
 import io
 import json
+import os
 import random
 import tarfile
 import wave
@@ -117,8 +118,8 @@ def compute_fbank(data, num_mel_bins=23, frame_length=25, frame_shift=10, dither
     """Log-mel filterbank of every sample (``feat``: (T, num_mel_bins) CUDA tensor).  Samples shorter than one
     window are dropped like the reference drops them (kaldi.py:142 raises, dataset.py:108-111)."""
     assert frame_length == 25 and frame_shift == 10, 'only 25 ms / 10 ms framing is built'
-    assert dither == 0.0, 'dither is stochastic and not built'
     fe = default_frontend(num_mel_bins)
+    seed = [int.from_bytes(os.urandom(8), 'little')]         # wav dither: Philox key, advanced per GPU batch
 
     def flush(group):
         waves = []
@@ -127,7 +128,9 @@ def compute_fbank(data, num_mel_bins=23, frame_length=25, frame_shift=10, dither
             waves.append(w.detach().reshape(-1).cpu().numpy() if torch.is_tensor(w) else np.asarray(w).reshape(-1))
         any_f32 = any(w.dtype.kind == 'f' for w in waves)
         buf, offs, lens = pack_waveforms(waves, dtype=np.float32 if any_f32 else np.int16)
-        out, frames = fe.fbank(buf.to(fe.device, non_blocking=True), offs, lens, layout='ragged')
+        seed[0] += 1
+        out, frames = fe.fbank(buf.to(fe.device, non_blocking=True), offs, lens, layout='ragged',
+                               wav_dither=float(dither), dither_seed=seed[0])
         r = 0
         for s, w, m in zip(group, waves, frames):
             if m == 0:

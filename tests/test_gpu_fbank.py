@@ -342,3 +342,35 @@ def test_single_pass_padding_rows_and_launch_count(fe, tables):
     n0 = fe.launches
     fe.fbank(dev, offs, ln, layout='padded', normalization=True, stats=stats)
     assert fe.launches - n0 == 4
+
+
+def test_wav_dither_statistics(fe, tables):
+    """kaldi.fbank(dither=d) adds d * N(0,1) to every frame element before DC removal (kaldi.py:179-181).  Stochastic
+    (torch's global generator there, Philox here), so the distribution is checked: an all-zero waveform with dither d
+    must have the per-bin mean log-mel of a sigma = d white-noise waveform (oracle fbank, no dither); same seed ->
+    bit-identical, other seed -> different; frames of one utterance draw independent noise; int16 and fp32 input."""
+    d = 3.0
+    n = 400 + 160 * 2999                                           # 3000 frames
+    zeros = np.zeros(n, np.int16)
+    y1, fr = run_raw(fe, [zeros], layout='ragged', wav_dither=d, dither_seed=1234)
+    y2, _ = run_raw(fe, [zeros], layout='ragged', wav_dither=d, dither_seed=1234)
+    y3, _ = run_raw(fe, [zeros], layout='ragged', wav_dither=d, dither_seed=1235)
+    y4, _ = run_raw(fe, [zeros.astype(np.float32)], dtype=np.float32, layout='ragged', wav_dither=d, dither_seed=1234)
+    assert fr.tolist() == [3000] and np.isfinite(y1).all()
+    assert np.array_equal(y1, y2) and not np.array_equal(y1, y3)
+    assert np.array_equal(y1, y4)                                   # same key, same frame elements: same noise
+    assert np.abs(y1[0] - y1[1]).max() > 0.1                        # frames are not copies of each other
+    noise = np.random.default_rng(0).normal(0.0, d, n).astype(np.float32)
+    ref = F.fbank(noise, window=tables[0], mel=tables[1])
+    # per-bin std of log-mel over frames is <= 1.3 (1-2 fft bins per mel bin at the low end): 3000 frames -> 0.024
+    assert np.abs(y1.mean(0) - ref.mean(0)).max() < 0.15
+    assert np.abs(y1.std(0) - ref.std(0)).max() < 0.15
+    # a real signal well above the dither level is barely moved
+    x = signals.make('speech', 16000, 5)
+    a, _ = run_raw(fe, [x], layout='ragged')
+    b, _ = run_raw(fe, [x], layout='ragged', wav_dither=1.0, dither_seed=7)
+    assert 0 < np.abs(a - b).max() and np.median(np.abs(a - b)) < 0.05
+    # fused speed perturb + dither is refused loudly (the dataset mirror resamples first in that case)
+    from openeat_b200._lib import FrontendError
+    with pytest.raises(FrontendError):
+        run_raw(fe, [x], layout='ragged', wav_dither=1.0, speed_ratios=np.array([[9, 10]]))

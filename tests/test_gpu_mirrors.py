@@ -373,3 +373,27 @@ def test_feature_dither_statistics_and_masks():
     assert np.abs(noise).max() <= a / 2 + 1e-5
     assert abs(noise.mean()) < 5 * a / np.sqrt(12 * noise.size) + 1e-6
     assert abs(noise.var() - a * a / 12) < 0.05 * a * a / 12
+
+
+def test_wav_dither_through_the_collate_mirror():
+    """feature_extraction_conf['wav_dither'] (dataset.py:98) through audio_collate_func: with dither the speed perturb is
+    not fused (the library refuses that combination), the mirror resamples first and dithers the fp32 result; frame
+    counts, ordering and the consumption of Python's `random` stream are those of the undithered run."""
+    import random
+    from openeat_b200.dataset import audio_collate_func
+    from oracle import signals
+    lens = [30000, 48000, 20000, 16000]
+    items = [('u%d' % i, signals.make('speech', n, 60 + i), [1, 2], s) for i, (n, s) in enumerate(zip(lens, (0.9, 1.0, 1.1, 1.0)))]
+    base = {'mel_bins': 80, 'speed_perturb_rate': 0, 'speeds': [1.0], 'wav_dither': 0.0}
+    outs = []
+    for d in (0.0, 1.0):
+        coll = audio_collate_func(data_type='wav', feature_extraction_conf=dict(base, wav_dither=d), normalization=False)
+        random.seed(5)
+        keys, out = coll(items)
+        outs.append((keys, out, random.random()))
+    (k0, o0, r0), (k1, o1, r1) = outs
+    assert k0 == k1 and r0 == r1
+    assert o0['features_length'].tolist() == o1['features_length'].tolist()
+    a, b = o0['features'].cpu().numpy(), o1['features'].cpu().numpy()
+    assert np.isfinite(b).all() and not np.array_equal(a, b)
+    assert np.median(np.abs(a - b)) < 0.05                         # speech at +/- 3000 vs dither 1.0
