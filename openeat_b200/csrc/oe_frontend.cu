@@ -347,27 +347,43 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
         }
         cmask[e] = m;
     }
-    const int64_t raw0 = P.frame_prefix[b];
-    const int64_t out0 = P.out_row[b];
+    // Lean row loop (the kernel was issue-bound at 118 instructions per row chunk: 70 % issue-slot utilisation at 34 %
+    // of the DRAM peak): 64-bit bases once, 32-bit row offsets, the first four time masks in registers, identities
+    // instead of branches ((x - 0) * 1 is exact), and the padding value precomputed per thread.
+    const float* const rsrc = P.raw + P.frame_prefix[b] * F + c;
+    float* const odst = P.out + P.out_row[b] * P.pitch + c;
+    const int pitch = (int)P.pitch;
     const int32_t* const fmap = P.frame_map ? P.frame_map + P.map_off[b] : nullptr;
     const int32_t* const tm = P.tmask + (int64_t)b * P.n_tmask * 2;
+    constexpr int kFinTm = 4;
+    int tm_lo[kFinTm], tm_hi[kFinTm];
+#pragma unroll
+    for (int j = 0; j < kFinTm; ++j) {
+        tm_lo[j] = j < P.n_tmask ? tm[2 * j] : 0;
+        tm_hi[j] = j < P.n_tmask ? tm[2 * j + 1] : 0;
+    }
+    float padv[VEC];                                      // padding rows: 0, or (0 - mean) * istd with CMVN on padding
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) padv[e] = (has_cm && P.cmvn_on_pad) ? (0.f - cm[e]) * ci[e] : 0.f;
     const int r_end = min(nrows, r0 + kFinRows);
+#pragma unroll 1
     for (int t = r0 + rl; t < r_end; t += lanes) {
-        const bool real = t < nfr;
         float v[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) v[e] = 0.f;
-        if (real) {
-            bool rmask = false;
-            for (int j = 0; j < P.n_tmask; ++j) rmask |= (t >= tm[2 * j]) & (t < tm[2 * j + 1]);
+        for (int e = 0; e < VEC; ++e) v[e] = padv[e];
+        if (t < nfr) {
             const int ts = fmap ? fmap[t] : t;
-            const float* const src = P.raw + (raw0 + ts) * F + c;
+            const float* const src = rsrc + ts * F;
             if (VEC == 4) {
                 const float4 x = *reinterpret_cast<const float4*>(src);
                 v[0] = x.x; v[1 % VEC] = x.y; v[2 % VEC] = x.z; v[3 % VEC] = x.w;
             } else {
                 v[0] = src[0];
             }
+            bool rmask = false;
+#pragma unroll
+            for (int j = 0; j < kFinTm; ++j) rmask |= (t >= tm_lo[j]) & (t < tm_hi[j]);
+            for (int j = kFinTm; j < P.n_tmask; ++j) rmask |= (t >= tm[2 * j]) & (t < tm[2 * j + 1]);
             float du[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) du[e] = 0.f;
@@ -380,19 +396,13 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
             }
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                float y = (norm ? (v[e] - mean[e]) * rstd[e] : v[e]) + du[e];
+                float y = (v[e] - mean[e]) * rstd[e];                  // mean = 0, rstd = 1 without normalisation: exact
+                if (DITHER) y += du[e];
                 if (rmask || cmask[e]) y = 0.f;
-                v[e] = y;
+                v[e] = (y - cm[e]) * ci[e];                            // cm = 0, ci = 1 without CMVN: exact
             }
         }
-        if (has_cm && (real || P.cmvn_on_pad)) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                v[e] = v[e] - cm[e];
-                if (has_ci) v[e] = v[e] * ci[e];
-            }
-        }
-        float* const dst = P.out + (out0 + t) * P.pitch + c;
+        float* const dst = odst + t * pitch;
         if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
         else dst[0] = v[0];
     }
