@@ -195,6 +195,33 @@ def main():
     with open(os.path.join(OUT, 'audio_dataset.json'), 'w', encoding='utf-8') as f:
         json.dump(ds_gold, f, ensure_ascii=False)
 
+    # 8. the reference's audio_collate_func on Kaldi-archive features (data_type != 'wav': _load_feature,
+    #    dataset.py:120-152, then the common chain :195-238), under the shim.  kaldi_io is a third-party package
+    #    that is not installed here: the shim's stub module gets read_mat from openeat_b200.kaldi_io, so this pins
+    #    the reference's handling of the matrices (sort order, the doubled label list, normalisation, masks,
+    #    padding) -- the binary format itself is only pinned by Kaldi's published layout (no Kaldi binaries here).
+    import sys
+    from openeat_b200 import kaldi_io as my_kaldi_io
+    sys.modules['kaldi_io'].read_mat = my_kaldi_io.read_mat
+    rng = np.random.default_rng(99)
+    T = [57, 120, 33, 240, 5, 120]
+    mats = [rng.normal(3.0, 2.0, (t, 80)).astype(np.float32) for t in T]
+    scp = my_kaldi_io.write_mat_ark(os.path.join(tmp, 'feats.ark'), [('k%d' % i, m) for i, m in enumerate(mats)])
+    kbatch = [('k%d' % i, scp['k%d' % i], [i + 1] * (i % 3 + 1), 1.0) for i in range(len(T))]
+    kc = {'mat%d' % i: m for i, m in enumerate(mats)}
+    kc['labels'] = np.array([len(x[2]) for x in kbatch])
+    for tag, kw in [('plain', dict(normalization=False)),
+                    ('norm_aug', dict(normalization=True, spec_aug=True,
+                                      spec_aug_conf=dict(num_t_mask=2, num_f_mask=2, max_t=20, max_f=8))),
+                    ('sub', dict(normalization=True, spec_sub=True, spec_sub_conf=dict(num_t_sub=3, max_t=10)))]:
+        fn = ref_ds.audio_collate_func(data_type='kaldi', **kw)
+        random.seed(777)
+        keys, out = fn([kbatch])
+        kc[tag + '_keys'] = np.array(keys)
+        for k2, v in out.items():
+            kc[tag + '_' + k2] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, 'kaldi_collate.npz'), **kc)
+
     with open(os.path.join(OUT, 'manifest.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(OUT)))

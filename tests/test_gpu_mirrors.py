@@ -397,3 +397,34 @@ def test_wav_dither_through_the_collate_mirror():
     a, b = o0['features'].cpu().numpy(), o1['features'].cpu().numpy()
     assert np.isfinite(b).all() and not np.array_equal(a, b)
     assert np.median(np.abs(a - b)) < 0.05                         # speech at +/- 3000 vs dither 1.0
+
+
+@pytest.mark.parametrize('tag,kw', [
+    ('plain', dict(normalization=False)),
+    ('norm_aug', dict(normalization=True, spec_aug=True, spec_aug_conf=dict(num_t_mask=2, num_f_mask=2, max_t=20, max_f=8))),
+    ('sub', dict(normalization=True, spec_sub=True, spec_sub_conf=dict(num_t_sub=3, max_t=10))),
+])
+def test_kaldi_collate_matches_reference_output(tmp_path, golden_dir, tag, kw):
+    """The REFERENCE's audio_collate_func(data_type='kaldi') run end to end under oracle/ref_shim.py
+    (tests/golden/kaldi_collate.npz, oracle/make_golden.py section 8) against this package's collate on the same
+    archive and `random` seed: key order (ties included), the doubled-label quirk of dataset.py:141-143, lengths,
+    padding, masks bit-exact, values within fp32 normalisation noise."""
+    import random
+    from openeat_b200 import kaldi_io
+    from openeat_b200.dataset import audio_collate_func
+    g = np.load(os.path.join(golden_dir, 'kaldi_collate.npz'))
+    n = len(g['labels'])
+    mats = [g['mat%d' % i] for i in range(n)]
+    scp = kaldi_io.write_mat_ark(str(tmp_path / 'feats.ark'), [('k%d' % i, m) for i, m in enumerate(mats)])
+    batch = [('k%d' % i, scp['k%d' % i], [i + 1] * int(g['labels'][i]), 1.0) for i in range(n)]
+    coll = audio_collate_func(data_type='kaldi', **kw)
+    random.seed(777)
+    keys, out = coll([batch])
+    assert keys == g[tag + '_keys'].tolist()
+    assert out['features_length'].tolist() == g[tag + '_features_length'].tolist()
+    assert out['targets'].cpu().numpy().tolist() == g[tag + '_targets'].tolist()
+    assert out['targets_length'].tolist() == g[tag + '_targets_length'].tolist()
+    got, ref = out['features'].cpu().numpy(), g[tag + '_features']
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.abs(got - ref).max() <= (0 if tag == 'plain' else 2e-5)
