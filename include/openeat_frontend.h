@@ -146,6 +146,13 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* batch, const void* d_wav, fl
  * library counts itself).  bench.py reports the difference over its timed region as `gpu_launches`. */
 int64_t oe_frontend_launch_count(const oe_frontend* fe);
 
+/* Measurement hook: with timing on, oe_fbank_batch brackets its fbank kernel launch with two CUDA events on the
+ * caller's stream (and launches that kernel and its successor without programmatic overlap, so the bracket holds
+ * exactly that kernel).  oe_frontend_fbank_kernel_ms waits for the end event of the most recent call and returns the
+ * kernel's duration.  bench.py uses it to report the dominant kernel's launch time INSIDE the timed step. */
+int oe_frontend_set_kernel_timing(oe_frontend* fe, int32_t on);
+int oe_frontend_fbank_kernel_ms(oe_frontend* fe, float* ms);
+
 int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
                   const float* d_istd, oe_stream stream);
 

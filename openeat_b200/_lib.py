@@ -64,6 +64,8 @@ SYMBOLS = {
                                           ctypes.POINTER(ctypes.c_void_p)]),
     'oe_frontend_destroy': (ctypes.c_int, [ctypes.c_void_p]),
     'oe_frontend_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
+    'oe_frontend_set_kernel_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    'oe_frontend_fbank_kernel_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     'oe_frontend_get_tables': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p]),
     'oe_num_frames': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int64]),
     'oe_fbank_workspace_bytes': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeBatch),

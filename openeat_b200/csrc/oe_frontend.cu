@@ -600,6 +600,9 @@ struct oe_frontend {
     bool std_mel;                  // the mel matrix has the baked mel80 structure -> fast kernel
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     long long launches;            // kernels launched through this handle
+    bool timing;                   // oe_frontend_set_kernel_timing
+    bool timed;                    // the events below bracket a kernel of the most recent call
+    cudaEvent_t ev_begin, ev_end;
     float mel_w_std[512];
 };
 
@@ -815,6 +818,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->device = device;
     fe->d_tab = nullptr;
     fe->launches = 0;
+    fe->timing = fe->timed = false;
+    fe->ev_begin = fe->ev_end = nullptr;
     fe->d_rs = nullptr;
     fe->d_rs_coefs = nullptr;
     fe->rs_fast_9_10 = fe->rs_fast_11_10 = -1;
@@ -919,6 +924,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
 
 int oe_frontend_destroy(oe_frontend* fe) {
     if (!fe) return OE_OK;
+    if (fe->ev_begin) cudaEventDestroy(fe->ev_begin);
+    if (fe->ev_end) cudaEventDestroy(fe->ev_end);
     cudaFree(fe->d_tab);
     cudaFree(fe->d_rs);
     cudaFree(fe->d_rs_coefs);
@@ -927,6 +934,26 @@ int oe_frontend_destroy(oe_frontend* fe) {
 }
 
 int64_t oe_frontend_launch_count(const oe_frontend* fe) { return fe ? fe->launches : 0; }
+
+int oe_frontend_set_kernel_timing(oe_frontend* fe, int32_t on) {
+    if (!fe) return fail(OE_ERR_INVALID, "null frontend");
+    if (on && !fe->ev_begin) {
+        OE_CUDA(cudaSetDevice(fe->device));
+        OE_CUDA(cudaEventCreate(&fe->ev_begin));
+        OE_CUDA(cudaEventCreate(&fe->ev_end));
+    }
+    fe->timing = on != 0;
+    fe->timed = false;
+    return OE_OK;
+}
+
+int oe_frontend_fbank_kernel_ms(oe_frontend* fe, float* ms) {
+    if (!fe || !ms) return fail(OE_ERR_INVALID, "null pointer");
+    if (!fe->timed) return fail(OE_ERR_INVALID, "no timed fbank kernel: enable oe_frontend_set_kernel_timing before oe_fbank_batch");
+    OE_CUDA(cudaEventSynchronize(fe->ev_end));
+    OE_CUDA(cudaEventElapsedTime(ms, fe->ev_begin, fe->ev_end));
+    return OE_OK;
+}
 
 int oe_frontend_get_tables(const oe_frontend* fe, float* window, float* mel) {
     if (!fe) return fail(OE_ERR_INVALID, "null frontend");
@@ -1079,6 +1106,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         ++fe->launches;
         P.wav_dither = bt->wav_dither;
         P.dither_seed = bt->dither_seed;
+        if (fe->timing) OE_CUDA(cudaEventRecord(fe->ev_begin, stream));   // an event between two kernels also ends their PDL overlap
         if (bt->wav_dither != 0.f) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
@@ -1094,6 +1122,10 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             if (f32) OE_CUDA(launch_dep(oe::oe_fbank_kernel<true, false, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
             else if (any_rs) OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
             else OE_CUDA(launch_dep(oe::oe_fbank_kernel<false, false, false>, dim3(grid), dim3(oe::kThreads), fe->fbank_smem, stream, P));
+        }
+        if (fe->timing) {
+            OE_CUDA(cudaEventRecord(fe->ev_end, stream));
+            fe->timed = true;
         }
         OE_CUDA(cudaGetLastError());
     }

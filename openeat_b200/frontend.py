@@ -332,6 +332,16 @@ class Frontend(object):
                                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
         return out, out_frames
 
+    def set_kernel_timing(self, on=True):
+        """Measurement hook: bracket the fbank kernel of every following ``fbank`` call with CUDA events."""
+        check(self.lib.oe_frontend_set_kernel_timing(self.handle, 1 if on else 0))
+
+    def fbank_kernel_ms(self):
+        """Duration of the fbank kernel of the most recent ``fbank`` call (waits for it); needs set_kernel_timing."""
+        ms = ctypes.c_float()
+        check(self.lib.oe_frontend_fbank_kernel_ms(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
     @property
     def launches(self):
         """Kernels launched through this handle, counted by the library at every launch site
