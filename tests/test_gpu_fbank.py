@@ -374,3 +374,21 @@ def test_wav_dither_statistics(fe, tables):
     from openeat_b200._lib import FrontendError
     with pytest.raises(FrontendError):
         run_raw(fe, [x], layout='ragged', wav_dither=1.0, speed_ratios=np.array([[9, 10]]))
+
+
+def test_kernel_timing_hook(fe):
+    """oe_frontend_set_kernel_timing / oe_frontend_fbank_kernel_ms: the events the library records around its fbank
+    kernel (bench.py's roofline.in_step); refused loudly when no timed call exists."""
+    from openeat_b200._lib import FrontendError
+    x = [signals.make('white', 160000, 3)] * 8
+    fe.set_kernel_timing(True)
+    with pytest.raises(FrontendError):
+        fe.fbank_kernel_ms()
+    y1, _ = run_raw(fe, x, layout='ragged')
+    ms = fe.fbank_kernel_ms()
+    assert 0.0 < ms < 5.0
+    fe.set_kernel_timing(False)
+    y2, _ = run_raw(fe, x, layout='ragged')
+    assert np.array_equal(y1, y2)
+    with pytest.raises(FrontendError):
+        fe.fbank_kernel_ms()
