@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                 const int shift = rs_first_input(rs, t0) - dp->in_first;   // 0..7
                 for (int mi = tid + 1; mi < kRsBlocks; mi += kThreads) {   // block mi -> tile samples 10 mi - 10 .. 10 mi - 1
                     float y[10];
-                    if (rs == 1) rs_block<9>(xin + shift + mi * 9, P.rs_coef[0], y);
-                    else rs_block<11>(xin + shift + mi * 11, P.rs_coef[1], y);
+                    if (rs == 1) rs_block_baked<9>(xin + shift + mi * 9, y);
+                    else rs_block_baked<11>(xin + shift + mi * 11, y);
                     float2* const dst = reinterpret_cast<float2*>(sTile + 10 * mi - 10);
 #pragma unroll
                     for (int j = 0; j < 5; ++j)

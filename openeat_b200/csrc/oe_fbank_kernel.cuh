@@ -195,6 +195,29 @@ __device__ __forceinline__ void rs_block(const float* __restrict__ xin, const fl
     });
 }
 
+// rs_block with the baked tables of oe_rs_coefs.h: every coefficient is a 32-bit immediate of its FFMA (a run-time
+// table costs a uniform constant load per two taps).  Same taps, same order: bitwise identical to rs_block on a
+// table that matches the baked bits (oe_add_resampler only fuses such tables).
+template <int ORIG>
+__device__ __forceinline__ void rs_block_baked(const float* __restrict__ xin, float (&y)[10]) {
+    constexpr int TAPS = 14 + ORIG;
+    float x[TAPS];
+#pragma unroll
+    for (int q = 0; q < TAPS; ++q) x[q] = xin[q];
+    static_for<0, 10>([&](auto pp) {
+        constexpr int p = decltype(pp)::value;
+        float acc = 0.f;
+        static_for<0, TAPS>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            if constexpr (rs_tap_nonzero(ORIG, 10, 7, p, q)) {
+                constexpr float c = rsbaked::coef<ORIG>(p * TAPS + q);
+                acc = fmaf(c, x[q], acc);
+            }
+        });
+        y[p] = acc;
+    });
+}
+
 __device__ __forceinline__ void prefetch_desc(TileDesc* dst, const TileDesc* src, int tid) {
     if (tid < 3) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16 * tid,
                             reinterpret_cast<const unsigned char*>(src) + 16 * tid, 16);

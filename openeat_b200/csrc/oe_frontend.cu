@@ -69,6 +69,7 @@ struct DevTables {
 }  // namespace oe
 
 #include "oe_mel80.h"
+#include "oe_rs_coefs.h"
 #include "oe_fbank_kernel.cuh"
 #include "oe_fbank2_kernel.cuh"
 
@@ -1277,6 +1278,12 @@ int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* ke
         for (int p = 0; p < neu && ok; ++p)
             for (int q = 0; q < ntaps && ok; ++q)
                 if (!oe::rs_tap_nonzero(orig, neu, width, p, q) && std::fabs(fe->rs_coefs[t.coef_off + p * ntaps + q]) > 1e-12f) ok = false;
+        // ... and the fused resampler of the gen-2 fbank kernel carries the torchaudio table as immediates: only a
+        // table with exactly those bits is fused (anything else still has the stand-alone resampling kernels)
+        for (int i = 0; i < neu * ntaps && ok; ++i) {
+            const float baked = orig == 9 ? oe::rsbaked::coef<9>(i) : oe::rsbaked::coef<11>(i);
+            if (memcmp(&baked, &fe->rs_coefs[t.coef_off + i], 4) != 0 && oe::rs_tap_nonzero(orig, neu, width, i / ntaps, i % ntaps)) ok = false;
+        }
         if (ok) (orig == 9 ? fe->rs_fast_9_10 : fe->rs_fast_11_10) = (int)fe->rs.size() - 1;
     }
     OE_CUDA(cudaSetDevice(fe->device));
