@@ -1,5 +1,6 @@
-// oe_fbank2_kernel: second-generation ragged-batch Kaldi fbank for sm_100a, standard 80-bin mel layout
-// (included by oe_frontend.cu; oe_fbank_kernel stays as the table-driven fallback for other bin counts).
+// oe_fbank2_kernel: second-generation ragged-batch Kaldi fbank for sm_100a, standard 80-bin mel matrix (torchaudio's
+// values, baked) -- included by oe_frontend.cu; oe_fbank_kernel stays for other matrices (same structure with other
+// weights: compile-time structure, parameter weights; anything else: table-driven).
 //
 // ncu on the first-generation kernel showed the shared-memory data pipe at 72 % of peak (162 wavefronts per
 // frame) and 31 % of the issued instructions spent on integer address arithmetic; HBM sat at 3 %.  This
@@ -78,8 +79,11 @@ __device__ __forceinline__ unsigned long long v2_bits(V2 a) {
 __device__ __forceinline__ V2 lds_v2(const unsigned char* p) { return v2_from_bits(*reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ void sts_v2(unsigned char* p, V2 v) { *reinterpret_cast<unsigned long long*>(p) = v2_bits(v); }
 
-// Standard-structure mel projection of one warp's bin group from the per-group power slices
-// (pcol[2 k] = 4 |X[k]|^2 of this lane's frame); weights are kernel-parameter constants.
+// Standard mel projection of one warp's bin group from the per-group power slices (pcol[2 k] = 4 |X[k]|^2 of this
+// lane's frame).  Structure AND weights are compile-time (oe_mel80.h: torchaudio's matrix, x 1/4): every weight is a
+// 32-bit immediate of its FFMA.  Kernel-parameter constants cost a uniform constant load for every third weight, each
+// worth ~15 cycles of the tile's critical path: immediates made the kernel 4 % faster.  Handles whose matrix has the
+// structure but other values run the first-generation kernel, which takes the weights as parameters.
 template <int G>
 __device__ __forceinline__ void mel_group2(const float* __restrict__ pcol, const FbankParams& P,
                                            float* __restrict__ orow, float log_floor) {
@@ -91,7 +95,7 @@ __device__ __forceinline__ void mel_group2(const float* __restrict__ pcol, const
         float a = 0.f;
         static_for<0, mel80::kLen[b]>([&](auto ii) {
             constexpr int i = decltype(ii)::value;
-            a = fmaf(P.mel_w[off + i], pcol[2 * (k0 + i)], a);
+            a = fmaf(mel80::weight(off + i), pcol[2 * (k0 + i)], a);
         });
         acc[b - b0] = a;
     });

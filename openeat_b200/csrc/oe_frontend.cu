@@ -598,7 +598,8 @@ struct oe_frontend {
     oe::RsTable* d_rs;
     float* d_rs_coefs;
     size_t fbank_smem;
-    bool std_mel;                  // the mel matrix has the baked mel80 structure -> fast kernel
+    bool std_mel;                  // the mel matrix has the baked mel80 structure -> kernels with a compile-time mel structure
+    bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     long long launches;            // kernels launched through this handle
     bool timing;                   // oe_frontend_set_kernel_timing
@@ -662,6 +663,16 @@ void default_window(int n, std::vector<float>& w) {
 // kaldi.py:436-511 (vtln_warp 1.0): scalar limits in double, per-bin arithmetic in fp32 like torch
 void default_mel(const oe_config& c, std::vector<float>& m) {
     const int nb = c.num_mel_bins, nf = c.fft_size / 2;
+    if (nb == oe::mel80::kBins && c.sample_rate == 16000 && c.fft_size == 512 && c.low_freq == 20.0f && c.high_freq <= 0.0f &&
+        c.high_freq + 8000.0f == 8000.0f) {
+        // the standard configuration gets torchaudio's own matrix, bit for bit (oe_mel80.h): same values as
+        // kaldi.get_mel_banks, and the handle qualifies for the kernel that carries the weights as immediates
+        m.assign((size_t)nb * nf, 0.f);
+        for (int b = 0; b < nb; ++b)
+            for (int i = 0; i < oe::mel80::kLen[b]; ++i)
+                m[(size_t)b * nf + oe::mel80::kStart[b] + i] = 4.0f * oe::mel80::weight(oe::mel80::kOff[b] + i);
+        return;
+    }
     const double nyq = 0.5 * c.sample_rate;
     double high = c.high_freq;
     if (high <= 0.0) high += nyq;
@@ -711,7 +722,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     if (pitch < F) return fail(OE_ERR_INVALID, "out_pitch smaller than num_mel_bins");
     if (bt->wav_dither != 0.f) {                         // validated here, before anything is launched
         if (feats) return fail(OE_ERR_INVALID, "wav_dither needs waveform input");
-        if (!fe->std_mel || fe->force_v1) return fail(OE_ERR_UNSUPPORTED, "wav_dither is built for the standard 80-bin kernel only");
+        if (!fe->mel_baked || fe->force_v1) return fail(OE_ERR_UNSUPPORTED, "wav_dither is built for the standard 80-bin kernel (torchaudio's mel matrix) only");
         for (int b = 0; bt->resample_ids && b < B; ++b)
             if (bt->resample_ids[b] >= 0)
                 return fail(OE_ERR_UNSUPPORTED, "wav_dither cannot be combined with a fused speed perturb: resample first (oe_resample)");
@@ -892,6 +903,11 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->std_mel = nb == oe::mel80::kBins && nnz == oe::mel80::kNnz;
     for (int b = 0; fe->std_mel && b < nb; ++b)
         fe->std_mel = h.mel_start[b] == oe::mel80::kStart[b] && h.mel_len[b] == oe::mel80::kLen[b];
+    fe->mel_baked = fe->std_mel;
+    for (int i = 0; fe->mel_baked && i < nnz; ++i) {
+        const float w = oe::mel80::weight(i);
+        fe->mel_baked = memcmp(&w, &h.mel_w[i], 4) == 0;
+    }
     memset(fe->mel_w_std, 0, sizeof(fe->mel_w_std));
     if (fe->std_mel) memcpy(fe->mel_w_std, h.mel_w, sizeof(float) * nnz);
     fe->fbank_smem = fe->std_mel ? align_up((size_t)oe::kSmStd, 16) : align_up((size_t)oe::kSmMelW + 4 * (size_t)nnz, 16);
@@ -1062,7 +1078,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
     // float4 row stores: gen-1 kernel needs dense rows (pitch == F), gen-2 any 16-byte aligned pitch
-    P.out_vec = (((fe->std_mel && !fe->force_v1) ? P.pitch % 4 == 0 : P.pitch == F) && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
+    P.out_vec = (((fe->mel_baked && !fe->force_v1) ? P.pitch % 4 == 0 : P.pitch == F) && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
     if (M.total_tiles > 0) {
         oe::TileDescParams T;
         T.tile_prefix = d_tile_prefix;
@@ -1111,7 +1127,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         if (bt->wav_dither != 0.f) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
-        } else if (fe->std_mel && !fe->force_v1) {
+        } else if (fe->mel_baked && !fe->force_v1) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else if (any_rs) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, true>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));

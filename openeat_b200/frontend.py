@@ -97,7 +97,10 @@ def _ptr(arr, ptype):
 class Frontend(object):
     """One CUDA front-end handle (tables + resampler taps) on one device."""
 
-    def __init__(self, mel_bins=80, sample_rate=16000, device=None, torch_tables=True):
+    def __init__(self, mel_bins=80, sample_rate=16000, device=None, torch_tables=True, mel=None):
+        """``torch_tables``: build the Povey window and the mel matrix with torch's own fp32 expressions (bit-identical to
+        torchaudio's); False leaves both to the C library (its standard 80-bin table is the same matrix).  ``mel``: a
+        custom (mel_bins, fft_size / 2) fp32 matrix instead."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise FrontendError('openeat_b200 needs a CUDA device: the front-end has no CPU path')
@@ -112,10 +115,14 @@ class Frontend(object):
         self.cfg = cfg
         self.mel_bins = int(mel_bins)
         self.sample_rate = int(sample_rate)
-        win = mel = None
+        custom_mel, win, mel = mel, None, None
         if torch_tables:
             win = np.ascontiguousarray(torch_povey_window(cfg.frame_length).numpy())
             mel = np.ascontiguousarray(torch_mel_banks(mel_bins, cfg.fft_size, float(sample_rate)).numpy())
+        if custom_mel is not None:
+            mel = np.ascontiguousarray(custom_mel, dtype=np.float32)
+            if mel.shape != (int(mel_bins), cfg.fft_size // 2):
+                raise FrontendError('mel must be (%d, %d)' % (mel_bins, cfg.fft_size // 2))
         handle = ctypes.c_void_p()
         check(self.lib.oe_frontend_create(ctypes.byref(cfg), _ptr(win, c_f32p), _ptr(mel, c_f32p),
                                           self.device.index, ctypes.byref(handle)))

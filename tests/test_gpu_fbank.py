@@ -392,3 +392,24 @@ def test_kernel_timing_hook(fe):
     assert np.array_equal(y1, y2)
     with pytest.raises(FrontendError):
         fe.fbank_kernel_ms()
+
+
+def test_custom_mel_weights_use_the_parameter_kernel(tables):
+    """A handle whose mel matrix has the standard sparsity structure but other VALUES must not get the kernel that
+    carries torchaudio's weights as immediates: it runs the first-generation kernel with the weights as parameters.
+    Parity against the oracle with that very matrix; the default handle (mel=None -> the library's own table) is
+    torchaudio's matrix bit for bit."""
+    from openeat_b200.frontend import Frontend
+    win, mel = tables
+    scale = (1.0 + 0.01 * np.cos(np.arange(80)))[:, None].astype(np.float32)
+    mel2 = (mel * scale).astype(np.float32)                      # same structure, every weight changed
+    fe2 = Frontend(mel_bins=80, sample_rate=16000, mel=mel2)
+    x = signals.make('speech', 48000, 9)
+    y, fr = run_raw(fe2, [x], layout='ragged')
+    ref = F.fbank(x.astype(np.float32), window=win, mel=mel2)
+    assert np.abs(y - ref).max() <= 1e-3
+    base = Frontend(mel_bins=80, sample_rate=16000, torch_tables=False)      # the C library's own tables
+    assert np.array_equal(base.tables()[1], mel)
+    y0, _ = run_raw(base, [x], layout='ragged')
+    assert np.abs(y0 - F.fbank(x.astype(np.float32), window=win, mel=mel)).max() <= 1e-3
+    assert np.abs(y - y0).max() > 1e-3                           # the custom weights really were used
