@@ -15,8 +15,11 @@
 //   * the conjugate-partner exchange moves HALF of Z: lane k1 keeps k2 = 0..7, publishes k2 = 8..15 and the
 //     pair untangle (oe_fft.h: untangle_pair) yields bins k and 256 - k from one (P, Q) pair;
 //   * every 16-thread group owns a private power-spectrum slice inside its own exchange area, so power is
-//     stored straight from the untangle (no register staging, one CTA barrier fewer).
-// Per frame: ~90 shared-memory wavefronts and ~330 warp instructions (was 162 and 459).
+//     stored straight from the untangle (no register staging, one CTA barrier fewer);
+//   * no constant loads on the tile's critical path: mel weights and resampler taps are FFMA immediates (baked
+//     torchaudio tables, oe_mel80.h / oe_rs_coefs.h), twiddles of the FFT stages are compile-time constants.
+// Measured per frame (ncu, profiles/): 106 shared-memory wavefronts and 374 warp instructions (was 162 and 459);
+// 98 us per 150 k frames (was 128 us).
 //
 // Work split: CTA = 256 threads = 16 groups of 16; 32-frame tile; warp w owns frames 4w .. 4w+3; group
 // g = 0/1 of the warp packs frames (4w + g, 4w + g + 2) into the two halves of f32x2 registers (the +2
