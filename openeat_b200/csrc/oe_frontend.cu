@@ -617,7 +617,7 @@ thread_local char g_err[512] = "";
 // (and every kernel of the chain does so, which keeps the ordering transitive).  OE_NO_PDL=1 disables it.
 template <class Params>
 cudaError_t launch_dep(void (*kern)(const Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params& prm) {
-    static const bool no_pdl = [] { const char* e = getenv("OE_NO_PDL"); return e && e[0] == '1'; }();
+    static bool pdl = [] { const char* e = getenv("OE_NO_PDL"); return !(e && e[0] == '1'); }();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -628,8 +628,15 @@ cudaError_t launch_dep(void (*kern)(const Params), dim3 grid, dim3 block, size_t
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, prm);
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
+    if (e != cudaSuccess && pdl && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+        (void)cudaGetLastError();             // a driver / device without programmatic launches: plain stream order from now on
+        pdl = false;
+        cfg.numAttrs = 0;
+        e = cudaLaunchKernelEx(&cfg, kern, prm);
+    }
+    return e;
 }
 
 
