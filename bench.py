@@ -175,6 +175,25 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU runs: pin this rank (and therefore its pinned staging buffers, first touch) to the CPUs NVML reports as
+    local to its GPU, so the H2D traffic of the e2e leg does not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -186,6 +205,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     fe = default_frontend(80, 16000, dev)
     lens, speeds = workload(rank)
     host_pool, offs = synth_pool_host(lens, rank, POOL)
@@ -362,7 +382,8 @@ def run_ours(args, rank, world, local_rank):
                        'timing': 'median of %d back-to-back repeats of the %d-step timed region (each bracketed by '
                                  'barrier + synchronize; repeats only lengthen the window nvidia-smi samples)' % (reps, args.steps),
                        'parallelism': 'utterance sharding, dp%d; one 161 x f64 NCCL all-reduce closes the timed region'
-                                      % world if world > 1 else 'single GPU'},
+                                      % world if world > 1 else 'single GPU',
+                       'host_binding': ('rank pinned to the %d CPUs local to its GPU (NVML affinity)' % numa) if numa else 'none'},
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': BATCH * 4 + 161 * 8, 'ms_per_step': ms_e2e / args.steps,
                     'api': 'openeat_b200.dataset.PrefetchingCollator over audio_collate_func.collate_packed (pinned int16 '
