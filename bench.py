@@ -175,25 +175,6 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------
-def bind_to_gpu_numa_node(index):
-    """Multi-GPU runs: pin this rank (and therefore its pinned staging buffers, first touch) to the CPUs NVML reports as
-    local to its GPU, so the H2D traffic of the e2e leg does not cross the socket interconnect.  Best effort."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
-    except Exception:
-        pass
-    return None
-
-
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -202,10 +183,11 @@ def run_ours(args, rank, world, local_rank):
     from openeat_b200.dataset import _plan_batch, _run_plan, audio_collate_func
     from openeat_b200 import planner
     from openeat_b200.frontend import default_frontend
+    from openeat_b200.sharding import bind_to_gpu_numa_node
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa = bind_to_gpu_numa_node(local_rank)
     fe = default_frontend(80, 16000, dev)
     lens, speeds = workload(rank)
     host_pool, offs = synth_pool_host(lens, rank, POOL)
