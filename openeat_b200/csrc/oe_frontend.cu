@@ -412,7 +412,9 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
 // Padding rows of the single-pass layout: the fbank kernel writes whole 32-frame tiles (real frames plus the padding
 // rows that share the last tile); rows [32 ceil(frames / 32), out_nrows) of every utterance are filled here with
 // 0 or (0 - mean) * istd (dataset.py:214-218 pad_sequence, then GlobalCMVN on the padded tensor).  Reads only the
-// launch metadata, so under a programmatic dependent launch it runs in the shadow of the fbank kernel's tail.
+// launch metadata, so under a programmatic dependent launch it runs in the shadow of the fbank kernel's tail: the
+// dependency wait comes LAST (work first, wait before exiting), which keeps the chain transitive -- this grid cannot
+// complete before the fbank grid has completed and flushed, so whatever waits on this grid also waits on that one.
 struct PadFillParams {
     const int32_t* n_frames;
     const int32_t* n_rows;
@@ -428,7 +430,10 @@ __global__ void __launch_bounds__(256) oe_pad_fill_kernel(const PadFillParams P)
     const int b = blockIdx.x;
     const int first = (P.n_frames[b] + kTileFrames - 1) / kTileFrames * kTileFrames + blockIdx.y * kPadRows;
     const int last = min(P.n_rows[b], first + kPadRows);
-    if (first >= last) return;
+    if (first >= last) {
+        grid_dep_wait();
+        return;
+    }
     float* const dst = P.out + (P.out_row[b] + first) * P.pitch;
     const int F = P.F;
     if (P.pitch == F && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) {      // dense rows: one flat float4 run
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(256) oe_pad_fill_kernel(const PadFillParams P)
             dst[(int64_t)r * P.pitch + f] = v;
         }
     }
+    grid_dep_wait();
 }
 
 // openeat/modules/cmvn.py:43-46
