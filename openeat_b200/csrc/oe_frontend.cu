@@ -50,6 +50,9 @@ constexpr int kRowO = 81;           // floats per output-tile row (80 + 1 pad); 
 // Programmatic dependent launch: blocks until the preceding grid in the stream has completed and its writes are
 // visible (returns immediately when the kernel was launched without the attribute).
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next grid of the stream be scheduled now (it still waits for this grid's completion in its own
+// grid_dep_wait before reading anything): its blocks become resident and run their prologues under this grid.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 struct DevTables {
     float window[kFft];             // zero beyond frame_length
@@ -95,6 +98,7 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
     // the binary search runs on a shared-memory copy of the prefix array (one coalesced read instead of
     // log2(B) dependent global loads per thread)
     __shared__ int32_t sh_prefix[kDescSmemUtts + 1];
+    grid_dep_launch();                         // the fbank kernel's table staging runs under this kernel
     const bool staged = P.B <= kDescSmemUtts;
     if (staged) {
         for (int i = threadIdx.x; i <= P.B; i += blockDim.x) sh_prefix[i] = P.tile_prefix[i];
@@ -158,6 +162,7 @@ template <int MAX_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) oe_utt_stats_kernel(const UttStatsParams P) {
     __shared__ double sh[kUttSlices][kMaxMel];
     const int f = threadIdx.x, y = threadIdx.y;
+    grid_dep_launch();                         // the finalize blocks become resident while this latency chain runs
     grid_dep_wait();
     if ((int)blockIdx.x >= P.B) {
         const int nthr = blockDim.x * kUttSlices, lanes = nthr / kGlobStats;   // lanes per statistic
