@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     const float dc_scale = (1.0f - preemph) * (1.0f / (float)kWin);
     const float log_floor = tab->log_floor;
     const bool fused = (P.n_tmask | P.n_fmask) != 0;
+    // two-phase pipeline: the raw rows are re-read by the finalize kernel two launches later -> keep them in L2
+    const unsigned long long out_policy = P.keep_out_in_l2 ? l2_policy_evict_last() : l2_policy_evict_normal();
     const bool is15 = tau == 15;
     const int src_lane = (lane & 16) | ((tau + 15) & 15);
     const float m12 = tau < 8 ? 1.f : 0.f;     // chunk n1 = 12 holds samples 384 + 2 tau (+1): only tau < 8 are inside the frame
@@ -459,7 +461,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                         const float* const src = sTile + r * rowO + 4 * q;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (r < nvalid) v = make_float4(src[0], src[1], src[2], src[3]);
-                        *reinterpret_cast<float4*>(dst0 + (int64_t)r * pitch + 4 * q) = v;
+                        float4* const d4 = reinterpret_cast<float4*>(dst0 + (int64_t)r * pitch + 4 * q);
+                        st_f4_hint(d4, v, out_policy);
                     }
                 }
             } else if (P.out_vec) {

@@ -1081,6 +1081,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     const int64_t* d_tile_out_row;
     if (M.two_phase) {
         P.out = reinterpret_cast<float*>(ws + M.raw);
+        P.keep_out_in_l2 = 1;
         d_tile_out_row = reinterpret_cast<const int64_t*>(ws + M.frame_prefix);
         P.pitch = F;
     } else {
