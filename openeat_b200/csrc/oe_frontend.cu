@@ -333,25 +333,38 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
     const int ncol = (F + VEC - 1) / VEC;                 // column chunks per row
     const int lanes = 256 / ncol;                         // row lanes per block
     const int cc = threadIdx.x % ncol, rl = threadIdx.x / ncol;
-    if (rl >= lanes) return;
     const int c = cc * VEC;
     const int nfr = P.n_frames[b];
     const bool norm = P.utt_mean != nullptr, has_cm = P.cmvn_mean != nullptr, has_ci = P.cmvn_istd != nullptr;
-    float mean[VEC], rstd[VEC], cm[VEC], ci[VEC];
-    bool cmask[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-        const int f = c + e < F ? c + e : F - 1;
-        mean[e] = norm ? P.utt_mean[(int64_t)b * F + f] : 0.f;
-        rstd[e] = norm ? 1.0f / P.utt_std[(int64_t)b * F + f] : 1.f;      // 0 variance: 1/0 = inf, 0 * inf = NaN like x/0
-        cm[e] = has_cm ? P.cmvn_mean[f] : 0.f;
-        ci[e] = has_ci ? P.cmvn_istd[f] : 1.f;
+    // per-column constants: computed once per block by F threads, shared through shared memory (every thread loading
+    // its own 16 constants and the mask ranges made the prologue 45 loads for 11 rows of work)
+    __shared__ __align__(16) float sh_c[4][kMaxMel + 4];
+    __shared__ __align__(4) unsigned char sh_m[kMaxMel + 4];
+    if ((int)threadIdx.x < F) {
+        const int f = threadIdx.x;
+        sh_c[0][f] = norm ? P.utt_mean[(int64_t)b * F + f] : 0.f;
+        sh_c[1][f] = norm ? 1.0f / P.utt_std[(int64_t)b * F + f] : 1.f;      // 0 variance: 1/0 = inf, 0 * inf = NaN like x/0
+        sh_c[2][f] = has_cm ? P.cmvn_mean[f] : 0.f;
+        sh_c[3][f] = has_ci ? P.cmvn_istd[f] : 1.f;
         bool m = false;
         for (int j = 0; j < P.n_fmask; ++j) {
             const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
             m |= (f >= r[0]) & (f < r[1]);
         }
-        cmask[e] = m;
+        sh_m[f] = m;
+    }
+    __syncthreads();
+    if (rl >= lanes) return;
+    float mean[VEC], rstd[VEC], cm[VEC], ci[VEC];
+    bool cmask[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int f = c + e < F ? c + e : F - 1;
+        mean[e] = sh_c[0][f];
+        rstd[e] = sh_c[1][f];
+        cm[e] = sh_c[2][f];
+        ci[e] = sh_c[3][f];
+        cmask[e] = sh_m[f] != 0;
     }
     // Lean row loop (the kernel was issue-bound at 118 instructions per row chunk: 70 % issue-slot utilisation at 34 %
     // of the DRAM peak): 64-bit bases once, 32-bit row offsets, the first four time masks in registers, identities
