@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define OE_ABI_VERSION 2    /* 2: oe_batch gained feature_dither / dither_seed / wav_dither (appended) */
+#define OE_ABI_VERSION 3    /* 2: oe_batch gained feature_dither / dither_seed / wav_dither (appended)
+                             * 3: prepared batches (oe_batch_prepare / oe_fbank_run), ingest (oe_ingest_*) */
 
 enum { OE_OK = 0, OE_ERR_INVALID = 1, OE_ERR_UNSUPPORTED = 2, OE_ERR_CUDA = 3, OE_ERR_WORKSPACE = 4 };
 /* OE_WAV_I16: PCM int16.  OE_WAV_F32: fp32 on the int16 scale (dataset.py:75).
@@ -141,6 +142,20 @@ int oe_fbank_workspace_bytes(const oe_frontend* fe, const oe_batch* batch, size_
 int oe_fbank_batch(oe_frontend* fe, const oe_batch* batch, const void* d_wav, float* d_out,
                    void* d_workspace, size_t workspace_bytes, oe_stream stream);
 
+/* Prepared batches.  oe_batch_prepare validates a batch description and packs its metadata ONCE (the library keeps
+ * its own copy: every host array of `batch` may be freed afterwards; the DEVICE pointers d_cmvn_mean / d_cmvn_istd /
+ * d_stats are kept as given); oe_fbank_run then costs one stream-ordered metadata copy plus the kernel launches -- the
+ * hot loop of a trainer that plans batch i+1 on a worker thread while batch i runs (the reference does the same work
+ * inside DataLoader workers, openeat/bin/train.py:110-116).  oe_fbank_batch == prepare + run + destroy.
+ * A prepared batch may be run any number of times, with different d_wav / d_out / workspace / stream. */
+typedef struct oe_prepared oe_prepared; /* opaque */
+int oe_batch_prepare(oe_frontend* fe, const oe_batch* batch, oe_prepared** out);
+int oe_prepared_destroy(oe_prepared* p);
+size_t oe_prepared_workspace_bytes(const oe_prepared* p);
+const int32_t* oe_prepared_frames(const oe_prepared* p);   /* [B] frames per utterance, valid until destroy */
+int oe_fbank_run(oe_frontend* fe, const oe_prepared* p, const void* d_wav, float* d_out, void* d_workspace,
+                 size_t workspace_bytes, oe_stream stream);
+
 /* GlobalCMVN.forward (openeat/modules/cmvn.py:43-46): y = (x - mean) [* istd], rows x dim fp32. */
 /* Number of kernels this handle has launched so far (oe_fbank_batch and oe_resample; every launch site of the
  * library counts itself).  bench.py reports the difference over its timed region as `gpu_launches`. */
@@ -152,6 +167,8 @@ int64_t oe_frontend_launch_count(const oe_frontend* fe);
  * kernel's duration.  bench.py uses it to report the dominant kernel's launch time INSIDE the timed step. */
 int oe_frontend_set_kernel_timing(oe_frontend* fe, int32_t on);
 int oe_frontend_fbank_kernel_ms(oe_frontend* fe, float* ms);
+/* same hook: duration of the whole launch sequence of the most recent call (metadata copy .. last kernel) */
+int oe_frontend_step_ms(oe_frontend* fe, float* ms);
 
 int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
                   const float* d_istd, oe_stream stream);

@@ -66,12 +66,19 @@ SYMBOLS = {
     'oe_frontend_launch_count': (ctypes.c_int64, [ctypes.c_void_p]),
     'oe_frontend_set_kernel_timing': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     'oe_frontend_fbank_kernel_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    'oe_frontend_step_ms': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     'oe_frontend_get_tables': (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p]),
     'oe_num_frames': (ctypes.c_int32, [ctypes.c_void_p, ctypes.c_int64]),
     'oe_fbank_workspace_bytes': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeBatch),
                                                 ctypes.POINTER(ctypes.c_size_t)]),
     'oe_fbank_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeBatch), ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    'oe_batch_prepare': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeBatch), ctypes.POINTER(ctypes.c_void_p)]),
+    'oe_prepared_destroy': (ctypes.c_int, [ctypes.c_void_p]),
+    'oe_prepared_workspace_bytes': (ctypes.c_size_t, [ctypes.c_void_p]),
+    'oe_prepared_frames': (c_i32p, [ctypes.c_void_p]),
+    'oe_fbank_run': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_size_t, ctypes.c_void_p]),
     'oe_cmvn_apply': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'oe_add_resampler': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_f32p,
@@ -100,6 +107,7 @@ def build(force=False, verbose=False):
     src = os.path.join(CSRC, 'oe_frontend.cu')
     deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
             os.path.join(CSRC, 'oe_fbank2_kernel.cuh'), os.path.join(CSRC, 'oe_mel80.h'),
+            os.path.join(CSRC, 'oe_rs_coefs.h'),
             os.path.join(os.path.dirname(CSRC), '..', 'include', 'openeat_frontend.h')]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
         cmd = ['nvcc'] + NVCC_FLAGS + ['-o', LIB_PATH, src]

@@ -54,8 +54,9 @@ struct Smem {
     static constexpr int TwU = TwA + 16 * 144;                         // float2 (cos, sin)(2 pi (k1 + 16 k2) / 512), k2 < 8: 16 rows x 80 B
     static constexpr int Mask = TwU + 16 * 80;                         // uchar rowmask[32], colmask[96]
     static constexpr int Desc = Mask + 128;                            // TileDesc[2]
-    static constexpr int Acc = Desc + 96;                              // double acc[3][2][80]
-    static constexpr int End = Acc + 3 * 2 * kF * 8;
+    static constexpr int Acc = Desc + 96;                              // long long acc[3][2][80]: fixed-point CMVN statistics
+    static constexpr int Flag = Acc + 3 * 2 * kF * 8;                  // int: "this is the last CTA"
+    static constexpr int End = Flag + 16;
     static_assert(Raw % 16 == 0 && Tile % 16 == 0 && TwA % 16 == 0 && TwU % 16 == 0 && Desc % 16 == 0 && Acc % 8 == 0, "align");
     static_assert(End + 1024 <= 116224, "two CTAs per SM");
     static_assert(!kRs || kRsMaxIn * 4 <= 16 * kXGroup, "fp32 resampler input must fit the exchange areas");
@@ -108,6 +109,16 @@ __device__ __forceinline__ void mel_group2(const float* __restrict__ pcol, const
     });
 }
 
+// Fixed-point scales of the CMVN-statistics accumulators (compute_cmvn_stats): integer adds commute, so the call's sums
+// are bitwise reproducible however the tiles are spread over CTAs, and the CTAs can add straight into one global
+// accumulator (no per-CTA partials, no reduction kernel).  Range per call: |sum| < 2^63 / 2^28 = 3.4e10 (log-mel
+// magnitudes <= 40: 8e8 frames), sum of squares < 2^63 / 2^24 = 5.5e11 (3e8 frames = 950 h of audio in one batch).
+constexpr double kFxSum = 268435456.0;      // 2^28
+constexpr double kFxSq = 16777216.0;        // 2^24
+__device__ __forceinline__ long long fx(double v, double scale) { return __double2ll_rn(v * scale); }
+// release / acquire fence at GPU scope
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // kDither: kaldi.fbank's dither (kaldi.py:179-181), one independent N(0,1) per frame element before DC removal; a
 // separate instantiation because the Philox + Box-Muller code roughly triples the front.
 template <bool kF32, bool kRs, bool kDither = false>
@@ -119,7 +130,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     unsigned char* const sRowMask = smem + S::Mask;
     unsigned char* const sColMask = sRowMask + 32;
     TileDesc* const sDesc = reinterpret_cast<TileDesc*>(smem + S::Desc);
-    double* const sAcc = reinterpret_cast<double*>(smem + S::Acc);
+    long long* const sAcc = reinterpret_cast<long long*>(smem + S::Acc);
+    int* const sFlag = reinterpret_cast<int*>(smem + S::Flag);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tau = tid & 15, grp = tid >> 4;
@@ -127,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     const DevTables* __restrict__ tab = P.tab;
     constexpr int F = kF, rowO = kOutRow;
 
-    if (P.cta_stats != nullptr)
-        for (int i = tid; i < 3 * 2 * F; i += kThreads) sAcc[i] = 0.0;
+    if (P.stat_acc != nullptr)
+        for (int i = tid; i < 3 * 2 * F; i += kThreads) sAcc[i] = 0;
 
     int tile = blockIdx.x;
     int slot = 0;
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                 }
             }
             __syncthreads();                                       // (5) output tile complete
-            if (P.tile_stats != nullptr || P.cta_stats != nullptr) {
+            if (P.tile_stats != nullptr || P.stat_acc != nullptr) {
                 for (int idx = tid; idx < 3 * F; idx += kThreads) {
                     const int rg = idx / F, f = idx - rg * F;
                     const int n = stats_rows(nvalid, rg);
@@ -419,9 +431,9 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
                             const float d = r < n ? x[r] - mean : 0.f;
                             m2 = fmaf(d, d, m2);
                         }
-                        if (P.cta_stats != nullptr) {          // sum x^2 = M2 + n mean^2, accumulated in fp64, fixed order
-                            sAcc[(rg * 2 + 0) * F + f] += (double)s;
-                            sAcc[(rg * 2 + 1) * F + f] += (double)m2 + (double)s * (double)mean;
+                        if (P.stat_acc != nullptr) {           // sum x^2 = M2 + n mean^2, fixed point: order-independent
+                            sAcc[(rg * 2 + 0) * F + f] += fx((double)s, kFxSum);
+                            sAcc[(rg * 2 + 1) * F + f] += fx((double)m2 + (double)s * (double)mean, kFxSq);
                         }
                     }
                     if (P.tile_stats != nullptr) {
@@ -524,12 +536,26 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
         }
     }
     cp_async_wait_all();
-    if (P.cta_stats != nullptr) {      // each accumulator is owned by one thread: no barrier needed
-        for (int idx = tid; idx < 3 * F; idx += kThreads) {
+    if (P.stat_acc != nullptr) {
+        for (int idx = tid; idx < 3 * F; idx += kThreads) {      // each accumulator is owned by one thread: no barrier needed
             const int rg = idx / F, f = idx - rg * F;
-            double* const dst = P.cta_stats + ((int64_t)blockIdx.x * 3 + rg) * 2 * F;
-            dst[f] = sAcc[(rg * 2 + 0) * F + f];
-            dst[F + f] = sAcc[(rg * 2 + 1) * F + f];
+            atomicAdd(P.stat_acc + f, (unsigned long long)sAcc[(rg * 2 + 0) * F + f]);
+            atomicAdd(P.stat_acc + F + f, (unsigned long long)sAcc[(rg * 2 + 1) * F + f]);
+        }
+        // the last CTA to get here converts the call's integer sums and adds them to the caller's accumulator
+        __syncthreads();
+        if (tid == 0) {
+            fence_gpu();
+            sFlag[0] = atomicAdd(P.sched, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (sFlag[0] && P.d_stats != nullptr) {
+            fence_gpu();
+            for (int i = tid; i < 2 * F; i += kThreads) {
+                const long long a = (long long)__ldcg(P.stat_acc + i);
+                P.d_stats[i] += (double)a * (i < F ? 1.0 / kFxSum : 1.0 / kFxSq);
+            }
+            if (tid == 0) P.d_stats[2 * F] += P.stat_count;
         }
     }
 }

@@ -83,6 +83,11 @@ struct FbankParams {
     float* tile_stats;              // [total_tiles][3][2][F]: per row-group column sum and sum of squared deviations
     double* cta_stats;              // [gridDim.x][3][2][F] or null: this CTA's running sum / sum of squares (fp64)
     const DevTables* tab;
+    // ---- gen-2 kernel: CMVN statistics (compute_cmvn_stats) accumulated inside the kernel ----
+    unsigned long long* stat_acc;   // [2F] fixed-point sum / sum of squares of this call (zeroed by the descriptor kernel); null = none
+    int32_t* sched;                 // [0]: CTAs that have finished (zeroed likewise): the last one converts stat_acc
+    double* d_stats;                // caller's accumulator [2F+1]: += the call's sums and frame count
+    double stat_count;
     float mel_w[512];               // standard-structure fast path: weights (x 1/4) in mel80::kOff order;
                                     // lives in the kernel-parameter constant bank -> FFMA constant operands
     float rs_coef[2][256];          // fused speed perturb: sinc taps [new = 10][taps] for 9:10 and 11:10

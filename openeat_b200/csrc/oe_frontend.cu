@@ -69,6 +69,10 @@ struct DevTables {
     float mel_w[kMaxNnz];           // already multiplied by 1/4 (see untangle_power)
 };
 
+// 1 / rows for rows = 0..11, correctly rounded (rows <= 11: one fp32 rounding on a partial mean)
+__constant__ float kInvRows[12] = {0.f, 1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.f / 5.f, 1.f / 6.f,
+                                   1.f / 7.f, 1.f / 8.f, 1.f / 9.f, 1.f / 10.f, 1.f / 11.f};
+
 }  // namespace oe
 
 #include "oe_mel80.h"
@@ -90,6 +94,10 @@ struct TileDescParams {
     TileDesc* tiles;
     int B, total_tiles;
     int feats;                   // the input already is features: offsets / lengths count rows
+    // per-call state of the gen-2 kernel's in-kernel CMVN statistics, reset here (stream-ordered before the fbank kernel)
+    int32_t* sched;              // [1] or null: CTAs done
+    unsigned long long* stat_acc;    // [n_acc] or null
+    int n_acc;
 };
 
 // Expands the per-utterance metadata into one self-contained descriptor per 32-frame tile.
@@ -105,6 +113,12 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
         __syncthreads();
     }
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        const int stride = gridDim.x * blockDim.x;
+        if (P.stat_acc != nullptr)
+            for (int i = tile; i < P.n_acc; i += stride) P.stat_acc[i] = 0ull;
+        if (P.sched != nullptr && tile == 0) P.sched[0] = 0;
+    }
     if (tile >= P.total_tiles) return;
     const int b = staged ? find_utt(sh_prefix, P.B, tile) : find_utt(P.tile_prefix, P.B, tile);
     const int t0 = (tile - P.tile_prefix[b]) * kTileFrames;
@@ -143,10 +157,6 @@ struct UttStatsParams {
 constexpr int kUttSlices = 8;
 constexpr int kUttMaxPart = 12;          // partial sums per slice held in registers: covers 32 tiles = 1 024 frames per utterance
 constexpr int kGlobStats = 8;            // statistics per global-role block
-
-// 1 / rows for rows = 0..11, correctly rounded (rows <= 11: one fp32 rounding on a partial mean)
-__constant__ float kInvRows[12] = {0.f, 1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.f / 5.f, 1.f / 6.f,
-                                   1.f / 7.f, 1.f / 8.f, 1.f / 9.f, 1.f / 10.f, 1.f / 11.f};
 
 // Block role 1 (blockIdx.x < B), feature_processor.py:5-8: mean and population std over the frames of one utterance,
 // merged from the per-tile partials in a fixed order (fp64): mean = S/N, M2 = sum_p [M2_p + n_p (mean_p - mean)^2]
@@ -427,6 +437,152 @@ __global__ void __launch_bounds__(256) oe_finalize_kernel(const FinalizeParams P
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// In-place completion of the padded tensor (gen-2 path without spec_sub): the fbank kernel has written the RAW log-mel
+// rows straight to their final place (L2 evict_last) together with the per-tile column statistics; this kernel
+//   1. merges the utterance's tile statistics itself (feature_processor.py:5-8: mean and population std per bin, fp64,
+//      fixed order: row group y of every tile in tile order, then y = 0, 1, 2; two passes, robust for constant features)
+//      -- no separate statistics kernel, no mean / std round trip through global memory;
+//   2. rewrites the rows in place: (x - mean) * (1 / std) -> [feature dither] -> [time / frequency masks -> 0] ->
+//      [(y - cmvn_mean) * cmvn_istd], and fills the padding rows [frames, nrows) with 0 or (0 - mean) * istd
+//      (dataset.py:195-218, cmvn.py:43-46).
+// No raw scratch: the step's DRAM traffic is the PCM in and the padded tensor out (the re-read hits L2).
+// grid = (utterance, part): every part redoes the (small) merge of its utterance and handles a contiguous share of the
+// rows; block = 512 threads = 25 row lanes x 20 float4 columns, four rows in flight per thread.
+struct Finalize2Params {
+    float* out;
+    int64_t pitch;
+    const int64_t* out_row;      // [B]
+    const int64_t* row_prefix;   // [B+1] output rows (frames + padding)
+    const int32_t* n_frames;
+    const int32_t* tile_prefix;  // [B+1]
+    const float* tile_stats;     // [tiles][3][2][F], null without normalisation
+    const int32_t* tmask;
+    const int32_t* fmask;
+    int n_tmask, n_fmask;
+    const float* cmvn_mean;
+    const float* cmvn_istd;
+    int cmvn_on_pad;
+    int parts;
+    float dither_a;
+    unsigned long long dither_seed;
+};
+constexpr int kFin2Threads = 512;
+template <bool DITHER>
+__global__ void __launch_bounds__(kFin2Threads, 2) oe_finalize2_kernel(const Finalize2Params P) {
+    constexpr int F = 80;
+    __shared__ double shD[3][F];
+    __shared__ float shC[2][F];
+    grid_dep_wait();
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nfr = P.n_frames[b];
+    const int nrows = (int)(P.row_prefix[b + 1] - P.row_prefix[b]);
+    const int per = (nrows + P.parts - 1) / P.parts;
+    const int r_lo = blockIdx.y * per, r_hi = min(nrows, r_lo + per);
+    if (r_lo >= r_hi) return;
+    const bool norm = P.tile_stats != nullptr && r_lo < nfr;           // a part that only holds padding needs no statistics
+    if (norm) {
+        const int f = tid % F, y = tid / F;                            // y < 3: row group y of every tile
+        const int tile0 = P.tile_prefix[b], ntiles = P.tile_prefix[b + 1] - tile0;
+        const float* const base = P.tile_stats + ((int64_t)tile0 * 3 + (y < 3 ? y : 0)) * 2 * F + f;
+        const int nt = y < 3 ? ntiles : 0;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int tl = 0; tl < nt; ++tl) acc += (double)__ldcg(base + tl * 6 * F);
+        if (y < 3) shD[y][f] = acc;
+        __syncthreads();
+        const double S = shD[0][f] + shD[1][f] + shD[2][f];
+        const double mean = S / (double)nfr;
+        __syncthreads();
+        acc = 0.0;
+#pragma unroll 8
+        for (int tl = 0; tl < nt; ++tl) {
+            const int rows = stats_rows(min(kTileFrames, nfr - tl * kTileFrames), y);
+            const float sp = __ldcg(base + tl * 6 * F), m2p = __ldcg(base + tl * 6 * F + F);
+            const double d = (double)(sp * kInvRows[rows]) - mean;
+            acc += rows > 0 ? (double)m2p + (double)rows * d * d : 0.0;
+        }
+        if (y < 3) shD[y][f] = acc;
+        __syncthreads();
+        if (y == 0) {
+            const double m2 = shD[0][f] + shD[1][f] + shD[2][f];
+            shC[0][f] = (float)mean;
+            shC[1][f] = 1.0f / (float)sqrt(m2 / (double)nfr);          // 0 variance: 1/0 = inf, 0 * inf = NaN like x/0
+        }
+        __syncthreads();
+    }
+    const int q = tid % 20, rl = tid / 20;                             // 25 row lanes x 20 float4 columns
+    constexpr int kLanes = 25;
+    if (rl >= kLanes) return;
+    const int c = 4 * q;
+    const bool has_cm = P.cmvn_mean != nullptr, has_ci = P.cmvn_istd != nullptr;
+    float mean4[4], rstd4[4], cm[4], ci[4], padv[4];
+    bool cmask[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        mean4[e] = norm ? shC[0][c + e] : 0.f;
+        rstd4[e] = norm ? shC[1][c + e] : 1.f;
+        cm[e] = has_cm ? __ldg(P.cmvn_mean + c + e) : 0.f;
+        ci[e] = has_ci ? __ldg(P.cmvn_istd + c + e) : 1.f;
+        padv[e] = (has_cm && P.cmvn_on_pad) ? (0.f - cm[e]) * ci[e] : 0.f;
+        bool m = false;
+        for (int j = 0; j < P.n_fmask; ++j) {
+            const int32_t* r = P.fmask + ((int64_t)b * P.n_fmask + j) * 2;
+            m |= (c + e >= __ldg(r)) & (c + e < __ldg(r + 1));
+        }
+        cmask[e] = m;
+    }
+    const int32_t* const tm = P.tmask + (int64_t)b * P.n_tmask * 2;
+    constexpr int kTm = 4;                                             // time masks held in registers
+    int tm_lo[kTm], tm_hi[kTm];
+#pragma unroll
+    for (int j = 0; j < kTm; ++j) {
+        tm_lo[j] = j < P.n_tmask ? __ldg(tm + 2 * j) : 0;
+        tm_hi[j] = j < P.n_tmask ? __ldg(tm + 2 * j + 1) : 0;
+    }
+    const int pitch = (int)P.pitch;
+    float* const odst = P.out + P.out_row[b] * P.pitch + c;
+    const int real_hi = min(r_hi, nfr);
+    constexpr int kU = 4;
+#pragma unroll 1
+    for (int t0 = r_lo + rl; t0 < real_hi; t0 += kLanes * kU) {
+        float4 x[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (t0 + kLanes * u < real_hi) x[u] = __ldcg(reinterpret_cast<const float4*>(odst + (int64_t)(t0 + kLanes * u) * pitch));
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int t = t0 + kLanes * u;
+            if (t < real_hi) {
+                bool rmask = false;
+#pragma unroll
+                for (int j = 0; j < kTm; ++j) rmask |= (t >= tm_lo[j]) & (t < tm_hi[j]);
+                for (int j = kTm; j < P.n_tmask; ++j) rmask |= (t >= __ldg(tm + 2 * j)) & (t < __ldg(tm + 2 * j + 1));
+                float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                float du[4] = {0.f, 0.f, 0.f, 0.f};
+                if (DITHER) {
+                    const uint4 rn = philox4x32_10(make_uint4((unsigned)q, (unsigned)t, (unsigned)b, 0u),
+                                                   make_uint2((unsigned)P.dither_seed, (unsigned)(P.dither_seed >> 32)));
+                    const unsigned w[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) du[e] = ((float)(w[e] >> 8) * (1.0f / 16777216.0f) - 0.5f) * P.dither_a;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float yv = (v[e] - mean4[e]) * rstd4[e];           // mean = 0, rstd = 1 without normalisation: exact
+                    if (DITHER) yv += du[e];
+                    if (rmask || cmask[e]) yv = 0.f;
+                    v[e] = (yv - cm[e]) * ci[e];                       // cm = 0, ci = 1 without CMVN: exact
+                }
+                *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    const float4 pv = make_float4(padv[0], padv[1], padv[2], padv[3]);
+#pragma unroll 4
+    for (int t = max(r_lo, nfr) + rl; t < r_hi; t += kLanes) *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = pv;
+}
+
 // Padding rows of the single-pass layout: the fbank kernel writes whole 32-frame tiles (real frames plus the padding
 // rows that share the last tile); rows [32 ceil(frames / 32), out_nrows) of every utterance are filled here with
 // 0 or (0 - mean) * istd (dataset.py:214-218 pad_sequence, then GlobalCMVN on the padded tensor).  Reads only the
@@ -625,10 +781,20 @@ struct oe_frontend {
     bool std_mel;                  // the mel matrix has the baked mel80 structure -> kernels with a compile-time mel structure
     bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
+    int fin2_parts;                // OE_FIN2_PARTS=n: blocks per utterance of oe_finalize2_kernel (tuning only; 0 = automatic)
+    bool no_inplace;               // OE_NO_INPLACE=1: raw scratch + statistics kernel + out-of-place finalize behind the gen-2 kernel (A/B timing only)
+    // pinned staging ring for the per-call metadata block (a pageable source would make cudaMemcpyAsync wait for the
+    // stream); a slot is reused once the copy that read it has completed
+    static constexpr int kMetaSlots = 4;
+    unsigned char* h_meta[kMetaSlots];
+    size_t h_meta_cap[kMetaSlots];
+    cudaEvent_t h_meta_ev[kMetaSlots];
+    int h_meta_next;
     long long launches;            // kernels launched through this handle
     bool timing;                   // oe_frontend_set_kernel_timing
     bool timed;                    // the events below bracket a kernel of the most recent call
     cudaEvent_t ev_begin, ev_end;
+    cudaEvent_t ev_step[2];        // timing on: the whole launch sequence of the most recent call
     float mel_w_std[512];
 };
 
@@ -729,12 +895,14 @@ struct Meta {               // device-side metadata block layout (byte offsets i
     size_t wav_off, out_row, frame_prefix, row_prefix, map_off;          // int64 arrays
     size_t wav_len, n_frames, n_rows, tile_prefix, rs_mode, tmask, fmask, fmap, tiles;   // int32 arrays
     size_t meta_bytes;
-    size_t raw, tile_stats, utt_mean, utt_std, stat_partial, total;
+    size_t raw, tile_stats, utt_mean, utt_std, stat_partial, sched, stat_acc, total;
     int max_rows;
     int64_t total_frames, total_rows, total_map;
     int64_t pad_rows;           // output rows behind the last 32-frame tile of each utterance
     int total_tiles;
     bool two_phase, need_stats, feats;
+    bool k2;                    // the gen-2 kernel (standard 80-bin mel matrix, waveform input) runs this batch
+    bool inplace_ok;            // ... writes the raw rows to their final place, oe_finalize2_kernel completes them there
 };
 
 int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t>* frames_out) {
@@ -761,6 +929,8 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.two_phase = feats || bt->norm_mode != OE_NORM_NONE || bt->frame_map != nullptr || bt->feature_dither != 0.f;
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
+    M.k2 = !feats && fe->mel_baked && !fe->force_v1;
+    M.inplace_ok = M.k2 && M.two_phase && !bt->frame_map && !fe->no_inplace && F % 4 == 0 && pitch % 4 == 0;
     M.total_frames = M.total_rows = M.total_map = 0;
     M.pad_rows = 0;
     M.max_rows = 0;
@@ -786,7 +956,7 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
         M.total_frames += nfr;
         M.total_rows += nrows;
         M.max_rows = std::max(M.max_rows, nrows);
-        tiles += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;      // padding rows behind the last tile: oe_pad_fill_kernel
+        tiles += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;      // single pass: padding rows behind the last tile: oe_pad_fill_kernel
         M.pad_rows += std::max(0, nrows - (nfr + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
         if (bt->frame_map) M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
     }
@@ -809,11 +979,14 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.fmap = take(4 * (size_t)M.total_map);
     M.meta_bytes = o;
     M.tiles = take(sizeof(oe::TileDesc) * (size_t)M.total_tiles);
-    M.raw = take(M.two_phase && !feats ? 4 * (size_t)M.total_frames * F : 0);
+    // raw log-mel scratch: not when the rows are finished in place
+    M.raw = take(M.two_phase && !feats && !M.inplace_ok ? 4 * (size_t)M.total_frames * F : 0);
     M.tile_stats = take(M.need_stats ? 4 * (size_t)M.total_tiles * 3 * 2 * F : 0);
-    M.utt_mean = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
-    M.utt_std = take(bt->norm_mode != OE_NORM_NONE ? 4 * (size_t)B * F : 0);
-    M.stat_partial = take(bt->d_stats ? 8 * (size_t)(fe->sm_count * 8) * 3 * 2 * F : 0);
+    M.utt_mean = take(bt->norm_mode != OE_NORM_NONE && !M.inplace_ok ? 4 * (size_t)B * F : 0);
+    M.utt_std = take(bt->norm_mode != OE_NORM_NONE && !M.inplace_ok ? 4 * (size_t)B * F : 0);
+    M.stat_partial = take(bt->d_stats && !M.k2 ? 8 * (size_t)(fe->sm_count * 8) * 3 * 2 * F : 0);
+    M.sched = take(M.k2 ? 16 : 0);
+    M.stat_acc = take(M.k2 && bt->d_stats ? 8 * (size_t)2 * F : 0);
     M.total = o;
     return OE_OK;
 }
@@ -863,9 +1036,16 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->launches = 0;
     fe->timing = fe->timed = false;
     fe->ev_begin = fe->ev_end = nullptr;
+    fe->ev_step[0] = fe->ev_step[1] = nullptr;
     fe->d_rs = nullptr;
     fe->d_rs_coefs = nullptr;
     fe->rs_fast_9_10 = fe->rs_fast_11_10 = -1;
+    fe->h_meta_next = 0;
+    for (int i = 0; i < oe_frontend::kMetaSlots; ++i) {
+        fe->h_meta[i] = nullptr;
+        fe->h_meta_cap[i] = 0;
+        fe->h_meta_ev[i] = nullptr;
+    }
     const int nb = cfg->num_mel_bins, nf = cfg->fft_size / 2;
     if (window) fe->window.assign(window, window + cfg->frame_length); else default_window(cfg->frame_length, fe->window);
     if (mel) fe->mel.assign(mel, mel + (size_t)nb * nf); else default_mel(*cfg, fe->mel);
@@ -957,6 +1137,10 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     {   // developer switch for A/B timing: OE_FBANK_V1=1 keeps the first-generation kernel on the standard mel layout
         const char* v1 = getenv("OE_FBANK_V1");
         fe->force_v1 = v1 && v1[0] == '1';
+        const char* fp_ = getenv("OE_FIN2_PARTS");
+        fe->fin2_parts = fp_ ? atoi(fp_) : 0;
+        const char* nf = getenv("OE_NO_INPLACE");
+        fe->no_inplace = nf && nf[0] == '1';
     }
     if (e != cudaSuccess) {
         if (fe->d_tab) cudaFree(fe->d_tab);
@@ -974,6 +1158,12 @@ int oe_frontend_destroy(oe_frontend* fe) {
     if (!fe) return OE_OK;
     if (fe->ev_begin) cudaEventDestroy(fe->ev_begin);
     if (fe->ev_end) cudaEventDestroy(fe->ev_end);
+    for (int i = 0; i < 2; ++i)
+        if (fe->ev_step[i]) cudaEventDestroy(fe->ev_step[i]);
+    for (int i = 0; i < oe_frontend::kMetaSlots; ++i) {
+        if (fe->h_meta_ev[i]) cudaEventDestroy(fe->h_meta_ev[i]);
+        if (fe->h_meta[i]) cudaFreeHost(fe->h_meta[i]);
+    }
     cudaFree(fe->d_tab);
     cudaFree(fe->d_rs);
     cudaFree(fe->d_rs_coefs);
@@ -989,6 +1179,8 @@ int oe_frontend_set_kernel_timing(oe_frontend* fe, int32_t on) {
         OE_CUDA(cudaSetDevice(fe->device));
         OE_CUDA(cudaEventCreate(&fe->ev_begin));
         OE_CUDA(cudaEventCreate(&fe->ev_end));
+        OE_CUDA(cudaEventCreate(&fe->ev_step[0]));
+        OE_CUDA(cudaEventCreate(&fe->ev_step[1]));
     }
     fe->timing = on != 0;
     fe->timed = false;
@@ -1000,6 +1192,14 @@ int oe_frontend_fbank_kernel_ms(oe_frontend* fe, float* ms) {
     if (!fe->timed) return fail(OE_ERR_INVALID, "no timed fbank kernel: enable oe_frontend_set_kernel_timing before oe_fbank_batch");
     OE_CUDA(cudaEventSynchronize(fe->ev_end));
     OE_CUDA(cudaEventElapsedTime(ms, fe->ev_begin, fe->ev_end));
+    return OE_OK;
+}
+
+int oe_frontend_step_ms(oe_frontend* fe, float* ms) {
+    if (!fe || !ms) return fail(OE_ERR_INVALID, "null pointer");
+    if (!fe->timed) return fail(OE_ERR_INVALID, "no timed call: enable oe_frontend_set_kernel_timing before oe_fbank_batch");
+    OE_CUDA(cudaEventSynchronize(fe->ev_step[1]));
+    OE_CUDA(cudaEventElapsedTime(ms, fe->ev_step[0], fe->ev_step[1]));
     return OE_OK;
 }
 
@@ -1019,29 +1219,50 @@ int oe_fbank_workspace_bytes(const oe_frontend* fe, const oe_batch* batch, size_
     return OE_OK;
 }
 
-int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float* d_out, void* d_ws,
-                   size_t ws_bytes, oe_stream stream_) {
-    Meta M;
-    std::vector<int32_t> frames;
-    int rc = plan(fe, bt, M, &frames);
-    if (rc != OE_OK) return rc;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int B = bt->batch, F = fe->cfg.num_mel_bins;
-    if (bt->out_frames) for (int b = 0; b < B; ++b) bt->out_frames[b] = frames[b];
-    if (B == 0) return OE_OK;
-    if (!d_wav) return fail(OE_ERR_INVALID, "null d_wav");
-    if (!d_out && !bt->d_stats) return fail(OE_ERR_INVALID, "nothing to produce: d_out and d_stats are both null");
-    if (!d_ws || ws_bytes < M.total) return fail(OE_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", M.total, ws_bytes);
-    if ((reinterpret_cast<uintptr_t>(d_ws) & 15) || (reinterpret_cast<uintptr_t>(d_wav) & 15))
-        return fail(OE_ERR_INVALID, "d_wav and d_workspace must be 16-byte aligned");
-    OE_CUDA(cudaSetDevice(fe->device));
+// Next slot of the handle's pinned metadata ring, at least `bytes` large; waits (normally not at all) until the copy
+// that last read the slot has completed.
+static int meta_slot(oe_frontend* fe, size_t bytes, unsigned char** out, int* slot_out) {
+    const int slot = fe->h_meta_next;
+    fe->h_meta_next = (slot + 1) % oe_frontend::kMetaSlots;
+    if (!fe->h_meta_ev[slot]) OE_CUDA(cudaEventCreateWithFlags(&fe->h_meta_ev[slot], cudaEventDisableTiming));
+    else OE_CUDA(cudaEventSynchronize(fe->h_meta_ev[slot]));
+    if (fe->h_meta_cap[slot] < bytes) {
+        if (fe->h_meta[slot]) OE_CUDA(cudaFreeHost(fe->h_meta[slot]));
+        fe->h_meta[slot] = nullptr;
+        fe->h_meta_cap[slot] = 0;
+        const size_t cap = align_up(bytes + bytes / 2 + 4096, 4096);
+        OE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&fe->h_meta[slot]), cap, cudaHostAllocDefault));
+        fe->h_meta_cap[slot] = cap;
+    }
+    *out = fe->h_meta[slot];
+    *slot_out = slot;
+    return OE_OK;
+}
 
-    // ---- pack metadata on the host, one stream-ordered copy to the workspace ----
-    std::vector<unsigned char> hm(M.meta_bytes, 0);
-    auto i64 = [&](size_t off) { return reinterpret_cast<int64_t*>(hm.data() + off); };
-    auto i32 = [&](size_t off) { return reinterpret_cast<int32_t*>(hm.data() + off); };
+// Scalars and device pointers of an oe_batch that the launch sequence needs (no host arrays): what a prepared batch keeps.
+struct LaunchInfo {
+    int B;
+    int wav_dtype, norm_mode, n_tmask, n_fmask, cmvn_on_padding;
+    int64_t out_pitch;
+    bool has_map, any_rs;
+    int max_pad;                 // single pass: most padding rows behind an utterance's last tile
+    const float* d_cmvn_mean;
+    const float* d_cmvn_istd;
+    double* d_stats;
+    float feature_dither, wav_dither;
+    unsigned long long dither_seed;
+};
+
+// Fills the metadata block `hm` (M.meta_bytes) and the launch scalars from the caller's batch description.
+static int pack_meta(const oe_frontend* fe, const oe_batch* bt, const Meta& M, const std::vector<int32_t>& frames,
+                     unsigned char* hm, LaunchInfo& L) {
+    const int B = bt->batch;
+    auto i64 = [&](size_t off) { return reinterpret_cast<int64_t*>(hm + off); };
+    auto i32 = [&](size_t off) { return reinterpret_cast<int32_t*>(hm + off); };
     int64_t fp = 0, rp = 0;
     int tp = 0;
+    L.max_pad = 0;
+    L.any_rs = false;
     for (int b = 0; b < B; ++b) {
         const int nfr = frames[b];
         const int nrows = bt->out_nrows ? bt->out_nrows[b] : nfr;
@@ -1054,7 +1275,10 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         i32(M.n_frames)[b] = nfr;
         i32(M.n_rows)[b] = M.two_phase ? nfr : nrows;
         i32(M.tile_prefix)[b] = tp;
-        i32(M.rs_mode)[b] = (bt->resample_ids && bt->resample_ids[b] >= 0) ? (bt->resample_ids[b] == fe->rs_fast_9_10 ? 1 : 2) : 0;
+        const bool rs = bt->resample_ids && bt->resample_ids[b] >= 0;
+        i32(M.rs_mode)[b] = rs ? (bt->resample_ids[b] == fe->rs_fast_9_10 ? 1 : 2) : 0;
+        L.any_rs |= rs;
+        L.max_pad = std::max(L.max_pad, nrows - (nfr + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
         fp += nfr;
         rp += nrows;
         tp += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;
@@ -1072,8 +1296,124 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             }
         memcpy(i32(M.fmap), bt->frame_map, 4 * (size_t)M.total_map);
     }
+    L.B = B;
+    L.wav_dtype = bt->wav_dtype;
+    L.norm_mode = bt->norm_mode;
+    L.n_tmask = bt->n_tmask;
+    L.n_fmask = bt->n_fmask;
+    L.cmvn_on_padding = bt->cmvn_on_padding;
+    L.out_pitch = bt->out_pitch;
+    L.has_map = bt->frame_map != nullptr;
+    L.d_cmvn_mean = bt->d_cmvn_mean;
+    L.d_cmvn_istd = bt->d_cmvn_istd;
+    L.d_stats = bt->d_stats;
+    L.feature_dither = bt->feature_dither;
+    L.wav_dither = bt->wav_dither;
+    L.dither_seed = bt->dither_seed;
+    return OE_OK;
+}
+
+static int launch_batch(oe_frontend* fe, const Meta& M, const LaunchInfo& L, const unsigned char* meta, const void* d_wav,
+                        float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
+
+int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float* d_out, void* d_ws,
+                   size_t ws_bytes, oe_stream stream_) {
+    Meta M;
+    std::vector<int32_t> frames;
+    int rc = plan(fe, bt, M, &frames);
+    if (rc != OE_OK) return rc;
+    const int B = bt->batch;
+    if (bt->out_frames) for (int b = 0; b < B; ++b) bt->out_frames[b] = frames[b];
+    if (B == 0) return OE_OK;
+    // the metadata is packed straight into a slot of the handle's pinned ring
+    OE_CUDA(cudaSetDevice(fe->device));
+    unsigned char* hm = nullptr;
+    int hslot = 0;
+    rc = meta_slot(fe, M.meta_bytes, &hm, &hslot);
+    if (rc != OE_OK) return rc;
+    LaunchInfo L;
+    rc = pack_meta(fe, bt, M, frames, hm, L);
+    if (rc != OE_OK) return rc;
+    return launch_batch(fe, M, L, nullptr, d_wav, d_out, d_ws, ws_bytes, (cudaStream_t)stream_) ;
+}
+
+// ---- prepared batches: validate + pack once, launch many times (or later) with no host work beyond one memcpy ----
+struct oe_prepared {
+    Meta M;
+    LaunchInfo L;
+    std::vector<int32_t> frames;
+    std::vector<unsigned char> meta;
+};
+
+int oe_batch_prepare(oe_frontend* fe, const oe_batch* bt, oe_prepared** out) {
+    if (!out) return fail(OE_ERR_INVALID, "null out");
+    *out = nullptr;
+    oe_prepared* p = new oe_prepared();
+    int rc = plan(fe, bt, p->M, &p->frames);
+    if (rc == OE_OK) {
+        p->meta.assign(p->M.meta_bytes, 0);
+        rc = pack_meta(fe, bt, p->M, p->frames, p->meta.data(), p->L);
+    }
+    if (rc != OE_OK) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return OE_OK;
+}
+
+int oe_prepared_destroy(oe_prepared* p) {
+    delete p;
+    return OE_OK;
+}
+
+size_t oe_prepared_workspace_bytes(const oe_prepared* p) { return p ? p->M.total + 256 : 0; }
+const int32_t* oe_prepared_frames(const oe_prepared* p) { return p ? p->frames.data() : nullptr; }
+
+int oe_fbank_run(oe_frontend* fe, const oe_prepared* p, const void* d_wav, float* d_out, void* d_ws, size_t ws_bytes,
+                 oe_stream stream) {
+    if (!fe || !p) return fail(OE_ERR_INVALID, "null frontend or prepared batch");
+    if (p->L.B == 0) return OE_OK;
+    OE_CUDA(cudaSetDevice(fe->device));
+    return launch_batch(fe, p->M, p->L, p->meta.data(), d_wav, d_out, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// `meta` null: the block has just been packed into the ring slot handed out last (oe_fbank_batch); otherwise it is
+// copied into the next slot first.
+static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L, const unsigned char* meta, const void* d_wav,
+                             float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t stream);
+static int launch_batch(oe_frontend* fe, const Meta& M, const LaunchInfo& L, const unsigned char* meta, const void* d_wav,
+                        float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t stream) {
+    if (fe->timing) OE_CUDA(cudaEventRecord(fe->ev_step[0], stream));
+    const int rc = launch_batch_impl(fe, M, L, meta, d_wav, d_out, d_ws, ws_bytes, stream);
+    if (fe->timing && rc == OE_OK) OE_CUDA(cudaEventRecord(fe->ev_step[1], stream));
+    return rc;
+}
+static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L, const unsigned char* meta, const void* d_wav,
+                             float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t stream) {
+    const LaunchInfo* const bt = &L;            // same field names as oe_batch below
+    const int B = L.B, F = fe->cfg.num_mel_bins;
+    if (!d_wav) return fail(OE_ERR_INVALID, "null d_wav");
+    if (!d_out && !bt->d_stats) return fail(OE_ERR_INVALID, "nothing to produce: d_out and d_stats are both null");
+    if (!d_ws || ws_bytes < M.total) return fail(OE_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", M.total, ws_bytes);
+    if ((reinterpret_cast<uintptr_t>(d_ws) & 15) || (reinterpret_cast<uintptr_t>(d_wav) & 15))
+        return fail(OE_ERR_INVALID, "d_wav and d_workspace must be 16-byte aligned");
+    const bool inplace = M.inplace_ok && d_out != nullptr;
+    if (inplace && (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return fail(OE_ERR_INVALID, "d_out must be 16-byte aligned (rows are finished in place with 16-byte accesses)");
+    unsigned char* hm = nullptr;
+    int hslot = 0;
+    if (meta) {
+        const int rc = meta_slot(fe, M.meta_bytes, &hm, &hslot);
+        if (rc != OE_OK) return rc;
+        memcpy(hm, meta, M.meta_bytes);
+    } else {
+        hslot = (fe->h_meta_next + oe_frontend::kMetaSlots - 1) % oe_frontend::kMetaSlots;
+        hm = fe->h_meta[hslot];
+    }
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
-    OE_CUDA(cudaMemcpyAsync(ws, hm.data(), M.meta_bytes, cudaMemcpyHostToDevice, stream));
+    OE_CUDA(cudaMemcpyAsync(ws, hm, M.meta_bytes, cudaMemcpyHostToDevice, stream));
+    OE_CUDA(cudaEventRecord(fe->h_meta_ev[hslot], stream));
 
     const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
     oe::FbankParams P;
@@ -1092,8 +1432,14 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
     P.tab = fe->d_tab;
     P.tile_stats = M.need_stats ? reinterpret_cast<float*>(ws + M.tile_stats) : nullptr;
     const int64_t* d_tile_out_row;
-    if (M.two_phase) {
-        P.out = reinterpret_cast<float*>(ws + M.raw);
+    if (inplace) {
+        // raw rows go straight to their final place; oe_finalize2_kernel completes them there
+        P.out = d_out;
+        P.keep_out_in_l2 = 1;
+        d_tile_out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        P.pitch = pitch;
+    } else if (M.two_phase) {
+        P.out = (d_out || !M.k2) ? reinterpret_cast<float*>(ws + M.raw) : nullptr;   // statistics only: no rows at all
         P.keep_out_in_l2 = 1;
         d_tile_out_row = reinterpret_cast<const int64_t*>(ws + M.frame_prefix);
         P.pitch = F;
@@ -1109,10 +1455,20 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         P.cmvn_istd = bt->d_cmvn_istd;
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
+    const int grid = M.feats ? 0 : std::min(M.total_tiles, 2 * fe->sm_count);
+    if (M.k2) {
+        P.sched = reinterpret_cast<int32_t*>(ws + M.sched);
+        if (bt->d_stats) {
+            P.stat_acc = reinterpret_cast<unsigned long long*>(ws + M.stat_acc);
+            P.d_stats = bt->d_stats;
+            P.stat_count = (double)M.total_frames;
+        }
+    }
     // float4 row stores: gen-1 kernel needs dense rows (pitch == F), gen-2 any 16-byte aligned pitch
-    P.out_vec = (((fe->mel_baked && !fe->force_v1) ? P.pitch % 4 == 0 : P.pitch == F) && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
+    P.out_vec = ((M.k2 ? P.pitch % 4 == 0 : P.pitch == F) && F % 4 == 0 && !(reinterpret_cast<uintptr_t>(P.out) & 15)) ? 1 : 0;
     if (M.total_tiles > 0) {
         oe::TileDescParams T;
+        memset(&T, 0, sizeof(T));
         T.tile_prefix = d_tile_prefix;
         T.wav_off = d_wav_off;
         T.wav_len = reinterpret_cast<const int32_t*>(ws + M.wav_len);
@@ -1124,6 +1480,9 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         T.B = B;
         T.total_tiles = M.total_tiles;
         T.feats = M.feats ? 1 : 0;
+        T.sched = P.sched;
+        T.stat_acc = P.stat_acc;
+        T.n_acc = 2 * F;
         oe::oe_tile_desc_kernel<<<(M.total_tiles + 127) / 128, 128, 0, stream>>>(T);
         ++fe->launches;
         OE_CUDA(cudaGetLastError());
@@ -1144,14 +1503,12 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             OE_CUDA(cudaGetLastError());
         }
     } else if (M.total_tiles > 0) {
-        const int grid = std::min(M.total_tiles, 2 * fe->sm_count);
         const bool f32 = bt->wav_dtype == OE_WAV_F32;
-        if (bt->d_stats) {
+        if (bt->d_stats && !M.k2) {
             P.cta_stats = reinterpret_cast<double*>(ws + M.stat_partial);
             n_stat_partials = 3 * grid;
         }
-        bool any_rs = false;
-        for (int b = 0; bt->resample_ids && b < B && !any_rs; ++b) any_rs = bt->resample_ids[b] >= 0;
+        const bool any_rs = bt->any_rs;
         ++fe->launches;
         P.wav_dither = bt->wav_dither;
         P.dither_seed = bt->dither_seed;
@@ -1159,7 +1516,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         if (bt->wav_dither != 0.f) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
-        } else if (fe->mel_baked && !fe->force_v1) {
+        } else if (M.k2) {
             if (f32) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<true, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<true, false>::End, stream, P));
             else if (any_rs) OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, true>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, true>::End, stream, P));
             else OE_CUDA(launch_dep(oe::k2::oe_fbank2_kernel<false, false>, dim3(grid), dim3(oe::kThreads), oe::k2::Smem<false, false>::End, stream, P));
@@ -1179,11 +1536,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         OE_CUDA(cudaGetLastError());
     }
     if (!M.two_phase && d_out && M.pad_rows > 0) {
-        int max_pad = 0;
-        for (int b = 0; b < B; ++b) {
-            const int nrows = bt->out_nrows ? bt->out_nrows[b] : frames[b];
-            max_pad = std::max(max_pad, nrows - (frames[b] + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
-        }
+        const int max_pad = bt->max_pad;
         oe::PadFillParams Q;
         Q.n_frames = d_n_frames;
         Q.n_rows = reinterpret_cast<const int32_t*>(ws + M.n_rows);
@@ -1196,8 +1549,40 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
         ++fe->launches;
         OE_CUDA(launch_dep(oe::oe_pad_fill_kernel, dim3(B, (max_pad + oe::kPadRows - 1) / oe::kPadRows), dim3(256), 0, stream, Q));
     }
+    if (inplace) {
+        if (M.total_rows == 0) return OE_OK;
+        oe::Finalize2Params Z;
+        memset(&Z, 0, sizeof(Z));
+        Z.out = d_out;
+        Z.pitch = pitch;
+        Z.out_row = reinterpret_cast<const int64_t*>(ws + M.out_row);
+        Z.row_prefix = reinterpret_cast<const int64_t*>(ws + M.row_prefix);
+        Z.n_frames = d_n_frames;
+        Z.tile_prefix = d_tile_prefix;
+        Z.tile_stats = bt->norm_mode != OE_NORM_NONE ? P.tile_stats : nullptr;
+        Z.tmask = reinterpret_cast<const int32_t*>(ws + M.tmask);
+        Z.fmask = reinterpret_cast<const int32_t*>(ws + M.fmask);
+        Z.n_tmask = bt->n_tmask;
+        Z.n_fmask = bt->n_fmask;
+        Z.cmvn_mean = bt->d_cmvn_mean;
+        Z.cmvn_istd = bt->d_cmvn_istd;
+        Z.cmvn_on_pad = bt->cmvn_on_padding;
+        Z.dither_a = bt->feature_dither;
+        Z.dither_seed = bt->dither_seed;
+        // parts per utterance: ~384 rows each, and at least four blocks per SM in total
+        int parts = std::max(1, (M.max_rows + 383) / 384);
+        parts = std::max(parts, (4 * fe->sm_count + B - 1) / B);
+        parts = std::min(parts, std::max(1, (M.max_rows + 31) / 32));
+        if (fe->fin2_parts > 0) parts = fe->fin2_parts;
+        Z.parts = parts;
+        ++fe->launches;
+        if (Z.dither_a != 0.f) OE_CUDA(launch_dep(oe::oe_finalize2_kernel<true>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+        else OE_CUDA(launch_dep(oe::oe_finalize2_kernel<false>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+        OE_CUDA(cudaGetLastError());
+        return OE_OK;
+    }
     {
-        const bool want_utt = bt->norm_mode != OE_NORM_NONE;
+        const bool want_utt = bt->norm_mode != OE_NORM_NONE && d_out != nullptr;
         const bool want_glob = bt->d_stats && n_stat_partials > 0;
         if (want_utt || want_glob) {
             oe::UttStatsParams U;
@@ -1237,7 +1622,7 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
             Z.utt_mean = reinterpret_cast<const float*>(ws + M.utt_mean);
             Z.utt_std = reinterpret_cast<const float*>(ws + M.utt_std);
         }
-        if (bt->frame_map) {
+        if (bt->has_map) {
             Z.frame_map = reinterpret_cast<const int32_t*>(ws + M.fmap);
             Z.map_off = reinterpret_cast<const int64_t*>(ws + M.map_off);
         }

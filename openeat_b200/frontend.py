@@ -94,6 +94,23 @@ def _ptr(arr, ptype):
     return arr.ctypes.data_as(ptype) if arr is not None else None
 
 
+class PreparedBatch(object):
+    """A batch description validated and packed by the library (``oe_batch_prepare``); see ``Frontend.prepare``."""
+
+    def __init__(self, fe, handle, batch, out_shape, needs_out, keep):
+        self.fe, self.handle, self.batch = fe, handle, batch
+        self.out_shape, self.needs_out, self._keep = out_shape, needs_out, keep
+        self.ws_bytes = int(fe.lib.oe_prepared_workspace_bytes(handle))
+        fr = fe.lib.oe_prepared_frames(handle)
+        self.frames = np.ctypeslib.as_array(fr, shape=(batch,)).copy() if batch else np.zeros(0, np.int32)
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.fe.lib.oe_prepared_destroy(h)
+            self.handle = None
+
+
 class Frontend(object):
     """One CUDA front-end handle (tables + resampler taps) on one device."""
 
@@ -247,17 +264,40 @@ class Frontend(object):
                   Box-Muller keyed by dither_seed (no value parity); not with speed_ratios (resample first).
         Returns (out tensor or None, frames int32 ndarray).
         """
+        if features_in:
+            dtype = OE_FEATS_F32
+        else:
+            if wav.dtype not in (torch.float32, torch.int16):
+                raise FrontendError('waveform must be int16 or float32, got %s' % wav.dtype)
+            dtype = OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16
+        prep = self.prepare(dtype, offsets, lens, layout=layout, out_shape=None if out is None else tuple(out.shape),
+                            max_rows=max_rows, out_rows=out_rows, out_nrows=out_nrows, normalization=normalization,
+                            tmask=tmask, fmask=fmask, frame_maps=frame_maps, cmvn=cmvn,
+                            cmvn_on_padding=cmvn_on_padding, stats=stats, want_out=want_out,
+                            speed_ratios=speed_ratios, feature_dither=feature_dither, dither_seed=dither_seed,
+                            wav_dither=wav_dither)
+        out = self.run(prep, wav, out=out, stream=stream)
+        return out, prep.frames
+
+    def prepare(self, wav_dtype, offsets, lens, *, layout='padded', out_shape=None, max_rows=None, out_rows=None,
+                out_nrows=None, normalization=False, tmask=None, fmask=None, frame_maps=None, cmvn=None,
+                cmvn_on_padding=False, stats=None, want_out=True, speed_ratios=None, feature_dither=0.0,
+                dither_seed=0, wav_dither=0.0):
+        """Validates and packs one batch description natively (``oe_batch_prepare``) and returns a ``PreparedBatch``
+        that ``run`` launches with no further host work -- same keywords as ``fbank`` (``wav_dtype``: OE_WAV_I16 /
+        OE_WAV_F32 / OE_FEATS_F32 or a torch dtype; ``out_shape``: shape of a caller-provided output tensor).  A
+        prepared batch can be run many times and on any stream; cmvn / stats tensors must outlive it."""
+        if isinstance(wav_dtype, torch.dtype):
+            wav_dtype = OE_WAV_F32 if wav_dtype == torch.float32 else OE_WAV_I16
+        features_in = wav_dtype == OE_FEATS_F32
         B = len(lens)
         F = self.mel_bins
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         lens = np.ascontiguousarray(lens, dtype=np.int32)
+        rs_ids = None
         if features_in:
-            dtype = OE_FEATS_F32
             frames = lens.copy()
         else:
-            dtype = OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16
-            if wav.dtype not in (torch.float32, torch.int16):
-                raise FrontendError('waveform must be int16 or float32, got %s' % wav.dtype)
             eff = lens.astype(np.int64)
             if speed_ratios is not None:
                 speed_ratios = np.asarray(speed_ratios, dtype=np.int64).reshape(B, 2)
@@ -270,17 +310,16 @@ class Frontend(object):
                     eff[sel] = (n * eff[sel] + o - 1) // o
             frames = self.num_frames_array(eff)
         nrows = None
+        shape = None
         if not want_out:
-            out = None
             out_rows = np.zeros(B, dtype=np.int64)
         elif layout == 'padded':
             tmax = int(frames.max()) if B else 0
             if max_rows is not None:
                 tmax = max(tmax, int(max_rows))
-            if out is None:
-                out = torch.empty((B, tmax, F), dtype=torch.float32, device=self.device)
-            else:
-                tmax = out.shape[1]
+            if out_shape is not None:
+                tmax = out_shape[1]
+            shape = (B, tmax, F)
             out_rows = np.arange(B, dtype=np.int64) * tmax
             nrows = np.full(B, tmax, dtype=np.int32)
         elif layout == 'ragged':
@@ -290,10 +329,9 @@ class Frontend(object):
                     out_rows[1:] = np.cumsum(frames[:-1].astype(np.int64))
             else:
                 out_rows = np.ascontiguousarray(out_rows, dtype=np.int64)
-            if out is None:
-                out = torch.empty((int(frames.sum()), F), dtype=torch.float32, device=self.device)
+            shape = (int(frames.sum()), F)
         elif layout == 'custom':
-            if out is None or out_rows is None:
+            if out_shape is None or out_rows is None:
                 raise FrontendError("layout='custom' needs out and out_rows")
             out_rows = np.ascontiguousarray(out_rows, dtype=np.int64)
             if out_nrows is not None:
@@ -313,8 +351,11 @@ class Frontend(object):
             fmap_off = np.zeros(B, dtype=np.int64)
             if B > 1:
                 fmap_off[1:] = np.cumsum(frames[:-1].astype(np.int64))
-            fmap = np.concatenate([np.asarray(m, dtype=np.int32) for m in frame_maps]) if B else np.zeros(0, np.int32)
-            fmap = np.ascontiguousarray(fmap, dtype=np.int32)
+            if isinstance(frame_maps, np.ndarray) and frame_maps.ndim == 1:      # already concatenated in batch order
+                fmap = np.ascontiguousarray(frame_maps, dtype=np.int32)
+            else:
+                fmap = np.concatenate([np.asarray(m, dtype=np.int32) for m in frame_maps]) if B else np.zeros(0, np.int32)
+                fmap = np.ascontiguousarray(fmap, dtype=np.int32)
             if fmap.shape[0] != int(frames.sum()):
                 raise FrontendError('frame_maps must have one entry per frame')
         mean_p = istd_p = None
@@ -322,22 +363,31 @@ class Frontend(object):
             mean, istd = cmvn
             mean_p = ctypes.c_void_p(mean.data_ptr())
             istd_p = ctypes.c_void_p(istd.data_ptr()) if istd is not None else None
-        out_frames = np.zeros(B, dtype=np.int32)
-        rs_p = _ptr(rs_ids, c_i32p) if (speed_ratios is not None and not features_in) else None
-        bt = OeBatch(B, dtype, _ptr(offsets, c_i64p), _ptr(lens, c_i32p), _ptr(out_rows, c_i64p),
+        bt = OeBatch(B, wav_dtype, _ptr(offsets, c_i64p), _ptr(lens, c_i32p), _ptr(out_rows, c_i64p),
                      _ptr(nrows, c_i32p), 0, OE_NORM_PER_UTT if normalization else OE_NORM_NONE, n_t, n_f,
                      _ptr(tm, c_i32p), _ptr(fm, c_i32p), _ptr(fmap, c_i32p), _ptr(fmap_off, c_i64p),
                      mean_p, istd_p, 1 if cmvn_on_padding else 0,
                      ctypes.c_void_p(stats.data_ptr()) if stats is not None else None,
-                     _ptr(out_frames, c_i32p), rs_p, float(feature_dither), int(dither_seed) & 0xFFFFFFFFFFFFFFFF, float(wav_dither))
-        need = ctypes.c_size_t()
-        check(self.lib.oe_fbank_workspace_bytes(self.handle, ctypes.byref(bt), ctypes.byref(need)))
+                     None, _ptr(rs_ids, c_i32p), float(feature_dither), int(dither_seed) & 0xFFFFFFFFFFFFFFFF,
+                     float(wav_dither))
+        handle = ctypes.c_void_p()
+        check(self.lib.oe_batch_prepare(self.handle, ctypes.byref(bt), ctypes.byref(handle)))
+        return PreparedBatch(self, handle, B, shape if want_out else None, layout == 'custom' and want_out,
+                             (cmvn, stats))
+
+    def run(self, prep, wav, out=None, stream=None):
+        """Launches a prepared batch on ``wav`` (packed device tensor).  Returns the output tensor (None when the batch
+        was prepared with want_out=False)."""
+        if out is None and prep.out_shape is not None:
+            out = torch.empty(prep.out_shape, dtype=torch.float32, device=self.device)
+        if prep.needs_out and out is None:
+            raise FrontendError("layout='custom' needs out")
         s, sp = self._stream(stream)
-        ws = self._workspace(('fb', s.cuda_stream), need.value)
-        check(self.lib.oe_fbank_batch(self.handle, ctypes.byref(bt), ctypes.c_void_p(wav.data_ptr()),
-                                      ctypes.c_void_p(out.data_ptr()) if out is not None else None,
-                                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
-        return out, out_frames
+        ws = self._workspace(('fb', s.cuda_stream), prep.ws_bytes)
+        check(self.lib.oe_fbank_run(self.handle, prep.handle, ctypes.c_void_p(wav.data_ptr()),
+                                    ctypes.c_void_p(out.data_ptr()) if out is not None else None,
+                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
+        return out
 
     def set_kernel_timing(self, on=True):
         """Measurement hook: bracket the fbank kernel of every following ``fbank`` call with CUDA events."""
@@ -347,6 +397,12 @@ class Frontend(object):
         """Duration of the fbank kernel of the most recent ``fbank`` call (waits for it); needs set_kernel_timing."""
         ms = ctypes.c_float()
         check(self.lib.oe_frontend_fbank_kernel_ms(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def step_ms(self):
+        """Duration of the whole launch sequence of the most recent call (waits for it); needs set_kernel_timing."""
+        ms = ctypes.c_float()
+        check(self.lib.oe_frontend_step_ms(self.handle, ctypes.byref(ms)))
         return float(ms.value)
 
     @property

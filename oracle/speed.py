@@ -98,3 +98,43 @@ def speed_perturb(wave, sample_rate, speed, dtype=np.float32):
         return wave
     orig, new = speed_ratio(speed, sample_rate)
     return resample(wave, orig, new, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Second, independent resampler oracle: a stand-in for libsox `rate` at its default quality.
+#
+# sox(1), `rate`: the default quality is -h ("high"): 95 % of the band preserved, 125 dB rejection, linear phase, and
+# without -a the stop band begins at the Nyquist frequency (no aliasing / imaging).  libsox is not available here, so
+# its multi-stage implementation cannot be run or pinned; what CAN be stated independently of any implementation is
+# the specification, and any linear-phase filter meeting it agrees with libsox's to ~1e-6 in the pass band -- the two
+# can only differ inside the 5 % transition band.  `soxlike_kernel` designs such a filter directly (Kaiser-windowed
+# sinc, pass-band edge 0.95 fn, stop-band edge fn, fn = the lower of the two Nyquist frequencies) in the polyphase
+# layout `resample` takes.  It is used to MEASURE how far the product's resampler (torchaudio's width-6 hann sinc, the
+# substitute oracle above) is from a sox-quality one (tests/test_oracle_augment_cmvn_speed.py);
+# parity against libsox itself stays unpinned.
+def soxlike_kernel(orig, new, passband=0.95, rejection_db=125.0, dtype=np.float32):
+    """Returns (kernel[new, 2*width+orig], width): y[m*new + p] = sum_q kernel[p][q] * xpad[m*orig + q]."""
+    fn = 0.5 * min(1.0, new / orig)                 # cycles per INPUT sample
+    f_pass, f_stop = passband * fn, fn
+    delta = f_stop - f_pass
+    beta = 0.1102 * (rejection_db - 8.7)            # Kaiser's formulas
+    half = int(math.ceil((rejection_db - 7.95) / (14.36 * delta) / 2.0))    # half length in input samples
+    width = half
+    fc = 0.5 * (f_pass + f_stop)
+    q = np.arange(-width, width + orig, dtype=np.float64)[None, :]
+    p = np.arange(new, dtype=np.float64)[:, None]
+    t = q - p * orig / new                          # input-sample distance from the output instant
+    with np.errstate(invalid='ignore', divide='ignore'):
+        h = np.where(t == 0, 2.0 * fc, np.sin(2.0 * math.pi * fc * t) / (math.pi * t))
+    r = np.clip(1.0 - (t / half) ** 2, 0.0, None)
+    w = np.where(np.abs(t) <= half, np.i0(beta * np.sqrt(r)) / np.i0(beta), 0.0)
+    return (h * w).astype(dtype), width
+
+
+def speed_perturb_soxlike(wave, sample_rate, speed, dtype=np.float64):
+    """`speed <s>` + `rate <sr>` with the sox-quality stand-in filter (see above)."""
+    if speed == 1.0:
+        return np.asarray(wave, dtype=dtype)
+    orig, new = speed_ratio(speed, sample_rate)
+    k, _ = soxlike_kernel(orig, new, dtype=dtype)
+    return resample(wave, orig, new, dtype=dtype, kernel=k)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.oe_abi_version() == 2
+    assert lib.oe_abi_version() == 3
     cfg = _lib.OeConfig()
     assert lib.oe_config_default(ctypes.byref(cfg)) == 0
     assert (cfg.sample_rate, cfg.frame_length, cfg.frame_shift, cfg.fft_size, cfg.num_mel_bins) == (16000, 400, 160, 512, 80)

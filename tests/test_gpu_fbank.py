@@ -337,11 +337,28 @@ def test_single_pass_padding_rows_and_launch_count(fe, tables):
                 ref = C.global_cmvn(F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1]), mean, istd)
                 assert np.abs(y[i, :frames[i]] - ref).max() <= 1e-3 * float(istd.max())
             assert np.array_equal(y[i, frames[i]:], np.broadcast_to(pad_val, (tmax - frames[i], 80)))
-    # two-phase chain of the benchmark configuration: descriptors, fbank, statistics (per-utterance + global), finalize
+    # the benchmark configuration (per-utterance normalisation + global statistics): descriptors, the fbank kernel (raw rows
+    # straight into the padded tensor, global statistics accumulated in the kernel) and the in-place completion
+    # (oe_finalize2_kernel: statistics merge + normalisation + padding); the dropped utterance (0 frames) gets its padding
     stats = torch.zeros(161, dtype=torch.float64, device='cuda')
     n0 = fe.launches
-    fe.fbank(dev, offs, ln, layout='padded', normalization=True, stats=stats)
-    assert fe.launches - n0 == 4
+    y, fr = fe.fbank(dev, offs, ln, layout='padded', normalization=True, stats=stats, max_rows=tmax)
+    assert fe.launches - n0 == 3
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    assert y.shape == (len(waves), tmax, 80) and int(stats[160].item()) == sum(frames)
+    raws = []
+    for i, w in enumerate(waves):
+        assert np.all(y[i, frames[i]:] == 0)
+        if frames[i] > 1:                   # one frame: std = 0 -> 0/0, no value parity
+            ref = F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1])
+            raws.append(ref)
+            assert np.abs(y[i, :frames[i]] - A.normalization(ref)).max() <= 2e-3
+        elif frames[i] == 1:
+            raws.append(F.fbank(w.astype(np.float32), window=tables[0], mel=tables[1]))
+    allr = np.concatenate(raws).astype(np.float64)
+    got = stats.cpu().numpy()
+    assert np.allclose(got[:80], allr.sum(0), rtol=1e-4) and np.allclose(got[80:160], (allr ** 2).sum(0), rtol=1e-4)
 
 
 def test_wav_dither_statistics(fe, tables):
