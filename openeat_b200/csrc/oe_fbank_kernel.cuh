@@ -139,9 +139,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
-// L2 residency hint (two-phase pipeline): the raw log-mel rows are read again by the finalize kernel two launches later
-// -> evict_last stores, so more of them are still in the 126 MB L2 then (-2 us per step; an evict_first hint on the
-// waveform's cp.async added nothing and cost the plain path 3 % through code generation).
+// L2 residency hints (two-phase pipeline): the raw log-mel rows are read again by the completion kernel right after this
+// one -> evict_last stores; the waveform is read once -> evict_first loads (prefetch_tile).  Together they keep the raw
+// rows in L2 between the two kernels (measured with single-metric ncu passes, profiles/r02_step_traffic.md).
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     unsigned long long p;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -155,6 +155,16 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
 __device__ __forceinline__ void st_f4_hint(float4* p, float4 v, unsigned long long policy) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 16-byte cp.async of data that is read exactly once (the waveform), with an L2 eviction policy
+__device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gmem_src, int src_bytes, unsigned long long policy) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -165,6 +175,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <bool kF32>
 __device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wav, const TileDesc* d, int tid) {
     const int in_first = d->in_first, in_len = d->in_len;
+    // the waveform is read once: L2 evict_first, so the PCM stream does not push the raw log-mel rows out of L2 before
+    // the completion kernel re-reads them (single-metric ncu passes: its DRAM reads fall from 14.7 MB to 2.3 MB per
+    // batch, the step's DRAM traffic from 1.6x to 1.28x the algorithmic bytes)
+    const unsigned long long pol = l2_policy_evict_first();
     if (kF32) {
         const float* w = reinterpret_cast<const float*>(wav) + d->wav_utt;
         for (int q = tid; q < 673 * 2; q += kThreads) {
@@ -172,14 +186,14 @@ __device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wa
             int valid = in_len - s;
             valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
             if (s < 0) valid = 0;
-            cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 4 * valid);
+            cp_async16_stream(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 4 * valid, pol);
         }
     } else {
         const int16_t* w = reinterpret_cast<const int16_t*>(wav) + d->wav_utt;
         const int pieces = d->rs ? kRsPieces : 673;
         if (in_first >= 0 && in_first + 8 * pieces <= in_len) {       // interior tile: every piece is whole
             const int16_t* const src = w + in_first;
-            for (int q = tid; q < pieces; q += kThreads) cp_async16(raw + 16 * q, src + 8 * q, 16);
+            for (int q = tid; q < pieces; q += kThreads) cp_async16_stream(raw + 16 * q, src + 8 * q, 16, pol);
             return;
         }
         for (int q = tid; q < pieces; q += kThreads) {
@@ -187,7 +201,7 @@ __device__ __forceinline__ void prefetch_tile(unsigned char* raw, const void* wa
             int valid = in_len - s;
             valid = valid < 0 ? 0 : (valid > 8 ? 8 : valid);
             if (s < 0) valid = 0;
-            cp_async16(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 2 * valid);
+            cp_async16_stream(raw + 16 * q, valid ? (const void*)(w + s) : (const void*)w, 2 * valid, pol);
         }
     }
 }
