@@ -10,10 +10,18 @@ utterances -- plus accumulation of the CMVN statistics.  With N > 1 every rank r
 workload on its own utterances (weak scaling, no data-path collective) and the one collective of the
 path, the 161-double CMVN-stats all-reduce, closes the timed region.
 
-Keys of the JSON line (see the task contract): value = device-resident whole-job throughput; e2e = same
-metric through the public collate API from pinned HOST memory (H2D + D2H inside the timed region);
-roofline = the fbank kernel alone against the measured HBM peak; cpu_baseline = the reference CPU path
-(oracle collate port calling torchaudio.compliance.kaldi.fbank) on the box's host cores.
+Keys of the JSON line (see the task contract):
+  value        device-resident whole-job throughput: PCM already in HBM, batches prepared (oe_batch_prepare), the timed
+               region holds the four kernel launches per step (metadata fetch, descriptors, fbank, in-place completion);
+  e2e          the same metric through the public collate API from pinned HOST memory, H2D inside the timed region;
+               `value` keeps the features on the GPU (collate for a GPU trainer), `to_host` also brings the padded
+               feature tensor back to pinned host memory -- the reference's own boundary (CPU tensors, dataset.py:232-238);
+               `h2d_ceiling_gbs`: plain cudaMemcpyAsync from pinned memory on every rank at once, measured in this run;
+  roofline     the dominant kernel as it runs INSIDE the timed step against the measured HBM peak;
+  configs      the other BASELINE configurations (device-resident): config 1 shape, 3 (LibriSpeech shape, one list cut
+               by shard_by_length, CMVN statistics + one all-reduce per pass), 4 (short utterances + spec_sub),
+               5 (16-frame streaming windows);
+  cpu_baseline the reference CPU path (oracle collate port calling torchaudio.compliance.kaldi.fbank) on the host cores.
 """
 import argparse
 import json
@@ -36,6 +44,7 @@ POOL = 8            # distinct batches cycled so the inputs (~0.4 GB) exceed the
 CONF = {'resample_rate': 16000, 'speed_perturb_rate': 0, 'speeds': [0.9, 1.1, 0.1], 'wav_dither': 0.0,
         'mel_bins': 80}
 AUG = dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10)
+SUB = dict(num_t_sub=3, max_t=30)
 SPEEDS = (0.9, 1.0, 1.1)
 JSON_OUT = sys.stdout
 
@@ -60,6 +69,18 @@ def synth_pool_host(lens, rank, count):
         x = (torch.randn(total, generator=gen) * 3000.0).round_().clamp_(-32768, 32767).to(torch.int16)
         pool.append(x.pin_memory())
     return pool, offs
+
+
+def synth_dev(total, dev, seed):
+    """int16 Gaussian sigma=3000 (clipped), generated on the device."""
+    import torch
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty(total, dtype=torch.int16, device=dev)
+    step = 1 << 26
+    for a in range(0, total, step):
+        n = min(step, total - a)
+        out[a:a + n] = (torch.randn(n, generator=gen, device=dev) * 3000.0).round_().clamp_(-32768, 32767).to(torch.int16)
+    return out
 
 
 class ClockSampler(object):
@@ -152,17 +173,18 @@ def cpu_reference_throughput(lens, speeds, steps, warmup):
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores: same config, metric and unit as our arm, the
+    requested --steps / --warmup (one step = one 256-utterance batch, ~0.1 s on 16 cores; capped at 50 steps)."""
     if rank != 0:
         return
     lens, speeds = workload(0)
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    steps = min(steps, 10)                       # bounded: each step is ~1-2 s of 16-core CPU work
+    steps, warmup = max(1, min(args.steps, 50)), max(1, min(args.warmup, 10))
     value, cores, ms, impl = cpu_reference_throughput(lens, speeds, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'fbank_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch': BATCH, 'note': 'CPU reference path, rank 0 only'},
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'note': 'CPU reference path, rank 0 only'},
         'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
                          'sample': 'one 256-utterance batch (%.0f audio-s) per step, %d steps; oracle collate port '
                                    'calling %s (the function the reference calls at dataset.py:93-100), torchaudio.functional.speed '
@@ -179,15 +201,17 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from openeat_b200.cmvn import all_reduce_stats
-    from openeat_b200.dataset import _plan_batch, _run_plan, audio_collate_func
     from openeat_b200 import planner
-    from openeat_b200.frontend import default_frontend
-    from openeat_b200.sharding import bind_to_gpu_numa_node
+    from openeat_b200._lib import OE_WAV_I16
+    from openeat_b200.cmvn import all_reduce_stats
+    from openeat_b200.dataset import PrefetchingCollator, _plan_batch, audio_collate_func
+    from openeat_b200.frontend import aligned_offsets, default_frontend
+    from openeat_b200.sharding import bind_to_gpu_numa_node, dynamic_batches, shard_by_length
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)
+    cpus_before = os.sched_getaffinity(0)
+    binding = bind_to_gpu_numa_node(local_rank)
     fe = default_frontend(80, 16000, dev)
     lens, speeds = workload(rank)
     host_pool, offs = synth_pool_host(lens, rank, POOL)
@@ -195,33 +219,43 @@ def run_ours(args, rank, world, local_rank):
     keys = ['utt%d' % i for i in range(BATCH)]
     labels = [[1, 2, 3]] * BATCH
     audio_s = float(lens.sum()) / 16000.0
-    job_audio_s = audio_s                    # audio seconds per step over ALL ranks (each rank has its own lengths)
-    if world > 1:
-        t = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+
+    def job_total(x):
+        """sum of a per-rank scalar over all ranks"""
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
-        job_audio_s = float(t.item())
+        return float(t.item())
+
+    job_audio_s = job_total(audio_s)          # audio seconds per step over ALL ranks (each rank has its own lengths)
     # synthetic global CMVN (any finite vectors exercise the same arithmetic)
     mean = torch.linspace(8.0, 12.0, 80, device=dev)
     istd = torch.linspace(0.4, 0.6, 80, device=dev)
     stats = torch.zeros(161, dtype=torch.float64, device=dev)
 
-    # ---- plans: the host RNG work is done once per pool entry and reused (value leg) ----
+    # ---- value leg: every pool entry is planned (host RNG) and prepared (oe_batch_prepare) once ----
     random.seed(4242 + rank)
-    plans = []
+    preps, sp_frames = [], []
     for _ in range(POOL):
         plan = _plan_batch(keys, labels, lens, [16000] * BATCH, speeds, CONF)
         _, tm, fm = planner.plan_augment(plan.frames, 80, None, AUG)
-        plans.append((plan, tm, fm))
+        preps.append(fe.prepare(OE_WAV_I16, offs[plan.src], lens[plan.src], layout='padded', normalization=True,
+                                tmask=tm, fmask=fm, cmvn=(mean, istd), cmvn_on_padding=True, stats=stats,
+                                speed_ratios=plan.stage2))
+        sp_frames.append(float(plan.frames.sum()))
 
     def step_resident(i):
-        plan, tm, fm = plans[i % POOL]
-        _run_plan(plan, 80, dev_pool[i % POOL], offs, lens, normalization=True, tmask=tm, fmask=fm,
-                  cmvn=(mean, istd), cmvn_on_padding=True, stats=stats)
+        return fe.run(preps[i % POOL], dev_pool[i % POOL])
 
     collate = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=True, spec_aug=True,
                                  spec_aug_conf=AUG, global_cmvn=(mean, istd), cmvn_stats=stats)
-
-    from openeat_b200.dataset import PrefetchingCollator
 
     def host_batches():
         i = 0
@@ -230,8 +264,10 @@ def run_ours(args, rank, world, local_rank):
             i += 1
 
     pipe = PrefetchingCollator(collate, host_batches())
+    pipe_host = PrefetchingCollator(collate, host_batches(), to_host=True)
     d2h = {'n': torch.empty(BATCH, dtype=torch.int32).pin_memory(),
            's': torch.empty(161, dtype=torch.float64).pin_memory()}
+    feat_bytes = [0]
 
     def step_e2e(i):
         """Public API from pinned host memory: H2D of this step's PCM (PrefetchingCollator: on a side stream,
@@ -239,6 +275,12 @@ def run_ours(args, rank, world, local_rank):
         statistics; the features stay on the GPU for the model)."""
         _, out = next(pipe)
         d2h['n'].copy_(out['features_length'], non_blocking=True)
+        d2h['s'].copy_(stats, non_blocking=True)
+
+    def step_e2e_host(i):
+        """The reference boundary: the padded feature tensor comes back to (pinned) host memory as well."""
+        _, out = next(pipe_host)
+        feat_bytes[0] = out['features'].numel() * 4
         d2h['s'].copy_(stats, non_blocking=True)
 
     def timed(fn, steps, warmup, with_allreduce):
@@ -265,13 +307,14 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), fe.launches - l0
 
-    def timed_repeated(fn, with_allreduce, min_seconds):
-        """Times EXACTLY args.steps steps (barrier + sync on both sides); the K-step region is repeated until
+    def timed_repeated(fn, with_allreduce, min_seconds, steps=None):
+        """Times EXACTLY `steps` steps (barrier + sync on both sides); the K-step region is repeated until
         `min_seconds` have passed so that nvidia-smi (100 ms period) sees the clocks under this very load; the
         median repeat is reported."""
+        steps = steps or args.steps
         runs, launches, t0 = [], 0, time.perf_counter()
         while True:
-            ms, launches = timed(fn, args.steps, warmup if not runs else 0, with_allreduce)
+            ms, launches = timed(fn, steps, warmup if not runs else 0, with_allreduce)
             runs.append(ms)
             go = torch.tensor([1.0 if time.perf_counter() - t0 < min_seconds and len(runs) < 400 else 0.0], device=dev)
             if world > 1:
@@ -291,69 +334,175 @@ def run_ours(args, rank, world, local_rank):
     random.seed(99 + rank)
     ms_e2e, _, _ = timed_repeated(step_e2e, world > 1, 0.5)
     e2e_value = job_audio_s * args.steps / (ms_e2e * 1e-3)
+    ms_e2e_host, _, _ = timed_repeated(step_e2e_host, world > 1, 0.5)
+    e2e_host_value = job_audio_s * args.steps / (ms_e2e_host * 1e-3)
 
-    # ---- roofline of the dominant kernel (k2::oe_fbank2_kernel), timed alone on its own stream position ----
+    # ---- the box's own H2D ceiling: plain cudaMemcpyAsync from pinned memory, every rank at once ----
+    h2d = int(host_pool[0].numel() * 2)
+    sink = torch.empty_like(dev_pool[0])
+
+    def step_copy(i):
+        sink.copy_(host_pool[i % POOL], non_blocking=True)
+
+    ms_copy, _, _ = timed_repeated(step_copy, False, 0.3)
+    h2d_job = job_total(h2d)                                                     # bytes per step over all ranks
+    h2d_ceiling = h2d_job * args.steps / (ms_copy * 1e-3) / 1e9                  # GB/s over all ranks
+
+    # ---- the other BASELINE configurations, device-resident ----
+    def run_config(name, make):
+        """make() -> (list of (prepared batch, device wav), audio seconds per pass on this rank, algorithmic bytes per
+        pass, needs the stats all-reduce).  One timed repeat = one pass over the list."""
+        items, secs, alg, collective = make()
+        n_items = len(items)
+
+        def one_pass(i):
+            for p, w in items:
+                fe.run(p, w)
+
+        ms, ln, _ = timed_repeated(one_pass, collective and world > 1, 0.4, steps=3)
+        ms /= 3.0
+        tot_s, tot_b = job_total(secs), job_total(alg)
+        return {'workload': name, 'audio_s_per_s': tot_s / (ms * 1e-3), 'ms_per_pass': ms, 'batches_per_pass_per_gpu': n_items,
+                'gpu_launches_per_batch': ln / 3.0 / max(1, n_items),
+                'alg_gb_s_per_gpu': tot_b / world / (ms * 1e-3) / 1e9, 'hbm_frac': tot_b / world / (ms * 1e-3) / 1e9 / peak}
+
+    def frames_of(n):
+        return fe.num_frames_array(n)
+
+    def make_cfg1():
+        # configs[0] shape: 1 000 x 5.000 s, static batches of 16, per-utt norm (recipe default) + global CMVN
+        n = np.full(16, 80000, dtype=np.int32)
+        o, total = aligned_offsets(n)
+        nb = 63                                                 # 1 008 utterances, 161 MB of PCM > L2
+        wav = synth_dev(total * nb, dev, 2001 + rank)
+        p = fe.prepare(OE_WAV_I16, o, n, layout='padded', normalization=True, cmvn=(mean, istd), cmvn_on_padding=True)
+        items = [(p, wav[i * total:(i + 1) * total]) for i in range(nb)]
+        fr = float(frames_of(n).sum())
+        return items, nb * 16 * 5.0, nb * (2.0 * float(n.sum()) + 320.0 * fr), False
+
+    def make_cfg3():
+        # configs[2] shape: ONE global list of U[1,35] s utterances (seed 1004; a 10 h sample of the 1 000 h set), cut
+        # by shard_by_length, sorted + length-bucketed like AudioDataset(sort=True, batch_type='dynamic'), fbank +
+        # per-utt norm + padded output + CMVN-statistics accumulation, one all-reduce per pass
+        rng = np.random.default_rng(1004)
+        all_lens = np.round(rng.uniform(1.0, 35.0, 2000) * 16000).astype(np.int64)
+        mine = shard_by_length(all_lens, world)[rank]
+        n = all_lens[mine].astype(np.int32)
+        fr = frames_of(n)
+        items, secs, alg = [], 0.0, 0.0
+        for b in dynamic_batches([int(v) for v in fr], 150000, sort=True):
+            nb_ = n[b][::-1].copy()                             # longest first, like the collate's sort
+            o, total = aligned_offsets(nb_)
+            wav = synth_dev(total, dev, 3001 + 17 * len(items) + rank)
+            p = fe.prepare(OE_WAV_I16, o, nb_, layout='padded', normalization=True, stats=stats)
+            items.append((p, wav))
+            secs += float(nb_.sum()) / 16000.0
+            alg += 2.0 * float(nb_.sum()) + 320.0 * float(frames_of(nb_).sum())
+        return items, secs, alg, True
+
+    def make_cfg4():
+        # configs[3] shape: 256 x U[0.5,3] s, 80-mel + per-utt norm + spec_sub (3, 30): launch / framing overhead
+        rng = np.random.default_rng(1005 + 7919 * rank)
+        n = np.sort(np.round(rng.uniform(0.5, 3.0, BATCH) * 16000).astype(np.int32))[::-1].copy()
+        o, total = aligned_offsets(n)
+        nb = 20                                                 # 287 MB of PCM > L2
+        wav = synth_dev(total * nb, dev, 4001 + rank)
+        fr = frames_of(n)
+        random.seed(777 + rank)
+        items = []
+        for i in range(nb):
+            fmap, _, _ = planner.plan_augment(fr, 80, SUB, None)
+            p = fe.prepare(OE_WAV_I16, o, n, layout='padded', normalization=True, frame_maps=fmap)
+            items.append((p, wav[i * total:(i + 1) * total]))
+        return items, nb * float(n.sum()) / 16000.0, nb * (2.0 * float(n.sum()) + 320.0 * float(fr.sum())), False
+
+    def make_cfg5():
+        # configs[4] shape: 20-minute streams (19.2 M samples) fed as 7 500 windows of 16 frames (2 800 samples, 240
+        # overlap: windows are views into the stream), 80-mel + global CMVN, ragged output == whole-stream fbank
+        nwin, hop, wl = 7500, 2560, 2800
+        total = hop * (nwin - 1) + wl + 8
+        nb = 4                                                  # 154 MB of PCM > L2
+        wav = synth_dev(total * nb, dev, 5001 + rank)
+        o = np.arange(nwin, dtype=np.int64) * hop
+        n = np.full(nwin, wl, dtype=np.int32)
+        p = fe.prepare(OE_WAV_I16, o, n, layout='ragged', cmvn=(mean, istd))
+        items = [(p, wav[i * total:(i + 1) * total]) for i in range(nb)]
+        return items, nb * nwin * 16 * 0.01, nb * (2.0 * (hop * nwin + 240) + 320.0 * 16 * nwin), False
+
+    configs = {}
+    for key, name, mk in (('config1_shape', 'configs[0] shape on the GPU: 1 008 x 5 s, static batch 16, per-utt norm + global CMVN', make_cfg1),
+                          ('config3', 'configs[2]: LibriSpeech shape, 2 000 x U[1,35] s (10 h sample), one list cut by shard_by_length, '
+                                      'dynamic batches of <= 150 k frames, per-utt norm + CMVN statistics, one all-reduce per pass', make_cfg3),
+                          ('config4', 'configs[3]: ASRU shape, 256 x U[0.5,3] s, per-utt norm + spec_sub(3,30)', make_cfg4),
+                          ('config5', 'configs[4]: 20-minute streams as 7 500 x 16-frame windows, global CMVN, ragged output', make_cfg5)):
+        stats.zero_()
+        configs[key] = run_config(name, mk)
+        torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (k2::oe_fbank2_kernel) ----
     roof = None
     cpu = None
     if rank == 0:
         frames = fe.num_frames_array(lens)
-        alg_bytes = 2.0 * float(lens.sum()) + 4.0 * 80 * float(frames.sum())       # int16 in, fp32 out
+        alg_plain = 2.0 * float(lens.sum()) + 4.0 * 80 * float(frames.sum())       # SURVEY 8(d): int16 in, fp32 out
         out = torch.empty((int(frames.sum()), 80), device=dev)
+        plain = fe.prepare(OE_WAV_I16, offs, lens, layout='ragged')
         for i in range(3):
-            fe.fbank(dev_pool[i % POOL], offs, lens, layout='ragged', out=out)
+            fe.run(plain, dev_pool[i % POOL], out=out)
         torch.cuda.synchronize()
         durs = []
         for rep in range(5):                         # 5 x 16 back-to-back launches: the GPU never waits for the host
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for i in range(16):
-                fe.fbank(dev_pool[i % POOL], offs, lens, layout='ragged', out=out)
+                fe.run(plain, dev_pool[i % POOL], out=out)
             b.record()
             torch.cuda.synchronize()
             durs.append(a.elapsed_time(b) / 16.0)
-        dur_ms = float(np.median(durs))
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        peak = float(peaks.get('hbm_gbs', 6650.0))
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'fbank_traffic.json'))).get('dram_bytes_per_launch')
-        except Exception:
-            pass
-        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-        # the same kernel as it runs INSIDE the timed step (fused speed perturb on 2/3 of the utterances, tile and global
-        # statistics, raw rows to the L2-resident scratch): the library brackets it with CUDA events on the stream
+        plain_ms = float(np.median(durs))
+        # the kernel as it runs INSIDE the timed step (fused speed perturb on 2/3 of the utterances, tile + global
+        # statistics, raw rows straight into the padded tensor): the library brackets it with CUDA events on the stream
         fe.set_kernel_timing(True)
-        in_step = []
+        in_step, whole = [], []
         for i in range(12):
             step_resident(i)
             in_step.append(fe.fbank_kernel_ms())
+            whole.append(fe.step_ms())
         fe.set_kernel_timing(False)
         step_ms = float(np.median(in_step[2:]))
-        sp_frames = np.array([p[0].frames.sum() for p in plans], dtype=np.float64).mean()   # frames after the speed perturb
-        alg_step = 2.0 * float(lens.sum()) + 4.0 * 80 * float(sp_frames)
+        alg_step = 2.0 * float(lens.sum()) + 4.0 * 80 * float(np.mean(sp_frames))   # frames after the speed perturb
+        traffic, traffic_note = None, None
+        try:
+            t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_step_traffic.json')))
+            traffic, traffic_note = t.get('fbank_dram_bytes_per_launch'), t.get('how')
+        except Exception:
+            pass
+        achieved = alg_step / (step_ms * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'kernel': 'k2::oe_fbank2_kernel<int16> (+ oe_tile_desc_kernel, PDL-overlapped)',
-                'launch_ms': dur_ms, 'alg_bytes_per_launch': alg_bytes,
-                'in_step': {'kernel': 'k2::oe_fbank2_kernel<int16, fused speed perturb> + tile / global statistics',
-                            'launch_ms': step_ms, 'alg_bytes_per_launch': alg_step,
-                            'achieved': alg_step / (step_ms * 1e-3) / 1e9, 'frac': alg_step / (step_ms * 1e-3) / 1e9 / peak,
-                            'share_of_step': step_ms / (ms_total / args.steps),
-                            'how': 'CUDA events recorded by the library around the kernel launch on the stream, median of 10 steps'},
+                'traffic': traffic, 'traffic_how': traffic_note,
+                'kernel': 'k2::oe_fbank2_kernel<int16, fused speed perturb> + tile / global statistics, as launched inside the timed step',
+                'launch_ms': step_ms, 'alg_bytes_per_launch': alg_step,
+                'share_of_step': step_ms / (ms_total / args.steps),
+                'how': 'CUDA events recorded by the library around the kernel launch on the stream, median of 10 steps '
+                       '(the events end the programmatic overlap with the neighbouring kernels, so the sum of the parts '
+                       'exceeds the step)',
+                'step_frac': alg_step / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                'launch_sequence_ms_with_events': float(np.median(whole[2:])),
+                'plain_instantiation': {'kernel': 'k2::oe_fbank2_kernel<int16> alone (ragged output, no resampler, no statistics)',
+                                        'launch_ms': plain_ms, 'alg_bytes_per_launch': alg_plain,
+                                        'achieved': alg_plain / (plain_ms * 1e-3) / 1e9,
+                                        'frac': alg_plain / (plain_ms * 1e-3) / 1e9 / peak},
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',
                 'note': 'not HBM-bound: FMA pipe, issue slots and the shared-memory pipe are each ~50 % busy '
                         '(10.6 k FP32 lane-ops and 106 smem wavefronts per frame); see DESIGN.md section 4.1'}
         if world == 1:
+            os.sched_setaffinity(0, cpus_before)         # the CPU baseline gets every core of the box, not the GPU-local ones
             v, cores, cms, impl = cpu_reference_throughput(lens, speeds, 3, 1)
             cpu = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
                    'sample': '3 x one 256-utterance batch (%.0f audio-s each); oracle collate port calling %s, torchaudio.functional.speed, '
                              'numpy norm/spec_aug on %d processes x 1 thread' % (audio_s, impl, cores)}
 
     if rank == 0:
-        h2d = int(host_pool[0].numel() * 2)
         line = {
             'metric': 'fbank_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
@@ -363,15 +512,24 @@ def run_ours(args, rank, world, local_rank):
                              (POOL, POOL * h2d / 1e6),
                        'timing': 'median of %d back-to-back repeats of the %d-step timed region (each bracketed by '
                                  'barrier + synchronize; repeats only lengthen the window nvidia-smi samples)' % (reps, args.steps),
+                       'value_leg': 'batches prepared once per pool entry (host RNG plan + oe_batch_prepare); a step = '
+                                    'oe_fbank_run: 4 kernels (metadata fetch from mapped pinned memory, descriptors, fbank, in-place completion)',
                        'parallelism': 'utterance sharding, dp%d; one 161 x f64 NCCL all-reduce closes the timed region'
                                       % world if world > 1 else 'single GPU',
-                       'host_binding': ('rank pinned to the %d CPUs local to its GPU (NVML affinity)' % numa) if numa else 'none'},
+                       'host_binding': binding or 'none'},
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': BATCH * 4 + 161 * 8, 'ms_per_step': ms_e2e / args.steps,
                     'api': 'openeat_b200.dataset.PrefetchingCollator over audio_collate_func.collate_packed (pinned int16 '
                            '-> GPU features; H2D of batch i+1 overlaps batch i; frame counts + CMVN stats read back '
-                           'every step)'},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
+                           'every step; the feature tensor stays on the GPU for the model)',
+                    'to_host': {'value': e2e_host_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_host / args.steps,
+                                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(feat_bytes[0]) + BATCH * 8 + 161 * 8,
+                                'api': 'the same with to_host=True: the padded feature tensor returns to pinned host memory '
+                                       'on a third stream (the reference boundary: audio_collate_func returns CPU tensors)'},
+                    'h2d_ceiling_gbs': h2d_ceiling,
+                    'h2d_achieved_gbs': h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9,
+                    'frac_of_h2d_ceiling': (h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9) / h2d_ceiling},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'configs': configs,
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu

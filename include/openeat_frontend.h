@@ -156,6 +156,13 @@ const int32_t* oe_prepared_frames(const oe_prepared* p);   /* [B] frames per utt
 int oe_fbank_run(oe_frontend* fe, const oe_prepared* p, const void* d_wav, float* d_out, void* d_workspace,
                  size_t workspace_bytes, oe_stream stream);
 
+/* Small host -> device transfer that does not use the copy engine: `bytes` of host memory land at d_dst (16-byte
+ * aligned, capacity rounded up to 16 bytes) through the handle's mapped pinned ring and a copy kernel, stream-ordered.
+ * The host buffer may be reused as soon as the call returns.  For the int32 vectors of a batch (features_length,
+ * targets, targets_length, dataset.py:221-231): a cudaMemcpy of those queues behind the next batch's PCM on the DMA
+ * engine and stalls the collate pipeline by a whole bulk copy. */
+int oe_upload_small(oe_frontend* fe, const void* host, size_t bytes, void* d_dst, oe_stream stream);
+
 /* GlobalCMVN.forward (openeat/modules/cmvn.py:43-46): y = (x - mean) [* istd], rows x dim fp32. */
 /* Number of kernels this handle has launched so far (oe_fbank_batch and oe_resample; every launch site of the
  * library counts itself).  bench.py reports the difference over its timed region as `gpu_launches`. */

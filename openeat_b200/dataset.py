@@ -369,20 +369,28 @@ class audio_collate_func(object):
 
     def _finish(self, keys, features, frames, ys):
         dev = torch.device(self.output_device)
-        features_length = torch.from_numpy(np.array(frames, dtype=np.int32))
+        flen = np.array(frames, dtype=np.int32)
         tlen = np.array([len(y) for y in ys], dtype=np.int32)
         if features is None:                                         # dataset.py:219-220
             features = torch.Tensor([])
-            targets = torch.Tensor([])
+            tpad = None
         else:                                                        # pad_sequence(..., True, IGNORE_ID), dataset.py:225-226
             tpad = np.full((len(ys), int(tlen.max()) if len(ys) else 0), IGNORE_ID, dtype=np.int32)
             if tpad.size:
                 tpad[np.arange(tpad.shape[1])[None, :] < tlen[:, None]] = np.concatenate(
                     [np.asarray(y, dtype=np.int32).reshape(-1) for y in ys])
-            targets = torch.from_numpy(tpad)
-        targets_length = torch.from_numpy(tlen)
-        inputs = {'features': features.to(dev), 'features_length': features_length.to(dev),
-                  'targets': targets.to(dev), 'targets_length': targets_length.to(dev)}
+        if dev.type == 'cuda' and features.is_cuda:
+            # the three int32 tensors travel as ONE block through the front-end's mapped pinned ring (oe_upload_small):
+            # torch's .to() of a pageable tensor is a synchronous cudaMemcpy that queues behind the next batch's PCM
+            fe = default_frontend((self.feature_extraction_conf or {}).get('mel_bins', features.shape[-1]))
+            n, m = len(flen), (tpad.size if tpad is not None else 0)
+            blob = fe.upload_small(np.concatenate([flen, tlen, tpad.reshape(-1)]) if m else np.concatenate([flen, tlen]))
+            inputs = {'features': features, 'features_length': blob[:n], 'targets': blob[2 * n:].view(tpad.shape),
+                      'targets_length': blob[n:2 * n]}
+            return keys, inputs
+        targets = torch.Tensor([]) if tpad is None else torch.from_numpy(tpad)
+        inputs = {'features': features.to(dev), 'features_length': torch.from_numpy(flen).to(dev),
+                  'targets': targets.to(dev), 'targets_length': torch.from_numpy(tlen).to(dev)}
         return keys, inputs
 
 
@@ -489,14 +497,25 @@ class PrefetchingCollator(object):
     CPU workers, done here for the one resource the GPU front-end is bound by: the H2D copy).
 
     ``batches`` yields tuples ``(pinned_wav, offsets, lens, keys, labels, speeds)``.
+
+    ``to_host=True`` is the reference boundary proper (dataset.py:232-238: CPU tensors): the padded feature tensor
+    of batch i goes back over PCIe on a third stream into a ring of pinned buffers while batch i+1 is being
+    copied in and computed (PCIe is full duplex); a batch is handed out once its copy has landed, i.e. one
+    batch later than it was launched.  The yielded ``features`` tensor is a view of a ring slot: it stays valid
+    until ``ring`` more batches have been drawn.
     """
 
-    def __init__(self, collate, batches):
+    def __init__(self, collate, batches, to_host=False, ring=3):
         self.collate = collate
         self.batches = iter(batches)
         fe = default_frontend(collate.feature_extraction_conf['mel_bins'])
         self.device = fe.device
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.to_host = bool(to_host)
+        self.out_stream = torch.cuda.Stream(device=self.device) if to_host else None
+        self._ring = [None] * max(2, int(ring))
+        self._slot = 0
+        self._pending = None                     # (keys, inputs, event): launched, features still crossing PCIe
         self._next = None
         self._stage()
 
@@ -516,12 +535,57 @@ class PrefetchingCollator(object):
     def __iter__(self):
         return self
 
-    def __next__(self):
-        if self._next is None:
-            raise StopIteration
+    def _launch(self):
         dev, ev, offs, lens, keys, labels, speeds = self._next
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
         dev.record_stream(cur)
         self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
         return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds)
+
+    def _to_host(self, keys, inputs):
+        """Enqueues the D2H copy of one finished batch on the output stream; returns (keys, inputs, event)."""
+        cur = torch.cuda.current_stream(self.device)
+        done = torch.cuda.Event()
+        done.record(cur)
+        host = {}
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(done)
+            for k, v in inputs.items():
+                if not v.is_cuda:
+                    host[k] = v
+                    continue
+                if k == 'features' and v.numel():
+                    slot = self._ring[self._slot]
+                    if slot is None or slot.numel() < v.numel():
+                        slot = torch.empty(int(v.numel() * 1.2) + 1024, dtype=v.dtype).pin_memory()
+                        self._ring[self._slot] = slot
+                    self._slot = (self._slot + 1) % len(self._ring)
+                    dst = slot[:v.numel()].view(v.shape)
+                else:
+                    dst = torch.empty(v.shape, dtype=v.dtype).pin_memory() if v.numel() else torch.empty(v.shape, dtype=v.dtype)
+                dst.copy_(v, non_blocking=True)
+                v.record_stream(self.out_stream)
+                host[k] = dst
+            ev = torch.cuda.Event()
+            ev.record(self.out_stream)
+        return keys, host, ev
+
+    def __next__(self):
+        if not self.to_host:
+            if self._next is None:
+                raise StopIteration
+            return self._launch()
+        if self._next is None and self._pending is None:
+            raise StopIteration
+        launched = None
+        if self._next is not None:
+            launched = self._to_host(*self._launch())
+        if self._pending is None:                # first call: nothing to hand out yet -> launch one more if there is one
+            self._pending, launched = launched, None
+            if self._next is not None:
+                launched = self._to_host(*self._launch())
+        keys, host, ev = self._pending
+        self._pending = launched
+        ev.synchronize()
+        return keys, host

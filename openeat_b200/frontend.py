@@ -389,6 +389,20 @@ class Frontend(object):
                                     ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp))
         return out
 
+    def upload_small(self, arr, stream=None):
+        """Small numpy array -> new device tensor without the copy engine (``oe_upload_small``): the transfer does not
+        queue behind a bulk H2D copy and the host never blocks."""
+        arr = np.ascontiguousarray(arr)
+        tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32}[arr.dtype]
+        n = arr.size
+        pad = (-n * arr.itemsize) % 16 // arr.itemsize
+        out = torch.empty(n + pad, dtype=tdt, device=self.device)
+        if n:
+            _, sp = self._stream(stream)
+            check(self.lib.oe_upload_small(self.handle, ctypes.c_void_p(arr.ctypes.data), arr.nbytes,
+                                           ctypes.c_void_p(out.data_ptr()), sp))
+        return out[:n].view(arr.shape)
+
     def set_kernel_timing(self, on=True):
         """Measurement hook: bracket the fbank kernel of every following ``fbank`` call with CUDA events."""
         check(self.lib.oe_frontend_set_kernel_timing(self.handle, 1 if on else 0))

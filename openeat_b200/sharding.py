@@ -47,12 +47,52 @@ def static_batches(count, batch_size):
     return [list(range(i, min(i + batch_size, count))) for i in range(0, count, batch_size)]
 
 
+def gpu_numa_node(index):
+    """NUMA node the PCIe root complex of GPU ``index`` hangs off, from sysfs (``/sys/bus/pci/devices/<bdf>/numa_node``);
+    None when the platform does not say (single-node hosts and most virtual machines report -1)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _node_cpus(node):
+    cpus = set()
+    with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+        for part in f.read().strip().split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+    return cpus
+
+
 def bind_to_gpu_numa_node(index):
-    """Pins the calling process (and therefore its pinned staging buffers: first touch) to the CPUs NVML reports as
-    local to GPU ``index``, so host-to-device copies do not cross the socket interconnect.  One process per GPU
-    (the reference's DDP launch, train_ddp.py) should call it before allocating pinned memory: on an 8 x B200 box it
-    took the end-to-end front-end from 3.67 M to 6.45 M audio-s/s at 4 GPUs.  Best effort: returns the number of
-    CPUs bound to, or None when NVML / the affinity call is unavailable."""
+    """Places the calling process next to GPU ``index``: CPU affinity AND memory policy (``set_mempolicy(MPOL_PREFERRED)``,
+    so that the pinned staging rings allocated afterwards live in the memory of the GPU's own PCIe root complex and
+    host-to-device copies do not cross the socket interconnect).  The node comes from sysfs (``gpu_numa_node``); NVML's
+    CPU affinity is the fallback (it names CPUs only, and some hosts report one set for every GPU).  One process per
+    GPU (the reference's DDP launch, train_ddp.py) should call it before allocating pinned memory.  Best effort:
+    returns a short description of what was bound, or None."""
+    node = gpu_numa_node(index)
+    if node is not None:
+        try:
+            import ctypes
+            cpus = _node_cpus(node) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))     # x86-64 set_mempolicy, MPOL_PREFERRED
+            return 'numa node %d (sysfs): %d cpus%s' % (node, len(cpus), ', memory preferred' if rc == 0 else '')
+        except Exception:
+            pass
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -61,9 +101,9 @@ def bind_to_gpu_numa_node(index):
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
         cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
         cpus &= os.sched_getaffinity(0)
-        if cpus:
+        if cpus and cpus != os.sched_getaffinity(0):
             os.sched_setaffinity(0, cpus)
-            return len(cpus)
+            return '%d cpus (NVML affinity)' % len(cpus)
     except Exception:
         pass
     return None

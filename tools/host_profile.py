@@ -44,7 +44,38 @@ def e2e(n):
         out['features_length'].cpu(), stats.cpu()
 
 
-for name, fn in (('resident', resident), ('e2e', e2e)):
+from openeat_b200._lib import OE_WAV_I16   # noqa: E402
+from openeat_b200.dataset import PrefetchingCollator   # noqa: E402
+
+prep = fe.prepare(OE_WAV_I16, offs[plan.src], lens[plan.src], layout='padded', normalization=True, tmask=tm, fmask=fm,
+                  cmvn=(mean, istd), cmvn_on_padding=True, stats=stats, speed_ratios=plan.stage2)
+
+
+def prepared(n):
+    for i in range(n):
+        fe.run(prep, dev_pool[i % 2])
+
+
+def batches():
+    i = 0
+    while True:
+        yield (host_pool[i % 2], offs, lens, keys, labels, speeds)
+        i += 1
+
+
+pipe = PrefetchingCollator(collate, batches())
+pin_n = torch.empty(bench.BATCH, dtype=torch.int32).pin_memory()
+pin_s = torch.empty(161, dtype=torch.float64).pin_memory()
+
+
+def pipelined(n):
+    for i in range(n):
+        _, out = next(pipe)
+        pin_n.copy_(out['features_length'], non_blocking=True)
+        pin_s.copy_(stats, non_blocking=True)
+
+
+for name, fn in (('prepared', prepared), ('resident', resident), ('pipelined e2e', pipelined), ('e2e', e2e)):
     fn(5)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
