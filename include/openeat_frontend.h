@@ -114,7 +114,10 @@ typedef struct {
     const int32_t* table_ids;    /* [B] */
     const int64_t* out_offsets;  /* [B] sample offsets in d_out (keep them multiples of 8) */
     int32_t* out_lens;           /* [B] out, or NULL: ceil(new*N/orig) */
+    const int32_t* orig_rates;   /* [B] or NULL: rates of the utterances whose table_id is OE_RS_DIRECT -- the built-in */
+    const int32_t* new_rates;    /* hann sinc evaluated on the fly, for ratios too long to tabulate (441:160, continuous speeds) */
 } oe_resample_batch;
+#define OE_RS_DIRECT (-2)
 
 const char* oe_last_error(void);
 int oe_abi_version(void);
@@ -180,11 +183,18 @@ int oe_frontend_step_ms(oe_frontend* fe, float* ms);
 int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
                   const float* d_istd, oe_stream stream);
 
-/* Registers a polyphase table: kernel[new_rate][taps], taps = 2*width + orig_rate
- * (torchaudio functional.py:1343-1398 layout), or NULL = hann-windowed sinc, lowpass width 6,
- * rolloff 0.99 computed in double.  Returns the table id in *table_id. */
+/* Registers a polyphase table: kernel[new_rate][taps], taps = 2*width + orig_rate for any width >= 0
+ * (torchaudio functional.py:1343-1398 layout; a long Kaiser design gives sox-quality resampling), or NULL =
+ * hann-windowed sinc, lowpass width 6, rolloff 0.99 computed in double (OE_ERR_UNSUPPORTED when that table would
+ * exceed 65 536 coefficients: use OE_RS_DIRECT).  Tables are kept for the life of the handle; storage grows on
+ * demand (a setup-time call: it may synchronise the device).  Returns the table id in *table_id. */
 int oe_add_resampler(oe_frontend* fe, int32_t orig_rate, int32_t new_rate, const float* kernel,
                      int32_t taps, int32_t* table_id);
+/* 1 when the table can be resampled inside the fbank kernel's staging (oe_batch.resample_ids): the 9:10 / 11:10
+ * tables whose bits equal the baked torchaudio tables.  oe_mel_is_baked: 1 when the handle runs the kernel that carries
+ * torchaudio's 80-bin mel matrix as immediates (needed by wav_dither). */
+int oe_resampler_fusable(const oe_frontend* fe, int32_t table_id);
+int oe_mel_is_baked(const oe_frontend* fe);
 int64_t oe_resample_out_len(int64_t n, int32_t orig_rate, int32_t new_rate);
 int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* batch, size_t* bytes);
 int oe_resample(oe_frontend* fe, const oe_resample_batch* batch, const void* d_in, float* d_out,

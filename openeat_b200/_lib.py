@@ -52,7 +52,10 @@ class OeBatch(ctypes.Structure):
 class OeResampleBatch(ctypes.Structure):
     _fields_ = [('batch', ctypes.c_int32), ('wav_dtype', ctypes.c_int32),
                 ('in_offsets', c_i64p), ('in_lens', c_i32p), ('table_ids', c_i32p),
-                ('out_offsets', c_i64p), ('out_lens', c_i32p)]
+                ('out_offsets', c_i64p), ('out_lens', c_i32p), ('orig_rates', c_i32p), ('new_rates', c_i32p)]
+
+
+OE_RS_DIRECT = -2
 
 
 # every symbol include/openeat_frontend.h declares: (restype, argtypes)
@@ -84,6 +87,8 @@ SYMBOLS = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'oe_add_resampler': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_f32p,
                                         ctypes.c_int32, c_i32p]),
+    'oe_resampler_fusable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    'oe_mel_is_baked': (ctypes.c_int, [ctypes.c_void_p]),
     'oe_resample_out_len': (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     'oe_resample_workspace_bytes': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(OeResampleBatch),
                                                    ctypes.POINTER(ctypes.c_size_t)]),

@@ -666,8 +666,7 @@ __global__ void __launch_bounds__(256) oe_cmvn_kernel(const float* __restrict__ 
 struct RsTable {
     int orig, neu, taps, width, coef_off;
 };
-constexpr int kMaxRsTables = 16;
-constexpr int kMaxRsCoefs = 16384;
+constexpr int kRsDirectCoefs = 1 << 16;     // registered tables above this many coefficients are evaluated on the fly
 
 struct ResampleParams {
     const void* in;
@@ -679,6 +678,8 @@ struct ResampleParams {
     const int32_t* out_len;
     const RsTable* tables;
     const float* coefs;
+    const int32_t* orig;         // [B] rates of the utterances with table_id == OE_RS_DIRECT (others ignored), or null
+    const int32_t* neu;
 };
 
 // torchaudio functional.py:1401-1432: y[m*new + p] = sum_q k[p][q] * xpad[m*orig + q], xpad = x shifted by width.
@@ -693,23 +694,53 @@ __global__ void __launch_bounds__(256) oe_resample_kernel(const ResampleParams P
     float* const out = P.out + P.out_off[b];
     const int64_t ioff = P.in_off[b];
     const int stride = gridDim.x * blockDim.x;
+    auto sample = [&](int xi) -> float {
+        return kF32 ? reinterpret_cast<const float*>(P.in)[ioff + xi] : (float)reinterpret_cast<const int16_t*>(P.in)[ioff + xi];
+    };
+    if (tid_ == OE_RS_DIRECT) {
+        // Ratios whose polyphase table would be huge (speeds drawn from a continuous range, 44.1 kHz sources): every
+        // coefficient is evaluated where it is used, with torchaudio's formula (functional.py:1343-1398: hann-windowed
+        // sinc, lowpass_filter_width 6, rolloff 0.99); only the ~13 orig/min(orig, new) taps inside the window are
+        // visited (the table holds exact zeros everywhere else).  The filter argument is formed from the exact integer
+        // j new - phase orig: torch's own fp32 grid (p/new + idx/orig, a difference of two numbers near 1) is noisy for
+        // long periods -- its resampled 953:1000 waveform sits 0.8 (int16 scale) from the float64 evaluation, this
+        // kernel 1e-3 (tests/test_gpu_mirrors.py::test_long_ratio_and_kaiser_resamplers).
+        const int orig = P.orig[b], neu = P.neu[b];
+        const float base = (float)(orig < neu ? orig : neu) * 0.99f;
+        const float halfw = 6.0f * (float)orig / base;                  // taps with |t| < 6 around the output instant
+        const float scale = base / (float)orig;
+        const float tscale = base / ((float)orig * (float)neu);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+            const int m = i / neu, ph = i - m * neu;
+            const float c = (float)ph * (float)orig / (float)neu;       // output instant, in input samples past m * orig
+            const int j_lo = (int)ceilf(c - halfw) - 1, j_hi = (int)floorf(c + halfw) + 1;
+            float acc = 0.f;
+            for (int j = j_lo; j <= j_hi; ++j) {
+                const int xi = m * orig + j;
+                if (xi < 0 || xi >= n_in) continue;
+                float t = (float)((long long)j * neu - (long long)ph * orig) * tscale;
+                t = fminf(6.0f, fmaxf(-6.0f, t));
+                const float w = cosf(t * 3.14159265358979323846f / 6.0f / 2.0f);
+                const float a = t * 3.14159265358979323846f;
+                const float k = (a == 0.f ? 1.0f : sinf(a) / a) * (w * w) * scale;
+                acc = fmaf(k, sample(xi), acc);
+            }
+            out[i] = acc;
+        }
+        return;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
         float acc = 0.f;
         if (tid_ < 0) {
-            acc = kF32 ? reinterpret_cast<const float*>(P.in)[ioff + i]
-                       : (float)reinterpret_cast<const int16_t*>(P.in)[ioff + i];
+            acc = sample(i);
         } else {
             const RsTable t = P.tables[tid_];
             const int m = i / t.neu, ph = i - m * t.neu;
-            const float* const k = P.coefs + t.coef_off + ph * t.taps;
+            const float* const k = P.coefs + (size_t)t.coef_off + (size_t)ph * t.taps;
             const int x0 = m * t.orig - t.width;
             for (int q = 0; q < t.taps; ++q) {
                 const int xi = x0 + q;
-                if (xi >= 0 && xi < n_in) {
-                    const float xv = kF32 ? reinterpret_cast<const float*>(P.in)[ioff + xi]
-                                          : (float)reinterpret_cast<const int16_t*>(P.in)[ioff + xi];
-                    acc = fmaf(k[q], xv, acc);
-                }
+                if (xi >= 0 && xi < n_in) acc = fmaf(k[q], sample(xi), acc);
             }
         }
         out[i] = acc;
@@ -783,10 +814,12 @@ struct oe_frontend {
     oe::DevTables* d_tab;
     std::vector<float> window, mel;
     std::vector<oe::RsTable> rs;
+    std::vector<char> rs_builtin;      // table i is the library's own hann sinc (found again by ratio), not a caller's kernel
     std::vector<float> rs_coefs;
     int rs_fast_9_10, rs_fast_11_10;   // table ids served by oe_resample_fast_kernel, or -1
     oe::RsTable* d_rs;
     float* d_rs_coefs;
+    size_t d_rs_cap, d_rs_coefs_cap;   // device capacities (tables / floats); grown in oe_add_resampler
     size_t fbank_smem;
     bool std_mel;                  // the mel matrix has the baked mel80 structure -> kernels with a compile-time mel structure
     bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
@@ -1050,6 +1083,7 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     fe->ev_step[0] = fe->ev_step[1] = nullptr;
     fe->d_rs = nullptr;
     fe->d_rs_coefs = nullptr;
+    fe->d_rs_cap = fe->d_rs_coefs_cap = 0;
     fe->rs_fast_9_10 = fe->rs_fast_11_10 = -1;
     fe->h_meta_next = 0;
     for (int i = 0; i < oe_frontend::kMetaSlots; ++i) {
@@ -1119,8 +1153,6 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
     }
     cudaError_t e = cudaMalloc(&fe->d_tab, sizeof(oe::DevTables));
     if (e == cudaSuccess) e = cudaMemcpy(fe->d_tab, &h, sizeof(h), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&fe->d_rs, sizeof(oe::RsTable) * oe::kMaxRsTables);
-    if (e == cudaSuccess) e = cudaMalloc(&fe->d_rs_coefs, sizeof(float) * oe::kMaxRsCoefs);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
     fe->std_mel = nb == oe::mel80::kBins && nnz == oe::mel80::kNnz;
@@ -1710,23 +1742,32 @@ int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* ke
     if (!fe || !table_id) return fail(OE_ERR_INVALID, "null pointer");
     if (orig <= 0 || neu <= 0) return fail(OE_ERR_INVALID, "rates must be positive");
     for (size_t i = 0; i < fe->rs.size(); ++i)
-        if (fe->rs[i].orig == orig && fe->rs[i].neu == neu && !kernel) {
+        if (fe->rs[i].orig == orig && fe->rs[i].neu == neu && !kernel && fe->rs_builtin[i]) {
             *table_id = (int)i;
             return OE_OK;
         }
-    if ((int)fe->rs.size() >= oe::kMaxRsTables) return fail(OE_ERR_UNSUPPORTED, "too many resampler tables");
     // functional.py:1343-1398
     const double lowpass = 6.0, rolloff = 0.99;
     const double base = std::min(orig, neu) * rolloff;
-    const int width = (int)std::ceil(lowpass * orig / base);
-    const int ntaps = 2 * width + orig;
-    if (kernel && taps != ntaps) return fail(OE_ERR_INVALID, "taps must be 2*width+orig = %d", ntaps);
-    if (fe->rs_coefs.size() + (size_t)neu * ntaps > (size_t)oe::kMaxRsCoefs) return fail(OE_ERR_UNSUPPORTED, "resampler table too large");
+    int width = (int)std::ceil(lowpass * orig / base);
+    int ntaps = 2 * width + orig;
+    if (kernel) {
+        // any polyphase table in torchaudio's layout: kernel[new][2 * width + orig] (e.g. a long Kaiser design of sox quality)
+        if (taps < orig || ((taps - orig) & 1)) return fail(OE_ERR_INVALID, "taps must be 2*width+orig with width >= 0; got %d for orig %d", taps, orig);
+        ntaps = taps;
+        width = (taps - orig) / 2;
+    } else if ((size_t)neu * ntaps > (size_t)oe::kRsDirectCoefs) {
+        // the built-in hann sinc of a ratio with a long period (441:160, speeds drawn from a continuous range) is not
+        // tabulated: oe_resample evaluates it on the fly for utterances marked OE_RS_DIRECT
+        return fail(OE_ERR_UNSUPPORTED, "the %d:%d table would hold %zu coefficients: pass table_ids[b] = OE_RS_DIRECT with "
+                                        "orig_rates / new_rates instead", orig, neu, (size_t)neu * ntaps);
+    }
     oe::RsTable t;
     t.orig = orig;
     t.neu = neu;
     t.taps = ntaps;
     t.width = width;
+    if (fe->rs_coefs.size() + (size_t)neu * ntaps > (size_t)INT32_MAX) return fail(OE_ERR_UNSUPPORTED, "resampler tables too large");
     t.coef_off = (int)fe->rs_coefs.size();
     for (int p = 0; p < neu; ++p)
         for (int q = 0; q < ntaps; ++q) {
@@ -1744,6 +1785,7 @@ int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* ke
             fe->rs_coefs.push_back(v);
         }
     fe->rs.push_back(t);
+    fe->rs_builtin.push_back(kernel == nullptr);
     if (width == 7 && neu == 10 && (orig == 9 || orig == 11)) {
         // the specialised kernel skips taps the hann-sinc formula makes zero: only valid if this table has them zero
         bool ok = true;
@@ -1759,16 +1801,34 @@ int oe_add_resampler(oe_frontend* fe, int32_t orig, int32_t neu, const float* ke
         if (ok) (orig == 9 ? fe->rs_fast_9_10 : fe->rs_fast_11_10) = (int)fe->rs.size() - 1;
     }
     OE_CUDA(cudaSetDevice(fe->device));
+    // device copies grow by doubling; a setup-time call: waiting for the device before the old block is freed is fine
+    if (fe->rs.size() > fe->d_rs_cap || fe->rs_coefs.size() > fe->d_rs_coefs_cap) {
+        OE_CUDA(cudaDeviceSynchronize());
+        if (fe->d_rs) cudaFree(fe->d_rs);
+        if (fe->d_rs_coefs) cudaFree(fe->d_rs_coefs);
+        fe->d_rs = nullptr;
+        fe->d_rs_coefs = nullptr;
+        fe->d_rs_cap = std::max<size_t>(16, 2 * fe->rs.size());
+        fe->d_rs_coefs_cap = std::max<size_t>(16384, 2 * fe->rs_coefs.size());
+        OE_CUDA(cudaMalloc(&fe->d_rs, sizeof(oe::RsTable) * fe->d_rs_cap));
+        OE_CUDA(cudaMalloc(&fe->d_rs_coefs, sizeof(float) * fe->d_rs_coefs_cap));
+    }
     OE_CUDA(cudaMemcpy(fe->d_rs, fe->rs.data(), sizeof(oe::RsTable) * fe->rs.size(), cudaMemcpyHostToDevice));
     OE_CUDA(cudaMemcpy(fe->d_rs_coefs, fe->rs_coefs.data(), sizeof(float) * fe->rs_coefs.size(), cudaMemcpyHostToDevice));
     *table_id = (int)fe->rs.size() - 1;
     return OE_OK;
 }
 
+int oe_resampler_fusable(const oe_frontend* fe, int32_t table_id) {
+    return fe && table_id >= 0 && (table_id == fe->rs_fast_9_10 || table_id == fe->rs_fast_11_10) ? 1 : 0;
+}
+
+int oe_mel_is_baked(const oe_frontend* fe) { return fe && fe->mel_baked && !fe->force_v1 ? 1 : 0; }
+
 int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* bt, size_t* bytes) {
     if (!fe || !bt || !bytes) return fail(OE_ERR_INVALID, "null pointer");
     const size_t B = (size_t)std::max(bt->batch, 0);
-    *bytes = align_up(8 * B, 16) * 2 + align_up(4 * B, 16) * 3 + 256;
+    *bytes = align_up(8 * B, 16) * 2 + align_up(4 * B, 16) * 5 + 256;
     return OE_OK;
 }
 
@@ -1784,12 +1844,22 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
     oe_resample_workspace_bytes(fe, bt, &need);
     if (!d_ws || ws_bytes < need) return fail(OE_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
     const size_t a8 = align_up(8 * (size_t)B, 16), a4 = align_up(4 * (size_t)B, 16);
-    std::vector<unsigned char> hm(2 * a8 + 3 * a4, 0);
-    int64_t* in_off = reinterpret_cast<int64_t*>(hm.data());
-    int64_t* out_off = reinterpret_cast<int64_t*>(hm.data() + a8);
-    int32_t* in_len = reinterpret_cast<int32_t*>(hm.data() + 2 * a8);
-    int32_t* tab = reinterpret_cast<int32_t*>(hm.data() + 2 * a8 + a4);
-    int32_t* out_len = reinterpret_cast<int32_t*>(hm.data() + 2 * a8 + 2 * a4);
+    const size_t hm_bytes = 2 * a8 + 5 * a4;
+    OE_CUDA(cudaSetDevice(fe->device));
+    unsigned char* hm = nullptr;
+    int hslot = 0;
+    {
+        const int rc = meta_slot(fe, hm_bytes, &hm, &hslot);
+        if (rc != OE_OK) return rc;
+    }
+    memset(hm, 0, hm_bytes);
+    int64_t* in_off = reinterpret_cast<int64_t*>(hm);
+    int64_t* out_off = reinterpret_cast<int64_t*>(hm + a8);
+    int32_t* in_len = reinterpret_cast<int32_t*>(hm + 2 * a8);
+    int32_t* tab = reinterpret_cast<int32_t*>(hm + 2 * a8 + a4);
+    int32_t* out_len = reinterpret_cast<int32_t*>(hm + 2 * a8 + 2 * a4);
+    int32_t* r_orig = reinterpret_cast<int32_t*>(hm + 2 * a8 + 3 * a4);
+    int32_t* r_neu = reinterpret_cast<int32_t*>(hm + 2 * a8 + 4 * a4);
     int max_out = 0;
     for (int b = 0; b < B; ++b) {
         const int id = bt->table_ids[b];
@@ -1799,15 +1869,22 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
         out_off[b] = bt->out_offsets[b];
         in_len[b] = bt->in_lens[b];
         tab[b] = id;
-        out_len[b] = id < 0 ? bt->in_lens[b] : (int32_t)oe_resample_out_len(bt->in_lens[b], fe->rs[id].orig, fe->rs[id].neu);
+        if (id == OE_RS_DIRECT) {
+            if (!bt->orig_rates || !bt->new_rates || bt->orig_rates[b] <= 0 || bt->new_rates[b] <= 0)
+                return fail(OE_ERR_INVALID, "table_ids[%d] = OE_RS_DIRECT needs positive orig_rates / new_rates", b);
+            r_orig[b] = bt->orig_rates[b];
+            r_neu[b] = bt->new_rates[b];
+            out_len[b] = (int32_t)oe_resample_out_len(bt->in_lens[b], r_orig[b], r_neu[b]);
+        } else {
+            out_len[b] = id < 0 ? bt->in_lens[b] : (int32_t)oe_resample_out_len(bt->in_lens[b], fe->rs[id].orig, fe->rs[id].neu);
+        }
         if (bt->out_lens) bt->out_lens[b] = out_len[b];
         max_out = std::max(max_out, out_len[b]);
     }
     if (max_out == 0) return OE_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    OE_CUDA(cudaSetDevice(fe->device));
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
-    OE_CUDA(cudaMemcpyAsync(ws, hm.data(), hm.size(), cudaMemcpyHostToDevice, stream));
+    OE_CUDA(fetch_small(fe, hslot, ws, hm_bytes, stream));
     oe::ResampleParams P;
     P.in = d_in;
     P.out = d_out;
@@ -1818,6 +1895,8 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* bt, const void* d_in, 
     P.out_len = reinterpret_cast<const int32_t*>(ws + 2 * a8 + 2 * a4);
     P.tables = fe->d_rs;
     P.coefs = fe->d_rs_coefs;
+    P.orig = reinterpret_cast<const int32_t*>(ws + 2 * a8 + 3 * a4);
+    P.neu = reinterpret_cast<const int32_t*>(ws + 2 * a8 + 4 * a4);
     const bool f32 = bt->wav_dtype == OE_WAV_F32;
     bool need_generic = false, need_9 = false, need_11 = false;
     for (int b = 0; b < B; ++b) {

@@ -70,7 +70,7 @@ class _Plan(object):
     position, in the packed input buffer, of the utterance that ends up i-th after the length sort;
     ``stage1`` / ``stage2`` are the (orig, new) resampling ratios of the resample_rate and speed stages
     (0, 0 = none)."""
-    __slots__ = ('keys', 'labels', 'src', 'stage1', 'stage2', 'frames', 'sample_rate', 'wav_dither')
+    __slots__ = ('keys', 'labels', 'src', 'stage1', 'stage2', 'frames', 'sample_rate', 'wav_dither', 'resampler')
 
 
 def _ceil_ratio(n, orig, new):
@@ -126,6 +126,9 @@ def _plan_batch(keys_in, labels_in, nsamples, sample_rates, speeds_in, conf, tar
     p.frames = frames[src].astype(np.int32)
     p.sample_rate = target_rate
     p.wav_dither = float(conf.get('wav_dither', 0.0) or 0.0)      # kaldi.fbank(dither=...), dataset.py:98
+    # extension: 'sinc' (default) = torchaudio's width-6 hann sinc; 'kaiser' = the long sox-quality filter
+    # (frontend.kaiser_sinc_kernel), for users who need the reference's libsox-grade speed perturb
+    p.resampler = conf.get('resampler', 'sinc')
     return p
 
 
@@ -171,8 +174,11 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
     if plan.wav_dither != 0.0:                               # Philox key per call; os.urandom: Python's `random` stream stays the reference's
         fused = dict(fused, wav_dither=plan.wav_dither,
                      dither_seed=fused.get('dither_seed') or int.from_bytes(os.urandom(8), 'little'))
+    # (the library fuses only tables whose bits equal its baked torchaudio tables: ask it, fall back to oe_resample)
     fusable = (plan.wav_dither == 0.0 and dev_wav.dtype == torch.int16 and not (plan.stage1[:, 0] != 0).any() and
-               np.isin(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1], (0, 9 * 65536 + 10, 11 * 65536 + 10)).all())
+               plan.resampler == 'sinc' and fe.mel_baked and
+               np.isin(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1], (0, 9 * 65536 + 10, 11 * 65536 + 10)).all() and
+               all(fe.fusable(o, n) for o, n in {(int(a), int(b)) for a, b in plan.stage2 if a}))
     if fusable and needs.any():
         kw = dict(fused)
         if kw.get('frame_map') is not None:
@@ -198,9 +204,9 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
         call(dev_wav, offs[plan.src[direct]], lens[plan.src[direct]], direct)
     if len(resamp):
         cur, cur_offs, cur_lens = dev_wav, offs[plan.src[resamp]], lens[plan.src[resamp]]
-        for stage in (plan.stage1[resamp], plan.stage2[resamp]):     # resample_rate stage, then speed stage
+        for stage, kind in ((plan.stage1[resamp], 'sinc'), (plan.stage2[resamp], plan.resampler)):   # resample_rate stage, then speed stage
             if (stage[:, 0] != 0).any():
-                cur, cur_offs, cur_lens = fe.resample(cur, cur_offs, cur_lens, stage)
+                cur, cur_offs, cur_lens = fe.resample(cur, cur_offs, cur_lens, stage, kind=kind)
         call(cur, cur_offs, cur_lens, resamp)
     return out, fe
 

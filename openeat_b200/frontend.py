@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (OE_FEATS_F32, OE_NORM_NONE, OE_NORM_PER_UTT, OE_WAV_F32, OE_WAV_I16, FrontendError,
+from ._lib import (OE_FEATS_F32, OE_NORM_NONE, OE_NORM_PER_UTT, OE_RS_DIRECT, OE_WAV_F32, OE_WAV_I16, FrontendError,
                    OeBatch, OeConfig, OeResampleBatch, c_f32p, c_i32p, c_i64p, check)
 
 ALIGN = 8  # samples; the kernels read 16-byte vectors (include/openeat_frontend.h: wav_offsets)
@@ -56,6 +56,27 @@ def torch_sinc_kernel(orig, new, lowpass_filter_width=6, rolloff=0.99):
     kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
     kernels *= window * scale
     return kernels[:, 0, :].contiguous(), width
+
+
+def kaiser_sinc_kernel(orig, new, passband=0.95, rejection_db=125.0):
+    """Polyphase table of a long linear-phase low-pass with the specification of ``sox rate`` at its default quality
+    (-h: 95 % of the band kept, 125 dB rejection, stop band from the lower Nyquist frequency): Kaiser-windowed sinc,
+    designed in float64, in the layout ``oe_add_resampler`` takes (kernel[new, 2*width+orig]).  libsox itself (the
+    reference's ``_speed_perturb``, audio_processor.py:31-34) is not reproducible here; this is the closest resampler the
+    front-end offers to it (``resampler='kaiser'``), at ~25x the arithmetic of the default width-6 hann sinc."""
+    fn = 0.5 * min(1.0, new / orig)                 # cycles per input sample
+    f_pass, f_stop = passband * fn, fn
+    beta = 0.1102 * (rejection_db - 8.7)
+    half = int(math.ceil((rejection_db - 7.95) / (14.36 * (f_stop - f_pass)) / 2.0))
+    fc = 0.5 * (f_pass + f_stop)
+    q = np.arange(-half, half + orig, dtype=np.float64)[None, :]
+    p = np.arange(new, dtype=np.float64)[:, None]
+    t = q - p * orig / new
+    with np.errstate(invalid='ignore', divide='ignore'):
+        h = np.where(t == 0, 2.0 * fc, np.sin(2.0 * math.pi * fc * t) / (math.pi * t))
+    r = np.clip(1.0 - (t / half) ** 2, 0.0, None)
+    w = np.where(np.abs(t) <= half, np.i0(beta * np.sqrt(r)) / np.i0(beta), 0.0)
+    return np.ascontiguousarray((h * w).astype(np.float32)), half
 
 
 def speed_ratio(speed, sample_rate=16000):
@@ -183,12 +204,22 @@ class Frontend(object):
         return ws
 
     # ------------------------------------------------------------------ speed perturb
-    def resampler_id(self, orig, new):
-        key = (int(orig), int(new))
+    def resampler_id(self, orig, new, kind='sinc'):
+        """Table id of the (orig, new) polyphase resampler.  kind 'sinc': torchaudio's width-6 hann sinc (the substitute
+        the path is pinned to); 'kaiser': the sox-quality design of ``kaiser_sinc_kernel``.  Returns OE_RS_DIRECT for a
+        'sinc' ratio too long to tabulate (evaluated on the fly by ``resample``)."""
+        key = (int(orig), int(new), kind)
         if key not in self._resamplers:
             tid = ctypes.c_int32(-1)
-            if self.torch_tables:
-                k, _ = torch_sinc_kernel(*key)
+            if kind == 'kaiser':
+                k, _ = kaiser_sinc_kernel(key[0], key[1])
+                check(self.lib.oe_add_resampler(self.handle, key[0], key[1], _ptr(k, c_f32p), k.shape[1], ctypes.byref(tid)))
+            elif kind != 'sinc':
+                raise ValueError(kind)
+            elif key[1] * (2 * math.ceil(6 * key[0] / (min(key[0], key[1]) * 0.99)) + key[0]) > 65536:
+                tid = ctypes.c_int32(OE_RS_DIRECT)
+            elif self.torch_tables:
+                k, _ = torch_sinc_kernel(key[0], key[1])
                 k = np.ascontiguousarray(k.numpy())
                 check(self.lib.oe_add_resampler(self.handle, key[0], key[1], _ptr(k, c_f32p), k.shape[1],
                                                 ctypes.byref(tid)))
@@ -197,29 +228,39 @@ class Frontend(object):
             self._resamplers[key] = tid.value
         return self._resamplers[key]
 
+    def fusable(self, orig, new):
+        """True when the (orig, new) 'sinc' resampler can run inside the fbank kernel's staging (speed_ratios)."""
+        tid = self.resampler_id(orig, new)
+        return tid >= 0 and bool(self.lib.oe_resampler_fusable(self.handle, tid))
+
+    @property
+    def mel_baked(self):
+        return bool(self.lib.oe_mel_is_baked(self.handle))
+
     def resample_out_len(self, n, orig, new):
         return int(self.lib.oe_resample_out_len(int(n), int(orig), int(new)))
 
-    def resample(self, wav, offsets, lens, ratios, out=None, out_offsets=None, stream=None):
+    def resample(self, wav, offsets, lens, ratios, out=None, out_offsets=None, stream=None, kind='sinc'):
         """Ragged polyphase resampling.  ``ratios[b]`` is (orig, new) or None (plain copy to fp32).
         Returns (fp32 device tensor, out_offsets, out_lens)."""
         B = len(lens)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         lens = np.ascontiguousarray(lens, dtype=np.int32)
-        if isinstance(ratios, np.ndarray):                       # [B, 2] int array, (0, 0) = plain copy
-            ids = np.full(B, -1, dtype=np.int32)
-            olens = lens.astype(np.int64)
-            key = ratios[:, 0] * 65536 + ratios[:, 1]
-            for k in np.unique(key[key != 0]):
-                o, n = int(k) >> 16, int(k) & 65535
-                sel = key == k
-                ids[sel] = self.resampler_id(o, n)
-                olens[sel] = (n * olens[sel] + o - 1) // o
-            olens = olens.astype(np.int32)
-        else:
-            ids = np.array([-1 if r is None else self.resampler_id(*r) for r in ratios], dtype=np.int32)
-            olens = np.array([n if r is None else self.resample_out_len(n, *r) for n, r in zip(lens, ratios)],
-                             dtype=np.int32)
+        if not isinstance(ratios, np.ndarray):                   # list of (orig, new) / None -> [B, 2], (0, 0) = plain copy
+            ratios = np.array([(0, 0) if r is None else tuple(r) for r in ratios], dtype=np.int64).reshape(B, 2)
+        ratios = np.asarray(ratios, dtype=np.int64)
+        ids = np.full(B, -1, dtype=np.int32)
+        olens = lens.astype(np.int64)
+        key = ratios[:, 0] * (1 << 32) + ratios[:, 1]
+        for k in np.unique(key[key != 0]):
+            o, n = int(k) >> 32, int(k) & 0xFFFFFFFF
+            sel = key == k
+            ids[sel] = self.resampler_id(o, n, kind)
+            olens[sel] = (n * olens[sel] + o - 1) // o
+        olens = olens.astype(np.int32)
+        direct = ids == OE_RS_DIRECT
+        r_orig = np.ascontiguousarray(ratios[:, 0], dtype=np.int32) if direct.any() else None
+        r_new = np.ascontiguousarray(ratios[:, 1], dtype=np.int32) if direct.any() else None
         if out_offsets is None:
             out_offsets, total = aligned_offsets(olens)
         else:
@@ -228,7 +269,8 @@ class Frontend(object):
         if out is None:
             out = torch.empty(max(total, ALIGN), dtype=torch.float32, device=self.device)   # gaps are never read
         rb = OeResampleBatch(B, OE_WAV_F32 if wav.dtype == torch.float32 else OE_WAV_I16, _ptr(offsets, c_i64p),
-                             _ptr(lens, c_i32p), _ptr(ids, c_i32p), _ptr(out_offsets, c_i64p), None)
+                             _ptr(lens, c_i32p), _ptr(ids, c_i32p), _ptr(out_offsets, c_i64p), None,
+                             _ptr(r_orig, c_i32p), _ptr(r_new, c_i32p))
         need = ctypes.c_size_t()
         check(self.lib.oe_resample_workspace_bytes(self.handle, ctypes.byref(rb), ctypes.byref(need)))
         s, sp = self._stream(stream)

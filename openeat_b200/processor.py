@@ -156,39 +156,71 @@ def compute_fbank(data, num_mel_bins=23, frame_length=25, frame_shift=10, dither
             yield s
 
 
-def _feat_op(sample, **kw):
-    x = sample['feat']
-    fe = default_frontend(x.shape[1])
-    x = x.to(fe.device, dtype=torch.float32).contiguous()
-    out, _ = fe.fbank(x, np.array([0], np.int64), np.array([x.shape[0]], np.int32), layout='ragged', features_in=True, **kw)
-    return dict(sample, feat=out)
+def _feat_ops(data, plan, batch_size=64):
+    """Runs one post-fbank operation over groups of ``batch_size`` samples with ONE launch sequence per group (the
+    features of a group are concatenated into a fresh, 16-byte aligned buffer; ``plan(frames, F)`` makes the group's
+    random draws, sample by sample in order, and returns the keywords of ``Frontend.fbank(features_in=True)``)."""
+    def flush(group):
+        xs = [s['feat'] for s in group]
+        F = int(xs[0].shape[1])
+        fe = default_frontend(F)
+        frames = np.array([x.shape[0] for x in xs], dtype=np.int32)
+        kw = plan(frames, F)
+        buf = torch.cat([x.to(fe.device, dtype=torch.float32) for x in xs]).contiguous()
+        offs = np.concatenate([[0], np.cumsum(frames[:-1].astype(np.int64))]).astype(np.int64)
+        out, _ = fe.fbank(buf, offs, frames, layout='ragged', features_in=True, **kw)
+        r = 0
+        for s, m in zip(group, frames):
+            yield dict(s, feat=out[r:r + int(m)])
+            r += int(m)
 
-
-def spec_sub(data, max_t=20, num_t_sub=3):
-    """feature_processor.py:44-64 per sample."""
+    group = []
     for sample in data:
-        yield _feat_op(sample, frame_maps=[plan_spec_substitute(sample['feat'].shape[0], max_t, num_t_sub)])
+        group.append(sample)
+        if len(group) == batch_size:
+            for s in flush(group):
+                yield s
+            group = []
+    if group:
+        for s in flush(group):
+            yield s
 
 
-def spec_aug(data, num_t_mask=2, num_f_mask=2, max_t=50, max_f=10):
-    """feature_processor.py:10-42 per sample."""
-    for sample in data:
-        t, f = plan_spec_augmentation(sample['feat'].shape[0], sample['feat'].shape[1], num_t_mask, num_f_mask, max_t, max_f)
-        yield _feat_op(sample, tmask=np.array([t], np.int32) if t else None, fmask=np.array([f], np.int32) if f else None)
+def spec_sub(data, max_t=20, num_t_sub=3, batch_size=64):
+    """feature_processor.py:44-64, one launch sequence per ``batch_size`` samples (draws: sample by sample, in order)."""
+    return _feat_ops(data, lambda frames, F: dict(frame_maps=[plan_spec_substitute(int(t), max_t, num_t_sub) for t in frames]),
+                     batch_size)
 
 
-def utt_normalize(data):
-    """feature_processor.py:5-8 per sample (OpenEAT's default ``normalization=True``)."""
-    for sample in data:
-        yield _feat_op(sample, normalization=True)
+def spec_aug(data, num_t_mask=2, num_f_mask=2, max_t=50, max_f=10, batch_size=64):
+    """feature_processor.py:10-42, one launch sequence per ``batch_size`` samples (draws: sample by sample, in order)."""
+    def plan(frames, F):
+        tm, fm = [], []
+        for t in frames:
+            a, b = plan_spec_augmentation(int(t), F, num_t_mask, num_f_mask, max_t, max_f)
+            tm.append(a)
+            fm.append(b)
+        return dict(tmask=np.array(tm, np.int32).reshape(len(frames), -1, 2) if num_t_mask else None,
+                    fmask=np.array(fm, np.int32).reshape(len(frames), -1, 2) if num_f_mask else None)
+    return _feat_ops(data, plan, batch_size)
 
 
-def global_cmvn(data, mean, istd, norm_var=True):
-    """modules/cmvn.py:35-46 per sample; ``mean`` / ``istd`` are fp32 tensors (any device)."""
-    for sample in data:
-        x = sample['feat']
-        fe = default_frontend(x.shape[1])
-        yield dict(sample, feat=fe.cmvn_apply(x.contiguous(), mean.to(fe.device), istd.to(fe.device) if norm_var else None))
+def utt_normalize(data, batch_size=64):
+    """feature_processor.py:5-8 (OpenEAT's default ``normalization=True``), one launch sequence per ``batch_size`` samples."""
+    return _feat_ops(data, lambda frames, F: dict(normalization=True), batch_size)
+
+
+def global_cmvn(data, mean, istd, norm_var=True, batch_size=64):
+    """modules/cmvn.py:35-46; ``mean`` / ``istd`` are fp32 tensors (any device); one launch sequence per ``batch_size`` samples."""
+    dev = {}
+
+    def plan(frames, F):
+        if not dev:
+            fe = default_frontend(F)
+            dev['cmvn'] = (mean.to(fe.device, dtype=torch.float32).contiguous(),
+                           istd.to(fe.device, dtype=torch.float32).contiguous() if norm_var else None)
+        return dict(cmvn=dev['cmvn'])
+    return _feat_ops(data, plan, batch_size)
 
 
 def batch(data, batch_size=16):

@@ -73,6 +73,25 @@ def test_config3_librispeech_shape_sharded_stats_are_linear(fe):
     np.testing.assert_allclose(summed[:160], everything[:160], rtol=1e-11)
     loads = [int(lens[s].sum()) for s in shards]
     assert max(loads) - min(loads) <= int(lens.max())
+    # oracle VALUES on four utterances (shortest, longest, two in between) of this very list: ragged features, and their
+    # sums against a statistics pass over just those four
+    from oracle import cmvn as C
+    order = np.argsort(lens)
+    pick = np.array([order[0], order[133], order[266], order[-1]])
+    got, fr4 = fe.fbank(x, offs[pick], lens[pick], layout='ragged')
+    got = got.cpu().numpy()
+    refs = [F.fbank(x[offs[i]:offs[i] + lens[i]].cpu().numpy().astype(np.float32)) for i in pick]
+    assert fr4.tolist() == [r.shape[0] for r in refs]
+    # 581 k cells of white noise: the lowest mel bins sit ~40 dB below the frame's energy after pre-emphasis, where two
+    # fp32 evaluations (this kernel's FFT, the oracle's pocketfft + matmul) differ by up to a few 1e-3 in the log -- the
+    # 1e-3 bound holds for all but a 1e-4 fraction of the cells (and on every golden file, test_gpu_fbank.py)
+    d = np.abs(got - np.concatenate(refs))
+    assert d.max() <= 4e-3 and (d > 1e-3).mean() <= 1e-4
+    s4, q4, n4 = C.compute_cmvn_stats(refs)
+    st4 = stats_of([pick])
+    assert st4[160] == n4
+    np.testing.assert_allclose(st4[:80], s4, rtol=1e-4)
+    np.testing.assert_allclose(st4[80:160], q4, rtol=1e-4)
     # mean / variance are sane numbers for Gaussian noise through the mel bank
     mean = everything[:80] / everything[160]
     var = everything[80:160] / everything[160] - mean ** 2
@@ -97,8 +116,14 @@ def test_config4_short_utterances_with_spec_sub_is_a_row_gather(fe):
     sub, _ = fe.fbank(x, offs, lens, layout='padded', frame_maps=maps)
     both, _ = fe.fbank(x, offs, lens, layout='padded', frame_maps=maps, tmask=tm, fmask=fm)
     raw, sub, both = raw.cpu().numpy(), sub.cpu().numpy(), both.cpu().numpy()
+    from oracle import augment as A
     for b in (0, 1, 17, 100, 255):
         t = int(frames[b])
+        # oracle VALUES: raw log-mel of this utterance, then the reference's own substitution / masking arithmetic
+        ref = F.fbank(x[offs[b]:offs[b] + lens[b]].cpu().numpy().astype(np.float32))
+        assert ref.shape[0] == t and np.abs(raw[b, :t] - ref).max() <= 1e-3
+        ref_both = A.apply_spec_augmentation(ref[maps[b]], [tuple(r) for r in tm[b]], [tuple(r) for r in fm[b]])
+        assert np.array_equal(both[b, :t] == 0, ref_both == 0) and np.abs(both[b, :t] - ref_both).max() <= 1e-3
         assert np.array_equal(sub[b, :t], raw[b, :t][maps[b]])
         expect = sub[b, :t].copy()
         for s, e in tm[b]:
@@ -143,6 +168,20 @@ def test_config2_full_batch_properties(fe):
             assert np.array_equal(a[i, :t, s:e], np.broadcast_to(zero_after[s:e], a[i, :t, s:e].shape))
         np.testing.assert_allclose(plain[i, :t].mean(0), 0.0, atol=2e-4)
         np.testing.assert_allclose(plain[i, :t].std(0), 1.0, atol=2e-4)
+        # oracle VALUES of the whole chain for this utterance: substitute speed oracle -> fbank -> _normalization ->
+        # masks -> GlobalCMVN (the resampler tolerance dominates: 0.05 on the int16 scale; the ill-conditioned top bins
+        # of speed 0.9 are bounded separately in test_gpu_fbank.py)
+        from oracle import augment as A, cmvn as C, speed as S
+        w = x[offs[i]:offs[i] + lens[i]].cpu().numpy().astype(np.float32)
+        if ratios[i, 0]:
+            w = S.resample(w, int(ratios[i, 0]), int(ratios[i, 1]))
+        ref = A.normalization(F.fbank(np.asarray(w, np.float32)))
+        assert ref.shape[0] == t
+        hi = 70 if ratios[i, 0] == 9 else 80
+        assert np.abs(plain[i, :t, :hi] - ref[:, :hi]).max() <= 5e-3
+        ref = C.global_cmvn(A.apply_spec_augmentation(ref, [tuple(r) for r in tm[i]], [tuple(r) for r in fm[i]]),
+                            mean.cpu().numpy(), istd.cpu().numpy())
+        assert np.abs(a[i, :t, :hi] - ref[:, :hi]).max() <= 5e-3
 
 
 def test_multi_tile_ctas_equal_one_utterance_at_a_time():

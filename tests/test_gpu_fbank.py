@@ -430,3 +430,65 @@ def test_custom_mel_weights_use_the_parameter_kernel(tables):
     y0, _ = run_raw(base, [x], layout='ragged')
     assert np.abs(y0 - F.fbank(x.astype(np.float32), window=win, mel=mel)).max() <= 1e-3
     assert np.abs(y - y0).max() > 1e-3                           # the custom weights really were used
+
+
+@pytest.mark.parametrize('case', ['fbank_mel23_speech_8000', 'fbank_mel23_white_560', 'fbank_mel40_white_8000',
+                                  'fbank_mel40_dcsine_8000'])
+def test_other_mel_bin_counts_against_torchaudio(golden_dir, case):
+    """feature_extraction_conf['mel_bins'] other than 80 (dataset.py:95) runs the table-driven first-generation kernel
+    (oe_fbank_kernel<.., false, ..>): torchaudio-generated goldens (oracle/make_golden_r02.py), int16 and fp32 input,
+    ragged and padded layout, plus the two-phase chain (per-utterance normalisation, masks) against the oracle."""
+    from openeat_b200.frontend import Frontend
+    g = np.load(os.path.join(golden_dir, case + '.npz'))
+    bins = int(g['mel'].shape[0])
+    fe = Frontend(mel_bins=bins, sample_rate=16000)
+    assert np.array_equal(fe.tables()[1], g['mel'])                    # torch-built table == torchaudio's, bit for bit
+    gap = float(np.abs(g['y32'] - g['y64']).max())
+    for dtype in (np.int16, np.float32):
+        y, fr = run_raw(fe, [g['pcm']], dtype=dtype, layout='ragged')
+        assert fr.tolist() == [g['y32'].shape[0]] and y.shape == g['y32'].shape
+        if 'dcsine' in case:
+            assert np.abs(y - g['y64']).max() <= max(1e-3, gap)
+        else:
+            assert np.abs(y - g['y32']).max() <= 1e-3
+    # batch of three copies with different lengths, padded, normalised, masked
+    waves = [g['pcm'], g['pcm'][:len(g['pcm']) // 2 + 400], g['pcm'][100:]]
+    tm = np.array([[[2, 5]], [[0, 1]], [[1, 30]]], np.int32)
+    fm = np.array([[[3, 9]], [[0, 2]], [[bins - 4, bins]]], np.int32)
+    y, fr = run_raw(fe, waves, layout='padded', normalization=True, tmask=tm, fmask=fm)
+    for i, w in enumerate(waves):
+        ref = A.normalization(F.fbank(w.astype(np.float32), num_mel_bins=bins, window=fe.tables()[0], mel=g['mel']))
+        t = ref.shape[0]
+        assert fr[i] == t
+        ref = A.apply_spec_augmentation(ref, [(int(tm[i, 0, 0]), min(int(tm[i, 0, 1]), t))], [tuple(fm[i, 0])])
+        assert np.array_equal(y[i, :t] == 0, ref == 0)
+        if 'dcsine' not in case and t > 2:
+            assert np.abs(y[i, :t] - ref).max() <= 5e-3
+        assert np.all(y[i, t:] == 0)
+
+
+def test_processor_chain_with_23_bins(golden_dir):
+    """The wenet-style processor chain at compute_fbank's own default (23 bins: 92-byte rows, so per-sample row slices
+    are not 16-byte aligned): utt_normalize -> spec_sub -> spec_aug -> global_cmvn, every stage one launch sequence per
+    group, against the oracle with the same random draws."""
+    from openeat_b200 import processor as P
+    from openeat_b200.frontend import Frontend
+    from oracle import cmvn as C
+    g = np.load(os.path.join(golden_dir, 'fbank_mel23_speech_8000.npz'))
+    fe = Frontend(mel_bins=23, sample_rate=16000)
+    win = fe.tables()[0]
+    pcm = g['pcm']
+    samples = [{'key': 'a', 'wav': pcm, 'sample_rate': 16000}, {'key': 'b', 'wav': pcm[:5000], 'sample_rate': 16000},
+               {'key': 'c', 'wav': pcm[33:7000], 'sample_rate': 16000}]
+    mean, istd = torch.linspace(5.0, 9.0, 23), torch.linspace(0.3, 0.5, 23)
+    random.seed(5)
+    out = list(P.global_cmvn(P.spec_aug(P.spec_sub(P.utt_normalize(P.compute_fbank(iter(samples))), max_t=10, num_t_sub=2),
+                                        num_t_mask=1, num_f_mask=1, max_t=8, max_f=4), mean, istd))
+    random.seed(5)
+    xs = [A.normalization(F.fbank(s['wav'].astype(np.float32), num_mel_bins=23, window=win, mel=g['mel'])) for s in samples]
+    xs = [A.spec_substitute(x, max_t=10, num_t_sub=2) for x in xs]
+    xs = [A.spec_augmentation(x, 1, 1, 8, 4) for x in xs]
+    for o, x in zip(out, xs):
+        ref = C.global_cmvn(x, mean.numpy(), istd.numpy())
+        got = o['feat'].cpu().numpy()
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 3e-3

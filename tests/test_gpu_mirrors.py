@@ -264,20 +264,16 @@ def test_wenet_style_processor_chain(gold, tmp_path, tables):
         P.speed_perturb(iter(samples)), num_mel_bins=80, batch_size=4)), max_t=30, num_t_sub=3),
         num_t_mask=3, num_f_mask=2, max_t=50, max_f=10), mean, istd), batch_size=16))
     keys, feats, labels, flen, llen = next(chain)
-    # the oracle replays the lazy generators' draw order in one pass: compute_fbank pulls a group of 4 samples
-    # through speed_perturb (4 speed draws), then every surviving sample of the group gets its spec_sub and
-    # spec_aug draws as it travels down the chain, then the next group is pulled
+    # the oracle replays the lazy generators' draw order: every feature operation works on groups of 64 samples, so the
+    # first one pulls the whole list through compute_fbank / speed_perturb (7 speed draws, in order), then every
+    # surviving sample gets its spec_sub draws (in order), then every one its spec_aug draws
     random.seed(77)
-    out = {}
-    for g in (samples[:4], samples[4:]):
-        pert = [S.speed_perturb(smp['wav'].astype(np.float32), 16000, random.choice([0.9, 1.0, 1.1])) for smp in g]
-        for smp, w in zip(g, pert):
-            if len(w) < 400:
-                continue
-            x = A.normalization(F.fbank(np.asarray(w, np.float32), window=tables[0], mel=tables[1]))
-            x = A.spec_substitute(x, max_t=30, num_t_sub=3)
-            x = A.spec_augmentation(x, 3, 2, 50, 10)
-            out[smp['key']] = C.global_cmvn(x, mean.numpy(), istd.numpy())
+    pert = [S.speed_perturb(smp['wav'].astype(np.float32), 16000, random.choice([0.9, 1.0, 1.1])) for smp in samples]
+    alive = [(smp, w) for smp, w in zip(samples, pert) if len(w) >= 400]
+    xs = [A.normalization(F.fbank(np.asarray(w, np.float32), window=tables[0], mel=tables[1])) for _, w in alive]
+    xs = [A.spec_substitute(x, max_t=30, num_t_sub=3) for x in xs]
+    xs = [A.spec_augmentation(x, 3, 2, 50, 10) for x in xs]
+    out = {smp['key']: C.global_cmvn(x, mean.numpy(), istd.numpy()) for (smp, _), x in zip(alive, xs)}
     assert 'k4' not in out and set(keys) == set(out)
     assert flen.tolist() == sorted(flen.tolist(), reverse=True)
     feats = feats.cpu().numpy()
@@ -428,3 +424,45 @@ def test_kaldi_collate_matches_reference_output(tmp_path, golden_dir, tag, kw):
     assert got.shape == ref.shape and got.dtype == ref.dtype
     assert np.array_equal(got == 0, ref == 0)
     assert np.abs(got - ref).max() <= (0 if tag == 'plain' else 2e-5)
+
+
+def test_long_ratio_and_kaiser_resamplers(golden_dir):
+    """Ratios whose polyphase table is too long to keep (44.1 kHz -> 16 kHz = 441:160; a speed drawn from a continuous
+    range, 953:1000) are evaluated on the fly (OE_RS_DIRECT) -- against torchaudio.functional.resample goldens
+    (oracle/make_golden_r02.py).  A caller-designed table with an arbitrary tap count (the sox-quality Kaiser filter)
+    registers and runs through the generic kernel -- against the oracle's own design of the same specification."""
+    from openeat_b200.frontend import Frontend, kaiser_sinc_kernel, pack_waveforms
+    from oracle import speed as S
+    fe = Frontend(mel_bins=80, sample_rate=16000)
+    g = np.load(os.path.join(golden_dir, 'resample_long.npz'))
+    for name, (o, n), tol in (('441_160', (441, 160), 0.1), ('953_1000', (953, 1000), 1.0)):
+        x, ref = g['x_' + name], g['y_' + name]
+        exact = S.resample(x, o, n, dtype=np.float64)                   # the same filter, evaluated in float64
+        for dtype in (np.float32, np.int16):
+            buf, offs, lens = pack_waveforms([x.astype(dtype)], dtype=dtype)
+            out, ooffs, olens = fe.resample(buf.cuda(), offs, lens, [(o, n)])
+            torch.cuda.synchronize()
+            got = out[ooffs[0]:ooffs[0] + int(olens[0])].cpu().numpy()
+            assert got.shape == ref.shape
+            assert np.abs(got - exact).max() <= 0.02                    # int16 scale
+            assert np.abs(got - ref).max() <= tol                       # torchaudio's fp32 kernel grid is that noisy (see the oracle test)
+    # the whole collate path with a 44.1 kHz source: resample_rate stage through the on-the-fly resampler
+    from openeat_b200.dataset import _extract_feature
+    from oracle import fbank as F
+    keys, feats, _ = _extract_feature([('u', (g['x_441_160'].astype(np.int16), 44100), [1], 1.0)],
+                                      {'mel_bins': 80, 'resample_rate': 16000, 'speed_perturb_rate': 0, 'wav_dither': 0.0})
+    ref = F.fbank(g['y_441_160'])
+    assert keys == ['u'] and feats[0].shape == ref.shape and np.abs(feats[0][:, :72] - ref[:, :72]).max() <= 5e-3
+    # Kaiser design: product vs oracle table, then the resampled waveform vs the oracle's float64 resampling
+    for sp in (0.9, 1.1):
+        o, n = S.speed_ratio(sp)
+        k, width = kaiser_sinc_kernel(o, n)
+        kr, wr = S.soxlike_kernel(o, n, dtype=np.float64)
+        assert width == wr and np.abs(k - kr).max() <= 1e-7
+        x = g['x_953_1000']
+        buf, offs, lens = pack_waveforms([x], dtype=np.float32)
+        out, ooffs, olens = fe.resample(buf.cuda(), offs, lens, [(o, n)], kind='kaiser')
+        torch.cuda.synchronize()
+        got = out[ooffs[0]:ooffs[0] + int(olens[0])].cpu().numpy()
+        ref = S.speed_perturb_soxlike(x, 16000, sp)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 0.05
