@@ -337,6 +337,44 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e_host, _, _ = timed_repeated(step_e2e_host, world > 1, 0.5)
     e2e_host_value = job_audio_s * args.steps / (ms_e2e_host * 1e-3)
 
+    # ---- the same from WAV FILES (tmpfs): native ingest (header parse + multi-threaded pread into a pinned ring) on a
+    # background thread -> H2D -> kernels; the reference reads its wavs inside DataLoader workers (train.py:110-116) ----
+    import shutil
+    import tempfile
+    import wave
+    from openeat_b200.ingest import ingest_batches
+    wav_dir = tempfile.mkdtemp(prefix='oe_bench_%d_' % rank, dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    file_batches = []
+    for bi in range(POOL):
+        pcm = host_pool[bi].numpy()
+        items = []
+        for u in range(BATCH):
+            path = os.path.join(wav_dir, 'b%d_u%d.wav' % (bi, u))
+            with wave.open(path, 'wb') as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(16000)
+                w.writeframes(pcm[offs[u]:offs[u] + lens[u]].tobytes())
+            items.append((keys[u], path, labels[u], speeds[u]))
+        file_batches.append(items)
+
+    def file_items():
+        i = 0
+        while True:
+            yield file_batches[i % POOL]
+            i += 1
+
+    pipe_files = PrefetchingCollator(collate, ingest_batches(file_items(), depth=3))
+
+    def step_e2e_files(i):
+        _, out = next(pipe_files)
+        d2h['n'].copy_(out['features_length'], non_blocking=True)
+        d2h['s'].copy_(stats, non_blocking=True)
+
+    ms_e2e_files, _, _ = timed_repeated(step_e2e_files, world > 1, 0.5)
+    e2e_files_value = job_audio_s * args.steps / (ms_e2e_files * 1e-3)
+    shutil.rmtree(wav_dir, ignore_errors=True)
+
     # ---- the box's own H2D ceiling: plain cudaMemcpyAsync from pinned memory, every rank at once ----
     h2d = int(host_pool[0].numel() * 2)
     sink = torch.empty_like(dev_pool[0])
@@ -526,6 +564,11 @@ def run_ours(args, rank, world, local_rank):
                                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(feat_bytes[0]) + BATCH * 8 + 161 * 8,
                                 'api': 'the same with to_host=True: the padded feature tensor returns to pinned host memory '
                                        'on a third stream (the reference boundary: audio_collate_func returns CPU tensors)'},
+                    'from_wav_files': {'value': e2e_files_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_files / args.steps,
+                                       'api': 'openeat_b200.ingest.ingest_batches (native RIFF parse + multi-threaded pread of %d wav '
+                                              'files per step from tmpfs into a pinned ring, background thread) -> '
+                                              'PrefetchingCollator -> the same kernels' % BATCH,
+                                       'frac_of_packed_e2e': e2e_files_value / e2e_value},
                     'h2d_ceiling_gbs': h2d_ceiling,
                     'h2d_achieved_gbs': h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9,
                     'frac_of_h2d_ceiling': (h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9) / h2d_ceiling},

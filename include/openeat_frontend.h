@@ -200,6 +200,31 @@ int oe_resample_workspace_bytes(const oe_frontend* fe, const oe_resample_batch* 
 int oe_resample(oe_frontend* fe, const oe_resample_batch* batch, const void* d_in, float* d_out,
                 void* d_workspace, size_t workspace_bytes, oe_stream stream);
 
+/* ---- native PCM ingest (host threads, no CUDA) ---------------------------------------------------------------
+ * Replaces the per-utterance sox_io_backend.info + torchaudio.load of _extract_feature (dataset.py:55-75), which the
+ * reference runs inside DataLoader worker processes (train.py:110-116): one call parses the RIFF/WAVE headers of a
+ * whole batch (probe), the caller lays the utterances out (offsets: multiples of 8 samples) in ONE packed buffer --
+ * normally the pinned staging buffer the H2D copy starts from -- and a second call reads every utterance's PCM
+ * straight into its place with a pool of reader threads (pread, no intermediate copy for mono files; channel 0 of
+ * multi-channel files, like torchaudio.load(...)[0]).
+ *   paths[i]            file name; starts / ends: seconds of a segmented entry ("path,start,end", dataset.py:56-70:
+ *                       frame_offset = int(start * sr), num_frames = int(end * sr) - frame_offset), starts[i] < 0
+ *                       (or NULL arrays) = the whole file
+ *   status[i]           OE_OK or an error code; oe_ingest_error(g, i) names the reason ("...: FLAC is not supported
+ *                       ...", "...: 24-bit samples ...", "...: No such file or directory").  Per-utterance failures do
+ *                       not fail the call: the caller prints the message and drops the utterance, the reference's
+ *                       convention (dataset.py:108-111).
+ * Only 16-bit integer PCM RIFF/WAVE is decoded (incl. WAVE_FORMAT_EXTENSIBLE); anything libsox reads beyond that
+ * (FLAC, 24-bit, float) is reported, not silently dropped. */
+typedef struct oe_ingest oe_ingest; /* opaque */
+int oe_ingest_create(int32_t threads, oe_ingest** out);      /* threads <= 0: one per hardware thread */
+int oe_ingest_destroy(oe_ingest* g);
+int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                    int32_t* n_samples, int32_t* sample_rates, int32_t* status);
+int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                   int16_t* dst, const int64_t* offsets, const int32_t* n_samples, int32_t* status);
+const char* oe_ingest_error(const oe_ingest* g, int32_t index);
+
 /* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
  * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).
  * These helpers continue that very generator natively: `mt_state` is `random.getstate()[1]` (624 state

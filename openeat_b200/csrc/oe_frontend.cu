@@ -31,6 +31,7 @@
 
 #include "../../include/openeat_frontend.h"
 #include "oe_fft.h"
+#include "oe_ingest.h"
 
 namespace oe {
 
@@ -2064,6 +2065,119 @@ int oe_plan_augment(uint32_t* mt_state, int32_t n, const int32_t* frames, int32_
             }
         }
     }
+    return OE_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// Native PCM ingest (host threads, no CUDA) -- oe_ingest.h
+// ==========================================================================================
+extern "C" {
+
+int oe_ingest_create(int32_t threads, oe_ingest** out) {
+    if (!out) return fail(OE_ERR_INVALID, "null out");
+    oe_ingest* g = new oe_ingest();
+    g->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    *out = g;
+    return OE_OK;
+}
+
+int oe_ingest_destroy(oe_ingest* g) {
+    delete g;
+    return OE_OK;
+}
+
+const char* oe_ingest_error(const oe_ingest* g, int32_t index) {
+    if (!g || index < 0 || index >= (int)g->errors.size()) return "";
+    return g->errors[index].c_str();
+}
+
+int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                    int32_t* n_samples, int32_t* sample_rates, int32_t* status) {
+    if (!g || n < 0 || (n > 0 && (!paths || !n_samples || !sample_rates || !status))) return fail(OE_ERR_INVALID, "null pointer");
+    g->errors.assign(n, std::string());
+    oe_ing::parallel_for(g->threads, n, [&](int i) {
+        n_samples[i] = sample_rates[i] = 0;
+        status[i] = OE_ERR_INVALID;
+        const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+        if (fd < 0) {
+            g->errors[i] = std::string(paths[i]) + ": " + strerror(errno);
+            return;
+        }
+        oe_ing::WavInfo w;
+        std::string err = oe_ing::parse_wav(fd, paths[i], w);
+        close(fd);
+        if (!err.empty()) {
+            g->errors[i] = err;
+            status[i] = OE_ERR_UNSUPPORTED;
+            return;
+        }
+        int64_t first, count;
+        const bool seg = starts && ends && !(starts[i] < 0.0);
+        oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
+        if (count > INT32_MAX) {
+            g->errors[i] = std::string(paths[i]) + ": more than 2^31 samples";
+            status[i] = OE_ERR_UNSUPPORTED;
+            return;
+        }
+        n_samples[i] = (int32_t)count;
+        sample_rates[i] = w.sample_rate;
+        status[i] = OE_OK;
+    });
+    return OE_OK;
+}
+
+int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                   int16_t* dst, const int64_t* offsets, const int32_t* n_samples, int32_t* status) {
+    if (!g || n < 0 || (n > 0 && (!paths || !dst || !offsets || !n_samples || !status))) return fail(OE_ERR_INVALID, "null pointer");
+    if ((int)g->errors.size() != n) g->errors.assign(n, std::string());
+    oe_ing::parallel_for(g->threads, n, [&](int i) {
+        if (status[i] != OE_OK || n_samples[i] <= 0) return;          // failed in the probe (message kept) or empty
+        const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+        if (fd < 0) {
+            g->errors[i] = std::string(paths[i]) + ": " + strerror(errno);
+            status[i] = OE_ERR_INVALID;
+            return;
+        }
+        oe_ing::WavInfo w;
+        std::string err = oe_ing::parse_wav(fd, paths[i], w);
+        int64_t first = 0, count = 0;
+        if (err.empty()) {
+            const bool seg = starts && ends && !(starts[i] < 0.0);
+            oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
+            if (count != n_samples[i]) err = std::string(paths[i]) + ": changed between probe and read";
+        }
+        if (err.empty()) {
+            int16_t* const out = dst + offsets[i];
+            if (w.channels == 1) {                                    // straight into the packed (pinned) buffer
+                int64_t done = 0;
+                const int64_t bytes = 2 * count;
+                while (done < bytes) {
+                    const ssize_t r = pread(fd, reinterpret_cast<char*>(out) + done, (size_t)(bytes - done), w.data_off + 2 * first + done);
+                    if (r <= 0) break;
+                    done += r;
+                }
+                if (done != bytes) err = std::string(paths[i]) + ": short read";
+            } else {                                                  // channel 0 of interleaved frames (torchaudio.load(...)[0])
+                std::vector<int16_t> tmp((size_t)65536 * w.channels);
+                for (int64_t f0 = 0; f0 < count && err.empty(); f0 += 65536) {
+                    const int64_t nf = std::min<int64_t>(65536, count - f0);
+                    const int64_t bytes = nf * 2 * w.channels;
+                    if (pread(fd, tmp.data(), (size_t)bytes, w.data_off + (first + f0) * 2 * w.channels) != bytes) {
+                        err = std::string(paths[i]) + ": short read";
+                        break;
+                    }
+                    for (int64_t f = 0; f < nf; ++f) out[f0 + f] = tmp[(size_t)f * w.channels];
+                }
+            }
+        }
+        close(fd);
+        if (!err.empty()) {
+            g->errors[i] = err;
+            status[i] = OE_ERR_INVALID;
+        }
+    });
     return OE_OK;
 }
 

@@ -298,6 +298,19 @@ class audio_collate_func(object):
         if self.data_type != 'wav':                                  # dataset.py:190-191
             keys, xs, ys = _load_feature(batch)
             return self.collate_features(keys, xs, ys)
+        if len(batch) and all(isinstance(x[1], str) for x in batch):
+            # wav files: native ingest (headers + multi-threaded pread straight into a pinned buffer, no per-utterance Python)
+            from .ingest import default_ingest
+            ing = default_ingest()
+            keys = [x[0] for x in batch]
+            buf, offs, lens, rates, loaded, slot = ing.load([x[1] for x in batch], keys)
+            out = self.collate_packed(buf, offs, lens, keys, [x[2] for x in batch], [x[3] for x in batch],
+                                      sample_rates=rates, loaded=loaded)
+            if torch.cuda.is_available():
+                ev = torch.cuda.Event()
+                ev.record()                      # behind the H2D copy of `buf`: the ring slot is reused after it
+                ing.release_after(slot, ev)
+            return out
         waves, rates, loaded = _load_batch(batch)
         buf, offs, lens = _pack_loaded(waves)
         return self.collate_packed(buf, offs, lens, [x[0] for x in batch], [x[2] for x in batch],
@@ -414,8 +427,9 @@ def _default_tokenizer(text):
 
 
 class AudioDataset(torch.utils.data.Dataset):
-    """openeat/dataset/dataset.py:241-376 for ``data_type='wav'``: parses ``format.data`` (one utterance per
-    line, tab-separated ``key:value`` fields ``utt feat feat_shape text`` [+ ``token tokenid token_shape``]),
+    """openeat/dataset/dataset.py:241-376: parses ``format.data`` (one utterance per line, tab-separated
+    ``key:value`` fields ``utt feat feat_shape text`` [+ ``token tokenid token_shape``]; ``feat_shape`` is seconds for
+    ``data_type='wav'`` and ``frames,dim`` for Kaldi-archive features, whose ``feat`` is ``file.ark:offset``),
     applies the length filters, the offline speed list, the optional sort and the static / dynamic / shuffle
     batching -- each item is a PRE-BUILT batch ``[(key, path, tokenid, speed), ...]`` for
     ``audio_collate_func`` -- including the reference's quirks (``num_frames *= speed``
@@ -430,8 +444,6 @@ class AudioDataset(torch.utils.data.Dataset):
                  speed_perturb=False, speeds=[0.9, 1.1, 0.1], data_type="kaldi", tokenizer=None):
         import codecs
         assert batch_type in ['static', 'dynamic', 'shuffle']
-        if data_type != 'wav':
-            raise NotImplementedError("openeat_b200.AudioDataset covers data_type='wav' (Kaldi-ark features: SURVEY 8f.4)")
         if bpe_model is not None and tokenizer is None:
             raise NotImplementedError('pass tokenizer= (e.g. a sentencepiece-backed callable); BPE is outside the front-end path')
         tokenizer = tokenizer or _default_tokenizer
@@ -456,7 +468,13 @@ class AudioDataset(torch.utils.data.Dataset):
                 else:
                     tokenid = arr[5].split(':')[1]                 # dataset.py:318-319 keeps the string
                 path = ':'.join(arr[1].split(':')[1:])
-                num_frames = int(float(arr[2].split(':')[1]) * 1000 / 10)                # dataset.py:324
+                if data_type == 'wav':
+                    num_frames = int(float(arr[2].split(':')[1]) * 1000 / 10)            # dataset.py:324
+                else:                                              # dataset.py:325-331: feat_shape:<frames>,<dim>
+                    feat_info = arr[2].split(':')[1].split(',')
+                    feat_dim = int(feat_info[1].strip())
+                    num_frames = int(feat_info[0].strip())
+                    self.input_size = feat_dim
                 length = num_frames
                 token_length = len(tokenid)
                 if min_length < length < max_length and token_min_length < token_length < token_max_length:
@@ -502,7 +520,9 @@ class PrefetchingCollator(object):
     ``collate_packed`` returns, in order (what torch's DataLoader prefetching does for the reference's
     CPU workers, done here for the one resource the GPU front-end is bound by: the H2D copy).
 
-    ``batches`` yields tuples ``(pinned_wav, offsets, lens, keys, labels, speeds)``.
+    ``batches`` yields tuples ``(pinned_wav, offsets, lens, keys, labels, speeds)``, optionally followed by
+    ``sample_rates, loaded, release`` (``openeat_b200.ingest.ingest_batches``: batches read from wav files by the native
+    ingest on a background thread; ``release(event)`` returns the pinned ring slot once the H2D copy has completed).
 
     ``to_host=True`` is the reference boundary proper (dataset.py:232-238: CPU tensors): the padded feature tensor
     of batch i goes back over PCIe on a third stream into a ring of pinned buffers while batch i+1 is being
@@ -536,17 +556,22 @@ class PrefetchingCollator(object):
             dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
-        self._next = (dev, ev) + tuple(item[1:])
+        if len(item) > 8 and item[8] is not None:
+            item[8](ev)                          # the ingest ring slot is free once this copy has completed
+        self._next = (dev, ev) + tuple(item[1:8])
 
     def __iter__(self):
         return self
 
     def _launch(self):
-        dev, ev, offs, lens, keys, labels, speeds = self._next
+        dev, ev, offs, lens, keys, labels, speeds = self._next[:7]
+        extra = self._next[7:]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
         dev.record_stream(cur)
         self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
+        if len(extra) >= 2:
+            return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds, sample_rates=extra[0], loaded=extra[1])
         return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds)
 
     def _to_host(self, keys, inputs):

@@ -1,0 +1,134 @@
+"""Native PCM ingest: the decode + pack step in front of the kernels (``oe_ingest_*`` of the C ABI).
+
+The reference decodes one utterance at a time with ``torchaudio.load`` inside DataLoader worker processes
+(``openeat/dataset/dataset.py:55-75``, ``openeat/bin/train.py:110-116``).  Here one native call parses the RIFF/WAVE
+headers of the whole batch, the utterances are laid out at 8-sample-aligned offsets of ONE pinned buffer, and a pool
+of reader threads ``pread``s every utterance straight into its place -- no per-utterance Python, no numpy pack, no GIL
+-- so the H2D copy can start from that buffer as it is.
+"""
+import ctypes
+import logging
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_f64p, c_i32p, c_i64p, check
+from .frontend import ALIGN, aligned_offsets
+
+
+def split_entry(entry):
+    """'path' or 'path,start,end' (dataset.py:56-58) -> (path, start, end) with start = -1 for a whole file."""
+    value = entry.strip().split(',')
+    assert len(value) == 1 or len(value) == 3
+    if len(value) == 3:
+        return value[0], float(value[1]), float(value[2])
+    return value[0], -1.0, 0.0
+
+
+class NativeIngest(object):
+    """``load(entries)`` -> (pinned int16 tensor, offsets, lens, sample_rates, loaded, slot).
+
+    The buffer is a slot of a small ring of pinned tensors (grown on demand); call ``release_after(slot, event)`` with
+    an event recorded behind the H2D copy that reads it, and the slot is reused only once that copy has completed.
+    Entries that cannot be ingested are reported the way the reference reports them (``print`` of the reason and
+    ``logging.warning('read utterance ... error')``, dataset.py:108-111) and come back with ``loaded[i] == False``;
+    the reason is explicit for formats libsox would have read (FLAC, 24-bit, float)."""
+
+    def __init__(self, threads=0, ring=4):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        check(self.lib.oe_ingest_create(int(threads), ctypes.byref(h)))
+        self.handle = h
+        self._ring = [None] * max(2, int(ring))
+        self._events = [None] * len(self._ring)
+        self._next = 0
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h:
+            self.lib.oe_ingest_destroy(h)
+            self.handle = None
+
+    def _slot(self, samples):
+        i = self._next
+        self._next = (i + 1) % len(self._ring)
+        if self._events[i] is not None:
+            self._events[i].synchronize()
+            self._events[i] = None
+        buf = self._ring[i]
+        if buf is None or buf.numel() < samples:
+            buf = torch.empty(int(samples * 1.25) + 4096, dtype=torch.int16)
+            if torch.cuda.is_available():
+                buf = buf.pin_memory()
+            self._ring[i] = buf
+        return i, buf
+
+    def release_after(self, slot, event):
+        self._events[slot] = event
+
+    def load(self, entries, keys=None):
+        n = len(entries)
+        parts = [split_entry(e) for e in entries]
+        paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
+        starts = np.array([p[1] for p in parts], dtype=np.float64)
+        ends = np.array([p[2] for p in parts], dtype=np.float64)
+        lens = np.zeros(n, dtype=np.int32)
+        rates = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        sp, ep = starts.ctypes.data_as(c_f64p), ends.ctypes.data_as(c_f64p)
+        check(self.lib.oe_ingest_probe(self.handle, n, paths, sp, ep, lens.ctypes.data_as(c_i32p),
+                                       rates.ctypes.data_as(c_i32p), status.ctypes.data_as(c_i32p)))
+        offs, total = aligned_offsets(lens)
+        slot, buf = self._slot(max(total, ALIGN))
+        check(self.lib.oe_ingest_read(self.handle, n, paths, sp, ep, ctypes.c_void_p(buf.data_ptr()),
+                                      offs.ctypes.data_as(c_i64p), lens.ctypes.data_as(c_i32p),
+                                      status.ctypes.data_as(c_i32p)))
+        loaded = status == 0
+        for i in np.nonzero(~loaded)[0]:                              # dataset.py:108-111: print, warn, drop
+            print(self.lib.oe_ingest_error(self.handle, int(i)).decode())
+            logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
+            lens[i] = 0
+        rates[~loaded] = 16000
+        return buf[:max(total, ALIGN)], offs, lens, rates, loaded, slot
+
+
+def ingest_batches(item_batches, ingest=None, depth=2):
+    """Generator over pre-built batches of ``(key, 'path[,start,end]', tokenid, speed)`` items (what ``AudioDataset``
+    yields): a background thread ingests up to ``depth`` batches ahead (the native call releases the GIL), so file
+    reading overlaps the H2D copy and the kernels of earlier batches.  Yields the tuples ``PrefetchingCollator`` takes:
+    ``(pinned_wav, offsets, lens, keys, labels, speeds, sample_rates, loaded, release)``; ``release(event)`` hands the
+    ring slot back once ``event`` (recorded behind the H2D copy) has completed."""
+    import queue
+    import threading
+    ing = ingest or NativeIngest(ring=depth + 3)
+    q = queue.Queue(maxsize=max(1, depth))
+    stop = object()
+
+    def work():
+        try:
+            for items in item_batches:
+                if len(items) == 1 and isinstance(items[0], list):          # DataLoader-style [batch] wrapping, dataset.py:186-187
+                    items = items[0]
+                keys = [x[0] for x in items]
+                buf, offs, lens, rates, loaded, slot = ing.load([x[1] for x in items], keys)
+                q.put((buf, offs, lens, keys, [x[2] for x in items], [x[3] for x in items], rates, loaded,
+                       (lambda ev, s=slot: ing.release_after(s, ev))))
+        finally:
+            q.put(stop)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is stop:
+            return
+        yield item
+
+
+_default = {}
+
+
+def default_ingest():
+    if 'g' not in _default:
+        _default['g'] = NativeIngest()
+    return _default['g']

@@ -492,3 +492,40 @@ def test_processor_chain_with_23_bins(golden_dir):
         ref = C.global_cmvn(x, mean.numpy(), istd.numpy())
         got = o['feat'].cpu().numpy()
         assert got.shape == ref.shape and np.abs(got - ref).max() <= 3e-3
+
+
+def test_output_canaries_stay_intact(fe):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are checked the blunt way: the output
+    tensor sits between two guard bands of a sentinel bit pattern, for every launch sequence (single pass with padding
+    fill, in-place completion, spec_sub through the scratch, ragged rows, odd row counts)."""
+    from openeat_b200.frontend import pack_waveforms
+    frames = [65, 1, 33, 0, 32, 97]
+    lens = [400 + 160 * (m - 1) if m else 300 for m in frames]
+    waves = [signals.make('white', n, 300 + i) for i, n in enumerate(lens)]
+    buf, offs, ln = pack_waveforms(waves)
+    dev = buf.cuda()
+    B, G, tmax = len(waves), 257, 101
+    sentinel = torch.tensor([0x7FC0DEAD], dtype=torch.int32).view(torch.float32).item()
+    mean = torch.linspace(8.0, 12.0, 80, device='cuda')
+    istd = torch.linspace(0.4, 0.6, 80, device='cuda')
+    maps = [np.arange(m, dtype=np.int32)[::-1].copy() for m in frames]
+    modes = [dict(), dict(cmvn=(mean, istd), cmvn_on_padding=True), dict(normalization=True),
+             dict(normalization=True, cmvn=(mean, istd), cmvn_on_padding=True, tmask=np.array([[[0, 3]]] * B, np.int32)),
+             dict(normalization=True, frame_maps=maps), dict(feature_dither=0.2, dither_seed=3)]
+    for kw in modes:
+        for layout in ('padded', 'ragged'):
+            rows = B * tmax if layout == 'padded' else sum(frames)
+            big = torch.empty((rows + 2 * G, 80), device='cuda')
+            big.view(torch.int32).fill_(0x7FC0DEAD)
+            out = big[G:G + rows]
+            if layout == 'padded':
+                o_rows, o_n = np.arange(B, dtype=np.int64) * tmax, np.full(B, tmax, np.int32)
+            else:
+                o_rows, o_n = np.concatenate([[0], np.cumsum(frames[:-1])]).astype(np.int64), np.array(frames, np.int32)
+            _, fr = fe.fbank(dev, offs, ln, layout='custom', out=out, out_rows=o_rows, out_nrows=o_n, **kw)
+            torch.cuda.synchronize()
+            assert fr.tolist() == frames
+            guard = torch.cat([big[:G], big[G + rows:]]).view(torch.int32)
+            assert bool((guard == 0x7FC0DEAD).all()), (kw.keys(), layout)
+            assert not bool((out.view(torch.int32) == 0x7FC0DEAD).any()), (kw.keys(), layout)     # every row was written
+    assert sentinel != sentinel                                        # (a NaN pattern: never a legitimate output)

@@ -177,7 +177,7 @@ def test_audio_dataset_matches_reference_batches(golden_dir):
         assert ds.batch_size == gold[tag + '_batch_size'] and len(ds) == len(gold[tag])
     ds = AudioDataset(path, char_dict, None, data_type='wav', batch_type='static', batch_size=4)
     assert any(',1.5,4.25' in item[1] for b in ds.data for item in b)        # segmented entries survive as path,start,end
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(IndexError):                # a wav list read as a Kaldi-feature list: feat_shape has no ",dim" -- the reference raises the same
         AudioDataset(path, char_dict, None, data_type='kaldi')
 
 
@@ -233,3 +233,58 @@ def test_tar_shard_reader(tmp_path):
     assert [s['key'] for s in got] == list(waves)
     for s in got:
         assert np.array_equal(s['wav'], waves[s['key']]) and s['sample_rate'] == 16000 and s['txt'] == 'text of ' + s['key']
+
+
+def test_native_ingest_matches_the_stdlib_reader(tmp_path):
+    """oe_ingest_probe / oe_ingest_read (dataset.py:55-75 natively): mono and stereo (channel 0) 16-bit PCM, segmented
+    entries 'path,start,end' incl. one that runs past the end of the file, 8-sample aligned packing -- equal to the
+    stdlib-`wave` reader sample for sample; formats libsox would read but this ingest does not (32-bit, FLAC) and a
+    missing file are reported with an explicit reason and marked not loaded (never silently dropped)."""
+    import wave
+    from openeat_b200.dataset import read_wav
+    from openeat_b200.ingest import NativeIngest
+    rng = np.random.default_rng(0)
+
+    def wr(path, pcm, ch=1, width=2, sr=16000):
+        with wave.open(str(path), 'wb') as w:
+            w.setnchannels(ch)
+            w.setsampwidth(width)
+            w.setframerate(sr)
+            w.writeframes(pcm.tobytes())
+    a = rng.integers(-3000, 3000, 16001).astype('<i2')
+    b = rng.integers(-3000, 3000, (9000, 2)).astype('<i2')
+    wr(tmp_path / 'a.wav', a)
+    wr(tmp_path / 'b.wav', b, ch=2, sr=8000)
+    wr(tmp_path / 'c.wav', rng.integers(-3000, 3000, 500).astype('<i4'), width=4)
+    (tmp_path / 'd.flac').write_bytes(b'fLaC' + b'\0' * 64)
+    p = str(tmp_path)
+    entries = [p + '/a.wav', p + '/b.wav', p + '/a.wav,0.25,0.75', p + '/c.wav', p + '/d.flac', p + '/missing.wav',
+               p + '/a.wav,0.9,5.0']
+    ing = NativeIngest(threads=3, ring=2)
+    for _ in range(3):                                            # walks the ring
+        buf, offs, lens, rates, loaded, slot = ing.load(entries, keys=['k%d' % i for i in range(7)])
+        x = buf.numpy()
+        assert loaded.tolist() == [True, True, True, False, False, False, True]
+        assert rates.tolist()[:3] == [16000, 8000, 16000] and (offs % 8 == 0).all()
+        assert lens.tolist() == [16001, 9000, 8000, 0, 0, 0, 1601]
+        assert np.array_equal(x[offs[0]:offs[0] + lens[0]], a)
+        assert np.array_equal(x[offs[1]:offs[1] + lens[1]], b[:, 0])
+        for i, (s, e) in ((2, (0.25, 0.75)), (6, (0.9, 5.0))):
+            ref, _ = read_wav(p + '/a.wav', s, e)
+            assert np.array_equal(x[offs[i]:offs[i] + lens[i]], ref)
+    errs = [ing.lib.oe_ingest_error(ing.handle, i).decode() for i in range(7)]
+    assert '32-bit' in errs[3] and 'FLAC' in errs[4] and 'No such file' in errs[5] and errs[0] == ''
+
+
+def test_audio_dataset_parses_kaldi_feature_lists(tmp_path):
+    """AudioDataset(data_type='kaldi') (dataset.py:325-331): ``feat:file.ark:offset`` and ``feat_shape:frames,dim``."""
+    from openeat_b200.dataset import AudioDataset
+    lines = ['utt:u%d\tfeat:/data/f.ark:%d\tfeat_shape:%d,80\ttext:a b' % (i, 17 + 100 * i, t)
+             for i, t in enumerate([120, 30, 500, 75])]
+    f = tmp_path / 'format.data'
+    f.write_text('\n'.join(lines) + '\n')
+    ds = AudioDataset(str(f), {'A': 1, 'B': 2, '<unk>': 0, ' ': 3}, data_type='kaldi', batch_type='static', batch_size=2,
+                      sort=True, max_length=400, min_length=40)
+    assert ds.input_size == 80
+    assert [[it[0] for it in b] for b in ds] == [['u3', 'u0']]    # 30 and 500 frames are filtered out, sorted by length
+    assert ds[0][0][1] == '/data/f.ark:317'

@@ -24,5 +24,14 @@ c, fr2 = fe.fbank(dev, offs, ln, layout='padded', normalization=True, speed_rati
                   fmask=np.array([[[10, 14]]] * 6, np.int32), cmvn=(mean, istd), cmvn_on_padding=True)
 r, ro, rl = fe.resample(dev, offs, ln, ratios)
 d, _ = fe.fbank(r, ro, rl, layout='ragged')                                                   # fp32 input path
+# spec_sub (scratch + out-of-place finalize), feature dither, the on-the-fly and Kaiser resamplers, 23 mel bins (gen-1 kernel)
+maps = [np.arange(int(t), dtype=np.int32)[::-1].copy() for t in fr]
+e, _ = fe.fbank(dev, offs, ln, layout='padded', normalization=True, frame_maps=maps, feature_dither=0.3, dither_seed=5)
+r2, _, _ = fe.resample(dev, offs, ln, [(441, 160)] * 6)
+r3, _, _ = fe.resample(dev, offs, ln, [(9, 10)] * 6, kind='kaiser')
+fe23 = Frontend(mel_bins=23)
+f23, _ = fe23.fbank(dev, offs, ln, layout='padded', normalization=True, stats=torch.zeros(47, dtype=torch.float64, device='cuda'))
+up = fe.upload_small(np.arange(37, dtype=np.int32))
 torch.cuda.synchronize()
+assert up.tolist() == list(range(37))
 print('ok', fr.tolist(), fr2.tolist(), float(stats[160]), bool(torch.isfinite(a).all()), bool(torch.isfinite(d).all()))
