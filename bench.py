@@ -358,9 +358,11 @@ def run_ours(args, rank, world, local_rank):
             items.append((keys[u], path, labels[u], speeds[u]))
         file_batches.append(items)
 
+    files_done = []
+
     def file_items():
         i = 0
-        while True:
+        while not files_done:
             yield file_batches[i % POOL]
             i += 1
 
@@ -373,7 +375,9 @@ def run_ours(args, rank, world, local_rank):
 
     ms_e2e_files, _, _ = timed_repeated(step_e2e_files, world > 1, 0.5)
     e2e_files_value = job_audio_s * args.steps / (ms_e2e_files * 1e-3)
-    shutil.rmtree(wav_dir, ignore_errors=True)
+    files_done.append(True)                     # the background reader stops; the files go at exit
+    import atexit
+    atexit.register(shutil.rmtree, wav_dir, ignore_errors=True)
 
     # ---- the box's own H2D ceiling: plain cudaMemcpyAsync from pinned memory, every rank at once ----
     h2d = int(host_pool[0].numel() * 2)

@@ -224,6 +224,19 @@ int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const dou
 int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
                    int16_t* dst, const int64_t* offsets, const int32_t* n_samples, int32_t* status);
 const char* oe_ingest_error(const oe_ingest* g, int32_t index);
+/* The same asynchronously: oe_ingest_submit copies the request and returns at once; a driver thread of the handle
+ * takes the jobs in order (probe -> 8-sample aligned layout -> read into dst, which must hold dst_capacity samples and
+ * stay valid until the wait); oe_ingest_wait blocks until the job is done and hands out its result arrays (owned by
+ * the job, valid until oe_ingest_job_release).  A destination that is too small fails the entries with
+ * OE_ERR_WORKSPACE and reports the samples needed in *total.  Do not mix with oe_ingest_probe / oe_ingest_read on the
+ * same handle while jobs are pending. */
+typedef struct oe_ingest_job oe_ingest_job; /* opaque */
+int oe_ingest_submit(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                     int16_t* dst, int64_t dst_capacity, oe_ingest_job** job);
+int oe_ingest_wait(oe_ingest_job* job, const int64_t** offsets, const int32_t** n_samples, const int32_t** sample_rates,
+                   const int32_t** status, int64_t* total);
+const char* oe_ingest_job_error(const oe_ingest_job* job, int32_t index);
+int oe_ingest_job_release(oe_ingest_job* job);
 
 /* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
  * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).

@@ -2078,12 +2078,32 @@ extern "C" {
 int oe_ingest_create(int32_t threads, oe_ingest** out) {
     if (!out) return fail(OE_ERR_INVALID, "null out");
     oe_ingest* g = new oe_ingest();
-    g->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    g->threads = threads > 0 ? threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    g->pool = new oe_ing::Pool(g->threads);
     *out = g;
     return OE_OK;
 }
 
+static void ingest_close_all(oe_ingest* g) {
+    for (int& fd : g->fds)
+        if (fd >= 0) {
+            close(fd);
+            fd = -1;
+        }
+}
+
 int oe_ingest_destroy(oe_ingest* g) {
+    if (!g) return OE_OK;
+    if (g->driver.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(g->qm);
+            g->quit = true;
+        }
+        g->qcv.notify_all();
+        g->driver.join();
+    }
+    ingest_close_all(g);
+    delete g->pool;
     delete g;
     return OE_OK;
 }
@@ -2096,8 +2116,12 @@ const char* oe_ingest_error(const oe_ingest* g, int32_t index) {
 int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
                     int32_t* n_samples, int32_t* sample_rates, int32_t* status) {
     if (!g || n < 0 || (n > 0 && (!paths || !n_samples || !sample_rates || !status))) return fail(OE_ERR_INVALID, "null pointer");
+    ingest_close_all(g);
     g->errors.assign(n, std::string());
-    oe_ing::parallel_for(g->threads, n, [&](int i) {
+    g->fds.assign(n, -1);
+    g->infos.assign(n, oe_ing::WavInfo());
+    g->first.assign(n, 0);
+    g->pool->run(n, [&](int i) {
         n_samples[i] = sample_rates[i] = 0;
         status[i] = OE_ERR_INVALID;
         const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
@@ -2105,22 +2129,22 @@ int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const dou
             g->errors[i] = std::string(paths[i]) + ": " + strerror(errno);
             return;
         }
-        oe_ing::WavInfo w;
+        oe_ing::WavInfo& w = g->infos[i];
         std::string err = oe_ing::parse_wav(fd, paths[i], w);
-        close(fd);
+        int64_t first = 0, count = 0;
+        if (err.empty()) {
+            const bool seg = starts && ends && !(starts[i] < 0.0);
+            oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
+            if (count > INT32_MAX) err = std::string(paths[i]) + ": more than 2^31 samples";
+        }
         if (!err.empty()) {
+            close(fd);
             g->errors[i] = err;
             status[i] = OE_ERR_UNSUPPORTED;
             return;
         }
-        int64_t first, count;
-        const bool seg = starts && ends && !(starts[i] < 0.0);
-        oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
-        if (count > INT32_MAX) {
-            g->errors[i] = std::string(paths[i]) + ": more than 2^31 samples";
-            status[i] = OE_ERR_UNSUPPORTED;
-            return;
-        }
+        g->fds[i] = fd;
+        g->first[i] = first;
         n_samples[i] = (int32_t)count;
         sample_rates[i] = w.sample_rate;
         status[i] = OE_OK;
@@ -2130,54 +2154,139 @@ int oe_ingest_probe(oe_ingest* g, int32_t n, const char* const* paths, const dou
 
 int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
                    int16_t* dst, const int64_t* offsets, const int32_t* n_samples, int32_t* status) {
+    (void)starts;
+    (void)ends;
     if (!g || n < 0 || (n > 0 && (!paths || !dst || !offsets || !n_samples || !status))) return fail(OE_ERR_INVALID, "null pointer");
-    if ((int)g->errors.size() != n) g->errors.assign(n, std::string());
-    oe_ing::parallel_for(g->threads, n, [&](int i) {
-        if (status[i] != OE_OK || n_samples[i] <= 0) return;          // failed in the probe (message kept) or empty
-        const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
-        if (fd < 0) {
-            g->errors[i] = std::string(paths[i]) + ": " + strerror(errno);
-            status[i] = OE_ERR_INVALID;
-            return;
-        }
-        oe_ing::WavInfo w;
-        std::string err = oe_ing::parse_wav(fd, paths[i], w);
-        int64_t first = 0, count = 0;
-        if (err.empty()) {
-            const bool seg = starts && ends && !(starts[i] < 0.0);
-            oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
-            if (count != n_samples[i]) err = std::string(paths[i]) + ": changed between probe and read";
-        }
-        if (err.empty()) {
-            int16_t* const out = dst + offsets[i];
-            if (w.channels == 1) {                                    // straight into the packed (pinned) buffer
-                int64_t done = 0;
-                const int64_t bytes = 2 * count;
-                while (done < bytes) {
-                    const ssize_t r = pread(fd, reinterpret_cast<char*>(out) + done, (size_t)(bytes - done), w.data_off + 2 * first + done);
-                    if (r <= 0) break;
-                    done += r;
+    if ((int)g->fds.size() != n) return fail(OE_ERR_INVALID, "oe_ingest_read must follow oe_ingest_probe of the same %d entries", n);
+    g->pool->run(n, [&](int i) {
+        const int fd = g->fds[i];
+        if (status[i] != OE_OK || fd < 0) return;                     // failed in the probe: message kept
+        const oe_ing::WavInfo& w = g->infos[i];
+        const int64_t first = g->first[i], count = n_samples[i];
+        std::string err;
+        int16_t* const out = dst + offsets[i];
+        if (w.channels == 1) {                                        // straight into the packed (pinned) buffer
+            int64_t done = 0;
+            const int64_t bytes = 2 * count;
+            while (done < bytes) {
+                const ssize_t r = pread(fd, reinterpret_cast<char*>(out) + done, (size_t)(bytes - done), w.data_off + 2 * first + done);
+                if (r <= 0) break;
+                done += r;
+            }
+            if (done != bytes) err = std::string(paths[i]) + ": short read";
+        } else {                                                      // channel 0 of interleaved frames (torchaudio.load(...)[0])
+            std::vector<int16_t> tmp((size_t)65536 * w.channels);
+            for (int64_t f0 = 0; f0 < count; f0 += 65536) {
+                const int64_t nf = std::min<int64_t>(65536, count - f0);
+                const int64_t bytes = nf * 2 * w.channels;
+                if (pread(fd, tmp.data(), (size_t)bytes, w.data_off + (first + f0) * 2 * w.channels) != bytes) {
+                    err = std::string(paths[i]) + ": short read";
+                    break;
                 }
-                if (done != bytes) err = std::string(paths[i]) + ": short read";
-            } else {                                                  // channel 0 of interleaved frames (torchaudio.load(...)[0])
-                std::vector<int16_t> tmp((size_t)65536 * w.channels);
-                for (int64_t f0 = 0; f0 < count && err.empty(); f0 += 65536) {
-                    const int64_t nf = std::min<int64_t>(65536, count - f0);
-                    const int64_t bytes = nf * 2 * w.channels;
-                    if (pread(fd, tmp.data(), (size_t)bytes, w.data_off + (first + f0) * 2 * w.channels) != bytes) {
-                        err = std::string(paths[i]) + ": short read";
-                        break;
-                    }
-                    for (int64_t f = 0; f < nf; ++f) out[f0 + f] = tmp[(size_t)f * w.channels];
-                }
+                for (int64_t f = 0; f < nf; ++f) out[f0 + f] = tmp[(size_t)f * w.channels];
             }
         }
-        close(fd);
         if (!err.empty()) {
             g->errors[i] = err;
             status[i] = OE_ERR_INVALID;
         }
     });
+    ingest_close_all(g);
+    return OE_OK;
+}
+
+// ---- asynchronous batches ----
+static void ingest_driver(oe_ingest* g) {
+    for (;;) {
+        oe_ingest_job* job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(g->qm);
+            g->qcv.wait(lk, [&] { return g->quit || !g->queue.empty(); });
+            if (g->queue.empty()) return;                              // quit and nothing left
+            job = g->queue.front();
+            g->queue.erase(g->queue.begin());
+        }
+        const int n = (int)job->paths.size();
+        oe_ingest_probe(g, n, job->cpaths.data(), job->starts.data(), job->ends.data(), job->lens.data(), job->rates.data(),
+                        job->status.data());
+        int64_t total = 0;
+        for (int i = 0; i < n; ++i) {                                  // 8-sample aligned packing (include/openeat_frontend.h: wav_offsets)
+            job->offsets[i] = total;
+            total += ((int64_t)job->lens[i] + 7) / 8 * 8;
+        }
+        job->total = total;
+        if (total > job->capacity) {
+            for (int i = 0; i < n; ++i)
+                if (job->status[i] == OE_OK) {
+                    job->status[i] = OE_ERR_WORKSPACE;
+                    g->errors[i] = "destination buffer too small";
+                }
+            ingest_close_all(g);
+        } else {
+            oe_ingest_read(g, n, job->cpaths.data(), job->starts.data(), job->ends.data(), job->dst, job->offsets.data(),
+                           job->lens.data(), job->status.data());
+        }
+        job->errors = g->errors;
+        {
+            std::lock_guard<std::mutex> lk(g->qm);
+            job->done = true;
+        }
+        g->dcv.notify_all();
+    }
+}
+
+int oe_ingest_submit(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                     int16_t* dst, int64_t dst_capacity, oe_ingest_job** out) {
+    if (!g || !out || n < 0 || (n > 0 && (!paths || !dst))) return fail(OE_ERR_INVALID, "null pointer");
+    oe_ingest_job* job = new oe_ingest_job();
+    job->owner = g;
+    job->paths.assign(paths, paths + n);
+    for (auto& p : job->paths) job->cpaths.push_back(p.c_str());
+    job->starts.assign(n, -1.0);
+    job->ends.assign(n, 0.0);
+    if (starts && ends) {
+        job->starts.assign(starts, starts + n);
+        job->ends.assign(ends, ends + n);
+    }
+    job->dst = dst;
+    job->capacity = dst_capacity;
+    job->offsets.assign(n, 0);
+    job->lens.assign(n, 0);
+    job->rates.assign(n, 0);
+    job->status.assign(n, OE_ERR_INVALID);
+    {
+        std::lock_guard<std::mutex> lk(g->qm);
+        if (!g->driver.joinable()) g->driver = std::thread(ingest_driver, g);
+        g->queue.push_back(job);
+    }
+    g->qcv.notify_all();
+    *out = job;
+    return OE_OK;
+}
+
+int oe_ingest_wait(oe_ingest_job* job, const int64_t** offsets, const int32_t** n_samples, const int32_t** sample_rates,
+                   const int32_t** status, int64_t* total) {
+    if (!job) return fail(OE_ERR_INVALID, "null job");
+    oe_ingest* g = job->owner;
+    {
+        std::unique_lock<std::mutex> lk(g->qm);
+        g->dcv.wait(lk, [&] { return job->done; });
+    }
+    if (offsets) *offsets = job->offsets.data();
+    if (n_samples) *n_samples = job->lens.data();
+    if (sample_rates) *sample_rates = job->rates.data();
+    if (status) *status = job->status.data();
+    if (total) *total = job->total;
+    return OE_OK;
+}
+
+const char* oe_ingest_job_error(const oe_ingest_job* job, int32_t index) {
+    if (!job || index < 0 || index >= (int)job->errors.size()) return "";
+    return job->errors[index].c_str();
+}
+
+int oe_ingest_job_release(oe_ingest_job* job) {
+    delete job;
     return OE_OK;
 }
 

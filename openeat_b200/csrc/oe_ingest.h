@@ -10,20 +10,121 @@
 
 #include <atomic>
 #include <cerrno>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 
-struct oe_ingest {
-    int threads;
-    std::vector<std::string> errors;        // per entry of the most recent probe / read
-};
-
 namespace oe_ing {
+
+// Persistent pool: the workers sleep between calls (creating 2 x 32 threads per batch costs more than reading it).
+class Pool {
+  public:
+    explicit Pool(int threads) : n_threads_(std::max(1, threads)) {
+        for (int i = 1; i < n_threads_; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // runs fn(i) for i in [0, n) on the pool (the caller takes part); returns when all are done
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            pending_ = n;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        int did = 0;
+        for (int i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) {
+            (*fn_)(i);
+            ++did;
+        }
+        if (did) {
+            std::lock_guard<std::mutex> lk(m_);
+            pending_ -= did;
+            if (pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return quit_ || epoch_ != seen; });
+                if (quit_) return;
+                seen = epoch_;
+            }
+            work();
+        }
+    }
+    int n_threads_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, pending_ = 0;
+    long epoch_ = 0;
+    bool quit_ = false;
+};
 
 struct WavInfo {
     int sample_rate = 0, channels = 0, bits = 0;
     int64_t data_off = 0, frames = 0;        // byte offset of the PCM, frames in the file
 };
+
+}  // namespace oe_ing
+
+// One asynchronous batch (oe_ingest_submit): owns copies of the request and the result arrays.
+struct oe_ingest_job {
+    oe_ingest* owner = nullptr;
+    std::vector<std::string> paths;
+    std::vector<const char*> cpaths;
+    std::vector<double> starts, ends;
+    int16_t* dst = nullptr;
+    int64_t capacity = 0, total = 0;
+    std::vector<int64_t> offsets;
+    std::vector<int32_t> lens, rates, status;
+    std::vector<std::string> errors;
+    bool done = false;
+};
+
+struct oe_ingest {
+    int threads;
+    oe_ing::Pool* pool;
+    std::vector<std::string> errors;        // per entry of the most recent probe / read
+    // the probe keeps every file open with its parsed header: the read that follows neither re-opens nor re-parses
+    std::vector<int> fds;
+    std::vector<oe_ing::WavInfo> infos;
+    std::vector<int64_t> first;
+    // asynchronous jobs: a driver thread takes them in order and runs probe -> layout -> read on the pool, so the
+    // caller (a Python thread holding the GIL) only submits and, later, waits
+    std::thread driver;
+    std::mutex qm;
+    std::condition_variable qcv, dcv;
+    std::vector<oe_ingest_job*> queue;
+    bool quit = false;
+};
+
+namespace oe_ing {
 
 inline uint32_t rd32(const unsigned char* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 inline uint32_t rd16(const unsigned char* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
@@ -83,19 +184,6 @@ inline void segment(const WavInfo& w, double start, double end, bool has_seg, in
     const int64_t s = (int64_t)(start * w.sample_rate), e = (int64_t)(end * w.sample_rate);
     first = std::min<int64_t>(std::max<int64_t>(s, 0), w.frames);
     count = std::max<int64_t>(0, std::min<int64_t>(e - s, w.frames - first));
-}
-
-template <class Fn>
-inline void parallel_for(int threads, int n, Fn fn) {
-    std::atomic<int> next(0);
-    auto work = [&]() {
-        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
-    };
-    const int t = std::max(1, std::min(threads, n));
-    std::vector<std::thread> pool;
-    for (int i = 1; i < t; ++i) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
 }
 
 }  // namespace oe_ing

@@ -67,6 +67,49 @@ class NativeIngest(object):
     def release_after(self, slot, event):
         self._events[slot] = event
 
+    def submit(self, entries, capacity=None):
+        """Starts reading a batch on the handle's driver thread; returns a ticket for ``wait``."""
+        n = len(entries)
+        parts = [split_entry(e) for e in entries]
+        paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
+        starts = np.array([p[1] for p in parts], dtype=np.float64)
+        ends = np.array([p[2] for p in parts], dtype=np.float64)
+        want = int(capacity or getattr(self, '_seen', 0) or (1 << 22))
+        slot, buf = self._slot(want)
+        job = ctypes.c_void_p()
+        check(self.lib.oe_ingest_submit(self.handle, n, paths, starts.ctypes.data_as(c_f64p), ends.ctypes.data_as(c_f64p),
+                                        ctypes.c_void_p(buf.data_ptr()), buf.numel(), ctypes.byref(job)))
+        return {'job': job, 'slot': slot, 'buf': buf, 'n': n, 'entries': entries, 'parts': parts}
+
+    def wait(self, ticket, keys=None):
+        """Blocks (GIL released) until the batch is in its buffer; same return value as ``load``."""
+        n = ticket['n']
+        o, l, r, st = c_i64p(), c_i32p(), c_i32p(), c_i32p()
+        total = ctypes.c_int64()
+        check(self.lib.oe_ingest_wait(ticket['job'], ctypes.byref(o), ctypes.byref(l), ctypes.byref(r), ctypes.byref(st),
+                                      ctypes.byref(total)))
+        if n:
+            offs = np.ctypeslib.as_array(o, shape=(n,)).copy()
+            lens = np.ctypeslib.as_array(l, shape=(n,)).copy()
+            rates = np.ctypeslib.as_array(r, shape=(n,)).copy()
+            status = np.ctypeslib.as_array(st, shape=(n,)).copy()
+        else:
+            offs, lens, rates, status = np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        self._seen = max(getattr(self, '_seen', 0), int(total.value * 1.25) + 4096)
+        if total.value > ticket['buf'].numel():                          # the ring slot was too small: once, synchronously, bigger
+            self.lib.oe_ingest_job_release(ticket['job'])
+            self._ring[ticket['slot']] = None
+            self._next = ticket['slot']
+            return self.load(ticket['entries'], keys)
+        loaded = status == 0
+        for i in np.nonzero(~loaded)[0]:                                 # dataset.py:108-111: print, warn, drop
+            print(self.lib.oe_ingest_job_error(ticket['job'], int(i)).decode())
+            logging.warning('read utterance {} error'.format(keys[i] if keys is not None else ticket['parts'][i][0]))
+            lens[i] = 0
+        rates[~loaded] = 16000
+        self.lib.oe_ingest_job_release(ticket['job'])
+        return ticket['buf'][:max(int(total.value), ALIGN)], offs, lens, rates, loaded, ticket['slot']
+
     def load(self, entries, keys=None):
         n = len(entries)
         parts = [split_entry(e) for e in entries]
@@ -95,34 +138,34 @@ class NativeIngest(object):
 
 def ingest_batches(item_batches, ingest=None, depth=2):
     """Generator over pre-built batches of ``(key, 'path[,start,end]', tokenid, speed)`` items (what ``AudioDataset``
-    yields): a background thread ingests up to ``depth`` batches ahead (the native call releases the GIL), so file
-    reading overlaps the H2D copy and the kernels of earlier batches.  Yields the tuples ``PrefetchingCollator`` takes:
-    ``(pinned_wav, offsets, lens, keys, labels, speeds, sample_rates, loaded, release)``; ``release(event)`` hands the
-    ring slot back once ``event`` (recorded behind the H2D copy) has completed."""
-    import queue
-    import threading
+    yields): up to ``depth`` batches are being read ahead by the handle's native driver thread (``oe_ingest_submit``; no
+    Python thread, so nothing competes for the GIL), i.e. file reading overlaps the H2D copy and the kernels of earlier
+    batches.  Yields the tuples ``PrefetchingCollator`` takes: ``(pinned_wav, offsets, lens, keys, labels, speeds,
+    sample_rates, loaded, release)``; ``release(event)`` hands the ring slot back once ``event`` (recorded behind the H2D
+    copy) has completed."""
     ing = ingest or NativeIngest(ring=depth + 3)
-    q = queue.Queue(maxsize=max(1, depth))
-    stop = object()
+    it = iter(item_batches)
+    pending = []
 
-    def work():
+    def submit():
         try:
-            for items in item_batches:
-                if len(items) == 1 and isinstance(items[0], list):          # DataLoader-style [batch] wrapping, dataset.py:186-187
-                    items = items[0]
-                keys = [x[0] for x in items]
-                buf, offs, lens, rates, loaded, slot = ing.load([x[1] for x in items], keys)
-                q.put((buf, offs, lens, keys, [x[2] for x in items], [x[3] for x in items], rates, loaded,
-                       (lambda ev, s=slot: ing.release_after(s, ev))))
-        finally:
-            q.put(stop)
+            items = next(it)
+        except StopIteration:
+            return False
+        if len(items) == 1 and isinstance(items[0], list):              # DataLoader-style [batch] wrapping, dataset.py:186-187
+            items = items[0]
+        pending.append((items, ing.submit([x[1] for x in items])))
+        return True
 
-    threading.Thread(target=work, daemon=True).start()
-    while True:
-        item = q.get()
-        if item is stop:
-            return
-        yield item
+    while len(pending) < depth and submit():
+        pass
+    while pending:
+        items, ticket = pending.pop(0)
+        keys = [x[0] for x in items]
+        buf, offs, lens, rates, loaded, slot = ing.wait(ticket, keys)
+        submit()
+        yield (buf, offs, lens, keys, [x[2] for x in items], [x[3] for x in items], rates, loaded,
+               (lambda ev, s=slot: ing.release_after(s, ev)))
 
 
 _default = {}

@@ -288,3 +288,38 @@ def test_audio_dataset_parses_kaldi_feature_lists(tmp_path):
     assert ds.input_size == 80
     assert [[it[0] for it in b] for b in ds] == [['u3', 'u0']]    # 30 and 500 frames are filtered out, sorted by length
     assert ds[0][0][1] == '/data/f.ark:317'
+
+
+def test_asynchronous_ingest_batches(tmp_path):
+    """ingest_batches: batches read ahead by the handle's native driver thread (oe_ingest_submit / oe_ingest_wait) arrive
+    in order and equal the files; a ring slot that is too small is replaced transparently; failures are reported."""
+    import wave
+    from openeat_b200.ingest import NativeIngest, ingest_batches
+    rng = np.random.default_rng(1)
+    data, batches = {}, []
+    for b in range(5):
+        items = []
+        for u in range(6):
+            x = rng.integers(-3000, 3000, int(rng.integers(500, 60000) * (8 if b == 3 else 1))).astype('<i2')
+            p = str(tmp_path / ('b%du%d.wav' % (b, u)))
+            with wave.open(p, 'wb') as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(16000)
+                w.writeframes(x.tobytes())
+            data[p] = x
+            items.append(('k%d_%d' % (b, u), p, [1, 2], 1.0))
+        items.append(('bad%d' % b, str(tmp_path / 'nope.wav'), [1], 1.0))
+        batches.append(items)
+    ing = NativeIngest(threads=2, ring=5)
+    ing._seen = 1 << 16                                            # small first guess: batch 3 (8x longer) outgrows its slot
+    seen = []
+    for buf, offs, lens, keys, labels, speeds, rates, loaded, release in ingest_batches(iter(batches), ing, depth=2):
+        x = buf.numpy()
+        seen.append(keys[0])
+        assert loaded.tolist() == [True] * 6 + [False] and lens[6] == 0 and (offs % 8 == 0).all()
+        for i in range(6):
+            p = batches[len(seen) - 1][i][1]
+            assert np.array_equal(x[offs[i]:offs[i] + lens[i]], data[p])
+        release(None)
+    assert seen == ['k%d_0' % b for b in range(5)]
