@@ -96,11 +96,13 @@ class NativeIngest(object):
         else:
             offs, lens, rates, status = np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)
         self._seen = max(getattr(self, '_seen', 0), int(total.value * 1.25) + 4096)
-        if total.value > ticket['buf'].numel():                          # the ring slot was too small: once, synchronously, bigger
-            self.lib.oe_ingest_job_release(ticket['job'])
+        if total.value > ticket['buf'].numel():                          # the ring slot was too small: once more, bigger (through the
+            self.lib.oe_ingest_job_release(ticket['job'])                # same queue: the driver thread owns the handle's state)
             self._ring[ticket['slot']] = None
-            self._next = ticket['slot']
-            return self.load(ticket['entries'], keys)
+            nxt, self._next = self._next, ticket['slot']                 # re-use this very slot; later slots belong to queued jobs
+            again = self.submit(ticket['entries'], capacity=int(total.value * 1.25) + 4096)
+            self._next = nxt
+            return self.wait(again, keys)
         loaded = status == 0
         for i in np.nonzero(~loaded)[0]:                                 # dataset.py:108-111: print, warn, drop
             print(self.lib.oe_ingest_job_error(ticket['job'], int(i)).decode())
