@@ -175,10 +175,11 @@ def _run_plan(plan, mel_bins, dev_wav, offs, lens, out_layout='padded', **fused)
         fused = dict(fused, wav_dither=plan.wav_dither,
                      dither_seed=fused.get('dither_seed') or int.from_bytes(os.urandom(8), 'little'))
     # (the library fuses only tables whose bits equal its baked torchaudio tables: ask it, fall back to oe_resample)
+    ratio_keys = np.unique(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1])
     fusable = (plan.wav_dither == 0.0 and dev_wav.dtype == torch.int16 and not (plan.stage1[:, 0] != 0).any() and
                plan.resampler == 'sinc' and fe.mel_baked and
-               np.isin(plan.stage2[:, 0] * 65536 + plan.stage2[:, 1], (0, 9 * 65536 + 10, 11 * 65536 + 10)).all() and
-               all(fe.fusable(o, n) for o, n in {(int(a), int(b)) for a, b in plan.stage2 if a}))
+               all(int(k) in (0, 9 * 65536 + 10, 11 * 65536 + 10) for k in ratio_keys) and
+               all(fe.fusable(int(k) >> 16, int(k) & 65535) for k in ratio_keys if k))
     if fusable and needs.any():
         kw = dict(fused)
         if kw.get('frame_map') is not None:
@@ -389,15 +390,16 @@ class audio_collate_func(object):
     def _finish(self, keys, features, frames, ys):
         dev = torch.device(self.output_device)
         flen = np.array(frames, dtype=np.int32)
-        tlen = np.array([len(y) for y in ys], dtype=np.int32)
+        tlen = np.fromiter(map(len, ys), dtype=np.int32, count=len(ys))
         if features is None:                                         # dataset.py:219-220
             features = torch.Tensor([])
             tpad = None
         else:                                                        # pad_sequence(..., True, IGNORE_ID), dataset.py:225-226
             tpad = np.full((len(ys), int(tlen.max()) if len(ys) else 0), IGNORE_ID, dtype=np.int32)
             if tpad.size:
-                tpad[np.arange(tpad.shape[1])[None, :] < tlen[:, None]] = np.concatenate(
-                    [np.asarray(y, dtype=np.int32).reshape(-1) for y in ys])
+                import itertools
+                tpad[np.arange(tpad.shape[1])[None, :] < tlen[:, None]] = np.fromiter(
+                    itertools.chain.from_iterable(ys), dtype=np.int32, count=int(tlen.sum()))
         if dev.type == 'cuda' and features.is_cuda:
             # the three int32 tensors travel as ONE block through the front-end's mapped pinned ring (oe_upload_small):
             # torch's .to() of a pageable tensor is a synchronous cudaMemcpy that queues behind the next batch's PCM

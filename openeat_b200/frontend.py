@@ -167,6 +167,8 @@ class Frontend(object):
         self.handle = handle
         self.torch_tables = torch_tables
         self._resamplers = {}
+        self._fusable = {}
+        self._mel_baked = None
         self._ws = {}
         self._extra_launches = 0     # oe_cmvn_apply takes no handle: counted here
 
@@ -230,12 +232,17 @@ class Frontend(object):
 
     def fusable(self, orig, new):
         """True when the (orig, new) 'sinc' resampler can run inside the fbank kernel's staging (speed_ratios)."""
-        tid = self.resampler_id(orig, new)
-        return tid >= 0 and bool(self.lib.oe_resampler_fusable(self.handle, tid))
+        key = (int(orig), int(new))
+        if key not in self._fusable:
+            tid = self.resampler_id(orig, new)
+            self._fusable[key] = tid >= 0 and bool(self.lib.oe_resampler_fusable(self.handle, tid))
+        return self._fusable[key]
 
     @property
     def mel_baked(self):
-        return bool(self.lib.oe_mel_is_baked(self.handle))
+        if self._mel_baked is None:
+            self._mel_baked = bool(self.lib.oe_mel_is_baked(self.handle))
+        return self._mel_baked
 
     def resample_out_len(self, n, orig, new):
         return int(self.lib.oe_resample_out_len(int(n), int(orig), int(new)))

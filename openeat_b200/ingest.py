@@ -19,6 +19,8 @@ from .frontend import ALIGN, aligned_offsets
 
 def split_entry(entry):
     """'path' or 'path,start,end' (dataset.py:56-58) -> (path, start, end) with start = -1 for a whole file."""
+    if ',' not in entry:
+        return entry.strip(), -1.0, 0.0
     value = entry.strip().split(',')
     assert len(value) == 1 or len(value) == 3
     if len(value) == 3:

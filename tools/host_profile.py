@@ -75,7 +75,44 @@ def pipelined(n):
         pin_s.copy_(stats, non_blocking=True)
 
 
-for name, fn in (('prepared', prepared), ('resident', resident), ('pipelined e2e', pipelined), ('e2e', e2e)):
+import tempfile   # noqa: E402
+import wave       # noqa: E402
+from openeat_b200.ingest import ingest_batches   # noqa: E402
+
+wav_dir = tempfile.mkdtemp(dir='/dev/shm')
+file_batches = []
+for bi in range(2):
+    pcm = host_pool[bi].numpy()
+    items = []
+    for u in range(bench.BATCH):
+        path = os.path.join(wav_dir, 'b%d_u%d.wav' % (bi, u))
+        with wave.open(path, 'wb') as w:
+            w.setnchannels(1)
+            w.setsampwidth(2)
+            w.setframerate(16000)
+            w.writeframes(pcm[offs[u]:offs[u] + lens[u]].tobytes())
+        items.append((keys[u], path, labels[u], speeds[u]))
+    file_batches.append(items)
+
+
+def file_items():
+    i = 0
+    while True:
+        yield file_batches[i % 2]
+        i += 1
+
+
+pipe_files = PrefetchingCollator(collate, ingest_batches(file_items(), depth=3))
+
+
+def from_files(n):
+    for i in range(n):
+        _, out = next(pipe_files)
+        pin_n.copy_(out['features_length'], non_blocking=True)
+        pin_s.copy_(stats, non_blocking=True)
+
+
+for name, fn in (('from wav files', from_files), ('pipelined e2e', pipelined)):
     fn(5)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
