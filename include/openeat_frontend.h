@@ -183,6 +183,17 @@ int oe_frontend_step_ms(oe_frontend* fe, float* ms);
 int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const float* d_mean,
                   const float* d_istd, oe_stream stream);
 
+/* GlobalCMVN fused into the first layer of Conv2dSubsampling4 (forward only): replaces
+ *   xs = global_cmvn(xs)                                  openeat/modules/encoder.py:221-222, cmvn.py:43-46
+ *   Conv2d(1, odim, 3, 2) + ReLU on xs.unsqueeze(1)       openeat/modules/subsampling.py:76-78, 110-111
+ * d_x (B, T, F) fp32 with row pitch `pitch` (0 = F) -- the padded tensor audio_collate_func returns; d_mean / d_istd [F]
+ * or NULL (d_istd NULL = norm_var False); d_w [odim][3][3] (the Conv2d weight (odim, 1, 3, 3), contiguous), d_bias [odim]
+ * or NULL; d_y (B, odim, (T-3)/2+1, (F-3)/2+1) fp32.  The normalised batch is never written: GlobalCMVN alone costs a
+ * read and a write of the whole batch. */
+int oe_cmvn_conv_subsample(const float* d_x, int64_t pitch, int32_t B, int32_t T, int32_t F, const float* d_mean,
+                           const float* d_istd, const float* d_w, const float* d_bias, int32_t odim, float* d_y,
+                           oe_stream stream);
+
 /* Registers a polyphase table: kernel[new_rate][taps], taps = 2*width + orig_rate for any width >= 0
  * (torchaudio functional.py:1343-1398 layout; a long Kaiser design gives sox-quality resampling), or NULL =
  * hann-windowed sinc, lowpass width 6, rolloff 0.99 computed in double (OE_ERR_UNSUPPORTED when that table would

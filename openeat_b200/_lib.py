@@ -85,6 +85,9 @@ SYMBOLS = {
     'oe_upload_small': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     'oe_cmvn_apply': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'oe_cmvn_conv_subsample': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
     'oe_add_resampler': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_f32p,
                                         ctypes.c_int32, c_i32p]),
     'oe_resampler_fusable': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),

@@ -650,6 +650,76 @@ __global__ void __launch_bounds__(256) oe_pad_fill_kernel(const PadFillParams P)
     grid_dep_wait();
 }
 
+// ------------------------------------------------------------------------------------------
+// The first consumer of the (B, T, F) feature tensor, fused with the step in front of it:
+//   encoder.py:221-222   xs = global_cmvn(xs)                    (x - mean) * istd on the padded batch, cmvn.py:43-46
+//   subsampling.py:76-78 Conv2d(1, odim, 3, 2) + ReLU on xs.unsqueeze(1)   (first layer of Conv2dSubsampling4, :110-111)
+// y[b][c][t][f] = relu(bias[c] + sum_{i,j<3} w[c][i][j] * cmvn(x)[b][2t + i][2f + j]),  t < (T-3)/2+1, f < (F-3)/2+1.
+// GlobalCMVN alone is a full read + write of the batch; here it costs two FMAs per staged input value.  The kernel is
+// bound by the stores of its output, odim/4 x (F'/F) ~ 31x the input (5 GB for a 256 x 1000 x 80 batch at odim 256):
+// thread = one output position (t, f) of the tile with its 9 inputs in registers, looping over the channels; the weights
+// are read as shared-memory broadcasts; a warp's stores of one channel are 32 consecutive floats of the (t, f) plane.
+struct ConvSubParams {
+    const float* x;              // (B, T, F) fp32, row pitch `pitch`
+    int64_t pitch;
+    int B, T, F, odim, T1, F1;
+    const float* w;              // [odim][9]
+    const float* bias;           // [odim]
+    const float* cmvn_mean;      // [F] or null
+    const float* cmvn_istd;      // [F] or null
+    float* y;                    // (B, odim, T1, F1)
+};
+constexpr int kConvTT = 8;       // output rows per block
+constexpr int kConvThreads = 320;
+__global__ void __launch_bounds__(kConvThreads) oe_conv_sub1_kernel(const ConvSubParams P) {
+    extern __shared__ __align__(16) float csm[];
+    float* const sw = csm;                                   // [odim][12]: 9 weights, bias, 2 pad -> three LDS.128 per channel
+    float* const sx = csm + (size_t)P.odim * 12;             // [2 kConvTT + 1][F] staged (CMVN'd) input rows
+    const int b = blockIdx.y, t0 = blockIdx.x * kConvTT;
+    const int rows = min(2 * kConvTT + 1, P.T - 2 * t0);
+    for (int i = threadIdx.x; i < P.odim; i += kConvThreads) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sw[i * 12 + k] = P.w[i * 9 + k];
+        sw[i * 12 + 9] = P.bias ? P.bias[i] : 0.f;
+        sw[i * 12 + 10] = sw[i * 12 + 11] = 0.f;
+    }
+    const float* const src = P.x + ((int64_t)b * P.T + 2 * t0) * P.pitch;
+    for (int i = threadIdx.x; i < rows * P.F; i += kConvThreads) {
+        const int r = i / P.F, f = i - r * P.F;
+        float v = src[(int64_t)r * P.pitch + f];
+        if (P.cmvn_mean) {
+            v = v - P.cmvn_mean[f];
+            if (P.cmvn_istd) v = v * P.cmvn_istd[f];
+        }
+        sx[i] = v;
+    }
+    __syncthreads();
+    const int npos = min(kConvTT, P.T1 - t0) * P.F1;
+    float* const ybase = P.y + (int64_t)b * P.odim * P.T1 * P.F1 + (int64_t)t0 * P.F1;
+    const int64_t plane = (int64_t)P.T1 * P.F1;
+    for (int pos = threadIdx.x; pos < npos; pos += kConvThreads) {
+        const int tl = pos / P.F1, f = pos - tl * P.F1;
+        float in[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) in[3 * i + j] = sx[(2 * tl + i) * P.F + 2 * f + j];
+        float* out = ybase + pos;
+#pragma unroll 4
+        for (int c = 0; c < P.odim; ++c) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + c * 12);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + c * 12 + 4);
+            const float4 w2 = *reinterpret_cast<const float4*>(sw + c * 12 + 8);
+            float a = w2.y;                                      // bias
+            a = fmaf(w0.x, in[0], a); a = fmaf(w0.y, in[1], a); a = fmaf(w0.z, in[2], a);
+            a = fmaf(w0.w, in[3], a); a = fmaf(w1.x, in[4], a); a = fmaf(w1.y, in[5], a);
+            a = fmaf(w1.z, in[6], a); a = fmaf(w1.w, in[7], a); a = fmaf(w2.x, in[8], a);
+            __stcs(out, fmaxf(a, 0.f));                          // written once, read by the next layer: streaming store
+            out += plane;
+        }
+    }
+}
+
 // openeat/modules/cmvn.py:43-46
 __global__ void __launch_bounds__(256) oe_cmvn_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                       int64_t n, int dim, const float* __restrict__ mean,
@@ -1730,6 +1800,38 @@ int oe_cmvn_apply(const float* d_x, float* d_y, int64_t rows, int32_t dim, const
     const int64_t n = rows * dim;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
     oe::oe_cmvn_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n, dim, d_mean, d_istd);
+    OE_CUDA(cudaGetLastError());
+    return OE_OK;
+}
+
+int oe_cmvn_conv_subsample(const float* d_x, int64_t pitch, int32_t B, int32_t T, int32_t F, const float* d_mean,
+                           const float* d_istd, const float* d_w, const float* d_bias, int32_t odim, float* d_y,
+                           oe_stream stream) {
+    if (B < 0 || T < 0 || F < 3 || odim <= 0) return fail(OE_ERR_INVALID, "bad shape");
+    if (pitch == 0) pitch = F;
+    if (pitch < F) return fail(OE_ERR_INVALID, "pitch smaller than F");
+    const int T1 = T >= 3 ? (T - 3) / 2 + 1 : 0, F1 = (F - 3) / 2 + 1;
+    if (B == 0 || T1 == 0) return OE_OK;
+    if (!d_x || !d_w || !d_y) return fail(OE_ERR_INVALID, "null pointer");
+    if (d_istd && !d_mean) return fail(OE_ERR_INVALID, "istd without mean");
+    const size_t smem = ((size_t)odim * 12 + (size_t)(2 * oe::kConvTT + 1) * F) * sizeof(float);
+    if (smem > 200 * 1024) return fail(OE_ERR_UNSUPPORTED, "odim * 48 + F * 68 bytes of shared memory exceed 200 KB");
+    if (smem > 48 * 1024) OE_CUDA(cudaFuncSetAttribute(oe::oe_conv_sub1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    oe::ConvSubParams P;
+    P.x = d_x;
+    P.pitch = pitch;
+    P.B = B;
+    P.T = T;
+    P.F = F;
+    P.odim = odim;
+    P.T1 = T1;
+    P.F1 = F1;
+    P.w = d_w;
+    P.bias = d_bias;
+    P.cmvn_mean = d_mean;
+    P.cmvn_istd = d_istd;
+    P.y = d_y;
+    oe::oe_conv_sub1_kernel<<<dim3((T1 + oe::kConvTT - 1) / oe::kConvTT, B), oe::kConvThreads, smem, (cudaStream_t)stream>>>(P);
     OE_CUDA(cudaGetLastError());
     return OE_OK;
 }

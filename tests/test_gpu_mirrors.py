@@ -466,3 +466,30 @@ def test_long_ratio_and_kaiser_resamplers(golden_dir):
         got = out[ooffs[0]:ooffs[0] + int(olens[0])].cpu().numpy()
         ref = S.speed_perturb_soxlike(x, 16000, sp)
         assert got.shape == ref.shape and np.abs(got - ref).max() <= 0.05
+
+
+def test_cmvn_conv_subsample_matches_torch():
+    """GlobalCMVN + Conv2d(1, odim, 3, 2) + ReLU in one kernel against the fp32 torch reference of the same
+    two operations (encoder.py:221-223, subsampling.py:76-78, 110-111) -- odd and even T, odim 256 and 32, with and
+    without CMVN / variance normalisation / bias, tolerance 1e-4 (nine-term fp32 dot products)."""
+    from openeat_b200.cmvn import GlobalCMVN
+    from openeat_b200.subsampling import CmvnConvSubsample
+    torch.manual_seed(3)
+    for B, T, F, odim, use_cmvn, norm_var, bias in ((3, 67, 80, 256, True, True, True), (2, 16, 80, 32, True, False, True),
+                                                  (1, 3, 80, 8, False, True, False), (2, 101, 40, 64, True, True, True)):
+        x = (torch.randn(B, T, F) * 4.0 + 10.0).cuda()
+        conv = torch.nn.Conv2d(1, odim, 3, 2, bias=bias).cuda()
+        cm = GlobalCMVN(torch.randn(F).cuda() + 10.0, torch.rand(F).cuda() + 0.2, norm_var=norm_var) if use_cmvn else None
+        got = CmvnConvSubsample(conv, cm)(x)
+        with torch.no_grad():
+            z = x
+            if cm is not None:
+                z = z - cm.mean
+                if norm_var:
+                    z = z * cm.istd
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            ref = torch.relu(conv(z.unsqueeze(1)))
+            torch.backends.cudnn.allow_tf32 = prev
+        assert got.shape == ref.shape == (B, odim, (T - 3) // 2 + 1, (F - 3) // 2 + 1)
+        assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
