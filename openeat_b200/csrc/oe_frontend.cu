@@ -119,7 +119,7 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
         const int stride = gridDim.x * blockDim.x;
         if (P.stat_acc != nullptr)
             for (int i = tile; i < P.n_acc; i += stride) P.stat_acc[i] = 0ull;
-        if (P.sched != nullptr && tile == 0) P.sched[0] = 0;
+        if (P.sched != nullptr && tile == 0) P.sched[0] = P.sched[1] = 0;      // CTAs done; tiles claimed (gen-2 kernel)
     }
     if (tile >= P.total_tiles) return;
     const int b = staged ? find_utt(sh_prefix, P.B, tile) : find_utt(P.tile_prefix, P.B, tile);
@@ -1711,9 +1711,11 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         Z.cmvn_on_pad = bt->cmvn_on_padding;
         Z.dither_a = bt->feature_dither;
         Z.dither_seed = bt->dither_seed;
-        // parts per utterance: ~384 rows each, and at least four blocks per SM in total
-        int parts = std::max(1, (M.max_rows + 383) / 384);
-        parts = std::max(parts, (4 * fe->sm_count + B - 1) / B);
+        // parts per utterance: every part redoes the statistics merge (two dependent rounds of L2 loads), so as few as
+        // fill the machine: <= 1024 rows each, and at least 1.5 blocks per SM in total (benchmark batch, same box:
+        // 1 part 163.6 us per step, 2: 164.6, 3: 167.3, 4: 172.5, 8: 186.6)
+        int parts = std::max(1, (M.max_rows + 1023) / 1024);
+        parts = std::max(parts, (3 * fe->sm_count / 2 + B - 1) / B);
         parts = std::min(parts, std::max(1, (M.max_rows + 31) / 32));
         if (fe->fin2_parts > 0) parts = fe->fin2_parts;
         Z.parts = parts;
