@@ -6,7 +6,7 @@ sequence per batch on the GPU instead of a per-utterance CPU loop.
 Differences a caller can observe (all deliberate):
   * tensors come back on the GPU by default (``output_device='cpu'`` restores the reference's CPU
     tensors); ``features`` are the same zero-padded (B, Tmax, F) fp32 tensor either way;
-  * wav decoding is built in for 16-bit PCM WAV (stdlib ``wave``; the reference needs libsox);
+  * wav decoding is built in for RIFF/WAVE files (integer PCM 8/16/24/32 bit, IEEE float; the reference needs libsox);
     an item's second field may also be an in-memory int16 / fp32 array or ``(array, sample_rate)``;
   * ``data_type != 'wav'`` reads binary Kaldi archives with the built-in ``openeat_b200.kaldi_io.read_mat``
     (the reference imports the third-party ``kaldi_io``); ``feature_dither`` draws its amplitude with the
@@ -18,7 +18,7 @@ Differences a caller can observe (all deliberate):
 import logging
 import os
 import random
-import wave
+import struct
 
 import numpy as np
 import torch
@@ -29,25 +29,80 @@ from .frontend import default_frontend, pack_waveforms, speed_ratio
 IGNORE_ID = -1  # openeat/utils/common.py:24
 
 
+def _riff_chunks(f):
+    """(format tag, channels, sample rate, bits, data offset, data bytes) of a RIFF/WAVE file object."""
+    head = f.read(12)
+    if len(head) < 12 or head[:4] != b'RIFF' or head[8:12] != b'WAVE':
+        if head[:4] == b'fLaC':
+            raise ValueError('FLAC is not decoded here: convert to wav (sox / ffmpeg) or pass decoded arrays')
+        raise ValueError('not a RIFF/WAVE file')
+    size = f.seek(0, 2)
+    fmt = None
+    pos = 12
+    while pos + 8 <= size:
+        f.seek(pos)
+        cid, csz = struct.unpack('<4sI', f.read(8))
+        if cid == b'fmt ':
+            body = f.read(min(csz, 40))
+            tag, nch, sr, _, _, bits = struct.unpack('<HHIIHH', body[:16])
+            if tag == 0xFFFE and len(body) >= 26:                  # WAVE_FORMAT_EXTENSIBLE: sub-format GUID
+                tag = struct.unpack('<H', body[24:26])[0]
+            fmt = (tag, nch, sr, bits)
+        elif cid == b'data':
+            if fmt is None:
+                raise ValueError('data chunk before fmt chunk')
+            avail = size - (pos + 8)
+            nbytes = avail if csz in (0, 0xFFFFFFFF) else min(csz, avail)   # streamed files write 0 / 0xFFFFFFFF sizes
+            return fmt + (pos + 8, nbytes)
+        pos += 8 + csz + (csz & 1)
+    raise ValueError('no data chunk')
+
+
 def read_wav(path, start=None, end=None):
-    """dataset.py:62-72 for 16-bit PCM WAV: returns (int16 samples of channel 0, sample_rate);
-    ``start`` / ``end`` are seconds (segmented wav.scp entries ``path,start,end``)."""
-    with wave.open(path, 'rb') as w:
-        sr = w.getframerate()
-        if w.getsampwidth() != 2:
-            raise ValueError('%s: only 16-bit PCM wav is supported' % path)
-        nch = w.getnchannels()
-        if start is not None:
-            s = int(float(start) * sr)
-            e = int(float(end) * sr)
-            w.setpos(min(s, w.getnframes()))
-            raw = w.readframes(max(0, e - s))
-        else:
-            raw = w.readframes(w.getnframes())
-    pcm = np.frombuffer(raw, dtype='<i2')
-    if nch > 1:
-        pcm = pcm.reshape(-1, nch)[:, 0]
-    return pcm, sr
+    """dataset.py:62-75 (``torchaudio.load`` then ``* (1 << 15)``) for RIFF/WAVE files: returns (samples of channel 0
+    on the int16 scale, sample_rate).  16-bit PCM comes back as int16 (the values the reference holds as fp32); 8-bit
+    (unsigned), 24- and 32-bit PCM and IEEE float come back as float32 ``normalised * 32768`` with torchaudio's
+    normalisation (``(s - 128) / 2^7``, ``s / 2^23``, ``s / 2^31``, float as is).  ``start`` / ``end`` are seconds
+    (segmented wav.scp entries ``path,start,end``: ``frame_offset = int(start * sr)``, ``num_frames = int(end * sr) -
+    frame_offset``)."""
+    with open(path, 'rb') as f:
+        return decode_wav(f, start, end, path)
+
+
+def decode_wav(f, start=None, end=None, name='<wav>'):
+    """``read_wav`` on an open (seekable) binary file object, e.g. a member of a shard tar."""
+    try:
+        tag, nch, sr, bits, off, nbytes = _riff_chunks(f)
+    except (ValueError, struct.error) as e:
+        raise ValueError('%s: %s' % (name, e))
+    if tag not in (1, 3) or (tag == 1 and bits not in (8, 16, 24, 32)) or (tag == 3 and bits not in (32, 64)) or nch < 1:
+        raise ValueError('%s: wav format tag %d with %d-bit samples is not supported (integer PCM 8/16/24/32 bit, '
+                         'IEEE float 32/64 bit)' % (name, tag, bits))
+    width = bits // 8 * nch
+    total = nbytes // width
+    first, count = 0, total
+    if start is not None:
+        s = int(float(start) * sr)
+        e = int(float(end) * sr)
+        first = min(max(s, 0), total)
+        count = max(0, min(e - s, total - first))
+    f.seek(off + first * width)
+    raw = f.read(count * width)
+    if tag == 1 and bits == 16:
+        pcm = np.frombuffer(raw, dtype='<i2')
+        return (pcm.reshape(-1, nch)[:, 0] if nch > 1 else pcm), sr
+    if tag == 3:
+        x = np.frombuffer(raw, dtype='<f4' if bits == 32 else '<f8').reshape(-1, nch)[:, 0].astype(np.float32)
+    elif bits == 8:
+        x = (np.frombuffer(raw, dtype=np.uint8).reshape(-1, nch)[:, 0].astype(np.float32) - 128.0) / 128.0
+    elif bits == 24:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, nch, 3)[:, 0, :].astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)
+        x = v.astype(np.float32) / np.float32(1 << 23)
+    else:
+        x = np.frombuffer(raw, dtype='<i4').reshape(-1, nch)[:, 0].astype(np.float32) / np.float32(2.0 ** 31)
+    return x * np.float32(1 << 15), sr
 
 
 def _load_item(x):

@@ -22,12 +22,11 @@ import json
 import os
 import random
 import tarfile
-import wave
 
 import numpy as np
 import torch
 
-from .dataset import IGNORE_ID, read_wav
+from .dataset import IGNORE_ID, decode_wav, read_wav
 from .feature_processor import plan_spec_augmentation, plan_spec_substitute
 from .frontend import default_frontend, pack_waveforms, speed_ratio
 
@@ -63,7 +62,7 @@ def parse_raw(lines):
 
 def tar_file_and_group(shards):
     """wenet shard lists: every line of ``data.list`` (``data_type='shard'``) names one tar file whose members are
-    ``<key>.wav`` (16-bit PCM) and ``<key>.txt``, stored next to each other.  Yields the same sample dicts as
+    ``<key>.wav`` (RIFF/WAVE, see ``dataset.read_wav``) and ``<key>.txt``, stored next to each other.  Yields the same sample dicts as
     ``parse_raw``.  A member that cannot be decoded is skipped with a message (dataset.py:108-111 convention)."""
     for shard in shards:
         shard = shard.strip() if isinstance(shard, str) else shard
@@ -85,12 +84,9 @@ def tar_file_and_group(shards):
                     if ext == 'txt':
                         sample['txt'] = blob.decode('utf8').strip()
                     elif ext == 'wav':
-                        with wave.open(io.BytesIO(blob)) as w:
-                            if w.getsampwidth() != 2:
-                                raise ValueError('only 16-bit PCM WAV members are supported')
-                            pcm = np.frombuffer(w.readframes(w.getnframes()), dtype='<i2')
-                            sample['wav'] = pcm.reshape(-1, w.getnchannels())[:, 0].copy()
-                            sample['sample_rate'] = w.getframerate()
+                        pcm, sr = decode_wav(io.BytesIO(blob), name=member.name)
+                        sample['wav'] = np.array(pcm)
+                        sample['sample_rate'] = sr
                 except Exception as e:
                     print(e)
                     print('read utterance {} error'.format(member.name))

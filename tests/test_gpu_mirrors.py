@@ -493,3 +493,33 @@ def test_cmvn_conv_subsample_matches_torch():
             torch.backends.cudnn.allow_tf32 = prev
         assert got.shape == ref.shape == (B, odim, (T - 3) // 2 + 1, (F - 3) // 2 + 1)
         assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_collate_reads_24bit_and_float_wav(gold, tmp_path):
+    """torchaudio.load reads more than 16-bit PCM (dataset.py:62-75); a batch mixing 24-bit PCM, IEEE-float and 16-bit
+    files goes through the fp32 waveform path and matches the oracle's fbank of the decoded values."""
+    import struct
+    from openeat_b200.dataset import audio_collate_func, read_wav
+
+    def riff(path, tag, bits, raw, sr=16000):
+        fmt = struct.pack('<HHIIHH', tag, 1, sr, sr * bits // 8, bits // 8, bits)
+        body = b'WAVE' + b'fmt ' + struct.pack('<I', len(fmt)) + fmt + b'data' + struct.pack('<I', len(raw)) + raw
+        with open(path, 'wb') as f:
+            f.write(b'RIFF' + struct.pack('<I', len(body)) + body)
+
+    pcm0, pcm1, pcm3 = gold['pcm0'], gold['pcm1'], gold['pcm3']
+    v24 = pcm0.astype(np.int64) * 256 + 77                                   # 24-bit samples that are not multiples of 256
+    raw24 = np.stack([v24 & 255, (v24 >> 8) & 255, (v24 >> 16) & 255], axis=-1).astype(np.uint8).tobytes()
+    riff(str(tmp_path / 'a24.wav'), 1, 24, raw24)
+    riff(str(tmp_path / 'bf.wav'), 3, 32, (pcm1.astype(np.float32) / 32768 * 0.5).astype('<f4').tobytes())
+    write_wav(tmp_path / 'c16.wav', pcm3)
+    batch = [('a', str(tmp_path / 'a24.wav'), [1], 1.0), ('b', str(tmp_path / 'bf.wav'), [2], 1.0),
+             ('c', str(tmp_path / 'c16.wav'), [3], 1.0)]
+    keys, out = audio_collate_func(data_type='wav', feature_extraction_conf=CONF, normalization=False)(batch)
+    assert keys == ['a', 'c', 'b']                                           # 16000, 12345, 9000 samples
+    feats = out['features'].cpu().numpy()
+    for row, name in enumerate(('a24.wav', 'c16.wav', 'bf.wav')):
+        x, sr = read_wav(str(tmp_path / name))
+        ref = F.fbank(np.asarray(x, dtype=np.float32))
+        assert np.abs(feats[row, :ref.shape[0]] - ref).max() < 1e-3
+    assert np.abs(read_wav(str(tmp_path / 'a24.wav'))[0] - (pcm0.astype(np.float32) + np.float32(77 / 256))).max() < 1e-2
