@@ -922,7 +922,10 @@ thread_local char g_err[512] = "";
 // (and every kernel of the chain does so, which keeps the ordering transitive).  OE_NO_PDL=1 disables it.
 template <class Params>
 cudaError_t launch_dep(void (*kern)(const Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params& prm) {
-    static bool pdl = [] { const char* e = getenv("OE_NO_PDL"); return !(e && e[0] == '1'); }();
+    // one flag per instantiation, shared by every host thread that launches through this library: atomic, relaxed (a
+    // thread that still sees `true` after another one switched it off merely repeats the fallback below)
+    static std::atomic<bool> pdl_flag([] { const char* e = getenv("OE_NO_PDL"); return !(e && e[0] == '1'); }());
+    const bool pdl = pdl_flag.load(std::memory_order_relaxed);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -937,7 +940,7 @@ cudaError_t launch_dep(void (*kern)(const Params), dim3 grid, dim3 block, size_t
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prm);
     if (e != cudaSuccess && pdl && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
         (void)cudaGetLastError();             // a driver / device without programmatic launches: plain stream order from now on
-        pdl = false;
+        pdl_flag.store(false, std::memory_order_relaxed);
         cfg.numAttrs = 0;
         e = cudaLaunchKernelEx(&cfg, kern, prm);
     }
