@@ -55,7 +55,7 @@ struct Smem {
     static constexpr int Mask = TwU + 16 * 80;                         // uchar rowmask[32], colmask[96]
     static constexpr int Desc = Mask + 128;                            // TileDesc[2]
     static constexpr int Acc = Desc + 96;                              // long long acc[3][2][80]: fixed-point CMVN statistics
-    static constexpr int Flag = Acc + 3 * 2 * kF * 8;                  // int: "this is the last CTA"
+    static constexpr int Flag = Acc + 3 * 2 * kF * 8;                  // int[0]: "this is the last CTA", int[1]: claimed tile, +8: mbarrier
     static constexpr int End = Flag + 16;
     static_assert(Raw % 16 == 0 && Tile % 16 == 0 && TwA % 16 == 0 && TwU % 16 == 0 && Desc % 16 == 0 && Acc % 8 == 0, "align");
     static_assert(End + 1024 <= 116224, "two CTAs per SM");
@@ -121,6 +121,49 @@ __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" 
 
 // kDither: kaldi.fbank's dither (kaldi.py:179-181), one independent N(0,1) per frame element before DC removal; a
 // separate instantiation because the Philox + Box-Muller code roughly triples the front.
+// ---- bulk-copy staging of interior tiles: one thread hands the whole contiguous PCM window of the next tile to the
+// copy unit (cp.async.bulk, completion counted in bytes on an mbarrier) instead of 256 threads issuing three 16-byte
+// cp.async each.  Tiles that touch an utterance's first or last samples keep the cp.async path (its src-size form
+// zero-fills what lies outside the utterance). ----
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                          unsigned long long policy) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic-proxy accesses of the buffer are ordered first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+// Stages the next tile's samples; returns true when the bulk path was taken (every thread computes the same answer from
+// the descriptor): the caller then waits on the mbarrier instead of its own cp.async group.
+template <bool kF32>
+__device__ __forceinline__ bool prefetch_tile2(unsigned char* raw, const void* wav, const TileDesc* d, unsigned long long* bar, int tid) {
+    const int in_first = d->in_first, in_len = d->in_len;
+    const int pieces = kF32 ? 673 * 2 : (d->rs ? kRsPieces : 673);
+    const int per = kF32 ? 4 : 8;                                      // samples per 16-byte piece
+    if (in_first >= 0 && in_first + per * pieces <= in_len) {
+        if (tid == 0) {
+            const unsigned char* const src = reinterpret_cast<const unsigned char*>(wav) + (d->wav_utt + in_first) * (kF32 ? 4 : 2);
+            bulk_load(raw, src, 16u * (unsigned)pieces, bar, l2_policy_evict_first());
+        }
+        return true;
+    }
+    prefetch_tile<kF32>(raw, wav, d, tid);
+    return false;
+}
+
 template <bool kF32, bool kRs, bool kDither = false>
 __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParams P) {
     using S = Smem<kF32, kRs>;
@@ -132,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     TileDesc* const sDesc = reinterpret_cast<TileDesc*>(smem + S::Desc);
     long long* const sAcc = reinterpret_cast<long long*>(smem + S::Acc);
     int* const sFlag = reinterpret_cast<int*>(smem + S::Flag);
+    unsigned long long* const sBar = reinterpret_cast<unsigned long long*>(smem + S::Flag + 8);    // bulk-copy completion
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tau = tid & 15, grp = tid >> 4;
@@ -166,13 +210,16 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     }
     // ---- everything above only read launch constants: with a programmatic dependent launch it overlaps the tail of
     // the descriptor kernel; the tile descriptors are touched from here on ----
+    if (tid == 0) mbar_init(sBar, 1);
+    unsigned bulk_parity = 0;                  // phase of the mbarrier the next bulk copy completes
+    bool bulk_pending = false;
     grid_dep_wait();
     if (tile < P.total_tiles) {                // first tile: descriptor, then its waveform
         prefetch_desc(sDesc, P.tiles + tile, tid);
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();
-        if (sDesc[0].nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, sDesc, tid);
+        if (sDesc[0].nvalid > 0) bulk_pending = prefetch_tile2<kF32>(sRaw, P.wav, sDesc, sBar, tid);
         cp_async_commit();
     }
     const float preemph = tab->preemph;
@@ -209,6 +256,11 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
     for (; tile < P.total_tiles; slot ^= 1) {
         const int next = kDyn ? next_dyn : tile + (int)gridDim.x;
         cp_async_wait_all();
+        if (bulk_pending) {
+            mbar_wait(sBar, bulk_parity);
+            bulk_parity ^= 1;
+            bulk_pending = false;
+        }
         __syncthreads();               // (1) raw samples + descriptor visible; previous tile's rows are out of smem
         const TileDesc* const dp = sDesc + slot;
         const int b = dp->b, t0 = dp->t0;
@@ -412,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
             __syncthreads();           // (4) power slices complete; the raw buffer has been consumed
             if (next < P.total_tiles) {
                 const TileDesc* const dn = sDesc + (slot ^ 1);
-                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
+                if (dn->nvalid > 0) bulk_pending = prefetch_tile2<kF32>(sRaw, P.wav, dn, sBar, tid);
             }
             cp_async_commit();
 
@@ -470,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 2) oe_fbank2_kernel(const FbankParam
             __syncthreads();
             if (next < P.total_tiles) {
                 const TileDesc* const dn = sDesc + (slot ^ 1);
-                if (dn->nvalid > 0) prefetch_tile<kF32>(sRaw, P.wav, dn, tid);
+                if (dn->nvalid > 0) bulk_pending = prefetch_tile2<kF32>(sRaw, P.wav, dn, sBar, tid);
             }
             cp_async_commit();
         }

@@ -105,6 +105,16 @@ def decode_wav(f, start=None, end=None, name='<wav>'):
     return x * np.float32(1 << 15), sr
 
 
+def _decodable(entry):
+    """True when ``read_wav`` can decode the file of a ``path[,start,end]`` entry."""
+    try:
+        with open(entry.strip().split(',')[0], 'rb') as f:
+            tag, nch, _, bits, _, _ = _riff_chunks(f)
+        return nch >= 1 and ((tag == 1 and bits in (8, 16, 24, 32)) or (tag == 3 and bits in (32, 64)))
+    except (OSError, ValueError, struct.error):
+        return False
+
+
 def _load_item(x):
     """(samples, sample_rate) for one batch item ``(key, path_or_array, tokenid, speed)``."""
     wav = x[1]
@@ -359,14 +369,18 @@ class audio_collate_func(object):
             from .ingest import default_ingest
             ing = default_ingest()
             keys = [x[0] for x in batch]
-            buf, offs, lens, rates, loaded, slot = ing.load([x[1] for x in batch], keys)
-            out = self.collate_packed(buf, offs, lens, keys, [x[2] for x in batch], [x[3] for x in batch],
-                                      sample_rates=rates, loaded=loaded)
-            if torch.cuda.is_available():
-                ev = torch.cuda.Event()
-                ev.record()                      # behind the H2D copy of `buf`: the ring slot is reused after it
-                ing.release_after(slot, ev)
-            return out
+            buf, offs, lens, rates, loaded, slot = ing.load([x[1] for x in batch], keys, report=False)
+            # the native ingest reads 16-bit PCM; a file it rejects but read_wav decodes (24-bit, float, ...: torchaudio.load
+            # reads those too) sends the whole batch through the general Python decoder below
+            if loaded.all() or not any(_decodable(batch[i][1]) for i in np.nonzero(~loaded)[0]):
+                ing.report_errors(keys)
+                out = self.collate_packed(buf, offs, lens, keys, [x[2] for x in batch], [x[3] for x in batch],
+                                          sample_rates=rates, loaded=loaded)
+                if torch.cuda.is_available():
+                    ev = torch.cuda.Event()
+                    ev.record()                  # behind the H2D copy of `buf`: the ring slot is reused after it
+                    ing.release_after(slot, ev)
+                return out
         waves, rates, loaded = _load_batch(batch)
         buf, offs, lens = _pack_loaded(waves)
         return self.collate_packed(buf, offs, lens, [x[0] for x in batch], [x[2] for x in batch],

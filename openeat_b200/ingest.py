@@ -114,7 +114,7 @@ class NativeIngest(object):
         self.lib.oe_ingest_job_release(ticket['job'])
         return ticket['buf'][:max(int(total.value), ALIGN)], offs, lens, rates, loaded, ticket['slot']
 
-    def load(self, entries, keys=None):
+    def load(self, entries, keys=None, report=True):
         n = len(entries)
         parts = [split_entry(e) for e in entries]
         paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
@@ -132,12 +132,20 @@ class NativeIngest(object):
                                       offs.ctypes.data_as(c_i64p), lens.ctypes.data_as(c_i32p),
                                       status.ctypes.data_as(c_i32p)))
         loaded = status == 0
+        self.last_errors = {int(i): self.lib.oe_ingest_error(self.handle, int(i)).decode() for i in np.nonzero(~loaded)[0]}
         for i in np.nonzero(~loaded)[0]:                              # dataset.py:108-111: print, warn, drop
-            print(self.lib.oe_ingest_error(self.handle, int(i)).decode())
-            logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
+            if report:
+                print(self.last_errors[int(i)])
+                logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
             lens[i] = 0
         rates[~loaded] = 16000
         return buf[:max(total, ALIGN)], offs, lens, rates, loaded, slot
+
+    def report_errors(self, keys):
+        """Prints what the last ``load(..., report=False)`` held back (dataset.py:108-111 convention)."""
+        for i, msg in sorted(getattr(self, 'last_errors', {}).items()):
+            print(msg)
+            logging.warning('read utterance {} error'.format(keys[i]))
 
 
 def ingest_batches(item_batches, ingest=None, depth=2):
