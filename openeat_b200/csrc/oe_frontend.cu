@@ -2187,6 +2187,10 @@ int oe_ingest_create(int32_t threads, oe_ingest** out) {
     oe_ingest* g = new oe_ingest();
     g->threads = threads > 0 ? threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     g->pool = new oe_ing::Pool(g->threads);
+    {
+        const char* d = getenv("OE_INGEST_DIRECT");
+        g->direct_read = d && d[0] == '1';
+    }
     *out = g;
     return OE_OK;
 }
@@ -2272,12 +2276,29 @@ int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const doub
         const int64_t first = g->first[i], count = n_samples[i];
         std::string err;
         int16_t* const out = dst + offsets[i];
-        if (w.channels == 1) {                                        // straight into the packed (pinned) buffer
+        if (w.channels == 1 && g->direct_read) {                      // straight into the packed (pinned) buffer
             int64_t done = 0;
             const int64_t bytes = 2 * count;
             while (done < bytes) {
                 const ssize_t r = pread(fd, reinterpret_cast<char*>(out) + done, (size_t)(bytes - done), w.data_off + 2 * first + done);
                 if (r <= 0) break;
+                done += r;
+            }
+            if (done != bytes) err = std::string(paths[i]) + ": short read";
+        } else if (w.channels == 1) {
+            // through a cache-resident bounce buffer, then streaming (non-temporal) stores into the packed buffer: a pread
+            // straight into the destination makes every destination line a read-for-ownership first -- three DRAM transfers
+            // per byte (page cache read, destination read, destination write) where two suffice, on a host whose memory the
+            // H2D copy engines are reading at full rate at the same time
+            static thread_local std::vector<char> bounce(oe_ing::kBounceBytes);
+            int64_t done = 0;
+            const int64_t bytes = 2 * count;
+            char* const o8 = reinterpret_cast<char*>(out);                // 16-byte aligned: offsets are multiples of 8 samples
+            while (done < bytes) {
+                const int64_t want = std::min<int64_t>(oe_ing::kBounceBytes, bytes - done);
+                const ssize_t r = pread(fd, bounce.data(), (size_t)want, w.data_off + 2 * first + done);
+                if (r <= 0) break;
+                oe_ing::stream_copy(o8 + done, bounce.data(), (size_t)r);
                 done += r;
             }
             if (done != bytes) err = std::string(paths[i]) + ": short read";

@@ -4,6 +4,7 @@
 // openeat/bin/train.py:110-116).  Included by oe_frontend.cu; the C ABI is declared in include/openeat_frontend.h.
 #pragma once
 
+#include <emmintrin.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -86,6 +87,32 @@ class Pool {
     bool quit_ = false;
 };
 
+constexpr int kBounceBytes = 128 * 1024;      // per reader thread: stays in the core's L2
+
+// dst may be unaligned only in its last partial 16 bytes' worth: the head is brought to 16-byte alignment with plain
+// stores, the body goes out with MOVNTDQ (no read-for-ownership of the destination lines), the tail with plain stores
+inline void stream_copy(char* dst, const char* src, size_t n) {
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    n -= head;
+    const size_t body = n & ~(size_t)63;
+    for (size_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    memcpy(dst + body, src + body, n - body);
+    _mm_sfence();
+}
+
 struct WavInfo {
     int sample_rate = 0, channels = 0, bits = 0;
     int64_t data_off = 0, frames = 0;        // byte offset of the PCM, frames in the file
@@ -109,6 +136,7 @@ struct oe_ingest_job {
 
 struct oe_ingest {
     int threads;
+    bool direct_read = false;               // OE_INGEST_DIRECT=1: pread straight into the destination (A/B timing only)
     oe_ing::Pool* pool;
     std::vector<std::string> errors;        // per entry of the most recent probe / read
     // the probe keeps every file open with its parsed header: the read that follows neither re-opens nor re-parses
