@@ -8,6 +8,7 @@ of reader threads ``pread``s every utterance straight into its place -- no per-u
 """
 import ctypes
 import logging
+import os
 
 import numpy as np
 import torch
@@ -40,6 +41,7 @@ class NativeIngest(object):
     def __init__(self, threads=0, ring=4):
         self.lib = _lib.load()
         h = ctypes.c_void_p()
+        threads = int(os.environ.get('OE_INGEST_THREADS', threads))       # 0: one reader per hardware thread
         check(self.lib.oe_ingest_create(int(threads), ctypes.byref(h)))
         self.handle = h
         self._ring = [None] * max(2, int(ring))
