@@ -264,7 +264,8 @@ def run_ours(args, rank, world, local_rank):
             i += 1
 
     pipe = PrefetchingCollator(collate, host_batches())
-    pipe_host = PrefetchingCollator(collate, host_batches(), to_host=True)
+    host_pad = os.environ.get('OE_BENCH_HOST_PAD') == '1'       # developer A/B: real rows over PCIe + padding on the host
+    pipe_host = PrefetchingCollator(collate, host_batches(), to_host=True, host_pad=host_pad)
     d2h = {'n': torch.empty(BATCH, dtype=torch.int32).pin_memory(),
            's': torch.empty(161, dtype=torch.float64).pin_memory()}
     feat_bytes = [0]
@@ -280,7 +281,10 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e_host(i):
         """The reference boundary: the padded feature tensor comes back to (pinned) host memory as well."""
         _, out = next(pipe_host)
-        feat_bytes[0] = out['features'].numel() * 4
+        if host_pad:
+            feat_bytes[0] = int(out['features_length'].sum().item()) * out['features'].shape[-1] * 4     # the rows that were copied
+        else:
+            feat_bytes[0] = out['features'].numel() * 4
         d2h['s'].copy_(stats, non_blocking=True)
 
     def timed(fn, steps, warmup, with_allreduce):
@@ -567,7 +571,9 @@ def run_ours(args, rank, world, local_rank):
                     'to_host': {'value': e2e_host_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_host / args.steps,
                                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(feat_bytes[0]) + BATCH * 8 + 161 * 8,
                                 'api': 'the same with to_host=True: the padded feature tensor returns to pinned host memory '
-                                       'on a third stream (the reference boundary: audio_collate_func returns CPU tensors)'},
+                                       'on a third stream (the reference boundary: audio_collate_func returns CPU tensors)'
+                                       + ('; OE_BENCH_HOST_PAD=1: only the real rows cross PCIe, oe_host_pad_rows completes '
+                                          'the padded tensor on the host' if host_pad else '')},
                     'from_wav_files': {'value': e2e_files_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_files / args.steps,
                                        'api': 'openeat_b200.ingest.ingest_batches (native RIFF parse + multi-threaded pread of %d wav '
                                               'files per step from tmpfs into a pinned ring, background thread) -> '

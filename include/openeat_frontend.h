@@ -249,6 +249,14 @@ int oe_ingest_wait(oe_ingest_job* job, const int64_t** offsets, const int32_t** 
 const char* oe_ingest_job_error(const oe_ingest_job* job, int32_t index);
 int oe_ingest_job_release(oe_ingest_job* job);
 
+/* Host half of the CPU-tensor boundary (dataset.py:214-218: pad_sequence of the per-utterance feature matrices, then
+ * GlobalCMVN on the padded tensor): scatters the ragged rows `src` (utterance b = frames[b] rows of F floats, one after
+ * the other) into the padded tensor dst[B][tmax][F] and fills the rows behind every utterance with `pad_row` (F floats;
+ * NULL = zeros), on the handle's reader threads with non-temporal stores.  Lets a pipeline bring back only the real rows
+ * over PCIe.  Blocking; do not call while ingest jobs are pending on the same handle (use a handle of its own). */
+int oe_host_pad_rows(oe_ingest* g, const float* src, const int32_t* frames, int32_t B, int32_t tmax, int32_t F,
+                     const float* pad_row, float* dst);
+
 /* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
  * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).
  * These helpers continue that very generator natively: `mt_state` is `random.getstate()[1]` (624 state

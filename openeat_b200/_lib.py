@@ -110,6 +110,8 @@ SYMBOLS = {
                                       ctypes.POINTER(c_i32p), ctypes.POINTER(ctypes.c_int64)]),
     'oe_ingest_job_error': (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int32]),
     'oe_ingest_job_release': (ctypes.c_int, [ctypes.c_void_p]),
+    'oe_host_pad_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     'oe_plan_speeds': (ctypes.c_int, [c_u32p, ctypes.c_int32, ctypes.c_double, c_f64p, ctypes.c_int32, c_f64p, c_u8p,
                                       c_f64p]),
     'oe_plan_augment': (ctypes.c_int, [c_u32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,

@@ -2418,4 +2418,32 @@ int oe_ingest_job_release(oe_ingest_job* job) {
     return OE_OK;
 }
 
+int oe_host_pad_rows(oe_ingest* g, const float* src, const int32_t* frames, int32_t B, int32_t tmax, int32_t F,
+                     const float* pad_row, float* dst) {
+    if (!g || B < 0 || tmax < 0 || F <= 0 || (B > 0 && tmax > 0 && (!src || !frames || !dst))) return fail(OE_ERR_INVALID, "null pointer / bad shape");
+    std::vector<int64_t> first((size_t)B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+        if (frames[b] < 0 || frames[b] > tmax) return fail(OE_ERR_INVALID, "frames[%d]=%d outside [0, %d]", b, frames[b], tmax);
+        first[b + 1] = first[b] + frames[b];
+    }
+    // work items: (utterance, chunk of kChunk padded rows): real rows are copied, rows behind them filled
+    constexpr int kChunk = 128;
+    const int per = (tmax + kChunk - 1) / kChunk;
+    const size_t row = (size_t)F * sizeof(float);
+    std::vector<float> zero;
+    if (!pad_row) {
+        zero.assign((size_t)F, 0.f);
+        pad_row = zero.data();
+    }
+    g->pool->run(B * per, [&](int item) {
+        const int b = item / per, t0 = (item - b * per) * kChunk, t1 = std::min(tmax, t0 + kChunk);
+        const int nf = frames[b];
+        char* const d = reinterpret_cast<char*>(dst + ((size_t)b * tmax + t0) * F);
+        const int real = std::max(0, std::min(nf, t1) - t0);
+        if (real > 0) oe_ing::stream_copy(d, reinterpret_cast<const char*>(src + (first[b] + t0) * F), (size_t)real * row);
+        for (int t = t0 + real; t < t1; ++t) oe_ing::stream_copy(d + (size_t)(t - t0) * row, reinterpret_cast<const char*>(pad_row), row);
+    });
+    return OE_OK;
+}
+
 }  // extern "C"

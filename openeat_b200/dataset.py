@@ -420,7 +420,7 @@ class audio_collate_func(object):
         fused.update(self._draw_dither())
         features = None
         if len(plan.src):
-            features, _ = _run_plan(plan, F, wav, offsets, lens, **fused)
+            features, _ = _run_plan(plan, F, wav, offsets, lens, out_layout=getattr(self, '_out_layout', 'padded'), **fused)
         return self._finish(plan.keys, features, frames, plan.labels)
 
     def _draw_dither(self):
@@ -600,20 +600,41 @@ class PrefetchingCollator(object):
     copied in and computed (PCIe is full duplex); a batch is handed out once its copy has landed, i.e. one
     batch later than it was launched.  The yielded ``features`` tensor is a view of a ring slot: it stays valid
     until ``ring`` more batches have been drawn.
+
+    ``host_pad=True`` (with ``to_host``) brings back only the REAL rows (the kernels write the ragged layout: about half
+    the bytes of the padded tensor for 2-10 s utterances) and lets a helper thread build the zero-padded
+    ``(B, Tmax, F)`` tensor on the host (``oe_host_pad_rows``: reader-pool threads, non-temporal stores; padding rows are
+    0, or ``(0 - mean) * istd`` with a fused GlobalCMVN); one more batch of latency.  It trades PCIe bytes for host
+    memory traffic: on the measured 16-core box, whose memory the two copy engines already keep busy, it is SLOWER
+    (0.69 M against 0.85 M audio-s/s) -- an option for hosts with a narrow link, not the default.
     """
 
-    def __init__(self, collate, batches, to_host=False, ring=3):
+    def __init__(self, collate, batches, to_host=False, ring=3, host_pad=False):
         self.collate = collate
         self.batches = iter(batches)
         fe = default_frontend(collate.feature_extraction_conf['mel_bins'])
         self.device = fe.device
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.to_host = bool(to_host)
+        self.host_pad = bool(to_host and host_pad)
         self.out_stream = torch.cuda.Stream(device=self.device) if to_host else None
-        self._ring = [None] * max(2, int(ring))
+        self._depth = 2 if self.host_pad else 1  # batches in flight behind the one being launched
+        self._ring = [None] * (max(2, int(ring)) + self._depth)
         self._slot = 0
-        self._pending = None                     # (keys, inputs, event): launched, features still crossing PCIe
+        self._stage_ring = [None] * (self._depth + 2)   # pinned landing buffers of the ragged rows
+        self._stage_slot = 0
+        self._pending = []                       # launched batches, oldest first: (keys, host dict, event, thread or None)
         self._next = None
+        self._pad_row = None
+        if self.host_pad:
+            import threading
+            from .ingest import NativeIngest
+            self._lock = threading.Lock()        # the helper threads of consecutive batches take ring slots
+            self._padder = NativeIngest(threads=int(os.environ.get('OE_PAD_THREADS', '0')), ring=2)
+            if getattr(collate, 'global_cmvn', None) is not None:
+                mean, istd = collate.global_cmvn
+                m = mean.detach().float().cpu().numpy()
+                self._pad_row = (np.float32(0.0) - m) if istd is None else (np.float32(0.0) - m) * istd.detach().float().cpu().numpy()
         self._stage()
 
     def _stage(self):
@@ -641,16 +662,22 @@ class PrefetchingCollator(object):
         cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
         dev.record_stream(cur)
         self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
-        if len(extra) >= 2:
-            return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds, sample_rates=extra[0], loaded=extra[1])
-        return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds)
+        self.collate._out_layout = 'ragged' if self.host_pad else 'padded'
+        try:
+            if len(extra) >= 2:
+                return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds, sample_rates=extra[0], loaded=extra[1])
+            return self.collate.collate_packed(dev, offs, lens, keys, labels, speeds)
+        finally:
+            self.collate._out_layout = 'padded'
 
     def _to_host(self, keys, inputs):
-        """Enqueues the D2H copy of one finished batch on the output stream; returns (keys, inputs, event)."""
+        """Enqueues the D2H copies of one finished batch on the output stream (and, with host padding, starts the thread
+        that completes the padded tensor); returns (keys, host dict, event, thread)."""
         cur = torch.cuda.current_stream(self.device)
         done = torch.cuda.Event()
         done.record(cur)
         host = {}
+        ragged = None
         with torch.cuda.stream(self.out_stream):
             self.out_stream.wait_event(done)
             for k, v in inputs.items():
@@ -658,12 +685,15 @@ class PrefetchingCollator(object):
                     host[k] = v
                     continue
                 if k == 'features' and v.numel():
-                    slot = self._ring[self._slot]
-                    if slot is None or slot.numel() < v.numel():
-                        slot = torch.empty(int(v.numel() * 1.2) + 1024, dtype=v.dtype).pin_memory()
-                        self._ring[self._slot] = slot
-                    self._slot = (self._slot + 1) % len(self._ring)
-                    dst = slot[:v.numel()].view(v.shape)
+                    if self.host_pad:
+                        slot = self._stage_ring[self._stage_slot]
+                        if slot is None or slot.numel() < v.numel():
+                            slot = torch.empty(int(v.numel() * 1.2) + 1024, dtype=v.dtype).pin_memory()
+                            self._stage_ring[self._stage_slot] = slot
+                        self._stage_slot = (self._stage_slot + 1) % len(self._stage_ring)
+                        dst = ragged = slot[:v.numel()].view(v.shape)
+                    else:
+                        dst = self._out_slot(v.numel(), v.dtype).view(v.shape)
                 else:
                     dst = torch.empty(v.shape, dtype=v.dtype).pin_memory() if v.numel() else torch.empty(v.shape, dtype=v.dtype)
                 dst.copy_(v, non_blocking=True)
@@ -671,23 +701,43 @@ class PrefetchingCollator(object):
                 host[k] = dst
             ev = torch.cuda.Event()
             ev.record(self.out_stream)
-        return keys, host, ev
+        thread = None
+        if ragged is not None:
+            import threading
+
+            def finish():
+                ev.synchronize()                     # the rows and the frame counts have landed (GIL released while waiting)
+                frames = host['features_length'].numpy()
+                tmax, F = int(frames.max()), int(ragged.shape[-1])
+                with self._lock:
+                    out = self._out_slot(len(frames) * tmax * F, ragged.dtype).view(len(frames), tmax, F)
+                    self._padder.pad_rows(ragged, frames, tmax, out, self._pad_row)
+                host['features'] = out
+            thread = threading.Thread(target=finish, daemon=True)
+            thread.start()
+        return keys, host, ev, thread
+
+    def _out_slot(self, numel, dtype):
+        slot = self._ring[self._slot]
+        if slot is None or slot.numel() < numel or slot.dtype != dtype:
+            slot = torch.empty(int(numel * 1.2) + 1024, dtype=dtype).pin_memory()
+            self._ring[self._slot] = slot
+        self._slot = (self._slot + 1) % len(self._ring)
+        return slot[:numel]
 
     def __next__(self):
         if not self.to_host:
             if self._next is None:
                 raise StopIteration
             return self._launch()
-        if self._next is None and self._pending is None:
+        if self._next is None and not self._pending:
             raise StopIteration
-        launched = None
-        if self._next is not None:
-            launched = self._to_host(*self._launch())
-        if self._pending is None:                # first call: nothing to hand out yet -> launch one more if there is one
-            self._pending, launched = launched, None
-            if self._next is not None:
-                launched = self._to_host(*self._launch())
-        keys, host, ev = self._pending
-        self._pending = launched
-        ev.synchronize()
+        # keep `_depth` batches in flight behind the one handed out
+        while self._next is not None and len(self._pending) <= self._depth:
+            self._pending.append(self._to_host(*self._launch()))
+        keys, host, ev, thread = self._pending.pop(0)
+        if thread is not None:
+            thread.join()
+        else:
+            ev.synchronize()
         return keys, host

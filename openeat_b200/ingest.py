@@ -68,6 +68,16 @@ class NativeIngest(object):
             self._ring[i] = buf
         return i, buf
 
+    def pad_rows(self, src, frames, tmax, dst, pad_row=None):
+        """``oe_host_pad_rows``: ragged host rows ``src`` (sum(frames), F) -> zero-padded host tensor ``dst`` (B, tmax, F)
+        on this handle's threads (non-temporal stores); ``pad_row`` (F,) float32 replaces the zeros (GlobalCMVN on the
+        padding).  Blocking, GIL released; the handle must not have ingest jobs pending."""
+        frames = np.ascontiguousarray(frames, dtype=np.int32)
+        pr = None if pad_row is None else np.ascontiguousarray(pad_row, dtype=np.float32)
+        check(self.lib.oe_host_pad_rows(self.handle, ctypes.c_void_p(src.data_ptr()), frames.ctypes.data_as(c_i32p),
+                                        len(frames), int(tmax), int(dst.shape[-1]),
+                                        None if pr is None else ctypes.c_void_p(pr.ctypes.data), ctypes.c_void_p(dst.data_ptr())))
+
     def release_after(self, slot, event):
         self._events[slot] = event
 

@@ -181,6 +181,41 @@ def test_prefetching_collator_equals_direct_calls(gold):
             assert torch.equal(o1[name], o2[name]), name
 
 
+@pytest.mark.parametrize('with_cmvn', [False, True])
+def test_prefetching_collator_to_host_pads_on_the_host(gold, golden_dir, with_cmvn):
+    """to_host=True (the reference boundary: CPU tensors, dataset.py:232-238): only the real rows cross PCIe and the
+    padded tensor is completed on the host (oe_host_pad_rows) -- must equal the padded tensor the GPU path produces,
+    bit for bit, padding rows included (0, or (0 - mean) * istd with a fused GlobalCMVN)."""
+    from openeat_b200.cmvn import load_cmvn
+    from openeat_b200.dataset import PrefetchingCollator, audio_collate_func
+    from openeat_b200.frontend import pack_waveforms
+    conf = dict(CONF, speed_perturb_rate=0.5)
+    kw = dict(data_type='wav', feature_extraction_conf=conf, normalization=True, spec_aug=True,
+              spec_aug_conf=dict(num_t_mask=3, num_f_mask=2, max_t=50, max_f=10))
+    if with_cmvn:
+        mean, istd = load_cmvn(os.path.join(golden_dir, 'cmvn_stats.json'), True)
+        kw['global_cmvn'] = (torch.from_numpy(mean).float().cuda(), torch.from_numpy(istd).float().cuda())
+    batches = []
+    for r in range(5):
+        ids = [(i + r) % 6 for i in range(5)]
+        buf, offs, lens = pack_waveforms([gold['pcm%d' % i] for i in ids])
+        batches.append((buf, offs, lens, ['u%d' % i for i in ids], [[i + 1] * 3 for i in ids], [1.0, 0.9, 1.1, 1.0, 1.0]))
+    fn = audio_collate_func(**kw)
+    random.seed(77)
+    direct = [fn.collate_packed(*b) for b in batches]
+    for host_pad in (True, False):
+        random.seed(77)
+        got = []
+        for keys, out in PrefetchingCollator(audio_collate_func(**kw), batches, to_host=True, host_pad=host_pad):
+            got.append((keys, {k: v.clone() for k, v in out.items()}))     # ring slots are reused
+        assert len(got) == 5
+        for (k1, o1), (k2, o2) in zip(direct, got):
+            assert k1 == k2
+            for name in o1:
+                assert not o2[name].is_cuda and o2[name].shape == o1[name].shape, name
+                assert torch.equal(o1[name].cpu(), o2[name]), (name, host_pad)
+
+
 def test_speed_processors(golden_dir):
     from openeat_b200.audio_processor import _speed_generator, _speed_perturb
     g = np.load(os.path.join(golden_dir, 'speed.npz'))

@@ -323,3 +323,28 @@ def test_asynchronous_ingest_batches(tmp_path):
             assert np.array_equal(x[offs[i]:offs[i] + lens[i]], data[p])
         release(None)
     assert seen == ['k%d_0' % b for b in range(5)]
+
+
+def test_host_pad_rows(tmp_path):
+    """oe_host_pad_rows (pad_sequence of dataset.py:214-218 on the reader pool): ragged rows -> (B, Tmax, F), padding rows
+    zero or a given row; odd row sizes and unaligned destinations take the head / tail paths of the streaming copy."""
+    torch = pytest.importorskip('torch')
+    from openeat_b200.ingest import NativeIngest
+    ing = NativeIngest(threads=4)
+    rng = np.random.default_rng(5)
+    for F, frames in ((80, [300, 129, 128, 1, 0]), (23, [7, 7, 3]), (3, [1000, 999])):
+        tmax = max(frames)
+        src = torch.from_numpy(rng.normal(size=(sum(frames), F)).astype(np.float32))
+        for pad_row in (None, rng.normal(size=F).astype(np.float32)):
+            raw = torch.full((len(frames) * tmax * F + 5,), 7.0)
+            dst = raw[3:3 + len(frames) * tmax * F].view(len(frames), tmax, F)      # 12-byte offset: unaligned rows
+            ing.pad_rows(src, frames, tmax, dst, pad_row)
+            want = np.zeros((len(frames), tmax, F), np.float32) if pad_row is None else np.broadcast_to(pad_row, (len(frames), tmax, F)).copy()
+            o = 0
+            for b, n in enumerate(frames):
+                want[b, :n] = src[o:o + n].numpy()
+                o += n
+            assert np.array_equal(dst.numpy(), want)
+            assert raw[:3].eq(7).all() and raw[-2:].eq(7).all()
+    with pytest.raises(Exception):
+        ing.pad_rows(src, [5000], 10, dst)                                          # frames > tmax
