@@ -477,6 +477,11 @@ struct Finalize2Params {
     int parts;
     float dither_a;
     unsigned long long dither_seed;
+    // compute_cmvn_stats: the fbank kernel in front of this one has added the batch's fixed-point sums into stat_acc; block
+    // (0, 0) converts them into the caller's fp64 accumulator (null = nothing to do)
+    const unsigned long long* stat_acc;      // [2F]
+    double* d_stats;                         // [2F+1]
+    double stat_count;
 };
 constexpr int kFin2Threads = 512;
 template <bool DITHER>
@@ -486,6 +491,10 @@ __global__ void __launch_bounds__(kFin2Threads, 2) oe_finalize2_kernel(const Fin
     __shared__ float shC[2][F];
     grid_dep_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (P.d_stats != nullptr && b == 0 && blockIdx.y == 0) {
+        if (tid < 2 * F) P.d_stats[tid] += (double)(long long)__ldcg(P.stat_acc + tid) * (tid < F ? 1.0 / k2::kFxSum : 1.0 / k2::kFxSq);
+        if (tid == 2 * F) P.d_stats[2 * F] += P.stat_count;
+    }
     const int nfr = P.n_frames[b];
     const int nrows = (int)(P.row_prefix[b + 1] - P.row_prefix[b]);
     const int per = (nrows + P.parts - 1) / P.parts;
@@ -1601,12 +1610,17 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         P.cmvn_on_pad = bt->cmvn_on_padding;
     }
     const int grid = M.feats ? 0 : std::min(M.total_tiles, 2 * fe->sm_count);
+    bool stats_by_completion = false;
     if (M.k2) {
         P.sched = reinterpret_cast<int32_t*>(ws + M.sched);
         if (bt->d_stats) {
             P.stat_acc = reinterpret_cast<unsigned long long*>(ws + M.stat_acc);
-            P.d_stats = bt->d_stats;
-            P.stat_count = (double)M.total_frames;
+            // with a completion kernel behind the fbank kernel, that kernel's first block converts the sums
+            stats_by_completion = inplace && M.total_rows > 0 && M.total_tiles > 0;
+            if (!stats_by_completion) {
+                P.d_stats = bt->d_stats;
+                P.stat_count = (double)M.total_frames;
+            }
         }
     }
     // float4 row stores: gen-1 kernel needs dense rows (pitch == F), gen-2 any 16-byte aligned pitch
@@ -1722,6 +1736,11 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         parts = std::min(parts, std::max(1, (M.max_rows + 31) / 32));
         if (fe->fin2_parts > 0) parts = fe->fin2_parts;
         Z.parts = parts;
+        if (stats_by_completion) {
+            Z.stat_acc = P.stat_acc;
+            Z.d_stats = bt->d_stats;
+            Z.stat_count = (double)M.total_frames;
+        }
         ++fe->launches;
         if (Z.dither_a != 0.f) OE_CUDA(launch_dep(oe::oe_finalize2_kernel<true>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
         else OE_CUDA(launch_dep(oe::oe_finalize2_kernel<false>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
