@@ -370,7 +370,10 @@ def run_ours(args, rank, world, local_rank):
             yield file_batches[i % POOL]
             i += 1
 
-    pipe_files = PrefetchingCollator(collate, ingest_batches(file_items(), depth=3))
+    # reader threads: every rank takes its share of the host cores (N ranks x all cores would oversubscribe the box)
+    from openeat_b200.ingest import NativeIngest
+    n_readers = max(2, len(os.sched_getaffinity(0)) // world)
+    pipe_files = PrefetchingCollator(collate, ingest_batches(file_items(), ingest=NativeIngest(threads=n_readers, ring=6), depth=3))
 
     def step_e2e_files(i):
         _, out = next(pipe_files)
@@ -576,8 +579,8 @@ def run_ours(args, rank, world, local_rank):
                                           'the padded tensor on the host' if host_pad else '')},
                     'from_wav_files': {'value': e2e_files_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_files / args.steps,
                                        'api': 'openeat_b200.ingest.ingest_batches (native RIFF parse + multi-threaded pread of %d wav '
-                                              'files per step from tmpfs into a pinned ring, background thread) -> '
-                                              'PrefetchingCollator -> the same kernels' % BATCH,
+                                              'files per step from tmpfs into a pinned ring, background thread, %d reader threads per rank) -> '
+                                              'PrefetchingCollator -> the same kernels' % (BATCH, n_readers),
                                        'frac_of_packed_e2e': e2e_files_value / e2e_value},
                     'h2d_ceiling_gbs': h2d_ceiling,
                     'h2d_achieved_gbs': h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9,
