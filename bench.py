@@ -430,11 +430,13 @@ def run_ours(args, rank, world, local_rank):
         return items, nb * 16 * 5.0, nb * (2.0 * float(n.sum()) + 320.0 * fr), False
 
     def make_cfg3():
-        # configs[2] shape: ONE global list of U[1,35] s utterances (seed 1004; a 10 h sample of the 1 000 h set), cut
-        # by shard_by_length, sorted + length-bucketed like AudioDataset(sort=True, batch_type='dynamic'), fbank +
-        # per-utt norm + padded output + CMVN-statistics accumulation, one all-reduce per pass
+        # configs[2] shape: ONE global list of U[1,35] s utterances (seed 1004; a sample of the 1 000 h set: 10 h per GPU,
+        # so that the work per GPU is the same at every N like the rest of this line -- the full set would give every GPU
+        # 125 h at N = 8, a 10 h total would leave each of eight GPUs 0.7 ms of work), cut by shard_by_length, sorted +
+        # length-bucketed like AudioDataset(sort=True, batch_type='dynamic'), fbank + per-utt norm + padded output +
+        # CMVN-statistics accumulation, one all-reduce per pass
         rng = np.random.default_rng(1004)
-        all_lens = np.round(rng.uniform(1.0, 35.0, 2000) * 16000).astype(np.int64)
+        all_lens = np.round(rng.uniform(1.0, 35.0, 2000 * world) * 16000).astype(np.int64)
         mine = shard_by_length(all_lens, world)[rank]
         n = all_lens[mine].astype(np.int32)
         fr = frames_of(n)
@@ -480,8 +482,8 @@ def run_ours(args, rank, world, local_rank):
 
     configs = {}
     for key, name, mk in (('config1_shape', 'configs[0] shape on the GPU: 1 008 x 5 s, static batch 16, per-utt norm + global CMVN', make_cfg1),
-                          ('config3', 'configs[2]: LibriSpeech shape, 2 000 x U[1,35] s (10 h sample), one list cut by shard_by_length, '
-                                      'dynamic batches of <= 150 k frames, per-utt norm + CMVN statistics, one all-reduce per pass', make_cfg3),
+                          ('config3', 'configs[2]: LibriSpeech shape, %d x U[1,35] s (10 h per GPU sample), one list cut by shard_by_length, '
+                                      'dynamic batches of <= 150 k frames, per-utt norm + CMVN statistics, one all-reduce per pass' % (2000 * world), make_cfg3),
                           ('config4', 'configs[3]: ASRU shape, 256 x U[0.5,3] s, per-utt norm + spec_sub(3,30)', make_cfg4),
                           ('config5', 'configs[4]: 20-minute streams as 7 500 x 16-frame windows, global CMVN, ragged output', make_cfg5)):
         stats.zero_()

@@ -77,7 +77,9 @@ typedef struct {
     const int32_t* fmask;        /* [B][n_fmask][2] half-open bin ranges, or NULL */
     const int32_t* frame_map;    /* composed _spec_substitute index map (:44-64): output frame t of
                                     utterance b is source frame frame_map[frame_map_offsets[b]+t];
-                                    NULL = identity */
+                                    NULL = identity.  Maps that only reach back (frame_map[t] <= t: what
+                                    spec_sub composes to) are applied in place, any other gather goes
+                                    through a raw scratch in the workspace */
     const int64_t* frame_map_offsets; /* [B] */
     const float* d_cmvn_mean;    /* DEVICE [num_mel_bins] or NULL (GlobalCMVN buffers) */
     const float* d_cmvn_istd;    /* DEVICE [num_mel_bins] or NULL (norm_var=False) */

@@ -477,6 +477,11 @@ struct Finalize2Params {
     int parts;
     float dither_a;
     unsigned long long dither_seed;
+    // spec_sub (feature_processor.py:44-64) as a composed frame map y[t] = x[map[t]], map[t] <= t (every substitution copies
+    // from EARLIER frames); null = none.  Handled in place by walking the utterance from its last rows to its first:
+    // whatever a row reads lies at or below it and is still raw.  One block per utterance (parts == 1).
+    const int32_t* frame_map;
+    const int64_t* map_off;      // [B]
     // compute_cmvn_stats: the fbank kernel in front of this one has added the batch's fixed-point sums into stat_acc; block
     // (0, 0) converts them into the caller's fp64 accumulator (null = nothing to do)
     const unsigned long long* stat_acc;      // [2F]
@@ -484,7 +489,7 @@ struct Finalize2Params {
     double stat_count;
 };
 constexpr int kFin2Threads = 512;
-template <bool DITHER>
+template <bool DITHER, bool SUB = false>
 __global__ void __launch_bounds__(kFin2Threads, 2) oe_finalize2_kernel(const Finalize2Params P) {
     constexpr int F = 80;
     __shared__ double shD[3][F];
@@ -533,7 +538,8 @@ __global__ void __launch_bounds__(kFin2Threads, 2) oe_finalize2_kernel(const Fin
     }
     const int q = tid % 20, rl = tid / 20;                             // 25 row lanes x 20 float4 columns
     constexpr int kLanes = 25;
-    if (rl >= kLanes) return;
+    const bool lane_ok = rl < kLanes;
+    if (!SUB && !lane_ok) return;
     const int c = 4 * q;
     const bool has_cm = P.cmvn_mean != nullptr, has_ci = P.cmvn_istd != nullptr;
     float mean4[4], rstd4[4], cm[4], ci[4], padv[4];
@@ -562,45 +568,103 @@ __global__ void __launch_bounds__(kFin2Threads, 2) oe_finalize2_kernel(const Fin
     }
     const int pitch = (int)P.pitch;
     float* const odst = P.out + P.out_row[b] * P.pitch + c;
-    const int real_hi = min(r_hi, nfr);
-    constexpr int kU = 4;
+    if constexpr (!SUB) {
+        const int real_hi = min(r_hi, nfr);
+        constexpr int kU = 4;
 #pragma unroll 1
-    for (int t0 = r_lo + rl; t0 < real_hi; t0 += kLanes * kU) {
-        float4 x[kU];
+        for (int t0 = r_lo + rl; t0 < real_hi; t0 += kLanes * kU) {
+            float4 x[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u)
-            if (t0 + kLanes * u < real_hi) x[u] = __ldcg(reinterpret_cast<const float4*>(odst + (int64_t)(t0 + kLanes * u) * pitch));
+            for (int u = 0; u < kU; ++u)
+                if (t0 + kLanes * u < real_hi) x[u] = __ldcg(reinterpret_cast<const float4*>(odst + (int64_t)(t0 + kLanes * u) * pitch));
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int t = t0 + kLanes * u;
-            if (t < real_hi) {
-                bool rmask = false;
+            for (int u = 0; u < kU; ++u) {
+                const int t = t0 + kLanes * u;
+                if (t < real_hi) {
+                    bool rmask = false;
 #pragma unroll
-                for (int j = 0; j < kTm; ++j) rmask |= (t >= tm_lo[j]) & (t < tm_hi[j]);
-                for (int j = kTm; j < P.n_tmask; ++j) rmask |= (t >= __ldg(tm + 2 * j)) & (t < __ldg(tm + 2 * j + 1));
-                float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-                float du[4] = {0.f, 0.f, 0.f, 0.f};
-                if (DITHER) {
-                    const uint4 rn = philox4x32_10(make_uint4((unsigned)q, (unsigned)t, (unsigned)b, 0u),
-                                                   make_uint2((unsigned)P.dither_seed, (unsigned)(P.dither_seed >> 32)));
-                    const unsigned w[4] = {rn.x, rn.y, rn.z, rn.w};
+                    for (int j = 0; j < kTm; ++j) rmask |= (t >= tm_lo[j]) & (t < tm_hi[j]);
+                    for (int j = kTm; j < P.n_tmask; ++j) rmask |= (t >= __ldg(tm + 2 * j)) & (t < __ldg(tm + 2 * j + 1));
+                    float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                    float du[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (DITHER) {
+                        const uint4 rn = philox4x32_10(make_uint4((unsigned)q, (unsigned)t, (unsigned)b, 0u),
+                                                       make_uint2((unsigned)P.dither_seed, (unsigned)(P.dither_seed >> 32)));
+                        const unsigned w[4] = {rn.x, rn.y, rn.z, rn.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) du[e] = ((float)(w[e] >> 8) * (1.0f / 16777216.0f) - 0.5f) * P.dither_a;
+                        for (int e = 0; e < 4; ++e) du[e] = ((float)(w[e] >> 8) * (1.0f / 16777216.0f) - 0.5f) * P.dither_a;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float yv = (v[e] - mean4[e]) * rstd4[e];           // mean = 0, rstd = 1 without normalisation: exact
+                        if (DITHER) yv += du[e];
+                        if (rmask || cmask[e]) yv = 0.f;
+                        v[e] = (yv - cm[e]) * ci[e];                       // cm = 0, ci = 1 without CMVN: exact
+                    }
+                    *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = make_float4(v[0], v[1], v[2], v[3]);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float yv = (v[e] - mean4[e]) * rstd4[e];           // mean = 0, rstd = 1 without normalisation: exact
-                    if (DITHER) yv += du[e];
-                    if (rmask || cmask[e]) yv = 0.f;
-                    v[e] = (yv - cm[e]) * ci[e];                       // cm = 0, ci = 1 without CMVN: exact
-                }
-                *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
-    }
-    const float4 pv = make_float4(padv[0], padv[1], padv[2], padv[3]);
+        const float4 pv = make_float4(padv[0], padv[1], padv[2], padv[3]);
 #pragma unroll 4
-    for (int t = max(r_lo, nfr) + rl; t < r_hi; t += kLanes) *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = pv;
+        for (int t = max(r_lo, nfr) + rl; t < r_hi; t += kLanes) *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = pv;
+    } else {
+        const int real_hi = min(r_hi, nfr);
+        constexpr int kU = 4;
+        constexpr int kChunk = kLanes * kU;
+        const int32_t* const fmap = SUB ? P.frame_map + P.map_off[b] : nullptr;
+        // without a frame map: chunks in ascending order; with one: from the LAST chunk down, loads of a chunk separated from
+        // its stores by a block barrier (a row of the chunk may be the source of a later row of the same chunk)
+        const int n_chunks = real_hi > r_lo ? (real_hi - r_lo + kChunk - 1) / kChunk : 0;
+#pragma unroll 1
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int t0 = r_lo + (SUB ? n_chunks - 1 - ch : ch) * kChunk + rl;
+            float4 x[kU];
+            int ts[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int t = t0 + kLanes * u;
+                ts[u] = t;
+                if (lane_ok && t < real_hi) {
+                    if (SUB) ts[u] = __ldg(fmap + t);
+                    x[u] = __ldcg(reinterpret_cast<const float4*>(odst + (int64_t)ts[u] * pitch));
+                }
+            }
+            if (SUB) __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int t = t0 + kLanes * u;
+                if (lane_ok && t < real_hi) {
+                    bool rmask = false;
+#pragma unroll
+                    for (int j = 0; j < kTm; ++j) rmask |= (t >= tm_lo[j]) & (t < tm_hi[j]);
+                    for (int j = kTm; j < P.n_tmask; ++j) rmask |= (t >= __ldg(tm + 2 * j)) & (t < __ldg(tm + 2 * j + 1));
+                    float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                    float du[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (DITHER) {              // keyed by the SOURCE frame: substituted rows carry their noise along
+                        const uint4 rn = philox4x32_10(make_uint4((unsigned)q, (unsigned)ts[u], (unsigned)b, 0u),
+                                                       make_uint2((unsigned)P.dither_seed, (unsigned)(P.dither_seed >> 32)));
+                        const unsigned w[4] = {rn.x, rn.y, rn.z, rn.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) du[e] = ((float)(w[e] >> 8) * (1.0f / 16777216.0f) - 0.5f) * P.dither_a;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float yv = (v[e] - mean4[e]) * rstd4[e];           // mean = 0, rstd = 1 without normalisation: exact
+                        if (DITHER) yv += du[e];
+                        if (rmask || cmask[e]) yv = 0.f;
+                        v[e] = (yv - cm[e]) * ci[e];                       // cm = 0, ci = 1 without CMVN: exact
+                    }
+                    *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+        if (lane_ok) {
+            const float4 pv = make_float4(padv[0], padv[1], padv[2], padv[3]);
+#pragma unroll 4
+            for (int t = max(r_lo, nfr) + rl; t < r_hi; t += kLanes) *reinterpret_cast<float4*>(odst + (int64_t)t * pitch) = pv;
+        }
+    }
 }
 
 // Padding rows of the single-pass layout: the fbank kernel writes whole 32-frame tiles (real frames plus the padding
@@ -905,6 +969,7 @@ struct oe_frontend {
     bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     int fin2_parts;                // OE_FIN2_PARTS=n: blocks per utterance of oe_finalize2_kernel (tuning only; 0 = automatic)
+    bool no_inplace_sub;           // OE_NO_INPLACE_SUB=1: spec_sub batches keep the ragged scratch + statistics kernel + out-of-place finalize (A/B timing only)
     bool no_inplace;               // OE_NO_INPLACE=1: raw scratch + statistics kernel + out-of-place finalize behind the gen-2 kernel (A/B timing only)
     // pinned staging ring for the per-call metadata block (a pageable source would make cudaMemcpyAsync wait for the
     // stream); a slot is reused once the copy that read it has completed
@@ -1057,7 +1122,8 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
     M.feats = feats;
     M.need_stats = bt->norm_mode != OE_NORM_NONE || (feats && bt->d_stats != nullptr);
     M.k2 = !feats && fe->mel_baked && !fe->force_v1;
-    M.inplace_ok = M.k2 && M.two_phase && !bt->frame_map && !fe->no_inplace && F % 4 == 0 && pitch % 4 == 0;
+    M.inplace_ok = M.k2 && M.two_phase && !fe->no_inplace && F % 4 == 0 && pitch % 4 == 0;
+    bool map_from_past = true;
     M.total_frames = M.total_rows = M.total_map = 0;
     M.pad_rows = 0;
     M.max_rows = 0;
@@ -1085,9 +1151,15 @@ int plan(const oe_frontend* fe, const oe_batch* bt, Meta& M, std::vector<int32_t
         M.max_rows = std::max(M.max_rows, nrows);
         tiles += (nfr + oe::kTileFrames - 1) / oe::kTileFrames;      // single pass: padding rows behind the last tile: oe_pad_fill_kernel
         M.pad_rows += std::max(0, nrows - (nfr + oe::kTileFrames - 1) / oe::kTileFrames * oe::kTileFrames);
-        if (bt->frame_map) M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
+        if (bt->frame_map) {
+            M.total_map = std::max<int64_t>(M.total_map, bt->frame_map_offsets[b] + nfr);
+            // spec_sub only ever copies from EARLIER frames (feature_processor.py:57-63): such a map can be applied in place
+            const int32_t* const mp = bt->frame_map + bt->frame_map_offsets[b];
+            for (int t = 0; t < nfr && map_from_past; ++t) map_from_past = mp[t] <= t;
+        }
     }
     if (tiles > INT32_MAX) return fail(OE_ERR_INVALID, "batch too large");
+    if (bt->frame_map && (!map_from_past || fe->no_inplace_sub)) M.inplace_ok = false;      // a general gather keeps the raw scratch
     M.total_tiles = (int)tiles;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 16); return r; };
@@ -1268,6 +1340,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
         fe->fin2_parts = fp_ ? atoi(fp_) : 0;
         const char* nf = getenv("OE_NO_INPLACE");
         fe->no_inplace = nf && nf[0] == '1';
+        const char* ns = getenv("OE_NO_INPLACE_SUB");
+        fe->no_inplace_sub = ns && ns[0] == '1';
     }
     if (e != cudaSuccess) {
         if (fe->d_tab) cudaFree(fe->d_tab);
@@ -1735,6 +1809,11 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         parts = std::max(parts, (3 * fe->sm_count / 2 + B - 1) / B);
         parts = std::min(parts, std::max(1, (M.max_rows + 31) / 32));
         if (fe->fin2_parts > 0) parts = fe->fin2_parts;
+        if (bt->has_map) {                      // spec_sub in place: one block walks the utterance from its last rows down
+            parts = 1;
+            Z.frame_map = reinterpret_cast<const int32_t*>(ws + M.fmap);
+            Z.map_off = reinterpret_cast<const int64_t*>(ws + M.map_off);
+        }
         Z.parts = parts;
         if (stats_by_completion) {
             Z.stat_acc = P.stat_acc;
@@ -1742,8 +1821,11 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
             Z.stat_count = (double)M.total_frames;
         }
         ++fe->launches;
-        if (Z.dither_a != 0.f) OE_CUDA(launch_dep(oe::oe_finalize2_kernel<true>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
-        else OE_CUDA(launch_dep(oe::oe_finalize2_kernel<false>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+        if (bt->has_map) {
+            if (Z.dither_a != 0.f) OE_CUDA(launch_dep(oe::oe_finalize2_kernel<true, true>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+            else OE_CUDA(launch_dep(oe::oe_finalize2_kernel<false, true>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+        } else if (Z.dither_a != 0.f) OE_CUDA(launch_dep(oe::oe_finalize2_kernel<true, false>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
+        else OE_CUDA(launch_dep(oe::oe_finalize2_kernel<false, false>, dim3(B, parts), dim3(oe::kFin2Threads), 0, stream, Z));
         OE_CUDA(cudaGetLastError());
         return OE_OK;
     }
