@@ -969,6 +969,7 @@ struct oe_frontend {
     bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     int fin2_parts;                // OE_FIN2_PARTS=n: blocks per utterance of oe_finalize2_kernel (tuning only; 0 = automatic)
+    bool no_coalesce;              // OE_NO_COALESCE=1: consecutive windows of one recording stay separate utterances (A/B timing only)
     bool no_inplace_sub;           // OE_NO_INPLACE_SUB=1: spec_sub batches keep the ragged scratch + statistics kernel + out-of-place finalize (A/B timing only)
     bool no_inplace;               // OE_NO_INPLACE=1: raw scratch + statistics kernel + out-of-place finalize behind the gen-2 kernel (A/B timing only)
     // pinned staging ring for the per-call metadata block (a pageable source would make cudaMemcpyAsync wait for the
@@ -1340,6 +1341,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
         fe->fin2_parts = fp_ ? atoi(fp_) : 0;
         const char* nf = getenv("OE_NO_INPLACE");
         fe->no_inplace = nf && nf[0] == '1';
+        const char* nz = getenv("OE_NO_COALESCE");
+        fe->no_coalesce = nz && nz[0] == '1';
         const char* ns = getenv("OE_NO_INPLACE_SUB");
         fe->no_inplace_sub = ns && ns[0] == '1';
     }
@@ -1411,10 +1414,63 @@ int oe_frontend_get_tables(const oe_frontend* fe, float* window, float* mel) {
     return OE_OK;
 }
 
+// ---- window coalescing: streaming front-ends feed a long recording as many short windows (BASELINE config 5: 7 500
+// windows of 16 frames, 2 800 samples each, 2 560 apart); a 16-frame window fills half a 32-frame tile.  When
+// consecutive utterances of a batch are CONTINUATIONS of each other -- the next one starts exactly `frames * shift`
+// samples behind the previous one in the waveform buffer and right behind its rows in the output -- and nothing in the
+// batch is per-utterance (no normalisation, masks, frame maps, dithers, resampling, padding rows), the run is the same
+// set of frames as one long utterance: fbank is frame-independent.  The batch is rewritten that way on the host, the
+// kernels see full tiles.  Frame counts are still reported per original utterance. ----
+struct Coalesced {
+    oe_batch b;
+    std::vector<int64_t> off, rows;
+    std::vector<int32_t> len;
+    std::vector<int32_t> frames_orig;
+};
+static bool coalesce_windows(const oe_frontend* fe, const oe_batch* bt, Coalesced& c) {
+    if (!fe || !bt || fe->no_coalesce || bt->batch < 4 || !bt->wav_offsets || !bt->wav_lens || !bt->out_rows) return false;
+    if (bt->wav_dtype != OE_WAV_I16 && bt->wav_dtype != OE_WAV_F32) return false;
+    if (bt->norm_mode != OE_NORM_NONE || bt->n_tmask || bt->n_fmask || bt->frame_map || bt->resample_ids ||
+        bt->feature_dither != 0.f || bt->wav_dither != 0.f)
+        return false;
+    const int B = bt->batch, shift = fe->cfg.frame_shift;
+    c.frames_orig.resize(B);
+    for (int b = 0; b < B; ++b) {
+        if (bt->wav_lens[b] < 0) return false;                          // reported by plan()
+        c.frames_orig[b] = oe_num_frames(fe, bt->wav_lens[b]);
+        if (bt->out_nrows && bt->out_nrows[b] != c.frames_orig[b]) return false;
+    }
+    c.off.clear();
+    c.rows.clear();
+    c.len.clear();
+    for (int b = 0; b < B;) {
+        int e = b;                                                      // run [b, e]
+        while (e + 1 < B && c.frames_orig[e] > 0 && c.frames_orig[e + 1] > 0 &&
+               bt->wav_offsets[e + 1] == bt->wav_offsets[e] + (int64_t)shift * c.frames_orig[e] &&
+               bt->out_rows[e + 1] == bt->out_rows[e] + c.frames_orig[e] &&
+               bt->wav_offsets[e + 1] + bt->wav_lens[e + 1] - bt->wav_offsets[b] <= INT32_MAX)
+            ++e;
+        c.off.push_back(bt->wav_offsets[b]);
+        c.rows.push_back(bt->out_rows[b]);
+        c.len.push_back((int32_t)(bt->wav_offsets[e] + bt->wav_lens[e] - bt->wav_offsets[b]));
+        b = e + 1;
+    }
+    if ((int)c.off.size() * 2 > B) return false;                       // not worth it
+    c.b = *bt;
+    c.b.batch = (int32_t)c.off.size();
+    c.b.wav_offsets = c.off.data();
+    c.b.wav_lens = c.len.data();
+    c.b.out_rows = c.rows.data();
+    c.b.out_nrows = nullptr;
+    c.b.out_frames = nullptr;
+    return true;
+}
+
 int oe_fbank_workspace_bytes(const oe_frontend* fe, const oe_batch* batch, size_t* bytes) {
     if (!bytes) return fail(OE_ERR_INVALID, "null bytes");
     Meta M;
-    const int rc = plan(fe, batch, M, nullptr);
+    Coalesced cz;
+    const int rc = plan(fe, coalesce_windows(fe, batch, cz) ? &cz.b : batch, M, nullptr);
     if (rc != OE_OK) return rc;
     *bytes = M.total + 256;
     return OE_OK;
@@ -1549,10 +1605,13 @@ int oe_fbank_batch(oe_frontend* fe, const oe_batch* bt, const void* d_wav, float
                    size_t ws_bytes, oe_stream stream_) {
     Meta M;
     std::vector<int32_t> frames;
+    Coalesced cz;
+    const oe_batch* const orig = bt;
+    if (coalesce_windows(fe, bt, cz)) bt = &cz.b;
     int rc = plan(fe, bt, M, &frames);
     if (rc != OE_OK) return rc;
     const int B = bt->batch;
-    if (bt->out_frames) for (int b = 0; b < B; ++b) bt->out_frames[b] = frames[b];
+    if (orig->out_frames) for (int b = 0; b < orig->batch; ++b) orig->out_frames[b] = bt == orig ? frames[b] : cz.frames_orig[b];
     if (B == 0) return OE_OK;
     // the metadata is packed straight into a slot of the handle's pinned ring
     OE_CUDA(cudaSetDevice(fe->device));
@@ -1578,10 +1637,15 @@ int oe_batch_prepare(oe_frontend* fe, const oe_batch* bt, oe_prepared** out) {
     if (!out) return fail(OE_ERR_INVALID, "null out");
     *out = nullptr;
     oe_prepared* p = new oe_prepared();
-    int rc = plan(fe, bt, p->M, &p->frames);
+    Coalesced cz;
+    const bool merged = coalesce_windows(fe, bt, cz);
+    if (merged) bt = &cz.b;
+    std::vector<int32_t> frames;
+    int rc = plan(fe, bt, p->M, &frames);
     if (rc == OE_OK) {
         p->meta.assign(p->M.meta_bytes, 0);
-        rc = pack_meta(fe, bt, p->M, p->frames, p->meta.data(), p->L);
+        rc = pack_meta(fe, bt, p->M, frames, p->meta.data(), p->L);
+        p->frames = merged ? cz.frames_orig : frames;                  // reported per ORIGINAL utterance
     }
     if (rc != OE_OK) {
         delete p;

@@ -45,6 +45,47 @@ def test_config5_twenty_minute_stream_in_16_frame_windows(fe):
     assert np.abs(parts[16 * 3000:16 * 3001].cpu().numpy() - ref).max() < 1e-3
 
 
+def test_window_coalescing_is_invisible(monkeypatch):
+    """Consecutive windows that continue each other in the waveform buffer and in the output are run as one long
+    utterance (full 32-frame tiles instead of half-filled ones): bitwise the same rows and per-window frame counts as with
+    OE_NO_COALESCE=1 (statistics to 1e-7); runs are only merged where they really are continuations, and never when something
+    per-utterance (normalisation, masks, padded rows) is asked for."""
+    from openeat_b200.frontend import Frontend
+    monkeypatch.setenv('OE_NO_COALESCE', '1')
+    fe_sep = Frontend(mel_bins=80, sample_rate=16000)
+    monkeypatch.delenv('OE_NO_COALESCE')
+    fe_co = Frontend(mel_bins=80, sample_rate=16000)
+    x = device_noise(2560 * 300 + 20000, 77)
+    # three streams of 100 / 150 / 49 windows, a stray window in between that is NOT a continuation, one too-short window
+    offs, lens = [], []
+    for base, count in ((0, 100), (2560 * 100 + 8, 150), (2560 * 251 + 4000, 49)):
+        offs += [base + 2560 * i for i in range(count)]
+        lens += [2800] * count
+    offs.insert(100, 64)
+    lens.insert(100, 4000)
+    offs.append(8)
+    lens.append(300)
+    offs, lens = np.array(offs, dtype=np.int64), np.array(lens, dtype=np.int32)
+    mean = torch.linspace(8.0, 12.0, 80, device='cuda')
+    istd = torch.linspace(0.4, 0.6, 80, device='cuda')
+    outs = []
+    for f in (fe_sep, fe_co):
+        st = torch.zeros(161, dtype=torch.float64, device='cuda')
+        n0 = f.launches
+        y, fr = f.fbank(x, offs, lens, layout='ragged', cmvn=(mean, istd), stats=st)
+        outs.append((y, fr, st, f.launches - n0))
+    assert np.array_equal(outs[0][1], outs[1][1]) and outs[0][1][100] == 23 and outs[0][1][-1] == 0
+    assert torch.equal(outs[0][0], outs[1][0])
+    # the statistics add per-tile fp32 partial sums: other tile boundaries, other roundings (1e-9 relative; the bar is 1e-4)
+    assert outs[0][2][160] == outs[1][2][160] and torch.allclose(outs[0][2], outs[1][2], rtol=1e-7, atol=0)
+    # per-utterance normalisation: windows must stay separate utterances (each one normalised on its own)
+    a, _ = fe_sep.fbank(x, offs[:50], lens[:50], layout='ragged', normalization=True)
+    b, _ = fe_co.fbank(x, offs[:50], lens[:50], layout='ragged', normalization=True)
+    assert torch.equal(a, b)
+    one, _ = fe_co.fbank(x, np.array([0]), np.array([2560 * 49 + 2800]), layout='ragged', normalization=True)
+    assert not torch.equal(b, one)
+
+
 def test_config3_librispeech_shape_sharded_stats_are_linear(fe):
     """Variable 1-35 s utterances, length-sorted dynamic batches (dataset.py:337-352), sharded over 8 'ranks':
     per-rank CMVN statistics add up (bitwise in the count, 1e-12 relative in the sums) to the single-rank pass,
