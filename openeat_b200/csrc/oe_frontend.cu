@@ -103,12 +103,9 @@ struct TileDescParams {
 
 // Expands the per-utterance metadata into one self-contained descriptor per 32-frame tile.
 constexpr int kDescSmemUtts = 4096;
-__global__ void oe_tile_desc_kernel(const TileDescParams P) {
+__device__ __forceinline__ void tile_desc_body(const TileDescParams& P, int32_t* sh_prefix) {
     // the binary search runs on a shared-memory copy of the prefix array (one coalesced read instead of
     // log2(B) dependent global loads per thread)
-    __shared__ int32_t sh_prefix[kDescSmemUtts + 1];
-    grid_dep_wait();                           // the metadata block (oe_fetch_kernel) has landed
-    grid_dep_launch();                         // the fbank kernel's table staging runs under this kernel
     const bool staged = P.B <= kDescSmemUtts;
     if (staged) {
         for (int i = threadIdx.x; i <= P.B; i += blockDim.x) sh_prefix[i] = P.tile_prefix[i];
@@ -138,6 +135,41 @@ __global__ void oe_tile_desc_kernel(const TileDescParams P) {
     d.out_start = P.out_row[b] + t0;
     d.pad = 0;
     P.tiles[tile] = d;
+}
+
+__global__ void oe_tile_desc_kernel(const TileDescParams P) {
+    __shared__ int32_t sh_prefix[kDescSmemUtts + 1];
+    grid_dep_wait();                           // the metadata block (oe_fetch_kernel) has landed
+    grid_dep_launch();                         // the fbank kernel's table staging runs under this kernel
+    tile_desc_body(P, sh_prefix);
+}
+
+// Small batches: the whole metadata block travels INSIDE the kernel parameters (it is a few hundred bytes for a batch of
+// 16 utterances), this kernel stores it into the workspace for the kernels behind it and builds the descriptors straight
+// from the parameter bank -- no oe_fetch_kernel, one latency-bound launch less in front of a 10 us fbank kernel.
+constexpr int kInlineMeta = 3072;
+struct TileDescInlineParams {
+    TileDescParams p;            // array pointers = byte offsets into `meta`
+    uint4* ws_meta;              // workspace copy for the fbank / completion kernels
+    int meta_bytes;
+    __align__(16) unsigned char meta[kInlineMeta];
+};
+__global__ void oe_tile_desc_inline_kernel(const __grid_constant__ TileDescInlineParams Q) {
+    __shared__ int32_t sh_prefix[kDescSmemUtts + 1];
+    grid_dep_launch();
+    const int n16 = (Q.meta_bytes + 15) / 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        Q.ws_meta[i] = reinterpret_cast<const uint4*>(Q.meta)[i];
+    TileDescParams P = Q.p;
+    const unsigned char* const m = Q.meta;
+    P.tile_prefix = reinterpret_cast<const int32_t*>(m + reinterpret_cast<uintptr_t>(Q.p.tile_prefix));
+    P.wav_off = reinterpret_cast<const int64_t*>(m + reinterpret_cast<uintptr_t>(Q.p.wav_off));
+    P.wav_len = reinterpret_cast<const int32_t*>(m + reinterpret_cast<uintptr_t>(Q.p.wav_len));
+    P.n_frames = reinterpret_cast<const int32_t*>(m + reinterpret_cast<uintptr_t>(Q.p.n_frames));
+    P.n_rows = reinterpret_cast<const int32_t*>(m + reinterpret_cast<uintptr_t>(Q.p.n_rows));
+    P.out_row = reinterpret_cast<const int64_t*>(m + reinterpret_cast<uintptr_t>(Q.p.out_row));
+    P.rs_mode = reinterpret_cast<const int32_t*>(m + reinterpret_cast<uintptr_t>(Q.p.rs_mode));
+    tile_desc_body(P, sh_prefix);
 }
 
 // Small host -> device transfers WITHOUT the copy engine: the source is pinned host memory mapped into the device's
@@ -969,6 +1001,7 @@ struct oe_frontend {
     bool mel_baked;                // ... and exactly torchaudio's weights (oe_mel80.h) -> gen-2 kernel, weights as FFMA immediates
     bool force_v1;                 // OE_FBANK_V1=1: first-generation kernel (A/B timing only)
     int fin2_parts;                // OE_FIN2_PARTS=n: blocks per utterance of oe_finalize2_kernel (tuning only; 0 = automatic)
+    bool no_inline_meta;           // OE_NO_INLINE_META=1: small batches send their metadata through oe_fetch_kernel too (A/B timing only)
     bool no_coalesce;              // OE_NO_COALESCE=1: consecutive windows of one recording stay separate utterances (A/B timing only)
     bool no_inplace_sub;           // OE_NO_INPLACE_SUB=1: spec_sub batches keep the ragged scratch + statistics kernel + out-of-place finalize (A/B timing only)
     bool no_inplace;               // OE_NO_INPLACE=1: raw scratch + statistics kernel + out-of-place finalize behind the gen-2 kernel (A/B timing only)
@@ -1341,6 +1374,8 @@ int oe_frontend_create(const oe_config* cfg, const float* window, const float* m
         fe->fin2_parts = fp_ ? atoi(fp_) : 0;
         const char* nf = getenv("OE_NO_INPLACE");
         fe->no_inplace = nf && nf[0] == '1';
+        const char* ni = getenv("OE_NO_INLINE_META");
+        fe->no_inline_meta = ni && ni[0] == '1';
         const char* nz = getenv("OE_NO_COALESCE");
         fe->no_coalesce = nz && nz[0] == '1';
         const char* ns = getenv("OE_NO_INPLACE_SUB");
@@ -1436,7 +1471,7 @@ static bool coalesce_windows(const oe_frontend* fe, const oe_batch* bt, Coalesce
     const int B = bt->batch, shift = fe->cfg.frame_shift;
     c.frames_orig.resize(B);
     for (int b = 0; b < B; ++b) {
-        if (bt->wav_lens[b] < 0) return false;                          // reported by plan()
+        if (bt->wav_lens[b] < 0 || bt->wav_offsets[b] < 0 || (bt->wav_offsets[b] & 7)) return false;    // plan() reports these on the caller's batch
         c.frames_orig[b] = oe_num_frames(fe, bt->wav_lens[b]);
         if (bt->out_nrows && bt->out_nrows[b] != c.frames_orig[b]) return false;
     }
@@ -1705,7 +1740,10 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         hm = fe->h_meta[hslot];
     }
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
-    OE_CUDA(fetch_small(fe, hslot, ws, M.meta_bytes, stream));
+    // small batches: the metadata rides in the descriptor kernel's parameters (oe_tile_desc_inline_kernel)
+    const bool inline_meta = M.meta_bytes <= (size_t)oe::kInlineMeta && M.total_tiles > 0 && !fe->no_inline_meta;
+    if (inline_meta) OE_CUDA(cudaEventRecord(fe->h_meta_ev[hslot], stream));      // the ring slot is free again at once
+    else OE_CUDA(fetch_small(fe, hslot, ws, M.meta_bytes, stream));
 
     const int64_t pitch = bt->out_pitch ? bt->out_pitch : F;
     oe::FbankParams P;
@@ -1781,7 +1819,25 @@ static int launch_batch_impl(oe_frontend* fe, const Meta& M, const LaunchInfo& L
         T.stat_acc = P.stat_acc;
         T.n_acc = 2 * F;
         ++fe->launches;
-        OE_CUDA(launch_dep(oe::oe_tile_desc_kernel, dim3((M.total_tiles + 127) / 128), dim3(128), 0, stream, T));
+        if (inline_meta) {
+            oe::TileDescInlineParams Q;
+            Q.p = T;
+            auto rel = [&](const void* dptr) { return reinterpret_cast<uintptr_t>(dptr) - reinterpret_cast<uintptr_t>(ws); };
+            Q.p.tile_prefix = reinterpret_cast<const int32_t*>(rel(T.tile_prefix));
+            Q.p.wav_off = reinterpret_cast<const int64_t*>(rel(T.wav_off));
+            Q.p.wav_len = reinterpret_cast<const int32_t*>(rel(T.wav_len));
+            Q.p.n_frames = reinterpret_cast<const int32_t*>(rel(T.n_frames));
+            Q.p.n_rows = reinterpret_cast<const int32_t*>(rel(T.n_rows));
+            Q.p.out_row = reinterpret_cast<const int64_t*>(rel(T.out_row));
+            Q.p.rs_mode = reinterpret_cast<const int32_t*>(rel(T.rs_mode));
+            Q.ws_meta = reinterpret_cast<uint4*>(ws);
+            Q.meta_bytes = (int)M.meta_bytes;
+            memcpy(Q.meta, hm, M.meta_bytes);
+            // plain stream order (like oe_fetch_kernel): the workspace may still be read by the previous call's kernels
+            oe::oe_tile_desc_inline_kernel<<<dim3((M.total_tiles + 127) / 128), dim3(128), 0, stream>>>(Q);
+        } else {
+            OE_CUDA(launch_dep(oe::oe_tile_desc_kernel, dim3((M.total_tiles + 127) / 128), dim3(128), 0, stream, T));
+        }
         OE_CUDA(cudaGetLastError());
     }
     int n_stat_partials = 0;
