@@ -223,12 +223,13 @@ int oe_resample(oe_frontend* fe, const oe_resample_batch* batch, const void* d_i
  *   paths[i]            file name; starts / ends: seconds of a segmented entry ("path,start,end", dataset.py:56-70:
  *                       frame_offset = int(start * sr), num_frames = int(end * sr) - frame_offset), starts[i] < 0
  *                       (or NULL arrays) = the whole file
- *   status[i]           OE_OK or an error code; oe_ingest_error(g, i) names the reason ("...: FLAC is not supported
+ *   status[i]           OE_OK or an error code; oe_ingest_error(g, i) names the reason ("...: 24-bit FLAC
  *                       ...", "...: 24-bit samples ...", "...: No such file or directory").  Per-utterance failures do
  *                       not fail the call: the caller prints the message and drops the utterance, the reference's
  *                       convention (dataset.py:108-111).
- * Only 16-bit integer PCM RIFF/WAVE is decoded (incl. WAVE_FORMAT_EXTENSIBLE); anything libsox reads beyond that
- * (FLAC, 24-bit, float) is reported, not silently dropped. */
+ * 16-bit integer PCM RIFF/WAVE (incl. WAVE_FORMAT_EXTENSIBLE) is copied, 16-bit FLAC (the LibriSpeech corpus) is decoded
+ * by the reader thread that owns the file (oe_flac_* below); anything libsox reads beyond that (24-bit, float, MP3) is
+ * reported, not silently dropped.  OE_FLAC_VERIFY_MD5=1 additionally checks every stream's MD5 signature. */
 typedef struct oe_ingest oe_ingest; /* opaque */
 int oe_ingest_create(int32_t threads, oe_ingest** out);      /* threads <= 0: one per hardware thread */
 int oe_ingest_destroy(oe_ingest* g);
@@ -258,6 +259,20 @@ int oe_ingest_job_release(oe_ingest_job* job);
  * over PCIe.  Blocking; do not call while ingest jobs are pending on the same handle (use a handle of its own). */
 int oe_host_pad_rows(oe_ingest* g, const float* src, const int32_t* frames, int32_t B, int32_t tmax, int32_t F,
                      const float* pad_row, float* dst);
+
+/* ---- FLAC streams (host code, no CUDA) ---------------------------------------------------------------------------
+ * Replaces torchaudio.load's libsox / libFLAC decode for .flac entries (openeat/dataset/dataset.py:62-72; the
+ * LibriSpeech recipe's corpus).  Decoder written from RFC 9639; the frame header CRC-8 and the frame CRC-16 are always
+ * checked, the STREAMINFO MD5 signature when verify_md5 != 0.  The native ingest above accepts 16-bit FLAC files next to
+ * 16-bit PCM wav (one reader thread decodes one file); these two calls serve in-memory streams (shard-tar members) and
+ * other sample sizes.  `data` is the whole .flac file.
+ *   oe_flac_info    sample rate, channel count, bits per sample, samples per channel (counted by a decode pass when
+ *                   STREAMINFO does not announce it)
+ *   oe_flac_decode  samples [first, first + count) of `channel` as int32 (the stream's own integer scale), *decoded =
+ *                   samples per channel in the stream */
+int oe_flac_info(const void* data, int64_t size, int32_t* sample_rate, int32_t* channels, int32_t* bits, int64_t* total_samples);
+int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t first, int64_t count, int32_t* out,
+                   int32_t verify_md5, int64_t* decoded);
 
 /* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
  * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).

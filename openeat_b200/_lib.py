@@ -112,6 +112,9 @@ SYMBOLS = {
     'oe_ingest_job_release': (ctypes.c_int, [ctypes.c_void_p]),
     'oe_host_pad_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    'oe_flac_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i64p]),
+    'oe_flac_decode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_void_p, ctypes.c_int32, c_i64p]),
     'oe_plan_speeds': (ctypes.c_int, [c_u32p, ctypes.c_int32, ctypes.c_double, c_f64p, ctypes.c_int32, c_f64p, c_u8p,
                                       c_f64p]),
     'oe_plan_augment': (ctypes.c_int, [c_u32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
@@ -129,7 +132,7 @@ class FrontendError(RuntimeError):
 def build(force=False, verbose=False):
     """nvcc -> csrc/libopeneat_frontend.so (sm_100a), g++ -> csrc/liboe_emul.so (test tooling)."""
     src = os.path.join(CSRC, 'oe_frontend.cu')
-    deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_ingest.h'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
+    deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_ingest.h'), os.path.join(CSRC, 'oe_flac.h'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
             os.path.join(CSRC, 'oe_fbank2_kernel.cuh'), os.path.join(CSRC, 'oe_mel80.h'),
             os.path.join(CSRC, 'oe_rs_coefs.h'),
             os.path.join(os.path.dirname(CSRC), '..', 'include', 'openeat_frontend.h')]

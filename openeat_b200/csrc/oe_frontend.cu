@@ -2411,6 +2411,8 @@ int oe_ingest_create(int32_t threads, oe_ingest** out) {
     {
         const char* d = getenv("OE_INGEST_DIRECT");
         g->direct_read = d && d[0] == '1';
+        const char* v = getenv("OE_FLAC_VERIFY_MD5");
+        g->flac_verify_md5 = v && v[0] == '1';
     }
     *out = g;
     return OE_OK;
@@ -2497,7 +2499,43 @@ int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const doub
         const int64_t first = g->first[i], count = n_samples[i];
         std::string err;
         int16_t* const out = dst + offsets[i];
-        if (w.channels == 1 && g->direct_read) {                      // straight into the packed (pinned) buffer
+        if (w.flac) {
+            // the whole compressed file (a LibriSpeech utterance: ~0.3 MB) -> channel 0 of the segment as int32 -> int16
+            // through the bounce buffer into the packed buffer, all on this reader thread
+            static thread_local std::vector<unsigned char> file;
+            static thread_local std::vector<int32_t> pcm;
+            static thread_local std::vector<char> bounce(oe_ing::kBounceBytes);
+            struct stat st;
+            if (fstat(fd, &st) != 0) err = std::string(paths[i]) + ": " + strerror(errno);
+            if (err.empty()) {
+                file.resize((size_t)st.st_size);
+                int64_t done = 0;
+                while (done < st.st_size) {
+                    const ssize_t r = pread(fd, file.data() + done, (size_t)(st.st_size - done), done);
+                    if (r <= 0) break;
+                    done += r;
+                }
+                if (done != st.st_size) err = std::string(paths[i]) + ": short read";
+            }
+            if (err.empty()) {
+                pcm.resize((size_t)std::max<int64_t>(count, 1));
+                oe_flac::Info fi;
+                int64_t total = 0;
+                const std::string e = oe_flac::decode(file.data(), (int64_t)file.size(), 0, first, count, pcm.data(), g->flac_verify_md5, fi, &total);
+                if (!e.empty()) err = std::string(paths[i]) + ": " + e;
+                else if (total < first + count) err = std::string(paths[i]) + ": the stream is shorter than its STREAMINFO block announces";
+            }
+            if (err.empty()) {
+                char* const o8 = reinterpret_cast<char*>(out);
+                int16_t* const b16 = reinterpret_cast<int16_t*>(bounce.data());
+                const int64_t chunk = oe_ing::kBounceBytes / 2;
+                for (int64_t s0 = 0; s0 < count; s0 += chunk) {
+                    const int64_t m = std::min<int64_t>(chunk, count - s0);
+                    for (int64_t k = 0; k < m; ++k) b16[k] = (int16_t)pcm[(size_t)(s0 + k)];
+                    oe_ing::stream_copy(o8 + 2 * s0, bounce.data(), (size_t)(2 * m));
+                }
+            }
+        } else if (w.channels == 1 && g->direct_read) {               // straight into the packed (pinned) buffer
             int64_t done = 0;
             const int64_t bytes = 2 * count;
             while (done < bytes) {
@@ -2541,6 +2579,36 @@ int oe_ingest_read(oe_ingest* g, int32_t n, const char* const* paths, const doub
         }
     });
     ingest_close_all(g);
+    return OE_OK;
+}
+
+// ---- FLAC streams in memory (shard-tar members, other sample sizes: the Python mirror scales them like torchaudio) ----
+int oe_flac_info(const void* data, int64_t size, int32_t* sample_rate, int32_t* channels, int32_t* bits, int64_t* total_samples) {
+    if (!data || size <= 0) return fail(OE_ERR_INVALID, "null / empty FLAC buffer");
+    oe_flac::Info fi;
+    std::string err = oe_flac::parse_streaminfo(static_cast<const unsigned char*>(data), size, fi);
+    if (err.empty() && fi.total == 0) {
+        int64_t n = 0;
+        err = oe_flac::decode(static_cast<const unsigned char*>(data), size, 0, 0, 0, nullptr, false, fi, &n);
+        fi.total = n;
+    }
+    if (!err.empty()) return fail(OE_ERR_UNSUPPORTED, "FLAC: %s", err.c_str());
+    if (sample_rate) *sample_rate = fi.sample_rate;
+    if (channels) *channels = fi.channels;
+    if (bits) *bits = fi.bits;
+    if (total_samples) *total_samples = fi.total;
+    return OE_OK;
+}
+
+int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t first, int64_t count, int32_t* out,
+                   int32_t verify_md5, int64_t* decoded) {
+    if (!data || size <= 0 || first < 0 || count < 0 || (count > 0 && !out)) return fail(OE_ERR_INVALID, "bad FLAC decode arguments");
+    oe_flac::Info fi;
+    int64_t n = 0;
+    const std::string err = oe_flac::decode(static_cast<const unsigned char*>(data), size, channel, first, count, out, verify_md5 != 0, fi, &n);
+    if (!err.empty()) return fail(OE_ERR_UNSUPPORTED, "FLAC: %s", err.c_str());
+    if (first + count > n) return fail(OE_ERR_INVALID, "FLAC: samples [%lld, %lld) requested, the stream holds %lld", (long long)first, (long long)(first + count), (long long)n);
+    if (decoded) *decoded = n;
     return OE_OK;
 }
 

@@ -17,6 +17,8 @@
 #include <string>
 #include <thread>
 
+#include "oe_flac.h"
+
 namespace oe_ing {
 
 // Persistent pool: the workers sleep between calls (creating 2 x 32 threads per batch costs more than reading it).
@@ -116,6 +118,7 @@ inline void stream_copy(char* dst, const char* src, size_t n) {
 struct WavInfo {
     int sample_rate = 0, channels = 0, bits = 0;
     int64_t data_off = 0, frames = 0;        // byte offset of the PCM, frames in the file
+    bool flac = false;                       // FLAC stream: decoded by the reader thread (oe_flac.h) instead of copied
 };
 
 }  // namespace oe_ing
@@ -137,6 +140,7 @@ struct oe_ingest_job {
 struct oe_ingest {
     int threads;
     bool direct_read = false;               // OE_INGEST_DIRECT=1: pread straight into the destination (A/B timing only)
+    bool flac_verify_md5 = false;           // OE_FLAC_VERIFY_MD5=1: also check the STREAMINFO signature (CRCs are always checked)
     oe_ing::Pool* pool;
     std::vector<std::string> errors;        // per entry of the most recent probe / read
     // the probe keeps every file open with its parsed header: the read that follows neither re-opens nor re-parses
@@ -161,12 +165,39 @@ inline uint32_t rd16(const unsigned char* p) { return (uint32_t)p[0] | (uint32_t
 inline std::string parse_wav(int fd, const char* path, WavInfo& w) {
     unsigned char h[12];
     if (pread(fd, h, 12, 0) != 12) return std::string(path) + ": too short for a RIFF header";
-    if (memcmp(h, "fLaC", 4) == 0)
-        return std::string(path) + ": FLAC is not supported by the native ingest (16-bit PCM RIFF/WAVE only): decode it first (sox / ffmpeg) or pass decoded arrays";
-    if (memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0)
-        return std::string(path) + ": not a RIFF/WAVE file (the native ingest reads 16-bit PCM wav only)";
     struct stat st;
     if (fstat(fd, &st) != 0) return std::string(path) + ": " + strerror(errno);
+    if (memcmp(h, "fLaC", 4) == 0) {
+        // STREAMINFO is always the first metadata block (RFC 9639 section 8.1): 4 + 4 + 34 bytes hold everything the
+        // probe needs; a stream that does not announce its length is decoded once to count it
+        unsigned char head[42];
+        if (pread(fd, head, 42, 0) != 42) return std::string(path) + ": too short for a FLAC STREAMINFO block";
+        oe_flac::Info fi;
+        unsigned char one[42];
+        memcpy(one, head, 42);
+        one[4] |= 0x80;                                                  // parse the first block only
+        std::string err = oe_flac::parse_streaminfo(one, 42, fi);
+        if (!err.empty()) return std::string(path) + ": " + err;
+        if (fi.bits != 16)
+            return std::string(path) + ": " + std::to_string(fi.bits) + "-bit FLAC (the native ingest fills an int16 buffer: 16-bit streams only; read_wav decodes the others to fp32)";
+        if (fi.total == 0) {
+            std::vector<unsigned char> all((size_t)st.st_size);
+            if (pread(fd, all.data(), all.size(), 0) != (ssize_t)all.size()) return std::string(path) + ": short read";
+            int64_t n = 0;
+            err = oe_flac::decode(all.data(), (int64_t)all.size(), 0, 0, 0, nullptr, false, fi, &n);
+            if (!err.empty()) return std::string(path) + ": " + err;
+            fi.total = n;
+        }
+        w.flac = true;
+        w.sample_rate = fi.sample_rate;
+        w.channels = fi.channels;
+        w.bits = fi.bits;
+        w.frames = fi.total;
+        w.data_off = 0;
+        return "";
+    }
+    if (memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0)
+        return std::string(path) + ": not a RIFF/WAVE or FLAC file (the native ingest reads 16-bit PCM wav and 16-bit FLAC)";
     int64_t pos = 12;
     bool have_fmt = false;
     while (pos + 8 <= st.st_size) {

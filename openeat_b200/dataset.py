@@ -6,7 +6,8 @@ sequence per batch on the GPU instead of a per-utterance CPU loop.
 Differences a caller can observe (all deliberate):
   * tensors come back on the GPU by default (``output_device='cpu'`` restores the reference's CPU
     tensors); ``features`` are the same zero-padded (B, Tmax, F) fp32 tensor either way;
-  * wav decoding is built in for RIFF/WAVE files (integer PCM 8/16/24/32 bit, IEEE float; the reference needs libsox);
+  * audio decoding is built in: RIFF/WAVE files (integer PCM 8/16/24/32 bit, IEEE float) and FLAC streams (RFC 9639,
+    the LibriSpeech corpus; decoded natively by ``oe_flac_decode``) -- the reference needs libsox;
     an item's second field may also be an in-memory int16 / fp32 array or ``(array, sample_rate)``;
   * ``data_type != 'wav'`` reads binary Kaldi archives with the built-in ``openeat_b200.kaldi_io.read_mat``
     (the reference imports the third-party ``kaldi_io``); ``feature_dither`` draws its amplitude with the
@@ -33,9 +34,7 @@ def _riff_chunks(f):
     """(format tag, channels, sample rate, bits, data offset, data bytes) of a RIFF/WAVE file object."""
     head = f.read(12)
     if len(head) < 12 or head[:4] != b'RIFF' or head[8:12] != b'WAVE':
-        if head[:4] == b'fLaC':
-            raise ValueError('FLAC is not decoded here: convert to wav (sox / ffmpeg) or pass decoded arrays')
-        raise ValueError('not a RIFF/WAVE file')
+        raise ValueError('not a RIFF/WAVE or FLAC file')
     size = f.seek(0, 2)
     fmt = None
     pos = 12
@@ -59,7 +58,7 @@ def _riff_chunks(f):
 
 
 def read_wav(path, start=None, end=None):
-    """dataset.py:62-75 (``torchaudio.load`` then ``* (1 << 15)``) for RIFF/WAVE files: returns (samples of channel 0
+    """dataset.py:62-75 (``torchaudio.load`` then ``* (1 << 15)``) for RIFF/WAVE files and FLAC streams: returns (samples of channel 0
     on the int16 scale, sample_rate).  16-bit PCM comes back as int16 (the values the reference holds as fp32); 8-bit
     (unsigned), 24- and 32-bit PCM and IEEE float come back as float32 ``normalised * 32768`` with torchaudio's
     normalisation (``(s - 128) / 2^7``, ``s / 2^23``, ``s / 2^31``, float as is).  ``start`` / ``end`` are seconds
@@ -69,8 +68,39 @@ def read_wav(path, start=None, end=None):
         return decode_wav(f, start, end, path)
 
 
+def _decode_flac(data, start, end, name):
+    """A whole FLAC stream in memory -> (channel 0 on the int16 scale, sample_rate); the decoder is the library's
+    ``oe_flac_decode`` (csrc/oe_flac.h: frame CRCs always checked).  16-bit streams come back as int16, other sample
+    sizes as float32 ``s / 2^(bits-1) * 32768`` (torchaudio's normalisation followed by dataset.py:75)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    sr, nch, bits, total = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+    if lib.oe_flac_info(buf.ctypes.data, buf.size, ctypes.byref(sr), ctypes.byref(nch), ctypes.byref(bits), ctypes.byref(total)):
+        raise ValueError('%s: %s' % (name, lib.oe_last_error().decode()))
+    sr, bits, total = sr.value, bits.value, total.value
+    first, count = 0, total
+    if start is not None:
+        s = int(float(start) * sr)
+        e = int(float(end) * sr)
+        first = min(max(s, 0), total)
+        count = max(0, min(e - s, total - first))
+    out = np.empty(max(count, 1), dtype=np.int32)
+    if lib.oe_flac_decode(buf.ctypes.data, buf.size, 0, first, count, out.ctypes.data, 0, None):
+        raise ValueError('%s: %s' % (name, lib.oe_last_error().decode()))
+    out = out[:count]
+    if bits == 16:
+        return out.astype(np.int16), sr
+    return out.astype(np.float32) / np.float32(2.0 ** (bits - 1)) * np.float32(1 << 15), sr
+
+
 def decode_wav(f, start=None, end=None, name='<wav>'):
     """``read_wav`` on an open (seekable) binary file object, e.g. a member of a shard tar."""
+    if f.read(4) == b'fLaC':
+        f.seek(0)
+        return _decode_flac(f.read(), start, end, name)
+    f.seek(0)
     try:
         tag, nch, sr, bits, off, nbytes = _riff_chunks(f)
     except (ValueError, struct.error) as e:
@@ -109,6 +139,9 @@ def _decodable(entry):
     """True when ``read_wav`` can decode the file of a ``path[,start,end]`` entry."""
     try:
         with open(entry.strip().split(',')[0], 'rb') as f:
+            if f.read(4) == b'fLaC':
+                return True
+            f.seek(0)
             tag, nch, _, bits, _, _ = _riff_chunks(f)
         return nch >= 1 and ((tag == 1 and bits in (8, 16, 24, 32)) or (tag == 3 and bits in (32, 64)))
     except (OSError, ValueError, struct.error):

@@ -238,8 +238,8 @@ def test_tar_shard_reader(tmp_path):
 def test_native_ingest_matches_the_stdlib_reader(tmp_path):
     """oe_ingest_probe / oe_ingest_read (dataset.py:55-75 natively): mono and stereo (channel 0) 16-bit PCM, segmented
     entries 'path,start,end' incl. one that runs past the end of the file, 8-sample aligned packing -- equal to the
-    stdlib-`wave` reader sample for sample; formats libsox would read but this ingest does not (32-bit, FLAC) and a
-    missing file are reported with an explicit reason and marked not loaded (never silently dropped)."""
+    stdlib-`wave` reader sample for sample; what this ingest cannot fill an int16 buffer from (32-bit samples, a damaged
+    FLAC stream; sound FLAC files: tests/test_flac.py) and a missing file are reported with an explicit reason and marked not loaded (never silently dropped)."""
     import wave
     from openeat_b200.dataset import read_wav
     from openeat_b200.ingest import NativeIngest
@@ -273,7 +273,7 @@ def test_native_ingest_matches_the_stdlib_reader(tmp_path):
             ref, _ = read_wav(p + '/a.wav', s, e)
             assert np.array_equal(x[offs[i]:offs[i] + lens[i]], ref)
     errs = [ing.lib.oe_ingest_error(ing.handle, i).decode() for i in range(7)]
-    assert '32-bit' in errs[3] and 'FLAC' in errs[4] and 'No such file' in errs[5] and errs[0] == ''
+    assert '32-bit' in errs[3] and 'STREAMINFO' in errs[4] and 'No such file' in errs[5] and errs[0] == ''
 
 
 def test_audio_dataset_parses_kaldi_feature_lists(tmp_path):

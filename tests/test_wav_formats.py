@@ -95,7 +95,7 @@ def test_read_wav_rejects_what_it_cannot_decode(tmp_path):
     p = str(tmp_path / 'x.flac')
     with open(p, 'wb') as f:
         f.write(b'fLaC' + bytes(64))
-    with pytest.raises(ValueError, match='FLAC'):
+    with pytest.raises(ValueError, match='STREAMINFO'):           # a damaged FLAC stream (sound ones: tests/test_flac.py)
         read_wav(p)
     q = str(tmp_path / 'adpcm.wav')
     _write(q, 2, 4, 1, 8000, np.zeros((8, 1)), junk=False)       # MS ADPCM tag
