@@ -274,6 +274,48 @@ int oe_flac_info(const void* data, int64_t size, int32_t* sample_rate, int32_t* 
 int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t first, int64_t count, int32_t* out,
                    int32_t verify_md5, int64_t* decoded);
 
+/* ---- FLAC decoded on the GPU -----------------------------------------------------------------------------------------
+ * For FLAC lists the compressed files cross PCIe (about half the bytes of their PCM for speech) and the GPU decodes
+ * them: one thread per audio frame, straight into the packed int16 buffer oe_fbank_batch reads (oe_flac_gpu.cuh).
+ *   oe_flac_pack          host: reads n files into `comp` (pinned; each file 16-byte aligned), walks every stream from
+ *                         frame header to frame header and writes one oe_flac_frame per frame that overlaps the entry's
+ *                         segment (starts / ends as for oe_ingest_probe), lays the utterances out at 8-sample aligned
+ *                         pcm_offsets.  status[i] != OE_OK: oe_ingest_error(g, i) says why; OE_ERR_UNSUPPORTED marks
+ *                         streams the GPU decoder does not take (more than one channel, more than 16 bits, no announced
+ *                         length) -- send those through oe_ingest_read / oe_flac_decode.  Returns OE_ERR_WORKSPACE with
+ *                         *comp_bytes / *n_frames set to what is needed when a buffer is too small (comp needs 16 spare
+ *                         bytes behind *comp_bytes).
+ *   oe_flac_decode_batch  device: decodes n_frames frames of d_comp into d_pcm; d_errors[utt] (caller-zeroed int32 per
+ *                         entry) collects OE_FLAC_ERR_* bits: the frame must end where the host found the next header and
+ *                         (verify_crc) match its CRC-16.  Stream-ordered, one launch.
+ *   oe_flac_encode        host: 16-bit mono PCM -> a FLAC stream (fixed predictors, partitioned Rice coding, MD5
+ *                         signature): writes the fixtures and the bench's corpus; returns OE_ERR_WORKSPACE with *bytes set
+ *                         when `capacity` is too small. */
+typedef struct oe_flac_frame {
+    int64_t comp_off;      /* byte offset of the frame's sync code in the compressed buffer */
+    int64_t out_off;       /* sample index in the PCM buffer of the first sample this frame contributes */
+    int32_t frame_bytes;   /* header + subframe + CRC-16; <= 0: unknown (last frame), -frame_bytes = bytes available */
+    int32_t hdr_bytes;     /* frame header incl. its CRC-8 */
+    int32_t block;         /* samples in the frame */
+    int32_t bps;           /* bits per sample */
+    int32_t skip, take;    /* samples [skip, skip + take) of the frame belong to the entry's segment */
+    int32_t utt;           /* entry index: errors are collected per entry */
+    int32_t reserved;
+} oe_flac_frame;
+#define OE_FLAC_ERR_END 1      /* the frame did not end where the next one starts */
+#define OE_FLAC_ERR_CRC 2      /* CRC-16 mismatch */
+#define OE_FLAC_ERR_HOST 4     /* legal FLAC outside the GPU decoder's range (predictor order > 12): use the host decoder */
+#define OE_FLAC_ERR_FORMAT 8   /* reserved codes / forbidden values */
+#define OE_FLAC_ERR_OVERRUN 16 /* the bit stream ran past the end of the buffer */
+int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                 void* comp, int64_t comp_capacity, oe_flac_frame* frames, int64_t frames_capacity,
+                 int64_t* comp_offsets, int64_t* pcm_offsets, int32_t* n_samples, int32_t* sample_rates, int32_t* status,
+                 int64_t* comp_bytes, int64_t* n_frames, int64_t* total_samples);
+int oe_flac_decode_batch(const void* d_comp, int64_t comp_bytes, const oe_flac_frame* d_frames, int64_t n_frames,
+                         int16_t* d_pcm, int32_t* d_errors, int32_t verify_crc, oe_stream stream);
+int oe_flac_encode(const int16_t* pcm, int64_t n, int32_t sample_rate, int32_t block, int32_t partition_order,
+                   void* out, int64_t capacity, int64_t* bytes);
+
 /* ---- host-side planning (no CUDA): the reference's random decisions, in its call order ----------
  * The reference draws every augmentation index from Python's global `random` module (Mersenne Twister).
  * These helpers continue that very generator natively: `mt_state` is `random.getstate()[1]` (624 state

@@ -15,6 +15,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '--shared', '-Xcompiler', '-fPIC', '-diag-suppress', '177,550']
 
 OE_OK = 0
+OE_ERR_INVALID, OE_ERR_UNSUPPORTED, OE_ERR_CUDA, OE_ERR_WORKSPACE = 1, 2, 3, 4
 OE_WAV_I16, OE_WAV_F32, OE_FEATS_F32 = 0, 1, 2
 OE_NORM_NONE, OE_NORM_PER_UTT = 0, 1
 
@@ -115,6 +116,13 @@ SYMBOLS = {
     'oe_flac_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i64p]),
     'oe_flac_decode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_int32, c_i64p]),
+    'oe_flac_pack': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), c_f64p, c_f64p,
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_i64p, c_i64p, c_i32p, c_i32p,
+                                    c_i32p, c_i64p, c_i64p, c_i64p]),
+    'oe_flac_decode_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    'oe_flac_encode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_void_p, ctypes.c_int64, c_i64p]),
     'oe_plan_speeds': (ctypes.c_int, [c_u32p, ctypes.c_int32, ctypes.c_double, c_f64p, ctypes.c_int32, c_f64p, c_u8p,
                                       c_f64p]),
     'oe_plan_augment': (ctypes.c_int, [c_u32p, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
@@ -132,7 +140,7 @@ class FrontendError(RuntimeError):
 def build(force=False, verbose=False):
     """nvcc -> csrc/libopeneat_frontend.so (sm_100a), g++ -> csrc/liboe_emul.so (test tooling)."""
     src = os.path.join(CSRC, 'oe_frontend.cu')
-    deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_ingest.h'), os.path.join(CSRC, 'oe_flac.h'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
+    deps = [src, os.path.join(CSRC, 'oe_fft.h'), os.path.join(CSRC, 'oe_ingest.h'), os.path.join(CSRC, 'oe_flac.h'), os.path.join(CSRC, 'oe_flac_gpu.cuh'), os.path.join(CSRC, 'oe_fbank_kernel.cuh'),
             os.path.join(CSRC, 'oe_fbank2_kernel.cuh'), os.path.join(CSRC, 'oe_mel80.h'),
             os.path.join(CSRC, 'oe_rs_coefs.h'),
             os.path.join(os.path.dirname(CSRC), '..', 'include', 'openeat_frontend.h')]
@@ -143,7 +151,7 @@ def build(force=False, verbose=False):
         subprocess.run(cmd, check=True, cwd=CSRC)
     emul = os.path.join(CSRC, 'oe_emul.cpp')
     if force or not os.path.exists(EMUL_PATH) or os.path.getmtime(emul) > os.path.getmtime(EMUL_PATH) \
-            or os.path.getmtime(deps[1]) > os.path.getmtime(EMUL_PATH):
+            or any(os.path.getmtime(os.path.join(CSRC, d)) > os.path.getmtime(EMUL_PATH) for d in ('oe_fft.h', 'oe_flac_gpu.cuh')):
         subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', EMUL_PATH, emul],
                        check=True, cwd=CSRC)
     return LIB_PATH

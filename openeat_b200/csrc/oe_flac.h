@@ -8,6 +8,8 @@
 #pragma once
 
 #include <cstdint>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -412,6 +414,243 @@ inline std::string decode(const unsigned char* d, int64_t size, int channel, int
     }
     if (decoded) *decoded = at;
     return "";
+}
+
+// ---- frame index for the GPU decoder (oe_flac_gpu.cuh): where every audio frame starts and ends -------------------
+// A frame does not announce its length (RFC 9639 section 9): a decoder learns it by decoding.  The host only needs the
+// boundaries, so it walks the stream from header to header: a header is accepted when its sync code, reserved bits,
+// blocking strategy, CRC-8 AND its coded frame / sample number (the predecessor's + 1 / + block size) all fit.  A false
+// positive inside compressed data needs ~2^-40 luck per byte; the GPU decoder still catches it, because each frame must
+// end exactly where the next one starts and carry a matching CRC-16.
+struct FrameHeader {
+    int block = 0, hdr_bytes = 0, ch_code = 0, bps = 0;
+    bool variable = false;
+    int64_t number = 0;                      // frame number (fixed block size) or first sample number (variable)
+};
+
+// Parses the header at p; returns false when p does not hold a valid header (no message: the scan probes candidates).
+inline bool parse_frame_header(const unsigned char* p, const unsigned char* end, const Info& info, FrameHeader& h) {
+    static const int kBlock[16] = {0, 192, 576, 1152, 2304, 4608, 0, 0, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768};
+    static const int kBps[8] = {0, 8, 12, -1, 16, 20, 24, 32};
+    if (end - p < 6 || p[0] != 0xFF || (p[1] & 0xFE) != 0xF8 || (p[3] & 1)) return false;
+    h.variable = p[1] & 1;
+    const int bs_code = p[2] >> 4, sr_code = p[2] & 15, bps_code = (p[3] >> 1) & 7;
+    h.ch_code = p[3] >> 4;
+    if (bs_code == 0 || sr_code == 15 || h.ch_code > 10) return false;
+    const unsigned char* q = p + 4;
+    int extra = 0;
+    while (extra < 8 && (q[0] & (0x80 >> extra))) ++extra;
+    if (extra == 1 || extra == 8) return false;
+    const int numlen = extra ? extra : 1;
+    if (end - q < numlen + 5) return false;
+    int64_t num = extra ? (q[0] & (0x7F >> extra)) : q[0];
+    for (int i = 1; i < numlen; ++i) {
+        if ((q[i] & 0xC0) != 0x80) return false;
+        num = num << 6 | (q[i] & 0x3F);
+    }
+    h.number = num;
+    q += numlen;
+    if (bs_code == 6) h.block = q[0] + 1, q += 1;
+    else if (bs_code == 7) h.block = (q[0] << 8 | q[1]) + 1, q += 2;
+    else h.block = kBlock[bs_code];
+    if (sr_code == 12) q += 1;
+    else if (sr_code == 13 || sr_code == 14) q += 2;
+    if (q >= end || crc8(p, (size_t)(q - p)) != q[0]) return false;
+    h.hdr_bytes = (int)(q + 1 - p);
+    h.bps = bps_code == 0 ? info.bits : kBps[bps_code];
+    return h.bps > 0;
+}
+
+struct FrameSpan {
+    int64_t off = 0, bytes = 0, first_sample = 0;   // byte offset in the stream, frame length incl. CRC-16 (<= 0: unknown,
+    FrameHeader h;                                  // -bytes = what is left of the stream), first sample it holds
+};
+
+// Walks the whole stream; returns "" or the reason.  The last frame's length is only bounded by the end of the stream
+// (trailing tags are legal), so it is reported as -(bytes left).
+inline std::string scan_frames(const unsigned char* d, int64_t size, const Info& info, std::vector<FrameSpan>& spans) {
+    spans.clear();
+    const unsigned char* const end = d + size;
+    const unsigned char* p = d + info.audio_off;
+    int64_t at = 0, index = 0;
+    FrameHeader h;
+    if (p >= end) return "";
+    if (!parse_frame_header(p, end, info, h)) return "lost frame sync at byte " + std::to_string(p - d);
+    for (;;) {
+        FrameSpan s;
+        s.off = p - d;
+        s.first_sample = at;
+        s.h = h;
+        // next header: first candidate behind this frame's smallest possible body that parses and continues the numbering
+        const unsigned char* q = p + h.hdr_bytes + 2;
+        FrameHeader nh;
+        bool found = false;
+        while (q < end) {
+            q = static_cast<const unsigned char*>(memchr(q, 0xFF, (size_t)(end - q)));
+            if (!q) break;
+            if (parse_frame_header(q, end, info, nh) && nh.variable == h.variable &&
+                nh.number == h.number + (h.variable ? h.block : 1)) {
+                found = true;
+                break;
+            }
+            ++q;
+        }
+        at += h.block;
+        ++index;
+        if (!found) {
+            s.bytes = -(int64_t)(end - p);
+            spans.push_back(s);
+            break;
+        }
+        s.bytes = q - p;
+        spans.push_back(s);
+        p = q;
+        h = nh;
+    }
+    return "";
+}
+
+// ---- encoder (fixed predictors, partitioned Rice coding; mono / 16 bit) ---------------------------------------------
+// Writes the streams the bench's FLAC legs and the tests read -- there is no FLAC encoder in the image.  Per frame: the
+// fixed predictor (order 0-4) with the smallest sum of |residual|, partition order `porder` (lowered until it divides the
+// block), per partition the Rice parameter floor(log2(mean folded residual)); STREAMINFO carries the MD5 signature.
+class BitWriter {
+  public:
+    std::vector<unsigned char>& out;
+    uint64_t acc = 0;
+    int fill = 0;
+    explicit BitWriter(std::vector<unsigned char>& o) : out(o) {}
+    inline void u(uint64_t v, int n) {       // n <= 32
+        if (n == 0) return;
+        acc = acc << n | (v & ((n == 64) ? ~0ull : ((1ull << n) - 1)));
+        fill += n;
+        while (fill >= 8) {
+            out.push_back((unsigned char)(acc >> (fill - 8)));
+            fill -= 8;
+        }
+    }
+    inline void unary(uint32_t q) {
+        while (q >= 32) u(0, 32), q -= 32;
+        u(1, (int)q + 1);
+    }
+    inline void align() {
+        if (fill) u(0, 8 - fill);
+    }
+};
+
+inline void encode(const int16_t* pcm, int64_t n, int sample_rate, int block, int porder, std::vector<unsigned char>& out) {
+    out.clear();
+    const unsigned char magic[4] = {'f', 'L', 'a', 'C'};
+    out.insert(out.end(), magic, magic + 4);
+    out.push_back(0x80);
+    out.push_back(0), out.push_back(0), out.push_back(34);
+    {
+        BitWriter w(out);
+        const uint64_t bs = (uint64_t)(n > block ? block : std::max<int64_t>(16, n));   // both bounds exclude a shorter last block
+        w.u(bs, 16);
+        w.u(bs, 16);
+        w.u(0, 24), w.u(0, 24);
+        w.u((uint64_t)sample_rate, 20);
+        w.u(0, 3);
+        w.u(15, 5);
+        w.u((uint64_t)(n >> 32), 4), w.u((uint64_t)(n & 0xFFFFFFFFu), 32);
+        Md5 md5;
+        md5.update(reinterpret_cast<const unsigned char*>(pcm), (size_t)n * 2);     // little-endian host
+        unsigned char sig[16];
+        md5.finish(sig);
+        for (int i = 0; i < 16; ++i) w.u(sig[i], 8);
+    }
+    std::vector<int32_t> res((size_t)block);
+    std::vector<unsigned char> frame;
+    int64_t index = 0;
+    for (int64_t at = 0; at < n; at += block, ++index) {
+        const int m = (int)std::min<int64_t>(block, n - at);
+        const int16_t* s = pcm + at;
+        frame.clear();
+        BitWriter w(frame);
+        w.u(0xFFF8, 16);
+        w.u(m <= 256 ? 6 : 7, 4);
+        w.u(0, 4);
+        w.u(0, 4);
+        w.u(4, 3);
+        w.u(0, 1);
+        {                                                                            // coded frame number
+            const uint64_t v = (uint64_t)index;
+            if (v < 0x80) w.u(v, 8);
+            else {
+                int len = 2;
+                while (len < 7 && v >= (1ull << (5 * len + 1))) ++len;
+                w.u((0xFF00u >> len & 0xFF) | (unsigned)(v >> (6 * (len - 1))), 8);
+                for (int i = len - 2; i >= 0; --i) w.u(0x80 | ((v >> (6 * i)) & 0x3F), 8);
+            }
+        }
+        if (m <= 256) w.u((uint64_t)m - 1, 8);
+        else w.u((uint64_t)m - 1, 16);
+        w.u(crc8(frame.data(), frame.size()), 8);
+        // predictor choice
+        int64_t cost[5] = {0, 0, 0, 0, 0};
+        for (int i = 4; i < m; ++i) {
+            const int64_t a = s[i], b = s[i - 1], c = s[i - 2], d = s[i - 3], e = s[i - 4];
+            cost[0] += std::llabs(a);
+            cost[1] += std::llabs(a - b);
+            cost[2] += std::llabs(a - 2 * b + c);
+            cost[3] += std::llabs(a - 3 * b + 3 * c - d);
+            cost[4] += std::llabs(a - 4 * b + 6 * c - 4 * d + e);
+        }
+        int order = 0;
+        for (int o = 1; o <= 4; ++o)
+            if (cost[o] < cost[order]) order = o;
+        if (order >= m) order = 0;
+        bool constant = true;
+        for (int i = 1; i < m && constant; ++i) constant = s[i] == s[0];
+        if (constant) {
+            w.u(0, 8);
+            w.u((uint64_t)(uint16_t)s[0], 16);
+        } else {
+            w.u((uint64_t)(8 + order) << 1, 8);
+            for (int i = 0; i < order; ++i) w.u((uint64_t)(uint16_t)s[i], 16);
+            for (int i = order; i < m; ++i) {
+                const int64_t a = s[i], b = i >= 1 ? s[i - 1] : 0, c = i >= 2 ? s[i - 2] : 0, d = i >= 3 ? s[i - 3] : 0, e = i >= 4 ? s[i - 4] : 0;
+                int64_t r = a;
+                if (order == 1) r = a - b;
+                else if (order == 2) r = a - 2 * b + c;
+                else if (order == 3) r = a - 3 * b + 3 * c - d;
+                else if (order == 4) r = a - 4 * b + 6 * c - 4 * d + e;
+                res[(size_t)i] = (int32_t)r;
+            }
+            int po = porder;
+            while (po && (((m >> po) << po) != m || (m >> po) <= order)) --po;
+            w.u(1, 2);                                                               // 5-bit Rice parameters
+            w.u((uint64_t)po, 4);
+            int at_r = order;
+            for (int part = 0; part < (1 << po); ++part) {
+                const int cnt = (m >> po) - (part == 0 ? order : 0);
+                uint64_t sum = 0;
+                for (int i = 0; i < cnt; ++i) {
+                    const int32_t r = res[(size_t)(at_r + i)];
+                    sum += ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
+                }
+                int k = 0;
+                if (cnt > 0) {
+                    const uint64_t mean = sum / (uint64_t)cnt;
+                    while (k < 30 && (2ull << k) <= mean) ++k;
+                }
+                w.u((uint64_t)k, 5);
+                for (int i = 0; i < cnt; ++i) {
+                    const int32_t r = res[(size_t)(at_r + i)];
+                    const uint32_t z = ((uint32_t)r << 1) ^ (uint32_t)(r >> 31);
+                    w.unary(z >> k);
+                    w.u(z & ((1u << k) - 1), k);
+                }
+                at_r += cnt;
+            }
+        }
+        w.align();
+        const uint16_t c16 = crc16(frame.data(), frame.size());
+        frame.push_back((unsigned char)(c16 >> 8));
+        frame.push_back((unsigned char)(c16 & 0xFF));
+        out.insert(out.end(), frame.begin(), frame.end());
+    }
 }
 
 }  // namespace oe_flac

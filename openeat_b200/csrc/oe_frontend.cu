@@ -80,6 +80,7 @@ __constant__ float kInvRows[12] = {0.f, 1.f, 1.f / 2.f, 1.f / 3.f, 1.f / 4.f, 1.
 #include "oe_rs_coefs.h"
 #include "oe_fbank_kernel.cuh"
 #include "oe_fbank2_kernel.cuh"
+#include "oe_flac_gpu.cuh"
 
 namespace oe {
 
@@ -2609,6 +2610,175 @@ int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t firs
     if (!err.empty()) return fail(OE_ERR_UNSUPPORTED, "FLAC: %s", err.c_str());
     if (first + count > n) return fail(OE_ERR_INVALID, "FLAC: samples [%lld, %lld) requested, the stream holds %lld", (long long)first, (long long)(first + count), (long long)n);
     if (decoded) *decoded = n;
+    return OE_OK;
+}
+
+// ---- FLAC decoded on the GPU: host-side packing (file bytes + frame index), the launch, and the fixture encoder ----
+int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends,
+                 void* comp, int64_t comp_capacity, oe_flac_frame* frames, int64_t frames_capacity,
+                 int64_t* comp_offsets, int64_t* pcm_offsets, int32_t* n_samples, int32_t* sample_rates, int32_t* status,
+                 int64_t* comp_bytes, int64_t* n_frames, int64_t* total_samples) {
+    if (!g || n < 0 || (n > 0 && (!paths || !comp_offsets || !pcm_offsets || !n_samples || !sample_rates || !status)) || !comp_bytes ||
+        !n_frames || !total_samples)
+        return fail(OE_ERR_INVALID, "null pointer");
+    ingest_close_all(g);
+    g->errors.assign(n, std::string());
+    g->fds.assign(n, -1);
+    g->first.assign(n, 0);
+    std::vector<int64_t> fsize((size_t)n, 0), fbound((size_t)n, 0);
+    std::vector<oe_flac::Info> infos((size_t)n);
+    // pass 1: open, STREAMINFO, segment
+    g->pool->run(n, [&](int i) {
+        n_samples[i] = sample_rates[i] = 0;
+        status[i] = OE_ERR_INVALID;
+        const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+        if (fd < 0) {
+            g->errors[i] = std::string(paths[i]) + ": " + strerror(errno);
+            return;
+        }
+        std::string err;
+        struct stat st;
+        unsigned char head[42];
+        oe_flac::Info& fi = infos[i];
+        if (fstat(fd, &st) != 0) err = strerror(errno);
+        else if (pread(fd, head, 42, 0) != 42 || memcmp(head, "fLaC", 4) != 0) err = "not a FLAC stream";
+        else {
+            head[4] |= 0x80;
+            err = oe_flac::parse_streaminfo(head, 42, fi);
+        }
+        int code = OE_ERR_INVALID;
+        if (err.empty()) {
+            code = OE_ERR_UNSUPPORTED;
+            if (fi.channels != 1) err = std::to_string(fi.channels) + " channels (the GPU decoder takes mono streams; the host decoder reads channel 0)";
+            else if (fi.bits > 16) err = std::to_string(fi.bits) + "-bit FLAC (the GPU decoder fills an int16 buffer)";
+            else if (fi.total == 0) err = "the stream does not announce its length (host decoder)";
+        }
+        int64_t first = 0, count = 0;
+        if (err.empty()) {
+            oe_ing::WavInfo w;
+            w.sample_rate = fi.sample_rate, w.channels = 1, w.bits = fi.bits, w.frames = fi.total;
+            const bool seg = starts && ends && !(starts[i] < 0.0);
+            oe_ing::segment(w, seg ? starts[i] : 0.0, seg ? ends[i] : 0.0, seg, first, count);
+            if (count > INT32_MAX) err = "more than 2^31 samples";
+        }
+        if (!err.empty()) {
+            close(fd);
+            g->errors[i] = std::string(paths[i]) + ": " + err;
+            status[i] = code;
+            return;
+        }
+        g->fds[i] = fd;
+        g->first[i] = first;
+        fsize[i] = st.st_size;
+        fbound[i] = fi.total / std::max(fi.min_block, 1) + 2;        // capacity planning only: checked again after the walk
+        n_samples[i] = (int32_t)count;
+        sample_rates[i] = fi.sample_rate;
+        status[i] = OE_OK;
+    });
+    int64_t cb = 0, fb = 0, total = 0;
+    for (int i = 0; i < n; ++i) {
+        comp_offsets[i] = cb;
+        cb += (fsize[i] + 15) / 16 * 16;
+        fb += fbound[i];
+        pcm_offsets[i] = total;
+        total += ((int64_t)n_samples[i] + 7) / 8 * 8;
+    }
+    *comp_bytes = cb;
+    *total_samples = total;
+    if (cb + 16 > comp_capacity || fb > frames_capacity || !comp || !frames) {
+        *n_frames = fb;
+        ingest_close_all(g);
+        return fail(OE_ERR_WORKSPACE, "compressed buffer / frame table too small: %lld + 16 bytes, %lld frames needed", (long long)cb, (long long)fb);
+    }
+    // pass 2: file bytes into the (pinned) buffer, frame index per file
+    std::vector<std::vector<oe_flac_frame>> per((size_t)n);
+    unsigned char* const cbase = static_cast<unsigned char*>(comp);
+    g->pool->run(n, [&](int i) {
+        const int fd = g->fds[i];
+        if (status[i] != OE_OK || fd < 0) return;
+        unsigned char* const d = cbase + comp_offsets[i];
+        int64_t done = 0;
+        while (done < fsize[i]) {
+            const ssize_t r = pread(fd, d + done, (size_t)(fsize[i] - done), done);
+            if (r <= 0) break;
+            done += r;
+        }
+        std::string err;
+        if (done != fsize[i]) err = "short read";
+        oe_flac::Info fi;
+        if (err.empty()) err = oe_flac::parse_streaminfo(d, fsize[i], fi);
+        std::vector<oe_flac::FrameSpan> spans;
+        if (err.empty()) err = oe_flac::scan_frames(d, fsize[i], fi, spans);
+        const int64_t first = g->first[i], last = first + n_samples[i];
+        int64_t covered = first;
+        if (err.empty()) {
+            for (const oe_flac::FrameSpan& s : spans) {
+                const int64_t a = std::max(first, s.first_sample), b = std::min(last, s.first_sample + s.h.block);
+                if (a >= b) continue;
+                if (s.h.ch_code != 0 || s.h.bps != fi.bits) {
+                    err = "channel layout / sample size changes inside the stream";
+                    break;
+                }
+                if (a != covered) break;
+                oe_flac_frame f;
+                f.comp_off = comp_offsets[i] + s.off;
+                f.out_off = pcm_offsets[i] + (a - first);
+                f.frame_bytes = (int32_t)s.bytes;
+                f.hdr_bytes = s.h.hdr_bytes;
+                f.block = s.h.block;
+                f.bps = s.h.bps;
+                f.skip = (int32_t)(a - s.first_sample);
+                f.take = (int32_t)(b - a);
+                f.utt = i;
+                f.reserved = 0;
+                per[i].push_back(f);
+                covered = b;
+            }
+            if (err.empty() && covered != last) err = "the frames hold fewer samples than STREAMINFO announces";
+            if (err.empty() && (int64_t)per[i].size() > fbound[i]) err = "more frames than STREAMINFO's minimum block size allows";
+        }
+        if (!err.empty()) {
+            g->errors[i] = std::string(paths[i]) + ": " + err;
+            status[i] = OE_ERR_INVALID;
+            n_samples[i] = 0;                                          // its slot in the PCM layout stays (unused)
+            per[i].clear();
+        }
+    });
+    ingest_close_all(g);
+    int64_t nf = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!per[i].empty()) memcpy(frames + nf, per[i].data(), per[i].size() * sizeof(oe_flac_frame));
+        nf += (int64_t)per[i].size();
+    }
+    memset(cbase + cb, 0, 16);
+    *n_frames = nf;
+    return OE_OK;
+}
+
+int oe_flac_decode_batch(const void* d_comp, int64_t comp_bytes, const oe_flac_frame* d_frames, int64_t n_frames,
+                         int16_t* d_pcm, int32_t* d_errors, int32_t verify_crc, oe_stream stream) {
+    if (n_frames < 0 || comp_bytes < 0) return fail(OE_ERR_INVALID, "negative size");
+    if (n_frames == 0) return OE_OK;
+    if (!d_comp || !d_frames || !d_pcm || !d_errors) return fail(OE_ERR_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(d_comp) & 15) || (comp_bytes & 15)) return fail(OE_ERR_INVALID, "d_comp and comp_bytes must be multiples of 16 (oe_flac_pack's layout)");
+    const int64_t blocks = (n_frames + 31) / 32;
+    if (blocks > INT32_MAX) return fail(OE_ERR_INVALID, "too many frames");
+    oe_flacgpu::oe_flac_decode_kernel<<<(unsigned)blocks, 32, 0, (cudaStream_t)stream>>>(
+        static_cast<const unsigned char*>(d_comp), comp_bytes + 16, d_frames, n_frames, d_pcm, d_errors, verify_crc);
+    OE_CUDA(cudaGetLastError());
+    return OE_OK;
+}
+
+int oe_flac_encode(const int16_t* pcm, int64_t n, int32_t sample_rate, int32_t block, int32_t partition_order, void* out,
+                   int64_t capacity, int64_t* bytes) {
+    if (n < 0 || (n > 0 && !pcm) || !bytes || sample_rate <= 0 || sample_rate >= (1 << 20) || block < 16 || block > 65535 ||
+        partition_order < 0 || partition_order > 8)
+        return fail(OE_ERR_INVALID, "bad FLAC encode arguments");
+    static thread_local std::vector<unsigned char> buf;
+    oe_flac::encode(pcm, n, sample_rate, block, partition_order, buf);
+    *bytes = (int64_t)buf.size();
+    if (!out || capacity < (int64_t)buf.size()) return fail(OE_ERR_WORKSPACE, "FLAC stream needs %lld bytes", (long long)buf.size());
+    memcpy(out, buf.data(), buf.size());
     return OE_OK;
 }
 

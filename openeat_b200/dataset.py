@@ -397,6 +397,23 @@ class audio_collate_func(object):
         if self.data_type != 'wav':                                  # dataset.py:190-191
             keys, xs, ys = _load_feature(batch)
             return self.collate_features(keys, xs, ys)
+        if (len(batch) and torch.cuda.is_available() and os.environ.get('OE_FLAC_GPU', '1') != '0'
+                and all(isinstance(x[1], str) and x[1].split(',')[0].strip().lower().endswith('.flac') for x in batch)):
+            # FLAC lists (the LibriSpeech recipe): the compressed files cross PCIe, the GPU decodes them (oe_flac_gpu.cuh);
+            # anything that decoder does not take (stereo, 24 bit, unreadable files) sends the batch to the host decoders below
+            from .ingest import default_flac_ingest
+            ing = default_flac_ingest()
+            keys = [x[0] for x in batch]
+            fb = ing.pack([x[1] for x in batch], keys, report=False)
+            if fb.loaded.all():
+                dev = fb.to_device(default_frontend(self.feature_extraction_conf['mel_bins']).device)
+                ev = torch.cuda.Event()
+                ev.record()
+                ing.release_after(fb.slot, ev)
+                lens = fb.drop_failed(fb.lens, fb.loaded, keys)
+                return self.collate_packed(dev, fb.offsets, lens, keys, [x[2] for x in batch], [x[3] for x in batch],
+                                           sample_rates=fb.rates, loaded=fb.loaded)
+            ing.release_after(fb.slot, None)
         if len(batch) and all(isinstance(x[1], str) for x in batch):
             # wav files: native ingest (headers + multi-threaded pread straight into a pinned buffer, no per-utterance Python)
             from .ingest import default_ingest
@@ -678,12 +695,16 @@ class PrefetchingCollator(object):
             return
         wav = item[0]
         with torch.cuda.stream(self.copy_stream):
-            dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
+            if hasattr(wav, 'to_device'):        # ingest.FlacBatch: compressed bytes cross PCIe, the decode kernel follows on this stream
+                dev = wav.to_device(self.device)
+            else:
+                dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
         if len(item) > 8 and item[8] is not None:
             item[8](ev)                          # the ingest ring slot is free once this copy has completed
         self._next = (dev, ev) + tuple(item[1:8])
+        self._next_flac = wav if hasattr(wav, 'to_device') else None
 
     def __iter__(self):
         return self
@@ -694,6 +715,10 @@ class PrefetchingCollator(object):
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
         dev.record_stream(cur)
+        if getattr(self, '_next_flac', None) is not None and len(extra) >= 2:
+            # streams that failed the GPU decoder's checks are dropped like any unreadable file (dataset.py:108-111); the
+            # batch was staged one step ahead, so its decode has normally finished by now
+            lens = self._next_flac.drop_failed(lens, extra[1], keys)
         self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
         self.collate._out_layout = 'ragged' if self.host_pad else 'padded'
         try:

@@ -199,3 +199,198 @@ def default_ingest():
     if 'g' not in _default:
         _default['g'] = NativeIngest()
     return _default['g']
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FLAC lists: compressed bytes over PCIe, decoded by the GPU (csrc/oe_flac_gpu.cuh)
+# ---------------------------------------------------------------------------------------------------------------------
+FRAME_BYTES = 48                                    # sizeof(oe_flac_frame), include/openeat_frontend.h
+FLAC_ERRORS = {1: 'a frame does not end where the next one starts', 2: 'frame CRC-16 mismatch',
+               4: 'predictor order above 12 (host decoder needed)', 8: 'reserved code in a subframe',
+               16: 'the bit stream runs past the end of the buffer'}
+
+
+class FlacBatch(object):
+    """One batch of FLAC files packed for the GPU decoder (``FlacGpuIngest.pack``): ``comp`` (pinned uint8: the files,
+    each 16-byte aligned) and ``frames`` (pinned uint8 holding ``n_frames`` ``oe_flac_frame`` records) cross PCIe instead
+    of the PCM; ``to_device`` enqueues the two copies and the decode kernel on the current stream and returns the packed
+    int16 PCM tensor ``collate_packed`` takes (utterance i at ``offsets[i]``, ``lens[i]`` samples)."""
+
+    def __init__(self, owner, slot, comp, frames, comp_bytes, n_frames, total, offsets, lens, rates, loaded, keys):
+        self.owner, self.slot = owner, slot
+        self.comp, self.frames = comp, frames
+        self.comp_bytes, self.n_frames, self.total = int(comp_bytes), int(n_frames), int(total)
+        self.offsets, self.lens, self.rates, self.loaded, self.keys = offsets, lens, rates, loaded, keys
+        self.errors = None                          # pinned int32 per entry, valid once `event` has completed
+        self.paths = None
+        self.event = None
+
+    is_cuda = False                                 # PrefetchingCollator: not a device tensor yet
+
+    @property
+    def h2d_bytes(self):
+        return self.comp_bytes + 16 + self.n_frames * FRAME_BYTES
+
+    def to_device(self, device, verify_crc=True):
+        lib = self.owner.lib
+        n = len(self.lens)
+        pcm = torch.empty(max(self.total, ALIGN), dtype=torch.int16, device=device)
+        if self.n_frames == 0:
+            return pcm
+        d_comp = self.comp[:self.comp_bytes + 16].to(device, non_blocking=True)
+        d_frames = self.frames[:self.n_frames * FRAME_BYTES].to(device, non_blocking=True)
+        d_err = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+        stream = torch.cuda.current_stream(device)
+        check(lib.oe_flac_decode_batch(ctypes.c_void_p(d_comp.data_ptr()), self.comp_bytes, ctypes.c_void_p(d_frames.data_ptr()),
+                                       self.n_frames, ctypes.c_void_p(pcm.data_ptr()), ctypes.c_void_p(d_err.data_ptr()),
+                                       1 if verify_crc else 0, ctypes.c_void_p(stream.cuda_stream)))
+        self.errors = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+        self.errors.copy_(d_err, non_blocking=True)
+        for t in (d_comp, d_frames, d_err):
+            t.record_stream(stream)
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+        self.owner._watch(self)
+        return pcm
+
+    def drop_failed(self, lens, loaded, keys=None):
+        """Waits for the decode; entries whose stream failed the kernel's checks are reported and dropped with the
+        reference's convention (print, ``logging.warning('read utterance ... error')``, dataset.py:108-111): their
+        ``lens`` become 0 and ``loaded`` False (both updated in place and returned as ``lens``)."""
+        if self.event is None:
+            return lens
+        self.event.synchronize()
+        bad = np.nonzero(self.errors.numpy()[:len(self.lens)])[0]
+        for i in bad:
+            print('%s: FLAC stream rejected by the GPU decoder: %s' % (
+                self.paths[i] if self.paths is not None else i, ', '.join(v for k, v in FLAC_ERRORS.items() if int(self.errors[i]) & k)))
+            logging.warning('read utterance {} error'.format(keys[i] if keys is not None else i))
+            lens[i] = 0
+            loaded[i] = False
+        self.errors[:len(self.lens)] = 0         # reported: the owner's deferred check stays quiet
+        return lens
+
+    def check(self):
+        """Waits for the decode and raises ``FrontendError`` naming every entry whose stream failed the GPU decoder's
+        checks (end-of-frame position, CRC-16) -- corrupted audio is never passed on silently."""
+        if self.event is None:
+            return
+        self.event.synchronize()
+        bad = np.nonzero(self.errors.numpy()[:len(self.lens)])[0]
+        if len(bad):
+            raise _lib.FrontendError('; '.join('%s: %s' % (self.keys[i] if self.keys is not None else i, ', '.join(
+                v for k, v in FLAC_ERRORS.items() if int(self.errors[i]) & k)) for i in bad))
+
+
+class FlacGpuIngest(NativeIngest):
+    """``pack(entries)`` -> ``FlacBatch``: the reader pool ``pread``s the FLAC files of a batch into one pinned buffer and
+    indexes their frames (``oe_flac_pack``); nothing is decoded on the host.  Entries the GPU decoder does not take
+    (stereo, 24-bit, streamed encodes without a length) are reported and dropped with the reference's convention
+    (dataset.py:108-111); decode them with ``NativeIngest`` / ``read_wav`` instead."""
+
+    def __init__(self, threads=0, ring=4):
+        super(FlacGpuIngest, self).__init__(threads, ring)
+        self._comp = [None] * len(self._ring)
+        self._frames = [None] * len(self._ring)
+        self._watched = []
+
+    def _watch(self, batch):
+        """Batches whose decode has finished are checked when the next one is launched (no extra synchronisation)."""
+        keep = []
+        for b in self._watched:
+            if b.event.query():
+                b.check()
+            else:
+                keep.append(b)
+        keep.append(batch)
+        self._watched = keep
+
+    def _buffers(self, comp_bytes, n_frames):
+        i = self._next
+        self._next = (i + 1) % len(self._ring)
+        if self._events[i] is not None:
+            self._events[i].synchronize()
+            self._events[i] = None
+
+        def grow(buf, need):
+            if buf is None or buf.numel() < need:
+                buf = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8)
+                if torch.cuda.is_available():
+                    buf = buf.pin_memory()
+            return buf
+        self._comp[i] = grow(self._comp[i], comp_bytes + 16)
+        self._frames[i] = grow(self._frames[i], n_frames * FRAME_BYTES)
+        return i, self._comp[i], self._frames[i]
+
+    def pack(self, entries, keys=None, report=True):
+        n = len(entries)
+        parts = [split_entry(e) for e in entries]
+        paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
+        starts = np.array([p[1] for p in parts], dtype=np.float64)
+        ends = np.array([p[2] for p in parts], dtype=np.float64)
+        coffs, offs = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        lens, rates, status = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        cb, nf, total = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        want = getattr(self, '_seen_flac', (1 << 20, 1 << 12))
+        for attempt in range(2):
+            slot, comp, frames = self._buffers(*want)
+            rc = self.lib.oe_flac_pack(self.handle, n, paths, starts.ctypes.data_as(c_f64p), ends.ctypes.data_as(c_f64p),
+                                       ctypes.c_void_p(comp.data_ptr()), comp.numel(), ctypes.c_void_p(frames.data_ptr()),
+                                       frames.numel() // FRAME_BYTES, coffs.ctypes.data_as(c_i64p), offs.ctypes.data_as(c_i64p),
+                                       lens.ctypes.data_as(c_i32p), rates.ctypes.data_as(c_i32p), status.ctypes.data_as(c_i32p),
+                                       ctypes.byref(cb), ctypes.byref(nf), ctypes.byref(total))
+            if rc != _lib.OE_ERR_WORKSPACE:
+                break
+            want = (cb.value, nf.value)                                # too small: once more with what the call asked for
+            self._next = slot
+        check(rc)
+        self._seen_flac = (max(want[0], cb.value), max(want[1], nf.value))
+        loaded = status == 0
+        for i in np.nonzero(~loaded)[0]:                               # dataset.py:108-111: print, warn, drop
+            if report:
+                print(self.lib.oe_ingest_error(self.handle, int(i)).decode())
+                logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
+            lens[i] = 0
+        rates[~loaded] = 16000
+        b = FlacBatch(self, slot, comp, frames, cb.value, nf.value, total.value, offs, lens, rates, loaded, keys)
+        b.paths = [p[0] for p in parts]
+        return b
+
+
+def flac_gpu_batches(item_batches, ingest=None, depth=2):
+    """``ingest_batches`` for FLAC lists decoded on the GPU: yields the tuples ``PrefetchingCollator`` takes with a
+    ``FlacBatch`` in the place of the pinned PCM tensor (the collator calls its ``to_device`` on the copy stream).  The next
+    ``depth`` batches are packed ahead by one helper thread (the work is inside ``oe_flac_pack``, GIL released)."""
+    from concurrent.futures import ThreadPoolExecutor
+    ing = ingest or FlacGpuIngest(ring=depth + 3)
+    pool = ThreadPoolExecutor(max_workers=1)
+    it = iter(item_batches)
+    pending = []
+
+    def submit():
+        try:
+            items = next(it)
+        except StopIteration:
+            return False
+        if len(items) == 1 and isinstance(items[0], list):
+            items = items[0]
+        pending.append((items, pool.submit(ing.pack, [x[1] for x in items], [x[0] for x in items])))
+        return True
+
+    while len(pending) < depth and submit():
+        pass
+    try:
+        while pending:
+            items, fut = pending.pop(0)
+            b = fut.result()
+            submit()
+            yield (b, b.offsets, b.lens, [x[0] for x in items], [x[2] for x in items], [x[3] for x in items], b.rates, b.loaded,
+                   (lambda ev, s=b.slot: ing.release_after(s, ev)))
+    finally:
+        pool.shutdown(wait=False)
+
+
+def default_flac_ingest():
+    if 'flac' not in _default:
+        _default['flac'] = FlacGpuIngest()
+    return _default['flac']

@@ -213,3 +213,151 @@ def test_read_wav_and_native_ingest_take_flac(tmp_path):
         assert np.array_equal(y[offs[2]:offs[2] + lens[2]], a[0, 4000:12000])
         assert np.array_equal(y[offs[4]:offs[4] + lens[4]], a[0, 14400:])
     assert '24-bit FLAC' in ing.lib.oe_ingest_error(ing.handle, 3).decode()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU decoder (csrc/oe_flac_gpu.cuh): host side (encoder, frame index) and the kernel body emulated on the host; the real
+# kernel runs in tests/test_gpu_mirrors.py (-m gpu) on the same streams.
+# ---------------------------------------------------------------------------------------------------------------------
+def lib_encode(pcm, rate=16000, block=4096, porder=3):
+    lib = _lib.load()
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    out = np.empty(2 * pcm.size + 8192, dtype=np.uint8)
+    nbytes = ctypes.c_int64()
+    assert lib.oe_flac_encode(pcm.ctypes.data, pcm.size, rate, block, porder, out.ctypes.data, out.size, ctypes.byref(nbytes)) == 0
+    return out[:nbytes.value].tobytes()
+
+
+def speechlike(rng, n, level=1500.0):
+    """Low-pass noise under a syllable-rate envelope with pauses: its FLAC stream is ~0.53 of the PCM, LibriSpeech's own
+    ratio (train-clean-100: 6.3 GB of FLAC for 100.6 h = 11.6 GB of PCM)."""
+    x = rng.normal(0, 1, n + 64)
+    for _ in range(3):
+        x = np.convolve(x, [0.25, 0.5, 0.25], mode='same')
+    x /= x.std()
+    env = np.clip(np.sin(2 * np.pi * np.arange(n + 64) / 5000.0 + rng.uniform(0, 6)), 0.02, None)
+    return np.clip(np.round(level * x * env)[:n], -32768, 32767).astype(np.int16)
+
+
+def flac_stream_matrix(rng):
+    """name -> (bytes, expected channel-0 int16 PCM): the product encoder's streams and the oracle encoder's (linear
+    predictors, escapes, wasted bits, 4-bit parameters, variable block sizes ...), all mono 16 bit."""
+    out = {}
+    for name, n, block, po in (('enc4096', 20000, 4096, 3), ('enc1152', 5000, 1152, 5), ('enc_short', 37, 4096, 3),
+                               ('enc_one', 1, 4096, 0), ('enc_odd', 4097, 4096, 2), ('enc256', 1000, 256, 8)):
+        x = speechlike(rng, n)
+        out[name] = (lib_encode(x, 16000, block, po), x)
+    x = np.full(3000, -1234, dtype=np.int16)
+    out['enc_constant'] = (lib_encode(x), x)
+    x = rng.integers(-32768, 32768, 3000).astype(np.int16)
+    out['enc_fullscale_noise'] = (lib_encode(x, block=576), x)
+    for i, kw in enumerate([dict(kind='lpc', order=8, porder=3, lpc=(12, 10, [1800, -900, 100, 20, -10, 5, 0, 3])),
+                            dict(kind='lpc', order=12, porder=2, pbits=5, lpc=(14, 12, [6000, -3000, 900, 20, -10, 5, 0, 3, 1, -1, 2, -2])),
+                            dict(kind='lpc', order=1, lpc=(5, 3, [7])), dict(kind='fixed', order=4, porder=4),
+                            dict(kind='fixed', order=0), dict(kind='fixed', order=1, escape=True, porder=2),
+                            dict(kind='verbatim', order=0), dict(kind='fixed', order=2, wasted=3),
+                            dict(kind='fixed', order=3, variable=True, block_sizes=[17, 256, 1, 400, 95, 2000]),
+                            dict(kind='fixed', order=2, pbits=4, block=192), dict(kind='fixed', order=2, padding_block=40, header_rate=True)]):
+        n = sum(kw['block_sizes']) if 'block_sizes' in kw else 2500
+        x = speechlike(rng, n).astype(np.int64)
+        if kw.get('wasted'):
+            x = (x >> 3) << 3
+        if kw['kind'] == 'verbatim' or kw.get('escape'):
+            x = rng.integers(-32768, 32768, n)
+        out['oracle%d' % i] = (oflac.encode(x[None], 16000, 16, **kw), x.astype(np.int16))
+    return out
+
+
+def test_product_encoder_streams_decode_with_the_oracle():
+    """oe_flac_encode -> valid streams: the oracle decoder (pinned by the RFC's examples) checks both CRCs and the MD5
+    signature and returns the PCM that went in; compression of the speech-like signal is reported by the bench."""
+    rng = np.random.default_rng(21)
+    for name, (data, pcm) in flac_stream_matrix(rng).items():
+        if not name.startswith('enc'):
+            continue
+        got, info = oflac.decode(data, verify_md5=True)
+        assert info['channels'] == 1 and info['bits'] == 16 and info['total'] == len(pcm), name
+        assert np.array_equal(got[0], pcm), name
+        out, _ = _lib_decode(data)
+        assert np.array_equal(out, pcm), name
+    x = speechlike(rng, 64000)
+    assert 0.45 * 2 * len(x) < len(lib_encode(x)) < 0.6 * 2 * len(x)
+
+
+def emul_decode(batch, verify=1):
+    """Runs the kernel body of oe_flac_gpu.cuh on the host (liboe_emul.so) over a packed batch."""
+    emul = ctypes.CDLL(_lib.EMUL_PATH)
+    pcm = np.full(max(batch.total, 8), 77, dtype=np.int16)
+    err = np.zeros(max(len(batch.lens), 1), dtype=np.int32)
+    emul.oe_emul_flac_decode(ctypes.c_void_p(batch.comp.data_ptr()), ctypes.c_longlong(batch.comp_bytes),
+                             ctypes.c_void_p(batch.frames.data_ptr()), ctypes.c_longlong(batch.n_frames),
+                             ctypes.c_void_p(pcm.ctypes.data), ctypes.c_void_p(err.ctypes.data), ctypes.c_int(verify))
+    return pcm, err
+
+
+def test_frame_index_and_emulated_kernel(tmp_path):
+    """oe_flac_pack + the kernel body (emulated thread per frame): every stream of the matrix, whole files and segments,
+    equals the PCM that was encoded; alignment padding between utterances is never written; a second pack re-uses the ring."""
+    from openeat_b200.ingest import FlacGpuIngest
+    rng = np.random.default_rng(22)
+    streams = flac_stream_matrix(rng)
+    entries, want = [], []
+    for name, (data, pcm) in streams.items():
+        f = tmp_path / (name + '.flac')
+        f.write_bytes(data)
+        entries.append(str(f))
+        want.append(pcm)
+    for name, s, e in (('enc4096', 0.25, 0.75), ('enc4096', 0.3, 5.0), ('enc1152', 0.07201, 0.07207), ('oracle8', 0.01, 0.1)):
+        entries.append('%s,%r,%r' % (tmp_path / (name + '.flac'), s, e))
+        pcm = streams[name][1]
+        a = int(s * 16000)
+        want.append(pcm[a:a + max(0, min(int(e * 16000) - a, len(pcm) - a))])
+    ing = FlacGpuIngest(threads=3, ring=2)
+    for _ in range(3):
+        b = ing.pack(entries)
+        assert b.loaded.all() and (b.offsets % 8 == 0).all()
+        assert b.lens.tolist() == [len(w) for w in want]
+        pcm, err = emul_decode(b)
+        assert not err.any()
+        for i, w in enumerate(want):
+            assert np.array_equal(pcm[b.offsets[i]:b.offsets[i] + b.lens[i]], w), entries[i]
+            pad = pcm[b.offsets[i] + b.lens[i]:(b.offsets[i + 1] if i + 1 < len(want) else b.total)]
+            assert (pad == 77).all()
+    assert b.h2d_bytes < 2 * sum(len(w) for w in want[:len(streams)]) + 64 * len(entries) + 48 * b.n_frames
+
+
+def test_emulated_kernel_flags_what_the_host_cannot_see(tmp_path):
+    """Corruption inside a frame's body is invisible to the header walk: the kernel's end-of-frame / CRC-16 checks flag the
+    entry (and only that entry).  Streams the GPU decoder does not take are reported by the pack, not dropped silently."""
+    from openeat_b200.ingest import FlacGpuIngest
+    rng = np.random.default_rng(23)
+    x = speechlike(rng, 12000)
+    good = lib_encode(x, block=1152)
+    _, pos = oflac.parse_streaminfo(good)
+    ing = FlacGpuIngest(threads=2, ring=2)
+    (tmp_path / 'good.flac').write_bytes(good)
+    flagged = 0
+    for trial in range(40):
+        bad = bytearray(good)
+        at = int(rng.integers(pos + 8, len(good) - 2))
+        bad[at] ^= 1 << int(rng.integers(0, 8))
+        (tmp_path / 'bad.flac').write_bytes(bytes(bad))
+        b = ing.pack([str(tmp_path / 'good.flac'), str(tmp_path / 'bad.flac')], report=False)
+        if not b.loaded[1]:                                       # the flip hit a header: the host walk already refuses it
+            continue
+        pcm, err = emul_decode(b)
+        assert err[0] == 0 and np.array_equal(pcm[b.offsets[0]:b.offsets[0] + b.lens[0]], x)
+        assert err[1] != 0
+        flagged += 1
+    assert flagged >= 30
+    # order-32 predictor: legal FLAC outside the kernel's range -> OE_FLAC_ERR_HOST; stereo / 24 bit: refused by the pack
+    y = speechlike(rng, 2000).astype(np.int64)
+    (tmp_path / 'o32.flac').write_bytes(oflac.encode(y[None], 16000, 16, kind='lpc', order=32, lpc=(8, 7, rng.integers(-50, 51, 32).tolist())))
+    (tmp_path / 'st.flac').write_bytes(oflac.encode(np.stack([y, y]), 16000, 16, kind='fixed', order=2))
+    (tmp_path / 'b24.flac').write_bytes(oflac.encode(y[None] * 200, 16000, 24, kind='fixed', order=2))
+    b = ing.pack([str(tmp_path / n) for n in ('o32.flac', 'st.flac', 'b24.flac', 'good.flac', 'missing.flac')], report=False)
+    assert b.loaded.tolist() == [True, False, False, True, False]
+    errs = [ing.lib.oe_ingest_error(ing.handle, i).decode() for i in range(5)]
+    assert 'channels' in errs[1] and '24-bit' in errs[2] and 'No such file' in errs[4]
+    pcm, err = emul_decode(b)
+    assert err[0] == 4 and err[3] == 0 and np.array_equal(pcm[b.offsets[3]:b.offsets[3] + b.lens[3]], x)
