@@ -121,48 +121,13 @@ void oe_emul_frame_pair_v2(const float* ha, const float* hb, float* pa, float* p
 
 }  // extern "C"
 
-// ---- the GPU FLAC decoder's kernel body run on the host, one emulated thread per frame (tests/test_flac.py checks it
+// ---- the GPU FLAC decoder's reader / predictor / CRC code run on the host, frame by frame (tests/test_flac.py checks it
 // against the host decoder without a GPU; `-m gpu` tests then run the real kernel) ----
-#include <cstring>
-namespace emul_cuda {
-struct Dim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local Dim3 threadIdx, blockIdx, blockDim;
-struct U4 { unsigned x, y, z, w; };
-inline U4 ldg(const U4* p) { return *p; }
-inline unsigned ldg(const unsigned* p) { return *p; }
-inline U4 make_u4(unsigned a, unsigned b, unsigned c, unsigned d) { return U4{a, b, c, d}; }
-inline unsigned byte_perm(unsigned a, unsigned, unsigned sel) {          // only the byte swap 0x0123 is used
-    (void)sel;
-    return __builtin_bswap32(a);
-}
-inline int clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
-inline int atomic_or(int* p, int v) { const int o = *p; *p |= v; return o; }
-}  // namespace emul_cuda
 #define __device__
-#define __global__
 #define __forceinline__ inline
-#define __shared__ static
-#define __align__(x)
-#define __restrict__
-#define __launch_bounds__(x)
-#define __ldg emul_cuda::ldg
-#define uint4 emul_cuda::U4
-#define make_uint4 emul_cuda::make_u4
-#define __byte_perm emul_cuda::byte_perm
-#define __clzll emul_cuda::clzll
-#define __syncthreads()
-#define atomicOr emul_cuda::atomic_or
-using emul_cuda::threadIdx;
-using emul_cuda::blockIdx;
-using emul_cuda::blockDim;
 #include "oe_flac_gpu.cuh"
 
 extern "C" void oe_emul_flac_decode(const unsigned char* comp, long long comp_bytes, const oe_flac_frame* frames, long long n_frames,
                                     short* pcm, int* errors, int verify_crc) {
-    emul_cuda::blockDim.x = 1;
-    emul_cuda::threadIdx.x = 0;
-    for (long long f = 0; f < n_frames; ++f) {
-        emul_cuda::blockIdx.x = (unsigned)f;
-        oe_flacgpu::oe_flac_decode_kernel(comp, comp_bytes + 16, frames, n_frames, pcm, errors, verify_crc);
-    }
+    for (long long f = 0; f < n_frames; ++f) oe_flacgpu::emulate_frame(comp, comp_bytes + 16, frames[f], pcm, errors, verify_crc);
 }

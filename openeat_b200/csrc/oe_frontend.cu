@@ -2763,7 +2763,7 @@ int oe_flac_decode_batch(const void* d_comp, int64_t comp_bytes, const oe_flac_f
     if ((reinterpret_cast<uintptr_t>(d_comp) & 15) || (comp_bytes & 15)) return fail(OE_ERR_INVALID, "d_comp and comp_bytes must be multiples of 16 (oe_flac_pack's layout)");
     const int64_t blocks = (n_frames + 31) / 32;
     if (blocks > INT32_MAX) return fail(OE_ERR_INVALID, "too many frames");
-    oe_flacgpu::oe_flac_decode_kernel<<<(unsigned)blocks, 32, 0, (cudaStream_t)stream>>>(
+    oe_flacgpu::oe_flac_decode_kernel<<<(unsigned)blocks, 96, 0, (cudaStream_t)stream>>>(
         static_cast<const unsigned char*>(d_comp), comp_bytes + 16, d_frames, n_frames, d_pcm, d_errors, verify_crc);
     OE_CUDA(cudaGetLastError());
     return OE_OK;

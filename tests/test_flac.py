@@ -257,7 +257,8 @@ def flac_stream_matrix(rng):
                             dict(kind='fixed', order=0), dict(kind='fixed', order=1, escape=True, porder=2),
                             dict(kind='verbatim', order=0), dict(kind='fixed', order=2, wasted=3),
                             dict(kind='fixed', order=3, variable=True, block_sizes=[17, 256, 1, 400, 95, 2000]),
-                            dict(kind='fixed', order=2, pbits=4, block=192), dict(kind='fixed', order=2, padding_block=40, header_rate=True)]):
+                            dict(kind='fixed', order=2, pbits=4, block=192), dict(kind='fixed', order=2, padding_block=40, header_rate=True),
+                            dict(kind='fixed', order=4, porder=6, block=256)]):
         n = sum(kw['block_sizes']) if 'block_sizes' in kw else 2500
         x = speechlike(rng, n).astype(np.int64)
         if kw.get('wasted'):
