@@ -26,7 +26,7 @@ namespace oe_flacgpu {
 
 constexpr int kMaxOrder = 12;
 
-constexpr int kRingWords = 64;               // per-lane staging ring in shared memory: two 128-byte lines of the lane's stream
+constexpr int kRingWords = 128;              // per-lane staging ring in shared memory: four 128-byte lines of the lane's stream
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void line_copy_async(void* smem_dst, const void* gmem_src, int chunks) {   // chunks x 16 bytes (<= 8), 16-byte aligned
@@ -70,21 +70,25 @@ struct Reader {
     uint64_t win;                            // next bits, left aligned; bits below `have` are zero
     int have;
     int wpos;                                // next stream word (from src16) to merge into the window
-    int next_issue;                          // when wpos reaches it, the ring half behind is refilled
+    int issued;                              // lines requested so far: line L lives in ring slot L & 3 until wpos passes its last word
     int start_bits;
     bool over;
 
-    __device__ __forceinline__ void issue_line(int line) {    // stream bytes [128 line, 128 line + 128) -> ring half (line & 1)
+    __device__ __forceinline__ void issue_line(int line) {    // stream bytes [128 line, 128 line + 128) -> ring slot (line & 3)
         const int64_t at = (int64_t)line * 128;
         const int64_t left = (src_bytes - at) >> 4;           // whole 16-byte chunks that exist (the buffer ends in a partial line)
-        line_copy_async(ring + (line & 1) * 32, src16 + at, (int)(left < 0 ? 0 : left > 8 ? 8 : left));
+        line_copy_async(ring + (line & 3) * 32, src16 + at, (int)(left < 0 ? 0 : left > 8 ? 8 : left));
         line_commit();
     }
+    // Keeps the ring as full as it can be: afterwards at least 96 words beyond wpos are staged or in flight, and everything
+    // but the newest request has landed, i.e. the next 64 words are readable.  Called once per round of the sample loop (a
+    // round's fast symbols consume at most 32 words) and by every slow-path read.
     __device__ __forceinline__ void service() {
-        if (wpos >= next_issue) {            // the half behind wpos is consumed: bring in the line after the one in use
-            issue_line((next_issue >> 5) + 1);
-            line_wait_all_but_one();         // the line requested one round ago (in use from now on) has landed
-            next_issue += 32;
+        if ((issued - 3) * 32 <= wpos) {
+            do issue_line(issued++);
+            while ((issued - 3) * 32 <= wpos);
+            line_wait_all_but_one();
+            if ((int64_t)wpos * 4 >= src_bytes) over = true;
         }
     }
     __device__ __forceinline__ uint32_t word() const { return big_endian(ring[wpos & (kRingWords - 1)]); }
@@ -93,7 +97,6 @@ struct Reader {
         const uint64_t add = (uint64_t)w << ((32 - have) & 63);
         win |= need ? add : 0ull;
         have += need ? 32 : 0;
-        if (need && (int64_t)wpos * 4 >= src_bytes) over = true;
         wpos += need ? 1 : 0;
     }
     __device__ __forceinline__ void init(const unsigned char* base, int64_t byte_off, int64_t limit, uint32_t* lane_ring) {
@@ -102,10 +105,8 @@ struct Reader {
         src16 = p - mis;
         src_bytes = (base + limit) - src16;
         ring = lane_ring;
-        issue_line(0);
-        issue_line(1);
+        for (issued = 0; issued < 4; ++issued) issue_line(issued);
         line_wait_all();
-        next_issue = 32;
         wpos = mis >> 2;
         start_bits = (mis & ~3) * 8 + (mis & 3) * 8;
         over = false;
@@ -150,21 +151,17 @@ struct Reader {
         }
     }
     // One Rice symbol with parameter k (<= 30): quotient in unary, then k bits.  When quotient + 1 + k <= 32 (almost always)
-    // the symbol is cut out of the window's top half in one step.
-    __device__ __forceinline__ uint32_t rice(int k) {
-        service();
-        const uint32_t w = word();
+    // the symbol is cut out of the window's top half in one step (rice_fast; the caller has checked n <= 32).
+    __device__ __forceinline__ uint32_t rice_fast(int k, int z, int n, uint32_t w) {
         const uint32_t hi = (uint32_t)(win >> 32);
-        const int z = clz32(hi);
-        const int n = z + 1 + k;
-        if (n <= 32) {
-            const uint32_t t = (hi << z) << 1;
-            const uint32_t rem = (t >> 1) >> (31 - k);
-            win <<= n;
-            have -= n;
-            top_up(w);
-            return ((uint32_t)z << k) | rem;
-        }
+        const uint32_t t = (hi << z) << 1;
+        const uint32_t rem = (t >> 1) >> (31 - k);
+        win <<= n;
+        have -= n;
+        top_up(w);
+        return ((uint32_t)z << k) | rem;
+    }
+    __device__ __forceinline__ uint32_t rice(int k) {
         const uint32_t q = unary();
         return (q << k) | take(k);
     }
@@ -184,10 +181,10 @@ constexpr int kErrOverrun = 16;              // the bit stream ran past the end 
 // frames.  Here lane l of warp 0 (the reader) turns frame l's bit stream into residuals, lane l of warp 1 (the predictor)
 // turns them into samples, lane l of warp 2 checks the frame's CRC-16 meanwhile; the three warps sit on three schedulers of
 // the SM.  Reader and predictor walk the sample index in lockstep, 32 samples per round, through a double-buffered
-// [2][32 samples][32 lanes] residual tile in shared memory with ONE named barrier per round.  Constant and verbatim
+// [2][48 samples][32 lanes] residual tile in shared memory with ONE named barrier per round.  Constant and verbatim
 // subframes, warm-up samples and escape partitions all travel as "residuals" of a predictor with zero coefficients, so the
 // predictor warp runs one uniform loop.
-constexpr int kChunk = 32;                   // samples per round
+constexpr int kChunk = 48;                   // samples per round (a multiple of kMaxOrder, see predictor_chunk)
 
 struct Hand {                                // reader -> predictor, per lane, written before the first barrier
     int32_t c[kMaxOrder];
@@ -196,7 +193,7 @@ struct Hand {                                // reader -> predictor, per lane, w
 
 struct ReaderState {
     Reader r;
-    int n, order, k, raw, cval, pbits, psize, part_end, part_base, err;
+    int n, order, k, raw, cval, pbits, psize, part_end, part_base, fast_until, err;
     bool rice;                               // false: every sample is `raw` bits (raw == 0: the constant cval)
 };
 
@@ -226,6 +223,7 @@ __device__ __forceinline__ void reader_prologue(ReaderState& st, Hand& hand, int
     st.psize = n;
     st.part_end = n;
     st.part_base = 0;
+    st.fast_until = 0;
     if (kind == 0) {
         st.cval = r.take_signed(bps);
     } else if (kind == 1) {
@@ -261,6 +259,7 @@ __device__ __forceinline__ void reader_prologue(ReaderState& st, Hand& hand, int
         err |= kErrFormat;
     }
     if (err) {                               // nothing more is read: the frame decodes to zeros and is reported
+        st.fast_until = 0;
         st.rice = false;
         st.raw = 0;
         st.cval = 0;
@@ -270,6 +269,7 @@ __device__ __forceinline__ void reader_prologue(ReaderState& st, Hand& hand, int
         for (int j = 0; j < kMaxOrder; ++j) hand.c[j] = 0;
     }
     st.order = order;
+    st.fast_until = order;                   // the first residual goes the slow way and reads its partition's parameter
     st.err = err;
     hand.order = order;
     hand.shift = shift;
@@ -277,31 +277,49 @@ __device__ __forceinline__ void reader_prologue(ReaderState& st, Hand& hand, int
     hand.err = err;
 }
 
-// Residuals i0 .. i0 + kChunk of this lane's frame into its tile column (stride 32 words).
+// One sample the slow way: partition parameters, escape / verbatim / constant values, long Rice symbols, samples outside
+// the residual range (nothing to do).  Returns the residual.
+__device__ __forceinline__ int32_t reader_slow_sample(ReaderState& st, int i) {
+    Reader& r = st.r;
+    if ((unsigned)(i - st.order) >= (unsigned)(st.n - st.order)) return 0;            // warm-up (already in the tile) or past the end
+    while (i == st.part_end) {               // a partition may be empty (predictor order == partition size): then the next one starts here too
+        const int k = (int)r.take(st.pbits);
+        st.rice = true;
+        st.k = k;
+        if (k == (1 << st.pbits) - 1) {
+            st.rice = false;
+            st.raw = (int)r.take(5);
+            st.cval = 0;
+        }
+        st.part_base += st.psize;
+        st.part_end = st.part_base;
+    }
+    st.fast_until = st.rice ? (st.part_end < st.n ? st.part_end : st.n) : st.order;     // == order: no fast samples
+    if (st.rice) {
+        const uint32_t v = r.rice(st.k);
+        return (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
+    }
+    return st.raw ? r.take_signed(st.raw) : st.cval;
+}
+
+// Residuals i0 .. i0 + kChunk of this lane's frame into its tile column (stride 32 words).  The hot path (a Rice symbol of
+// at most 32 bits inside a partition) is straight-line code behind ONE test; everything else goes through reader_slow_sample.
 __device__ __forceinline__ void reader_chunk(ReaderState& st, int32_t* tile, int i0) {
     Reader& r = st.r;
+    r.service();
 #pragma unroll 1
     for (int j = 0; j < kChunk; ++j) {
         const int i = i0 + j;
-        if ((unsigned)(i - st.order) >= (unsigned)(st.n - st.order)) continue;        // warm-up (already in the tile) or past the end
-        while (i == st.part_end) {           // a partition may be empty (predictor order == partition size): then the next one starts here too
-            const int k = (int)r.take(st.pbits);
-            st.rice = true;
-            st.k = k;
-            if (k == (1 << st.pbits) - 1) {
-                st.rice = false;
-                st.raw = (int)r.take(5);
-                st.cval = 0;
-            }
-            st.part_base += st.psize;
-            st.part_end = st.part_base;
-        }
+        const uint32_t w = r.word();
+        const int z = clz32((uint32_t)(r.win >> 32));
+        const int n = z + 1 + st.k;
         int32_t res;
-        if (st.rice) {
-            const uint32_t v = r.rice(st.k);
+        if ((unsigned)(i - st.order) < (unsigned)(st.fast_until - st.order) && n <= 32) {
+            const uint32_t v = r.rice_fast(st.k, z, n, w);
             res = (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
         } else {
-            res = st.raw ? r.take_signed(st.raw) : st.cval;
+            res = reader_slow_sample(st, i);
+            if (i < st.order) continue;      // warm-up samples are in the tile already
         }
         tile[j * 32] = res;
     }
@@ -324,26 +342,28 @@ __device__ __forceinline__ void predictor_init(PredictorState& p, const Hand& ha
     if (hand.err) p.lo = p.hi = 0;           // a rejected frame writes nothing
 }
 
+// kChunk is a multiple of kMaxOrder: inside a group of 12 samples the history slots rotate at compile time (sample u of
+// the group overwrites slot 11 - u, tap t of the next sample reads slot (12 - u + t) % 12 ... ), so no register is moved.
 __device__ __forceinline__ void predictor_chunk(PredictorState& p, const int32_t* tile, int i0) {
-#pragma unroll 4
-    for (int j = 0; j < kChunk; ++j) {
-        const int i = i0 + j;
-        if (i >= p.n) break;
-        const int32_t res = tile[j * 32];
-        // the taps that do not wait for the newest sample were summed one step ahead (`ahead`): the recursion's chain per
-        // sample is one multiply-add, one shift and one add
-        const int32_t pred = (int32_t)(mad_wide(p.c[0], p.h[0], p.ahead) >> p.shift);
-        const int32_t s = res + (i >= p.order ? pred : 0);
-        if (i >= p.lo && i < p.hi) p.out[i] = (int16_t)(s << p.wasted);
+#pragma unroll 1
+    for (int g = 0; g < kChunk; g += kMaxOrder) {
+        if (i0 + g >= p.n) break;
 #pragma unroll
-        for (int t = kMaxOrder - 1; t > 0; --t) p.h[t] = p.h[t - 1];
-        p.h[0] = s;
-        int64_t a0 = 0, a1 = 0;
+        for (int u = 0; u < kMaxOrder; ++u) {
+            // slot of the sample t steps back, before sample u of the group is stored: (kMaxOrder - u + t) % kMaxOrder
+            const int i = i0 + g + u;
+            const int32_t res = tile[(g + u) * 32];
+            const int32_t pred = (int32_t)(mad_wide(p.c[0], p.h[(kMaxOrder - u) % kMaxOrder], p.ahead) >> p.shift);
+            const int32_t s = res + (i >= p.order ? pred : 0);
+            if ((unsigned)(i - p.lo) < (unsigned)(p.hi - p.lo)) p.out[i] = (int16_t)(s << p.wasted);
+            p.h[kMaxOrder - 1 - u] = s;      // overwrites the oldest sample; it is now "0 steps back" for sample u + 1
+            int64_t a0 = 0, a1 = 0;
 #pragma unroll
-        for (int t = 1; t < kMaxOrder; t += 2) a0 = mad_wide(p.c[t], p.h[t], a0);
+            for (int t = 1; t < kMaxOrder; t += 2) a0 = mad_wide(p.c[t], p.h[(kMaxOrder - (u + 1) + t) % kMaxOrder], a0);
 #pragma unroll
-        for (int t = 2; t < kMaxOrder; t += 2) a1 = mad_wide(p.c[t], p.h[t], a1);
-        p.ahead = a0 + a1;
+            for (int t = 2; t < kMaxOrder; t += 2) a1 = mad_wide(p.c[t], p.h[(kMaxOrder - (u + 1) + t) % kMaxOrder], a1);
+            p.ahead = a0 + a1;
+        }
     }
 }
 
@@ -404,7 +424,7 @@ __global__ void __launch_bounds__(96) oe_flac_decode_kernel(const unsigned char*
         st.order = 0;
         st.err = 0;
         st.part_end = st.n;
-        st.rice = false, st.raw = 0, st.cval = 0, st.k = 0, st.pbits = 4, st.psize = 1;
+        st.rice = false, st.raw = 0, st.cval = 0, st.k = 0, st.pbits = 4, st.psize = 1, st.part_base = 0, st.fast_until = 0;
         if (live) {
             st.r.init(comp, fr.comp_off + fr.hdr_bytes, comp_limit, rings[lane]);
             reader_prologue(st, hands[lane], &tile[0][0][lane], fr.bps);
@@ -469,7 +489,7 @@ inline void emulate_frame(const unsigned char* comp, int64_t comp_limit, const o
     st.order = 0;
     st.err = 0;
     st.part_end = st.n;
-    st.rice = false, st.raw = 0, st.cval = 0, st.k = 0, st.pbits = 4, st.psize = 1;
+    st.rice = false, st.raw = 0, st.cval = 0, st.k = 0, st.pbits = 4, st.psize = 1, st.part_base = 0, st.fast_until = 0;
     st.r.init(comp, fr.comp_off + fr.hdr_bytes, comp_limit, ring);
     reader_prologue(st, hand, &tile[0][0][0], fr.bps);
     PredictorState p;
