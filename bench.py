@@ -386,6 +386,82 @@ def run_ours(args, rank, world, local_rank):
     import atexit
     atexit.register(shutil.rmtree, wav_dir, ignore_errors=True)
 
+    # ---- the same from FLAC FILES (the LibriSpeech recipe's corpus format): the compressed bytes cross PCIe and the GPU
+    # decodes them (oe_flac_pack -> oe_flac_decode_batch -> the same kernels).  White noise does not compress, so this leg
+    # has its own corpus of the same shape: low-pass noise under a syllable-rate envelope whose FLAC stream is ~0.53 of the
+    # PCM (LibriSpeech's own ratio), written by the library's encoder.  Next to it: the same files decoded on the host by the
+    # reader threads (what a libsox-style loader does), same pipeline behind. ----
+    import ctypes
+    from openeat_b200 import _lib as oe_lib
+    from openeat_b200.ingest import FlacGpuIngest, flac_gpu_batches
+    lib = oe_lib.load()
+    FLAC_POOL = 4
+    flac_batches, flac_bytes, pcm_bytes = [], 0, 0
+    rng_f = np.random.default_rng(1234 + rank)
+    enc_out = np.empty(2 * int(max(lens)) + 65536, dtype=np.uint8)
+    for bi in range(FLAC_POOL):
+        total_n = int(sum(lens)) + 64
+        x = rng_f.normal(0.0, 1.0, total_n).astype(np.float32)
+        for _ in range(3):
+            x = np.convolve(x, np.array([0.25, 0.5, 0.25], dtype=np.float32), mode='same')
+        x /= x.std()
+        env = np.clip(np.sin(2 * np.pi * np.arange(total_n, dtype=np.float32) / 5000.0), 0.02, None)
+        sig = np.clip(np.round(1500.0 * x * env), -32768, 32767).astype(np.int16)
+        items, at = [], 0
+        for u in range(BATCH):
+            seg = np.ascontiguousarray(sig[at:at + lens[u]])
+            at += int(lens[u])
+            nb = ctypes.c_int64()
+            oe_lib.check(lib.oe_flac_encode(seg.ctypes.data, seg.size, 16000, 4096, 3, enc_out.ctypes.data, enc_out.size, ctypes.byref(nb)))
+            path = os.path.join(wav_dir, 'b%d_u%d.flac' % (bi, u))
+            with open(path, 'wb') as f:
+                f.write(enc_out[:nb.value].tobytes())
+            flac_bytes += nb.value
+            pcm_bytes += 2 * seg.size
+            items.append((keys[u], path, labels[u], speeds[u]))
+        flac_batches.append(items)
+    flac_done = []
+
+    def flac_items():
+        i = 0
+        while not flac_done:
+            yield flac_batches[i % FLAC_POOL]
+            i += 1
+
+    pipe_flac = PrefetchingCollator(collate, flac_gpu_batches(flac_items(), depth=3, workers=2, threads=n_readers))
+
+    def step_e2e_flac(i):
+        _, out = next(pipe_flac)
+        d2h['n'].copy_(out['features_length'], non_blocking=True)
+        d2h['s'].copy_(stats, non_blocking=True)
+
+    ms_e2e_flac, _, _ = timed_repeated(step_e2e_flac, world > 1, 0.5)
+    e2e_flac_value = job_audio_s * args.steps / (ms_e2e_flac * 1e-3)
+    flac_done.append(True)
+    g_tmp = FlacGpuIngest(threads=n_readers, ring=2)
+    fb_tmp = g_tmp.pack([x[1] for x in flac_batches[0]], report=False)
+    flac_h2d_bytes, flac_frames = int(fb_tmp.h2d_bytes), int(fb_tmp.n_frames)
+    del fb_tmp, g_tmp
+    flac_host_done = []
+
+    def flac_host_items():
+        i = 0
+        while not flac_host_done:
+            yield flac_batches[i % FLAC_POOL]
+            i += 1
+
+    pipe_flac_host = PrefetchingCollator(collate, ingest_batches(flac_host_items(), ingest=NativeIngest(threads=n_readers, ring=6), depth=3))
+
+    def step_e2e_flac_host(i):
+        _, out = next(pipe_flac_host)
+        d2h['n'].copy_(out['features_length'], non_blocking=True)
+        d2h['s'].copy_(stats, non_blocking=True)
+
+    flac_host_steps = max(2, min(args.steps, 5))
+    ms_e2e_flac_host, _, _ = timed_repeated(step_e2e_flac_host, world > 1, 0.3, steps=flac_host_steps)
+    e2e_flac_host_value = job_audio_s * flac_host_steps / (ms_e2e_flac_host * 1e-3)
+    flac_host_done.append(True)
+
     # ---- the box's own H2D ceiling: plain cudaMemcpyAsync from pinned memory, every rank at once ----
     h2d = int(host_pool[0].numel() * 2)
     sink = torch.empty_like(dev_pool[0])
@@ -584,6 +660,20 @@ def run_ours(args, rank, world, local_rank):
                                               'files per step from tmpfs into a pinned ring, background thread, %d reader threads per rank) -> '
                                               'PrefetchingCollator -> the same kernels' % (BATCH, n_readers),
                                        'frac_of_packed_e2e': e2e_files_value / e2e_value},
+                    'from_flac_files': {'value': e2e_flac_value, 'unit': 'audio-s/s', 'ms_per_step': ms_e2e_flac / args.steps,
+                                        'h2d_bytes_per_step': flac_h2d_bytes, 'flac_over_pcm_bytes': flac_bytes / pcm_bytes,
+                                        'frames_per_step': flac_frames,
+                                        'corpus': 'same utterance lengths, speech-like synthetic signal (low-pass noise under a '
+                                                  'syllable-rate envelope), oe_flac_encode block 4096',
+                                        'api': 'openeat_b200.ingest.flac_gpu_batches (oe_flac_pack: pread of %d FLAC files per step + frame '
+                                               'index, nothing decoded on the host) -> PrefetchingCollator: compressed bytes over PCIe, '
+                                               'oe_flac_decode_batch (one kernel, end-of-frame + CRC-16 checks) -> the same kernels' % BATCH,
+                                        'frac_of_packed_e2e': e2e_flac_value / e2e_value,
+                                        'host_decode': {'value': e2e_flac_host_value, 'unit': 'audio-s/s',
+                                                        'ms_per_step': ms_e2e_flac_host / flac_host_steps,
+                                                        'api': 'the same files through ingest_batches: %d reader threads decode FLAC on the '
+                                                               'host (oe_flac.h), PCM over PCIe' % n_readers},
+                                        'gpu_over_host_decode': e2e_flac_value / e2e_flac_host_value},
                     'h2d_ceiling_gbs': h2d_ceiling,
                     'h2d_achieved_gbs': h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9,
                     'frac_of_h2d_ceiling': (h2d_job * args.steps / (ms_e2e * 1e-3) / 1e9) / h2d_ceiling},

@@ -296,7 +296,10 @@ __device__ __forceinline__ int32_t reader_slow_sample(ReaderState& st, int i) {
     }
     st.fast_until = st.rice ? (st.part_end < st.n ? st.part_end : st.n) : st.order;     // == order: no fast samples
     if (st.rice) {
-        const uint32_t v = r.rice(st.k);
+        r.service();
+        const int z = clz32((uint32_t)(r.win >> 32));
+        const int n = z + 1 + st.k;
+        const uint32_t v = n <= 32 ? r.rice_fast(st.k, z, n, r.word()) : r.rice(st.k);   // a partition's first symbol is as short as any
         return (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
     }
     return st.raw ? r.take_signed(st.raw) : st.cval;

@@ -16,6 +16,7 @@ Differences a caller can observe (all deliberate):
   * optional extras the reference applies later on the device can be fused in:
     ``global_cmvn=(mean, istd)`` (GlobalCMVN, encoder.py:221-222) and ``cmvn_stats`` accumulation.
 """
+import collections
 import logging
 import os
 import random
@@ -675,6 +676,9 @@ class PrefetchingCollator(object):
         self._stage_slot = 0
         self._pending = []                       # launched batches, oldest first: (keys, host dict, event, thread or None)
         self._next = None
+        self._staged = collections.deque()
+        self._stage_depth = 1
+        self._exhausted = False
         self._pad_row = None
         if self.host_pad:
             import threading
@@ -688,37 +692,44 @@ class PrefetchingCollator(object):
         self._stage()
 
     def _stage(self):
-        try:
-            item = next(self.batches)
-        except StopIteration:
-            self._next = None
-            return
-        wav = item[0]
-        with torch.cuda.stream(self.copy_stream):
-            if hasattr(wav, 'to_device'):        # ingest.FlacBatch: compressed bytes cross PCIe, the decode kernel follows on this stream
-                dev = wav.to_device(self.device)
-            else:
-                dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(self.copy_stream)
-        if len(item) > 8 and item[8] is not None:
-            item[8](ev)                          # the ingest ring slot is free once this copy has completed
-        self._next = (dev, ev) + tuple(item[1:8])
-        self._next_flac = wav if hasattr(wav, 'to_device') else None
+        """Keeps ``_stage_depth`` batches staged (copies enqueued) ahead of the one being launched: 1 for PCM; 2 for FLAC
+        batches, whose H2D copy (copy stream) and decode kernel (decode stream) then overlap the previous batch's."""
+        while not self._exhausted and len(self._staged) < self._stage_depth:
+            try:
+                item = next(self.batches)
+            except StopIteration:
+                self._exhausted = True
+                break
+            wav = item[0]
+            flac = wav if hasattr(wav, 'to_device') else None
+            with torch.cuda.stream(self.copy_stream):
+                if flac is not None:             # ingest.FlacBatch: compressed bytes cross PCIe, the decode kernel follows on its own stream
+                    self._stage_depth = 2
+                    dev = flac.to_device(self.device, wait=False)
+                    ev = flac.event
+                else:
+                    dev = wav if wav.is_cuda else wav.to(self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy_stream)
+            if len(item) > 8 and item[8] is not None:
+                item[8](ev)                      # the ingest ring slot is free once this copy has completed
+            self._staged.append(((dev, ev) + tuple(item[1:8]), flac))
+        self._next = self._staged[0][0] if self._staged else None
 
     def __iter__(self):
         return self
 
     def _launch(self):
-        dev, ev, offs, lens, keys, labels, speeds = self._next[:7]
-        extra = self._next[7:]
+        (dev, ev, offs, lens, keys, labels, speeds), flac = self._staged[0][0][:7], self._staged[0][1]
+        extra = self._staged[0][0][7:]
+        self._staged.popleft()
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)                       # kernels of this batch start when its PCM has landed
         dev.record_stream(cur)
-        if getattr(self, '_next_flac', None) is not None and len(extra) >= 2:
+        if flac is not None and len(extra) >= 2:
             # streams that failed the GPU decoder's checks are dropped like any unreadable file (dataset.py:108-111); the
-            # batch was staged one step ahead, so its decode has normally finished by now
-            lens = self._next_flac.drop_failed(lens, extra[1], keys)
+            # batch was staged two steps ahead, so its decode has normally finished by now
+            lens = flac.drop_failed(lens, extra[1], keys)
         self._stage()                            # next batch's copy is in flight before this batch's kernels are enqueued
         self.collate._out_layout = 'ragged' if self.host_pad else 'padded'
         try:

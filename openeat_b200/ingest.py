@@ -231,7 +231,7 @@ class FlacBatch(object):
     def h2d_bytes(self):
         return self.comp_bytes + 16 + self.n_frames * FRAME_BYTES
 
-    def to_device(self, device, verify_crc=True):
+    def to_device(self, device, verify_crc=True, wait=True):
         lib = self.owner.lib
         n = len(self.lens)
         pcm = torch.empty(max(self.total, ALIGN), dtype=torch.int16, device=device)
@@ -240,16 +240,25 @@ class FlacBatch(object):
         d_comp = self.comp[:self.comp_bytes + 16].to(device, non_blocking=True)
         d_frames = self.frames[:self.n_frames * FRAME_BYTES].to(device, non_blocking=True)
         d_err = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
-        stream = torch.cuda.current_stream(device)
+        # copies on the caller's (current) stream, the kernel on the ingest's decode stream behind them: the next batch's copy
+        # does not queue behind this batch's decode
+        cur = torch.cuda.current_stream(device)
+        stream = self.owner.decode_stream(device)
+        copied = torch.cuda.Event()
+        copied.record(cur)
+        stream.wait_event(copied)
         check(lib.oe_flac_decode_batch(ctypes.c_void_p(d_comp.data_ptr()), self.comp_bytes, ctypes.c_void_p(d_frames.data_ptr()),
                                        self.n_frames, ctypes.c_void_p(pcm.data_ptr()), ctypes.c_void_p(d_err.data_ptr()),
                                        1 if verify_crc else 0, ctypes.c_void_p(stream.cuda_stream)))
         self.errors = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
-        self.errors.copy_(d_err, non_blocking=True)
-        for t in (d_comp, d_frames, d_err):
+        with torch.cuda.stream(stream):
+            self.errors.copy_(d_err, non_blocking=True)
+        for t in (d_comp, d_frames, d_err, pcm):
             t.record_stream(stream)
         self.event = torch.cuda.Event()
         self.event.record(stream)
+        if wait:
+            cur.wait_event(self.event)           # stream-ordered for the caller: the PCM is ready for whatever it enqueues next
         self.owner._watch(self)
         return pcm
 
@@ -293,6 +302,13 @@ class FlacGpuIngest(NativeIngest):
         self._comp = [None] * len(self._ring)
         self._frames = [None] * len(self._ring)
         self._watched = []
+        self._decode_streams = {}
+
+    def decode_stream(self, device):
+        key = str(device)
+        if key not in self._decode_streams:
+            self._decode_streams[key] = torch.cuda.Stream(device=device)
+        return self._decode_streams[key]
 
     def _watch(self, batch):
         """Batches whose decode has finished are checked when the next one is launched (no extra synchronisation)."""
@@ -357,15 +373,22 @@ class FlacGpuIngest(NativeIngest):
         return b
 
 
-def flac_gpu_batches(item_batches, ingest=None, depth=2):
+def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
     """``ingest_batches`` for FLAC lists decoded on the GPU: yields the tuples ``PrefetchingCollator`` takes with a
     ``FlacBatch`` in the place of the pinned PCM tensor (the collator calls its ``to_device`` on the copy stream).  The next
-    ``depth`` batches are packed ahead by one helper thread (the work is inside ``oe_flac_pack``, GIL released)."""
+    ``depth`` batches are packed ahead by ``workers`` helper threads, each with its own ``FlacGpuIngest`` (the work is
+    inside ``oe_flac_pack``, GIL released; ``threads`` reader threads in total, 0 = one per core)."""
     from concurrent.futures import ThreadPoolExecutor
-    ing = ingest or FlacGpuIngest(ring=depth + 3)
-    pool = ThreadPoolExecutor(max_workers=1)
+    if ingest is not None:
+        ings = [ingest]
+    else:
+        total = int(threads) or len(os.sched_getaffinity(0))
+        workers = max(1, min(int(workers), total))
+        ings = [FlacGpuIngest(threads=max(1, total // workers), ring=depth + 4) for _ in range(workers)]
+    pool = ThreadPoolExecutor(max_workers=len(ings))
     it = iter(item_batches)
     pending = []
+    count = [0]
 
     def submit():
         try:
@@ -374,6 +397,8 @@ def flac_gpu_batches(item_batches, ingest=None, depth=2):
             return False
         if len(items) == 1 and isinstance(items[0], list):
             items = items[0]
+        ing = ings[count[0] % len(ings)]
+        count[0] += 1
         pending.append((items, pool.submit(ing.pack, [x[1] for x in items], [x[0] for x in items])))
         return True
 
@@ -385,7 +410,7 @@ def flac_gpu_batches(item_batches, ingest=None, depth=2):
             b = fut.result()
             submit()
             yield (b, b.offsets, b.lens, [x[0] for x in items], [x[2] for x in items], [x[3] for x in items], b.rates, b.loaded,
-                   (lambda ev, s=b.slot: ing.release_after(s, ev)))
+                   (lambda ev, s=b.slot, g=b.owner: g.release_after(s, ev)))
     finally:
         pool.shutdown(wait=False)
 
