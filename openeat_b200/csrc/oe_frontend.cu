@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -2703,6 +2704,8 @@ int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double
             if (r <= 0) break;
             done += r;
         }
+        close(fd);                                                     // by the thread that read it: 256 serial close() calls cost 0.1 ms
+        g->fds[i] = -1;
         std::string err;
         if (done != fsize[i]) err = "short read";
         oe_flac::Info fi;

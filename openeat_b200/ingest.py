@@ -412,7 +412,11 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
             yield (b, b.offsets, b.lens, [x[0] for x in items], [x[2] for x in items], [x[3] for x in items], b.rates, b.loaded,
                    (lambda ev, s=b.slot, g=b.owner: g.release_after(s, ev)))
     finally:
-        pool.shutdown(wait=False)
+        # packs still queued are dropped, the ones running finish before the ingest handles can go (a handle destroyed under a
+        # running oe_flac_pack would take the reader pool away from it)
+        for _, fut in pending:
+            fut.cancel()
+        pool.shutdown(wait=True)
 
 
 def default_flac_ingest():
