@@ -210,6 +210,14 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    t_start = time.perf_counter()
+
+    def mark(what):                              # progress on stderr (one line per leg and rank): a stuck leg names itself
+        print('[bench rank %d +%.1fs] %s' % (rank, time.perf_counter() - t_start, what), file=sys.stderr, flush=True)
+
+    if os.environ.get('OE_BENCH_WATCHDOG'):      # dump every thread's stack and exit if the run takes longer than this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['OE_BENCH_WATCHDOG']), exit=True)
     cpus_before = os.sched_getaffinity(0)
     binding = bind_to_gpu_numa_node(local_rank)
     fe = default_frontend(80, 16000, dev)
@@ -331,13 +339,16 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    mark('device-resident')
     ms_total, launches, reps = timed_repeated(step_resident, world > 1, 1.5)
     clocks = sampler.stop() if rank == 0 else None
     value = job_audio_s * args.steps / (ms_total * 1e-3)
     stats.zero_()
     random.seed(99 + rank)
+    mark('e2e packed')
     ms_e2e, _, _ = timed_repeated(step_e2e, world > 1, 0.5)
     e2e_value = job_audio_s * args.steps / (ms_e2e * 1e-3)
+    mark('e2e to_host')
     ms_e2e_host, _, _ = timed_repeated(step_e2e_host, world > 1, 0.5)
     e2e_host_value = job_audio_s * args.steps / (ms_e2e_host * 1e-3)
 
@@ -380,6 +391,7 @@ def run_ours(args, rank, world, local_rank):
         d2h['n'].copy_(out['features_length'], non_blocking=True)
         d2h['s'].copy_(stats, non_blocking=True)
 
+    mark('e2e from wav files')
     ms_e2e_files, _, _ = timed_repeated(step_e2e_files, world > 1, 0.5)
     e2e_files_value = job_audio_s * args.steps / (ms_e2e_files * 1e-3)
     files_done.append(True)                     # the background reader stops; the files go at exit
@@ -435,6 +447,7 @@ def run_ours(args, rank, world, local_rank):
         d2h['n'].copy_(out['features_length'], non_blocking=True)
         d2h['s'].copy_(stats, non_blocking=True)
 
+    mark('e2e from flac files (GPU decode)')
     ms_e2e_flac, _, _ = timed_repeated(step_e2e_flac, world > 1, 0.5)
     e2e_flac_value = job_audio_s * args.steps / (ms_e2e_flac * 1e-3)
     flac_done.append(True)
@@ -458,6 +471,7 @@ def run_ours(args, rank, world, local_rank):
         d2h['s'].copy_(stats, non_blocking=True)
 
     flac_host_steps = max(2, min(args.steps, 5))
+    mark('e2e from flac files (host decode)')
     ms_e2e_flac_host, _, _ = timed_repeated(step_e2e_flac_host, world > 1, 0.3, steps=flac_host_steps)
     e2e_flac_host_value = job_audio_s * flac_host_steps / (ms_e2e_flac_host * 1e-3)
     flac_host_done.append(True)
@@ -469,10 +483,12 @@ def run_ours(args, rank, world, local_rank):
     def step_copy(i):
         sink.copy_(host_pool[i % POOL], non_blocking=True)
 
+    mark('h2d ceiling')
     ms_copy, _, _ = timed_repeated(step_copy, False, 0.3)
     h2d_job = job_total(h2d)                                                     # bytes per step over all ranks
     h2d_ceiling = h2d_job * args.steps / (ms_copy * 1e-3) / 1e9                  # GB/s over all ranks
 
+    mark('other configs')
     # ---- the other BASELINE configurations, device-resident ----
     def run_config(name, make):
         """make() -> (list of (prepared batch, device wav), audio seconds per pass on this rank, algorithmic bytes per

@@ -133,6 +133,13 @@ SYMBOLS = {
 _lib = None
 
 
+class OeFlacFrame(ctypes.Structure):
+    """``oe_flac_frame`` (include/openeat_frontend.h): one audio frame of a packed FLAC batch."""
+    _fields_ = [('comp_off', ctypes.c_int64), ('out_off', ctypes.c_int64), ('frame_bytes', ctypes.c_int32),
+                ('hdr_bytes', ctypes.c_int32), ('block', ctypes.c_int32), ('bps', ctypes.c_int32), ('skip', ctypes.c_int32),
+                ('take', ctypes.c_int32), ('utt', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
 class FrontendError(RuntimeError):
     pass
 

@@ -385,7 +385,9 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
         total = int(threads) or len(os.sched_getaffinity(0))
         workers = max(1, min(int(workers), total))
         ings = [FlacGpuIngest(threads=max(1, total // workers), ring=depth + 4) for _ in range(workers)]
-    pool = ThreadPoolExecutor(max_workers=len(ings))
+    # one single-thread executor per handle: a handle runs one pack at a time (its reader pool and per-batch state are not
+    # re-entrant), consecutive batches alternate between the handles
+    pools = [ThreadPoolExecutor(max_workers=1) for _ in ings]
     it = iter(item_batches)
     pending = []
     count = [0]
@@ -397,9 +399,9 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
             return False
         if len(items) == 1 and isinstance(items[0], list):
             items = items[0]
-        ing = ings[count[0] % len(ings)]
+        k = count[0] % len(ings)
         count[0] += 1
-        pending.append((items, pool.submit(ing.pack, [x[1] for x in items], [x[0] for x in items])))
+        pending.append((items, pools[k].submit(ings[k].pack, [x[1] for x in items], [x[0] for x in items])))
         return True
 
     while len(pending) < depth and submit():
@@ -416,7 +418,8 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
         # running oe_flac_pack would take the reader pool away from it)
         for _, fut in pending:
             fut.cancel()
-        pool.shutdown(wait=True)
+        for pool in pools:
+            pool.shutdown(wait=True)
 
 
 def default_flac_ingest():

@@ -51,6 +51,11 @@ def test_struct_layout_matches_header():
         body = re.search(r'typedef struct \{([^{}]*)\}\s*' + cname + ';', src).group(1)
         fields = [re.search(r'(\w+)\s*$', d.strip()).group(1) for d in body.split(';') if d.strip()]
         assert fields == [f[0] for f in cls._fields_], cname
+    body = re.search(r'typedef struct oe_flac_frame \{([^{}]*)\}\s*oe_flac_frame;', src).group(1)
+    fields = [n.strip() for d in body.split(';') if d.strip() for n in re.sub(r'^\s*\w+\s+', '', d.strip()).split(',')]
+    assert fields == [f[0] for f in _lib.OeFlacFrame._fields_]
+    from openeat_b200.ingest import FRAME_BYTES
+    assert ctypes.sizeof(_lib.OeFlacFrame) == FRAME_BYTES == 48
 
 
 def test_product_has_no_cpu_fallback():

@@ -362,3 +362,29 @@ def test_emulated_kernel_flags_what_the_host_cannot_see(tmp_path):
     assert 'channels' in errs[1] and '24-bit' in errs[2] and 'No such file' in errs[4]
     pcm, err = emul_decode(b)
     assert err[0] == 4 and err[3] == 0 and np.array_equal(pcm[b.offsets[3]:b.offsets[3] + b.lens[3]], x)
+
+
+def test_pack_ahead_generator_is_race_free(tmp_path):
+    """flac_gpu_batches: batches packed ahead by two workers (one handle each, one pack at a time per handle) arrive in
+    order and decode (emulated kernel) to the PCM that was encoded, over many small batches."""
+    from openeat_b200.ingest import flac_gpu_batches
+    rng = np.random.default_rng(41)
+    pcm, items = {}, []
+    for i in range(12):
+        x = speechlike(rng, int(rng.integers(300, 9000)))
+        p = tmp_path / ('f%d.flac' % i)
+        p.write_bytes(lib_encode(x, block=576))
+        pcm[str(p)] = x
+        items.append(('k%d' % i, str(p), [1], 1.0))
+    batches = [[items[j] for j in rng.permutation(12)[:int(rng.integers(1, 8))]] for _ in range(150)]
+    seen = 0
+    for want, got in zip(batches, flac_gpu_batches(iter(batches), depth=3, workers=2, threads=4)):
+        b = got[0]
+        assert got[3] == [x[0] for x in want] and b.loaded.all()
+        out, err = emul_decode(b)
+        assert not err.any()
+        for i, it in enumerate(want):
+            assert np.array_equal(out[b.offsets[i]:b.offsets[i] + b.lens[i]], pcm[it[1]])
+        got[8](None)
+        seen += 1
+    assert seen == 150
