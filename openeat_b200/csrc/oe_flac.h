@@ -139,6 +139,15 @@ struct Bits {
     bool over = false;
     Bits(const unsigned char* b, const unsigned char* e) : p(b), end(e) {}
     inline void refill() {
+        if (end - p >= 8) {                  // eight bytes at once: the bits below `have` are the stream's own next bits, so
+            uint64_t w;                      // OR-ing them in again at the next refill changes nothing
+            memcpy(&w, p, 8);
+            win |= __builtin_bswap64(w) >> have;
+            const int nb = (64 - have) >> 3;
+            p += nb;
+            have += nb * 8;
+            return;
+        }
         while (have <= 56) {
             uint64_t byte = 0;
             if (p < end) byte = *p;
