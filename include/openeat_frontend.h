@@ -311,6 +311,14 @@ int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double
                  void* comp, int64_t comp_capacity, oe_flac_frame* frames, int64_t frames_capacity,
                  int64_t* comp_offsets, int64_t* pcm_offsets, int32_t* n_samples, int32_t* sample_rates, int32_t* status,
                  int64_t* comp_bytes, int64_t* n_frames, int64_t* total_samples);
+/* oe_flac_pack on the handle's driver thread (like oe_ingest_submit / oe_ingest_wait: the caller -- a Python thread holding
+ * the GIL -- only submits and, later, waits); buffers must stay valid until the wait returns.  oe_flac_wait returns what
+ * oe_flac_pack returned (OE_ERR_WORKSPACE with *comp_bytes / *n_frames set: submit again with larger buffers); per-entry
+ * messages through oe_ingest_job_error, release with oe_ingest_job_release. */
+int oe_flac_submit(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends, void* comp,
+                   int64_t comp_capacity, oe_flac_frame* frames, int64_t frames_capacity, oe_ingest_job** out);
+int oe_flac_wait(oe_ingest_job* job, const int64_t** pcm_offsets, const int32_t** n_samples, const int32_t** sample_rates,
+                 const int32_t** status, int64_t* comp_bytes, int64_t* n_frames, int64_t* total_samples);
 int oe_flac_decode_batch(const void* d_comp, int64_t comp_bytes, const oe_flac_frame* d_frames, int64_t n_frames,
                          int16_t* d_pcm, int32_t* d_errors, int32_t verify_crc, oe_stream stream);
 int oe_flac_encode(const int16_t* pcm, int64_t n, int32_t sample_rate, int32_t block, int32_t partition_order,

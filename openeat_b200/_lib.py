@@ -119,6 +119,10 @@ SYMBOLS = {
     'oe_flac_pack': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), c_f64p, c_f64p,
                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, c_i64p, c_i64p, c_i32p, c_i32p,
                                     c_i32p, c_i64p, c_i64p, c_i64p]),
+    'oe_flac_submit': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), c_f64p, c_f64p,
+                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
+    'oe_flac_wait': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_i64p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),
+                                    ctypes.POINTER(c_i32p), c_i64p, c_i64p, c_i64p]),
     'oe_flac_decode_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                             ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     'oe_flac_encode': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,

@@ -2797,6 +2797,19 @@ static void ingest_driver(oe_ingest* g) {
             g->queue.erase(g->queue.begin());
         }
         const int n = (int)job->paths.size();
+        if (job->flac) {
+            job->rc = oe_flac_pack(g, n, job->cpaths.data(), job->starts.data(), job->ends.data(), job->comp, job->comp_capacity,
+                                   job->frames, job->frames_capacity, job->comp_offsets.data(), job->offsets.data(), job->lens.data(),
+                                   job->rates.data(), job->status.data(), &job->comp_bytes, &job->n_frames, &job->total);
+            if (job->rc != OE_OK) job->message = oe_last_error();
+            job->errors = g->errors;
+            {
+                std::lock_guard<std::mutex> lk(g->qm);
+                job->done = true;
+            }
+            g->dcv.notify_all();
+            continue;
+        }
         oe_ingest_probe(g, n, job->cpaths.data(), job->starts.data(), job->ends.data(), job->lens.data(), job->rates.data(),
                         job->status.data());
         int64_t total = 0;
@@ -2867,6 +2880,58 @@ int oe_ingest_wait(oe_ingest_job* job, const int64_t** offsets, const int32_t** 
     if (sample_rates) *sample_rates = job->rates.data();
     if (status) *status = job->status.data();
     if (total) *total = job->total;
+    return OE_OK;
+}
+
+int oe_flac_submit(oe_ingest* g, int32_t n, const char* const* paths, const double* starts, const double* ends, void* comp,
+                   int64_t comp_capacity, oe_flac_frame* frames, int64_t frames_capacity, oe_ingest_job** out) {
+    if (!g || !out || n < 0 || (n > 0 && !paths)) return fail(OE_ERR_INVALID, "null pointer");
+    oe_ingest_job* job = new oe_ingest_job();
+    job->owner = g;
+    job->flac = true;
+    job->paths.assign(paths, paths + n);
+    for (auto& p : job->paths) job->cpaths.push_back(p.c_str());
+    job->starts.assign(n, -1.0);
+    job->ends.assign(n, 0.0);
+    if (starts && ends) {
+        job->starts.assign(starts, starts + n);
+        job->ends.assign(ends, ends + n);
+    }
+    job->comp = comp;
+    job->comp_capacity = comp_capacity;
+    job->frames = frames;
+    job->frames_capacity = frames_capacity;
+    job->comp_offsets.assign(n, 0);
+    job->offsets.assign(n, 0);
+    job->lens.assign(n, 0);
+    job->rates.assign(n, 0);
+    job->status.assign(n, OE_ERR_INVALID);
+    {
+        std::lock_guard<std::mutex> lk(g->qm);
+        if (!g->driver.joinable()) g->driver = std::thread(ingest_driver, g);
+        g->queue.push_back(job);
+    }
+    g->qcv.notify_all();
+    *out = job;
+    return OE_OK;
+}
+
+int oe_flac_wait(oe_ingest_job* job, const int64_t** pcm_offsets, const int32_t** n_samples, const int32_t** sample_rates,
+                 const int32_t** status, int64_t* comp_bytes, int64_t* n_frames, int64_t* total_samples) {
+    if (!job || !job->flac) return fail(OE_ERR_INVALID, "not a job of oe_flac_submit");
+    oe_ingest* g = job->owner;
+    {
+        std::unique_lock<std::mutex> lk(g->qm);
+        g->dcv.wait(lk, [&] { return job->done; });
+    }
+    if (pcm_offsets) *pcm_offsets = job->offsets.data();
+    if (n_samples) *n_samples = job->lens.data();
+    if (sample_rates) *sample_rates = job->rates.data();
+    if (status) *status = job->status.data();
+    if (comp_bytes) *comp_bytes = job->comp_bytes;
+    if (n_frames) *n_frames = job->n_frames;
+    if (total_samples) *total_samples = job->total;
+    if (job->rc != OE_OK) return fail(job->rc, "%s", job->message.c_str());
     return OE_OK;
 }
 

@@ -135,6 +135,14 @@ struct oe_ingest_job {
     std::vector<int32_t> lens, rates, status;
     std::vector<std::string> errors;
     bool done = false;
+    // FLAC batches for the GPU decoder (oe_flac_submit): the driver runs oe_flac_pack instead of probe + read
+    bool flac = false;
+    void* comp = nullptr;
+    struct oe_flac_frame* frames = nullptr;
+    int64_t comp_capacity = 0, frames_capacity = 0, comp_bytes = 0, n_frames = 0;
+    std::vector<int64_t> comp_offsets;
+    int rc = 0;
+    std::string message;
 };
 
 struct oe_ingest {

@@ -338,12 +338,29 @@ class FlacGpuIngest(NativeIngest):
         self._frames[i] = grow(self._frames[i], n_frames * FRAME_BYTES)
         return i, self._comp[i], self._frames[i]
 
-    def pack(self, entries, keys=None, report=True):
+    def _request(self, entries):
         n = len(entries)
         parts = [split_entry(e) for e in entries]
         paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
         starts = np.array([p[1] for p in parts], dtype=np.float64)
         ends = np.array([p[2] for p in parts], dtype=np.float64)
+        return n, parts, paths, starts, ends
+
+    def _finish(self, n, parts, keys, report, slot, comp, frames, cb, nf, total, offs, lens, rates, status, error_of):
+        self._seen_flac = (max(getattr(self, '_seen_flac', (0, 0))[0], cb), max(getattr(self, '_seen_flac', (0, 0))[1], nf))
+        loaded = status == 0
+        for i in np.nonzero(~loaded)[0]:                               # dataset.py:108-111: print, warn, drop
+            if report:
+                print(error_of(int(i)))
+                logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
+            lens[i] = 0
+        rates[~loaded] = 16000
+        b = FlacBatch(self, slot, comp, frames, cb, nf, total, offs, lens, rates, loaded, keys)
+        b.paths = [p[0] for p in parts]
+        return b
+
+    def pack(self, entries, keys=None, report=True):
+        n, parts, paths, starts, ends = self._request(entries)
         coffs, offs = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
         lens, rates, status = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
         cb, nf, total = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
@@ -360,34 +377,61 @@ class FlacGpuIngest(NativeIngest):
             want = (cb.value, nf.value)                                # too small: once more with what the call asked for
             self._next = slot
         check(rc)
-        self._seen_flac = (max(want[0], cb.value), max(want[1], nf.value))
-        loaded = status == 0
-        for i in np.nonzero(~loaded)[0]:                               # dataset.py:108-111: print, warn, drop
-            if report:
-                print(self.lib.oe_ingest_error(self.handle, int(i)).decode())
-                logging.warning('read utterance {} error'.format(keys[i] if keys is not None else parts[i][0]))
-            lens[i] = 0
-        rates[~loaded] = 16000
-        b = FlacBatch(self, slot, comp, frames, cb.value, nf.value, total.value, offs, lens, rates, loaded, keys)
-        b.paths = [p[0] for p in parts]
+        return self._finish(n, parts, keys, report, slot, comp, frames, cb.value, nf.value, total.value, offs, lens, rates, status,
+                            lambda i: self.lib.oe_ingest_error(self.handle, i).decode())
+
+    def submit(self, entries, keys=None):
+        """Starts packing a batch on the handle's native driver thread (``oe_flac_submit``: no Python thread, nothing competes
+        for the GIL); returns a ticket for ``wait``."""
+        n, parts, paths, starts, ends = self._request(entries)
+        want = getattr(self, '_seen_flac', (1 << 20, 1 << 12))
+        slot, comp, frames = self._buffers(*want)
+        job = ctypes.c_void_p()
+        check(self.lib.oe_flac_submit(self.handle, n, paths, starts.ctypes.data_as(c_f64p), ends.ctypes.data_as(c_f64p),
+                                      ctypes.c_void_p(comp.data_ptr()), comp.numel(), ctypes.c_void_p(frames.data_ptr()),
+                                      frames.numel() // FRAME_BYTES, ctypes.byref(job)))
+        return {'job': job, 'slot': slot, 'comp': comp, 'frames': frames, 'entries': entries, 'keys': keys, 'n': n, 'parts': parts}
+
+    def wait(self, ticket, report=True):
+        """Blocks (GIL released) until the batch is packed; returns the ``FlacBatch``."""
+        n = ticket['n']
+        o, l, r, st = c_i64p(), c_i32p(), c_i32p(), c_i32p()
+        cb, nf, total = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        rc = self.lib.oe_flac_wait(ticket['job'], ctypes.byref(o), ctypes.byref(l), ctypes.byref(r), ctypes.byref(st),
+                                   ctypes.byref(cb), ctypes.byref(nf), ctypes.byref(total))
+        if rc == _lib.OE_ERR_WORKSPACE:                                  # the ring slot was too small: once more, bigger, through the
+            self.lib.oe_ingest_job_release(ticket['job'])                # same queue (the driver thread owns the handle's state)
+            seen = getattr(self, '_seen_flac', (0, 0))
+            self._seen_flac = (max(seen[0], int(cb.value * 1.25) + 65536), max(seen[1], int(nf.value * 1.25) + 256))
+            nxt, self._next = self._next, ticket['slot']                 # re-use this very slot; later slots belong to queued jobs
+            again = self.submit(ticket['entries'], ticket['keys'])
+            self._next = nxt
+            return self.wait(again, report)
+        if rc != 0:
+            self.lib.oe_ingest_job_release(ticket['job'])
+            check(rc)
+        take = lambda p, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)   # noqa: E731
+        offs, lens, rates, status = take(o, np.int64), take(l, np.int32), take(r, np.int32), take(st, np.int32)
+        job = ticket['job']
+        b = self._finish(n, ticket['parts'], ticket['keys'], report, ticket['slot'], ticket['comp'], ticket['frames'], cb.value,
+                         nf.value, total.value, offs, lens, rates, status, lambda i: self.lib.oe_ingest_job_error(job, i).decode())
+        self.lib.oe_ingest_job_release(job)
         return b
 
 
 def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
     """``ingest_batches`` for FLAC lists decoded on the GPU: yields the tuples ``PrefetchingCollator`` takes with a
     ``FlacBatch`` in the place of the pinned PCM tensor (the collator calls its ``to_device`` on the copy stream).  The next
-    ``depth`` batches are packed ahead by ``workers`` helper threads, each with its own ``FlacGpuIngest`` (the work is
-    inside ``oe_flac_pack``, GIL released; ``threads`` reader threads in total, 0 = one per core)."""
-    from concurrent.futures import ThreadPoolExecutor
+    ``depth`` batches are being packed ahead on the native driver threads of ``workers`` ``FlacGpuIngest`` handles
+    (``oe_flac_submit`` / ``oe_flac_wait``; consecutive batches alternate between the handles, each handle packs one batch at
+    a time; ``threads`` reader threads in total, 0 = one per core).  No Python threads: helper threads that need the GIL
+    between their native calls were measured to stall the collate thread for whole switch intervals."""
     if ingest is not None:
         ings = [ingest]
     else:
         total = int(threads) or len(os.sched_getaffinity(0))
         workers = max(1, min(int(workers), total))
         ings = [FlacGpuIngest(threads=max(1, total // workers), ring=depth + 4) for _ in range(workers)]
-    # one single-thread executor per handle: a handle runs one pack at a time (its reader pool and per-batch state are not
-    # re-entrant), consecutive batches alternate between the handles
-    pools = [ThreadPoolExecutor(max_workers=1) for _ in ings]
     it = iter(item_batches)
     pending = []
     count = [0]
@@ -399,27 +443,23 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
             return False
         if len(items) == 1 and isinstance(items[0], list):
             items = items[0]
-        k = count[0] % len(ings)
+        ing = ings[count[0] % len(ings)]
         count[0] += 1
-        pending.append((items, pools[k].submit(ings[k].pack, [x[1] for x in items], [x[0] for x in items])))
+        pending.append((items, ing, ing.submit([x[1] for x in items], [x[0] for x in items])))
         return True
 
     while len(pending) < depth and submit():
         pass
     try:
         while pending:
-            items, fut = pending.pop(0)
-            b = fut.result()
+            items, ing, ticket = pending.pop(0)
+            b = ing.wait(ticket)
             submit()
             yield (b, b.offsets, b.lens, [x[0] for x in items], [x[2] for x in items], [x[3] for x in items], b.rates, b.loaded,
-                   (lambda ev, s=b.slot, g=b.owner: g.release_after(s, ev)))
+                   (lambda ev, s=b.slot, g=ing: g.release_after(s, ev)))
     finally:
-        # packs still queued are dropped, the ones running finish before the ingest handles can go (a handle destroyed under a
-        # running oe_flac_pack would take the reader pool away from it)
-        for _, fut in pending:
-            fut.cancel()
-        for pool in pools:
-            pool.shutdown(wait=True)
+        for _, ing, ticket in pending:           # packs in flight finish before their handles (and pinned buffers) can go
+            ing.wait(ticket, report=False)
 
 
 def default_flac_ingest():
