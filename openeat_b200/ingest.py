@@ -459,7 +459,11 @@ def flac_gpu_batches(item_batches, ingest=None, depth=3, workers=2, threads=0):
                    (lambda ev, s=b.slot, g=ing: g.release_after(s, ev)))
     finally:
         for _, ing, ticket in pending:           # packs in flight finish before their handles (and pinned buffers) can go
-            ing.wait(ticket, report=False)
+            try:
+                ing.lib.oe_flac_wait(ticket['job'], None, None, None, None, None, None, None)
+                ing.lib.oe_ingest_job_release(ticket['job'])
+            except Exception:                    # interpreter shutdown: modules are already gone
+                pass
 
 
 def default_flac_ingest():

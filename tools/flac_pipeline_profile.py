@@ -1,8 +1,6 @@
-"""Developer tool: where the time of the FLAC end-to-end leg goes (host profile of the pipelined step, pack timings)."""
-import cProfile
-import ctypes
+"""Developer tool: where the time of the FLAC end-to-end leg goes: per-step wall time distribution and the time spent
+waiting for the pack (oe_flac_wait), enqueueing copies + decode (to_device), waiting for the decode (drop_failed)."""
 import os
-import pstats
 import random
 import sys
 import time
@@ -13,8 +11,8 @@ import torch
 
 import bench
 from openeat_b200 import _lib
+from openeat_b200 import ingest as ING
 from openeat_b200.dataset import PrefetchingCollator, audio_collate_func
-from openeat_b200.ingest import FlacGpuIngest, flac_gpu_batches
 from tools.flac_gpu_bench import encode, speechlike
 
 dev = torch.device('cuda', 0)
@@ -39,6 +37,24 @@ istd = torch.linspace(0.4, 0.6, 80, device=dev)
 stats = torch.zeros(161, dtype=torch.float64, device=dev)
 collate = audio_collate_func(data_type='wav', feature_extraction_conf=bench.CONF, normalization=True, spec_aug=True,
                              spec_aug_conf=bench.AUG, global_cmvn=(mean, istd), cmvn_stats=stats)
+acc = {}
+
+
+def timed(cls, name):
+    fn = getattr(cls, name)
+
+    def wrap(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return fn(*a, **k)
+        finally:
+            acc.setdefault(name, []).append(time.perf_counter() - t0)
+    setattr(cls, name, wrap)
+
+
+for cls, name in ((ING.FlacGpuIngest, 'wait'), (ING.FlacGpuIngest, 'submit'), (ING.FlacGpuIngest, '_buffers'), (ING.FlacBatch, 'to_device'),
+                  (ING.FlacBatch, 'drop_failed'), (audio_collate_func, 'collate_packed')):
+    timed(cls, name)
 
 
 def forever():
@@ -48,34 +64,26 @@ def forever():
         i += 1
 
 
-for workers, threads in ((1, 16), (2, 16), (2, 8), (4, 16)):
-    g = FlacGpuIngest(threads=threads // workers, ring=3)
-    for _ in range(3):
-        g.pack([x[1] for x in batches[0]], report=False)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        g.pack([x[1] for x in batches[0]], report=False)
-    print('pack alone, %2d threads: %.2f ms' % (threads // workers, (time.perf_counter() - t0) / 20 * 1e3))
-    del g
-    pipe = PrefetchingCollator(collate, flac_gpu_batches(forever(), depth=3, workers=workers, threads=threads))
+for workers, threads in ((2, 16), (1, 16), (2, 8)):
+    pipe = PrefetchingCollator(collate, ING.flac_gpu_batches(forever(), depth=3, workers=workers, threads=threads))
     pin_n = torch.empty(bench.BATCH, dtype=torch.int32).pin_memory()
-
-    def run(n):
-        for i in range(n):
-            _, out = next(pipe)
-            pin_n.copy_(out['features_length'], non_blocking=True)
-
     random.seed(1)
-    run(20)
+    for i in range(30):
+        next(pipe)
     torch.cuda.synchronize()
+    acc.clear()
+    steps = []
     t0 = time.perf_counter()
-    run(100)
+    for i in range(200):
+        _, out = next(pipe)
+        pin_n.copy_(out['features_length'], non_blocking=True)
+        t1 = time.perf_counter()
+        steps.append(t1 - t0)
+        t0 = t1
     torch.cuda.synchronize()
-    print('pipeline, workers=%d threads=%d: %.3f ms per step' % (workers, threads, (time.perf_counter() - t0) / 100 * 1e3))
-    if workers == 2 and threads == 16:
-        pr = cProfile.Profile()
-        pr.enable()
-        run(100)
-        torch.cuda.synchronize()
-        pr.disable()
-        pstats.Stats(pr).sort_stats('tottime').print_stats(18)
+    s = np.array(steps) * 1e3
+    print('workers=%d threads=%d: step ms median %.3f mean %.3f p90 %.3f max %.3f' % (workers, threads, np.median(s), s.mean(), np.percentile(s, 90), s.max()))
+    for k, v in sorted(acc.items()):
+        v = np.array(v) * 1e3
+        print('   %-16s calls %4d  median %.3f  mean %.3f  max %.3f ms' % (k, len(v), np.median(v), v.mean(), v.max()))
+    del pipe
