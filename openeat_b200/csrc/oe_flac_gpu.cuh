@@ -46,6 +46,9 @@ __device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
 }
 __device__ __forceinline__ uint32_t big_endian(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
 __device__ __forceinline__ int clz32(uint32_t v) { return __clz((int)v); }
+// high / low word of a 64-bit pair shifted by 0..32 (the shift clamps at 32, unlike C's << and >>)
+__device__ __forceinline__ uint32_t shl_pair_hi(uint32_t hi, uint32_t lo, int n) { return __funnelshift_lc(lo, hi, n); }
+__device__ __forceinline__ uint32_t shr_pair_lo(uint32_t hi, uint32_t lo, int n) { return __funnelshift_rc(lo, hi, n); }
 #else   // host emulation (oe_emul.cpp): same arithmetic, copies are immediate
 inline void line_copy_async(void* d, const void* s, int chunks) { memcpy(d, s, 16 * (size_t)(chunks < 0 ? 0 : chunks > 8 ? 8 : chunks)); }
 inline void line_commit() {}
@@ -54,12 +57,14 @@ inline void line_wait_all_but_one() {}
 inline int64_t mad_wide(int32_t a, int32_t b, int64_t c) { return (int64_t)a * b + c; }
 inline uint32_t big_endian(uint32_t w) { return __builtin_bswap32(w); }
 inline int clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline uint32_t shl_pair_hi(uint32_t hi, uint32_t lo, int n) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (n > 32 ? 32 : n)) >> 32); }
+inline uint32_t shr_pair_lo(uint32_t hi, uint32_t lo, int n) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (n > 32 ? 32 : n)); }
 #endif
 
 // Bit reader of one lane.  The lane's stream is staged through a private 256-byte ring in shared memory, refilled a
 // 128-byte line at a time with cp.async one line AHEAD of use (issued ~100 samples before its first word is read, so no
 // lane ever waits for L2 / HBM: the 32 lanes of a warp walk 32 different streams and every line is a first touch for
-// somebody).  The bit window is a left-aligned 64-bit register with at least 32 valid bits; it is topped up from the ring
+// somebody).  The bit window is a left-aligned register pair (hi:lo) with at least 32 valid bits; it is topped up from the ring
 // without a branch (the next word is loaded speculatively, merged under a predicate), because a warp whose lanes branch
 // independently executes every side of every branch in every iteration.  A first version that loaded words on demand with
 // branches measured 1.8 ms for 6 000 frames (~850 cycles per sample: ~200 dependent instructions at one warp per scheduler).
@@ -67,7 +72,7 @@ struct Reader {
     const unsigned char* src16;              // 16-byte aligned address that holds the stream's first byte
     uint32_t* ring;                          // this lane's kRingWords words of shared memory
     int64_t src_bytes;                       // bytes readable from src16 (multiple of 16)
-    uint64_t win;                            // next bits, left aligned; bits below `have` are zero
+    uint32_t hi, lo;                         // next bits, left aligned in the pair hi:lo; bits below `have` are zero
     int have;
     int wpos;                                // next stream word (from src16) to merge into the window
     int issued;                              // lines requested so far: line L lives in ring slot L & 3 until wpos passes its last word
@@ -92,12 +97,21 @@ struct Reader {
         }
     }
     __device__ __forceinline__ uint32_t word() const { return big_endian(ring[wpos & (kRingWords - 1)]); }
-    __device__ __forceinline__ void top_up(uint32_t w) {      // branch-free: merge `w` (= word()) when 32 bits or fewer are left
+    // Branch-free: merges `w` (= word()) behind the valid bits when 32 or fewer are left (then lo is empty: all of them sit in
+    // hi).  Two funnel shifts and two predicated moves.
+    __device__ __forceinline__ void top_up(uint32_t w) {
         const bool need = have <= 32;
-        const uint64_t add = (uint64_t)w << ((32 - have) & 63);
-        win |= need ? add : 0ull;
+        const uint32_t a = shr_pair_lo(0u, w, have);           // w >> have          (0 when have == 32)
+        const uint32_t b = shr_pair_lo(w, 0u, have);           // w << (32 - have)   (0 when have == 0)
+        hi |= need ? a : 0u;
+        lo = need ? b : lo;
         have += need ? 32 : 0;
         wpos += need ? 1 : 0;
+    }
+    __device__ __forceinline__ void drop(int n) {             // 0 <= n <= 32 bits consumed
+        hi = shl_pair_hi(hi, lo, n);
+        lo = shl_pair_hi(lo, 0u, n);
+        have -= n;
     }
     __device__ __forceinline__ void init(const unsigned char* base, int64_t byte_off, int64_t limit, uint32_t* lane_ring) {
         const unsigned char* p = base + byte_off;
@@ -110,12 +124,12 @@ struct Reader {
         wpos = mis >> 2;
         start_bits = (mis & ~3) * 8 + (mis & 3) * 8;
         over = false;
-        win = (uint64_t)word() << 32;
+        hi = word();
         ++wpos;
-        win |= word();
+        lo = word();
         ++wpos;
-        have = 64 - (mis & 3) * 8;
-        win <<= (mis & 3) * 8;
+        have = 64;
+        drop((mis & 3) * 8);
         top_up(word());
     }
     // bits consumed since init
@@ -123,9 +137,8 @@ struct Reader {
     __device__ __forceinline__ uint32_t take(int n) {          // 0 <= n <= 32
         service();
         const uint32_t w = word();
-        const uint32_t v = (uint32_t)((win >> 1) >> (63 - n));
-        win <<= n;
-        have -= n;
+        const uint32_t v = shr_pair_lo(0u, hi, 32 - n);          // the top n bits (n == 0: nothing)
+        drop(n);
         top_up(w);
         return v;
     }
@@ -136,7 +149,7 @@ struct Reader {
     __device__ __forceinline__ uint32_t unary() {              // zeros before the next one bit (any length)
         uint32_t q = 0;
         for (;;) {
-            const int z = clz32((uint32_t)(win >> 32));         // at least 32 valid bits: a one among them ends the run
+            const int z = clz32(hi);                            // at least 32 valid bits: a one among them ends the run
             if (z < 32) {
                 q += (uint32_t)z;
                 take(z + 1);
@@ -153,11 +166,8 @@ struct Reader {
     // One Rice symbol with parameter k (<= 30): quotient in unary, then k bits.  When quotient + 1 + k <= 32 (almost always)
     // the symbol is cut out of the window's top half in one step (rice_fast; the caller has checked n <= 32).
     __device__ __forceinline__ uint32_t rice_fast(int k, int z, int n, uint32_t w) {
-        const uint32_t hi = (uint32_t)(win >> 32);
-        const uint32_t t = (hi << z) << 1;
-        const uint32_t rem = (t >> 1) >> (31 - k);
-        win <<= n;
-        have -= n;
+        const uint32_t rem = (hi >> (32 - n)) & ((1u << k) - 1u);    // the k bits behind the quotient's terminating one
+        drop(n);
         top_up(w);
         return ((uint32_t)z << k) | rem;
     }
@@ -297,7 +307,7 @@ __device__ __forceinline__ int32_t reader_slow_sample(ReaderState& st, int i) {
     st.fast_until = st.rice ? (st.part_end < st.n ? st.part_end : st.n) : st.order;     // == order: no fast samples
     if (st.rice) {
         r.service();
-        const int z = clz32((uint32_t)(r.win >> 32));
+        const int z = clz32(r.hi);
         const int n = z + 1 + st.k;
         const uint32_t v = n <= 32 ? r.rice_fast(st.k, z, n, r.word()) : r.rice(st.k);   // a partition's first symbol is as short as any
         return (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
@@ -310,21 +320,22 @@ __device__ __forceinline__ int32_t reader_slow_sample(ReaderState& st, int i) {
 __device__ __forceinline__ void reader_chunk(ReaderState& st, int32_t* tile, int i0) {
     Reader& r = st.r;
     r.service();
+    unsigned fast_span = (unsigned)(st.fast_until - st.order);       // refreshed whenever the slow path moved fast_until
 #pragma unroll 1
-    for (int j = 0; j < kChunk; ++j) {
-        const int i = i0 + j;
+    for (int i = i0; i < i0 + kChunk; ++i, tile += 32) {
         const uint32_t w = r.word();
-        const int z = clz32((uint32_t)(r.win >> 32));
+        const int z = clz32(r.hi);
         const int n = z + 1 + st.k;
         int32_t res;
-        if ((unsigned)(i - st.order) < (unsigned)(st.fast_until - st.order) && n <= 32) {
+        if ((unsigned)(i - st.order) < fast_span && n <= 32) {
             const uint32_t v = r.rice_fast(st.k, z, n, w);
             res = (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
         } else {
             res = reader_slow_sample(st, i);
+            fast_span = (unsigned)(st.fast_until - st.order);
             if (i < st.order) continue;      // warm-up samples are in the tile already
         }
-        tile[j * 32] = res;
+        *tile = res;
     }
 }
 
