@@ -235,7 +235,10 @@ class FlacBatch(object):
         lib = self.owner.lib
         n = len(self.lens)
         pcm = torch.empty(max(self.total, ALIGN), dtype=torch.int16, device=device)
-        if self.n_frames == 0:
+        if self.n_frames == 0:                   # nothing decodable in the batch: still an event for whoever orders behind it
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(device))
+            self.errors = torch.zeros(max(n, 1), dtype=torch.int32)
             return pcm
         d_comp = self.comp[:self.comp_bytes + 16].to(device, non_blocking=True)
         d_frames = self.frames[:self.n_frames * FRAME_BYTES].to(device, non_blocking=True)

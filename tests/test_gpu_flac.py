@@ -119,3 +119,18 @@ def test_collate_of_flac_files_equals_collate_of_their_pcm(tmp_path, capsys):
     keys3, out3 = fn([batch])
     assert 'utt3' not in list(keys3) and len(keys3) == len(keys) - 1
     assert 'rejected by the GPU decoder' in capsys.readouterr().out
+
+
+def test_batch_without_a_decodable_file(tmp_path, capsys):
+    """Every entry unreadable (missing file, damaged header): the batch comes back empty through both entry points instead
+    of failing (dataset.py:108-111 drops unreadable utterances one by one)."""
+    from openeat_b200.dataset import PrefetchingCollator, audio_collate_func
+    from openeat_b200.ingest import flac_gpu_batches
+    (tmp_path / 'bad.flac').write_bytes(b'fLaC' + bytes(64))
+    batch = [('a', str(tmp_path / 'bad.flac'), [1], 1.0), ('b', str(tmp_path / 'missing.flac'), [2], 1.0)]
+    fn = audio_collate_func(data_type='wav', feature_extraction_conf=CONF)
+    keys, out = fn([batch])
+    assert len(keys) == 0
+    got = list(PrefetchingCollator(fn, flac_gpu_batches([batch, batch])))
+    assert len(got) == 2 and all(len(k) == 0 for k, _ in got)
+    assert 'STREAMINFO' in capsys.readouterr().out
