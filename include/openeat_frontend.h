@@ -284,7 +284,8 @@ int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t firs
  *                         streams the GPU decoder does not take (more than one channel, more than 16 bits, no announced
  *                         length) -- send those through oe_ingest_read / oe_flac_decode.  Returns OE_ERR_WORKSPACE with
  *                         *comp_bytes / *n_frames set to what is needed when a buffer is too small (comp needs 16 spare
- *                         bytes behind *comp_bytes).
+ *                         bytes behind *comp_bytes).  Uses the handle's reader pool and per-batch state: one call at a
+ *                         time per handle, and not while jobs of oe_flac_submit / oe_ingest_submit are in flight on it.
  *   oe_flac_decode_batch  device: decodes n_frames frames of d_comp into d_pcm; d_errors[utt] (caller-zeroed int32 per
  *                         entry) collects OE_FLAC_ERR_* bits: the frame must end where the host found the next header and
  *                         (verify_crc) match its CRC-16.  Stream-ordered, one launch.
