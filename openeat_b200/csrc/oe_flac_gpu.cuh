@@ -1,20 +1,24 @@
-// FLAC frames decoded on the GPU: the compressed corpus crosses PCIe (about half the bytes of its PCM for speech), one
-// thread decodes one frame straight into the packed int16 buffer the fbank kernels read.  Replaces the per-utterance
-// libsox / libFLAC decode behind torchaudio.load (openeat/dataset/dataset.py:62-72) for the LibriSpeech-style lists;
-// the format is RFC 9639 (section 9: frames, subframes, partitioned Rice residuals), the arithmetic is integer and the
-// result is bit-exact with the host decoder in oe_flac.h.
+// FLAC frames decoded on the GPU: the compressed corpus crosses PCIe (about half the bytes of its PCM for speech) and is
+// decoded straight into the packed int16 buffer the fbank kernels read.  Replaces the per-utterance libsox / libFLAC decode
+// behind torchaudio.load (openeat/dataset/dataset.py:62-72) for the LibriSpeech-style lists; the format is RFC 9639
+// (section 9: frames, subframes, partitioned Rice residuals), the arithmetic is integer and the result is bit-exact with
+// the host decoder in oe_flac.h.
 //
-// Why one thread per frame: frames are the format's only independent units (each starts with its own header and warm-up
-// samples); inside a frame both the entropy code (variable-length, no resynchronisation points) and the predictor (an
-// IIR recursion) are serial.  A batch of 256 utterances holds ~6 000 frames = ~190 warps, one or two per SM scheduler,
-// each a latency-bound serial chain of ~60 instructions per sample; HBM is not the limit (2 bytes out per sample), the
-// dependent chain clz -> shift -> extract -> predict is.  Every thread runs the SAME code whatever its frame's predictor
-// is: fixed predictors are rewritten as linear predictors, every order runs the 12-tap body with zero coefficients
-// (orders above 12 exist only outside the format's streamable subset and are sent back to the host decoder), so warps
-// only diverge at partition boundaries and in the rare escape / verbatim / constant subframes.
+// Parallelism: frames are the format's only independent units (each starts with its own header and warm-up samples);
+// inside a frame both the entropy code (variable-length, no resynchronisation points) and the predictor (an IIR
+// recursion) are serial.  A batch of 256 utterances holds ~6 000 frames, so this is a latency problem -- a few hundred
+// warps on 592 schedulers, HBM is not the limit (2 bytes out per sample) -- and the design cuts the dependent chain per
+// sample: a block takes 32 frames; lane l of warp 0 turns frame l's bit stream into residuals, lane l of warp 1 runs the
+// predictor and stores PCM, lane l of warp 2 checks the CRC-16 meanwhile (see "three warps per block" below).  Every lane
+// runs the SAME code whatever its frame's predictor is: fixed predictors are rewritten as linear predictors, every order
+// runs the 12-tap body with zero coefficients (orders above 12 exist only outside the format's streamable subset and are
+// sent back to the host decoder), constant / verbatim subframes travel as residuals of a zero predictor.
 //
 // The host (oe_flac_pack) finds the frame boundaries by walking header to header; the kernel checks what the host
 // could not: each frame must end exactly where the next one starts and its CRC-16 must match.
+//
+// The reader / predictor / CRC code below also compiles for the host (no __CUDACC__: oe_emul.cpp), where the CPU test
+// suite runs it frame by frame over every stream of the test matrix.
 #pragma once
 
 #include <cstdint>
