@@ -247,7 +247,10 @@ __device__ __forceinline__ void reader_prologue(ReaderState& st, Hand& hand, int
         if (order > kMaxOrder) err |= kErrHost, order = 0;
         else if (order > n) err |= kErrFormat, order = 0;
         else {
-            for (int i = 0; i < order; ++i) tile0[i * 32] = r.take_signed(bps);      // order <= 12 < kChunk
+            for (int i = 0; i < order; ++i) {                                        // order <= 12 < kChunk; folded like every tile entry
+                const int32_t ws = r.take_signed(bps);
+                tile0[i * 32] = (int32_t)(((uint32_t)ws << 1) ^ (uint32_t)(ws >> 31));
+            }
             if (kind >= 32) {
                 const int prec = (int)r.take(4) + 1;
                 if (prec == 16) err |= kErrFormat;
@@ -330,16 +333,18 @@ __device__ __forceinline__ void reader_chunk(ReaderState& st, int32_t* tile, int
         const uint32_t w = r.word();
         const int z = clz32(r.hi);
         const int n = z + 1 + st.k;
-        int32_t res;
+        // the tile carries FOLDED residuals (the Rice code's own unsigned form, 2r for r >= 0 and -2r - 1 for r < 0): unfolding
+        // costs the predictor warp three instructions it has time for, and takes four off this warp, which is the critical one
+        uint32_t v;
         if ((unsigned)(i - st.order) < fast_span && n <= 32) {
-            const uint32_t v = r.rice_fast(st.k, z, n, w);
-            res = (int32_t)(v >> 1) ^ -(int32_t)(v & 1);
+            v = r.rice_fast(st.k, z, n, w);
         } else {
-            res = reader_slow_sample(st, i);
+            const int32_t res = reader_slow_sample(st, i);
+            v = ((uint32_t)res << 1) ^ (uint32_t)(res >> 31);
             fast_span = (unsigned)(st.fast_until - st.order);
             if (i < st.order) continue;      // warm-up samples are in the tile already
         }
-        *tile = res;
+        *tile = (int32_t)v;
     }
 }
 
@@ -370,7 +375,8 @@ __device__ __forceinline__ void predictor_chunk(PredictorState& p, const int32_t
         for (int u = 0; u < kMaxOrder; ++u) {
             // slot of the sample t steps back, before sample u of the group is stored: (kMaxOrder - u + t) % kMaxOrder
             const int i = i0 + g + u;
-            const int32_t res = tile[(g + u) * 32];
+            const uint32_t fv = (uint32_t)tile[(g + u) * 32];
+            const int32_t res = (int32_t)(fv >> 1) ^ -(int32_t)(fv & 1);
             const int32_t pred = (int32_t)(mad_wide(p.c[0], p.h[(kMaxOrder - u) % kMaxOrder], p.ahead) >> p.shift);
             const int32_t s = res + (i >= p.order ? pred : 0);
             if ((unsigned)(i - p.lo) < (unsigned)(p.hi - p.lo)) p.out[i] = (int16_t)(s << p.wasted);
