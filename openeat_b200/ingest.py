@@ -68,6 +68,32 @@ class NativeIngest(object):
             self._ring[i] = buf
         return i, buf
 
+    def _request(self, entries):
+        """entries -> (n, parts, char** array, starts, ends).  The pointer array is built with numpy over ONE encoded blob
+        (a ctypes array of 256 c_char_p costs ~90 us of the collate thread per batch); `parts` keeps the blob alive."""
+        n = len(entries)
+        joined = '\0'.join(entries)
+        if ',' in joined or ' ' in joined or '\n' in joined or '\t' in joined:    # segments / stray whitespace: entry by entry
+            parts = [split_entry(e) for e in entries]
+            starts = np.array([p[1] for p in parts], dtype=np.float64)
+            ends = np.array([p[2] for p in parts], dtype=np.float64)
+            joined = '\0'.join(p[0] for p in parts)
+        else:
+            parts = [(e, -1.0, 0.0) for e in entries]
+            starts = np.full(n, -1.0, dtype=np.float64)
+            ends = np.zeros(n, dtype=np.float64)
+        blob = (joined + '\0').encode()
+        ptrs = np.zeros(max(n, 1), dtype=np.uint64)
+        if n:
+            base = ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value
+            ends_at = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0)
+            assert len(ends_at) == n, 'a path contains a NUL byte'
+            ptrs[0] = base
+            ptrs[1:n] = base + ends_at[:-1].astype(np.uint64) + np.uint64(1)
+        paths = ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_char_p))
+        parts.append((blob, ptrs))               # keep-alive for the duration of the native call
+        return n, parts, paths, starts, ends
+
     def pad_rows(self, src, frames, tmax, dst, pad_row=None):
         """``oe_host_pad_rows``: ragged host rows ``src`` (sum(frames), F) -> zero-padded host tensor ``dst`` (B, tmax, F)
         on this handle's threads (non-temporal stores); ``pad_row`` (F,) float32 replaces the zeros (GlobalCMVN on the
@@ -83,11 +109,7 @@ class NativeIngest(object):
 
     def submit(self, entries, capacity=None):
         """Starts reading a batch on the handle's driver thread; returns a ticket for ``wait``."""
-        n = len(entries)
-        parts = [split_entry(e) for e in entries]
-        paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
-        starts = np.array([p[1] for p in parts], dtype=np.float64)
-        ends = np.array([p[2] for p in parts], dtype=np.float64)
+        n, parts, paths, starts, ends = self._request(entries)
         want = int(capacity or getattr(self, '_seen', 0) or (1 << 22))
         slot, buf = self._slot(want)
         job = ctypes.c_void_p()
@@ -127,11 +149,7 @@ class NativeIngest(object):
         return ticket['buf'][:max(int(total.value), ALIGN)], offs, lens, rates, loaded, ticket['slot']
 
     def load(self, entries, keys=None, report=True):
-        n = len(entries)
-        parts = [split_entry(e) for e in entries]
-        paths = (ctypes.c_char_p * n)(*[p[0].encode() for p in parts])
-        starts = np.array([p[1] for p in parts], dtype=np.float64)
-        ends = np.array([p[2] for p in parts], dtype=np.float64)
+        n, parts, paths, starts, ends = self._request(entries)
         lens = np.zeros(n, dtype=np.int32)
         rates = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.int32)
@@ -340,32 +358,6 @@ class FlacGpuIngest(NativeIngest):
         self._comp[i] = grow(self._comp[i], comp_bytes + 16)
         self._frames[i] = grow(self._frames[i], n_frames * FRAME_BYTES)
         return i, self._comp[i], self._frames[i]
-
-    def _request(self, entries):
-        """entries -> (n, parts, char** array, starts, ends).  The pointer array is built with numpy over ONE encoded blob
-        (a ctypes array of 256 c_char_p costs ~90 us of the collate thread per batch); `parts` keeps the blob alive."""
-        n = len(entries)
-        joined = '\0'.join(entries)
-        if ',' in joined or ' ' in joined or '\n' in joined or '\t' in joined:    # segments / stray whitespace: entry by entry
-            parts = [split_entry(e) for e in entries]
-            starts = np.array([p[1] for p in parts], dtype=np.float64)
-            ends = np.array([p[2] for p in parts], dtype=np.float64)
-            joined = '\0'.join(p[0] for p in parts)
-        else:
-            parts = [(e, -1.0, 0.0) for e in entries]
-            starts = np.full(n, -1.0, dtype=np.float64)
-            ends = np.zeros(n, dtype=np.float64)
-        blob = (joined + '\0').encode()
-        ptrs = np.zeros(max(n, 1), dtype=np.uint64)
-        if n:
-            base = ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value
-            ends_at = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0)
-            assert len(ends_at) == n, 'a path contains a NUL byte'
-            ptrs[0] = base
-            ptrs[1:n] = base + ends_at[:-1].astype(np.uint64) + np.uint64(1)
-        paths = ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_char_p))
-        parts.append((blob, ptrs))               # keep-alive for the duration of the native call
-        return n, parts, paths, starts, ends
 
     def _finish(self, n, parts, keys, report, slot, comp, frames, cb, nf, total, offs, lens, rates, status, error_of):
         self._seen_flac = (max(getattr(self, '_seen_flac', (0, 0))[0], cb), max(getattr(self, '_seen_flac', (0, 0))[1], nf))

@@ -388,3 +388,28 @@ def test_pack_ahead_generator_is_race_free(tmp_path):
         got[8](None)
         seen += 1
     assert seen == 150
+
+
+def test_async_pack_reports_bad_entries_and_grows_its_buffers(tmp_path, capsys):
+    """oe_flac_submit / oe_flac_wait: a first batch larger than the initial ring slot is re-submitted with larger buffers;
+    unreadable entries come back not loaded with their reason printed (dataset.py:108-111), the others decode."""
+    from openeat_b200.ingest import FlacGpuIngest
+    rng = np.random.default_rng(51)
+    x = speechlike(rng, 900000)                                    # ~0.9 MB of FLAC: with the others, more than the 1 MB first slot
+    y = speechlike(rng, 5000)
+    (tmp_path / 'big.flac').write_bytes(lib_encode(x))
+    (tmp_path / 'big2.flac').write_bytes(lib_encode(x[::-1].copy()))
+    (tmp_path / 'small.flac').write_bytes(lib_encode(y))
+    (tmp_path / 'bad.flac').write_bytes(b'fLaC' + bytes(64))
+    names = [str(tmp_path / n) for n in ('big.flac', 'bad.flac', 'small.flac', 'missing.flac', 'big2.flac')]
+    ing = FlacGpuIngest(threads=2, ring=3)
+    tickets = [ing.submit(names, keys=list('abcde')) for _ in range(2)]
+    for t in tickets:
+        b = ing.wait(t)
+        assert b.loaded.tolist() == [True, False, True, False, True] and b.lens.tolist() == [900000, 0, 5000, 0, 900000]
+        out, err = emul_decode(b)
+        assert not err.any()
+        assert np.array_equal(out[b.offsets[0]:b.offsets[0] + 900000], x) and np.array_equal(out[b.offsets[2]:b.offsets[2] + 5000], y)
+        assert np.array_equal(out[b.offsets[4]:b.offsets[4] + 900000], x[::-1])
+    text = capsys.readouterr().out
+    assert 'STREAMINFO' in text and 'No such file' in text
