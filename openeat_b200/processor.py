@@ -62,7 +62,7 @@ def parse_raw(lines):
 
 def tar_file_and_group(shards):
     """wenet shard lists: every line of ``data.list`` (``data_type='shard'``) names one tar file whose members are
-    ``<key>.wav`` (RIFF/WAVE, see ``dataset.read_wav``) and ``<key>.txt``, stored next to each other.  Yields the same sample dicts as
+    ``<key>.wav`` / ``<key>.flac`` (RIFF/WAVE or FLAC, see ``dataset.read_wav``) and ``<key>.txt``, stored next to each other.  Yields the same sample dicts as
     ``parse_raw``.  A member that cannot be decoded is skipped with a message (dataset.py:108-111 convention)."""
     for shard in shards:
         shard = shard.strip() if isinstance(shard, str) else shard
@@ -83,7 +83,7 @@ def tar_file_and_group(shards):
                     blob = tar.extractfile(member).read()
                     if ext == 'txt':
                         sample['txt'] = blob.decode('utf8').strip()
-                    elif ext == 'wav':
+                    elif ext in ('wav', 'flac'):
                         pcm, sr = decode_wav(io.BytesIO(blob), name=member.name)
                         sample['wav'] = np.array(pcm)
                         sample['sample_rate'] = sr

@@ -413,3 +413,22 @@ def test_async_pack_reports_bad_entries_and_grows_its_buffers(tmp_path, capsys):
         assert np.array_equal(out[b.offsets[4]:b.offsets[4] + 900000], x[::-1])
     text = capsys.readouterr().out
     assert 'STREAMINFO' in text and 'No such file' in text
+
+
+def test_shard_tar_with_flac_members(tmp_path):
+    """wenet-style shards (data_type='shard'): <key>.flac members are decoded like <key>.wav ones."""
+    import io
+    import tarfile
+    from openeat_b200.processor import tar_file_and_group
+    rng = np.random.default_rng(61)
+    x, y = speechlike(rng, 7000), speechlike(rng, 3000)
+    shard = tmp_path / 's0.tar'
+    with tarfile.open(shard, 'w') as tar:
+        for name, blob in (('u1.flac', lib_encode(x, block=1152)), ('u1.txt', 'hello world'.encode()),
+                           ('u2.txt', 'b'.encode()), ('u2.flac', lib_encode(y))):
+            info = tarfile.TarInfo(name)
+            info.size = len(blob)
+            tar.addfile(info, io.BytesIO(blob))
+    got = list(tar_file_and_group([str(shard)]))
+    assert [s['key'] for s in got] == ['u1', 'u2'] and [s['txt'] for s in got] == ['hello world', 'b']
+    assert np.array_equal(got[0]['wav'], x) and np.array_equal(got[1]['wav'], y) and got[0]['sample_rate'] == 16000
