@@ -281,7 +281,7 @@ int oe_flac_decode(const void* data, int64_t size, int32_t channel, int64_t firs
  *                         frame header to frame header and writes one oe_flac_frame per frame that overlaps the entry's
  *                         segment (starts / ends as for oe_ingest_probe), lays the utterances out at 8-sample aligned
  *                         pcm_offsets.  status[i] != OE_OK: oe_ingest_error(g, i) says why; OE_ERR_UNSUPPORTED marks
- *                         streams the GPU decoder does not take (more than one channel, more than 16 bits, no announced
+ *                         streams the GPU decoder does not take (more than one channel, other than 16 bits per sample, no announced
  *                         length) -- send those through oe_ingest_read / oe_flac_decode.  Returns OE_ERR_WORKSPACE with
  *                         *comp_bytes / *n_frames set to what is needed when a buffer is too small (comp needs 16 spare
  *                         bytes behind *comp_bytes).  Uses the handle's reader pool and per-batch state: one call at a

@@ -2651,7 +2651,7 @@ int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double
         if (err.empty()) {
             code = OE_ERR_UNSUPPORTED;
             if (fi.channels != 1) err = std::to_string(fi.channels) + " channels (the GPU decoder takes mono streams; the host decoder reads channel 0)";
-            else if (fi.bits > 16) err = std::to_string(fi.bits) + "-bit FLAC (the GPU decoder fills an int16 buffer)";
+            else if (fi.bits != 16) err = std::to_string(fi.bits) + "-bit FLAC (the GPU decoder fills an int16 buffer with 16-bit streams; read_wav scales the others like torchaudio)";
             else if (fi.total == 0) err = "the stream does not announce its length (host decoder)";
         }
         int64_t first = 0, count = 0;

@@ -356,6 +356,9 @@ def test_emulated_kernel_flags_what_the_host_cannot_see(tmp_path):
     (tmp_path / 'o32.flac').write_bytes(oflac.encode(y[None], 16000, 16, kind='lpc', order=32, lpc=(8, 7, rng.integers(-50, 51, 32).tolist())))
     (tmp_path / 'st.flac').write_bytes(oflac.encode(np.stack([y, y]), 16000, 16, kind='fixed', order=2))
     (tmp_path / 'b24.flac').write_bytes(oflac.encode(y[None] * 200, 16000, 24, kind='fixed', order=2))
+    (tmp_path / 'b8.flac').write_bytes(oflac.encode(y[None] >> 6, 16000, 8, kind='fixed', order=1))
+    b8 = ing.pack([str(tmp_path / 'b8.flac')], report=False)
+    assert not b8.loaded[0] and '8-bit' in ing.lib.oe_ingest_error(ing.handle, 0).decode()
     b = ing.pack([str(tmp_path / n) for n in ('o32.flac', 'st.flac', 'b24.flac', 'good.flac', 'missing.flac')], report=False)
     assert b.loaded.tolist() == [True, False, False, True, False]
     errs = [ing.lib.oe_ingest_error(ing.handle, i).decode() for i in range(5)]
