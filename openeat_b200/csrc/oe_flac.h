@@ -207,9 +207,17 @@ struct Bits {
     }
 };
 
+// Length of an ID3v2 tag in front of the stream (some taggers prepend one; libFLAC skips it too), 0 if there is none.
+// `d` needs to hold the tag's 10-byte header only.
+inline int64_t id3v2_bytes(const unsigned char* d, int64_t size) {
+    if (size < 10 || d[0] != 'I' || d[1] != 'D' || d[2] != '3' || d[3] == 0xFF || d[4] == 0xFF || ((d[6] | d[7] | d[8] | d[9]) & 0x80)) return 0;
+    return 10 + ((int64_t)d[6] << 21 | (int64_t)d[7] << 14 | (int64_t)d[8] << 7 | d[9]) + ((d[5] & 0x10) ? 10 : 0);
+}
+
 inline std::string parse_streaminfo(const unsigned char* d, int64_t size, Info& info) {
-    if (size < 42 || memcmp(d, "fLaC", 4) != 0) return "not a FLAC stream";
-    int64_t pos = 4;
+    int64_t pos = id3v2_bytes(d, size);
+    if (size - pos < 42 || memcmp(d + pos, "fLaC", 4) != 0) return "not a FLAC stream";
+    pos += 4;
     bool have = false;
     for (;;) {
         if (pos + 4 > size) return "truncated metadata";

@@ -2642,7 +2642,9 @@ int oe_flac_pack(oe_ingest* g, int32_t n, const char* const* paths, const double
         unsigned char head[42];
         oe_flac::Info& fi = infos[i];
         if (fstat(fd, &st) != 0) err = strerror(errno);
-        else if (pread(fd, head, 42, 0) != 42 || memcmp(head, "fLaC", 4) != 0) err = "not a FLAC stream";
+        else if (pread(fd, head, 42, 0) != 42) err = "not a FLAC stream";
+        else if (const int64_t id3 = oe_flac::id3v2_bytes(head, 42); id3 > 0 && pread(fd, head, 42, id3) != 42) err = "not a FLAC stream";
+        else if (memcmp(head, "fLaC", 4) != 0) err = "not a FLAC stream";
         else {
             head[4] |= 0x80;
             err = oe_flac::parse_streaminfo(head, 42, fi);

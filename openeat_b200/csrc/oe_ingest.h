@@ -175,11 +175,14 @@ inline std::string parse_wav(int fd, const char* path, WavInfo& w) {
     if (pread(fd, h, 12, 0) != 12) return std::string(path) + ": too short for a RIFF header";
     struct stat st;
     if (fstat(fd, &st) != 0) return std::string(path) + ": " + strerror(errno);
-    if (memcmp(h, "fLaC", 4) == 0) {
+    const int64_t id3 = oe_flac::id3v2_bytes(h, 12);                     // a tag in front of a FLAC stream is skipped
+    unsigned char magic[4] = {0, 0, 0, 0};
+    if (id3 > 0 && pread(fd, magic, 4, id3) != 4) memset(magic, 0, 4);
+    if (memcmp(h, "fLaC", 4) == 0 || memcmp(magic, "fLaC", 4) == 0) {
         // STREAMINFO is always the first metadata block (RFC 9639 section 8.1): 4 + 4 + 34 bytes hold everything the
         // probe needs; a stream that does not announce its length is decoded once to count it
         unsigned char head[42];
-        if (pread(fd, head, 42, 0) != 42) return std::string(path) + ": too short for a FLAC STREAMINFO block";
+        if (pread(fd, head, 42, memcmp(h, "fLaC", 4) == 0 ? 0 : id3) != 42) return std::string(path) + ": too short for a FLAC STREAMINFO block";
         oe_flac::Info fi;
         unsigned char one[42];
         memcpy(one, head, 42);

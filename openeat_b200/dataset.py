@@ -96,12 +96,21 @@ def _decode_flac(data, start, end, name):
     return out.astype(np.float32) / np.float32(2.0 ** (bits - 1)) * np.float32(1 << 15), sr
 
 
+def _is_flac(f):
+    """True when the (seekable) file object holds a native FLAC stream, possibly behind an ID3v2 tag; rewinds."""
+    head = f.read(10)
+    ok = head[:4] == b'fLaC'
+    if not ok and len(head) == 10 and head[:3] == b'ID3' and not any(b & 0x80 for b in head[6:10]):
+        f.seek(10 + (head[6] << 21 | head[7] << 14 | head[8] << 7 | head[9]) + (10 if head[5] & 0x10 else 0))
+        ok = f.read(4) == b'fLaC'
+    f.seek(0)
+    return ok
+
+
 def decode_wav(f, start=None, end=None, name='<wav>'):
     """``read_wav`` on an open (seekable) binary file object, e.g. a member of a shard tar."""
-    if f.read(4) == b'fLaC':
-        f.seek(0)
+    if _is_flac(f):
         return _decode_flac(f.read(), start, end, name)
-    f.seek(0)
     try:
         tag, nch, sr, bits, off, nbytes = _riff_chunks(f)
     except (ValueError, struct.error) as e:
@@ -140,9 +149,8 @@ def _decodable(entry):
     """True when ``read_wav`` can decode the file of a ``path[,start,end]`` entry."""
     try:
         with open(entry.strip().split(',')[0], 'rb') as f:
-            if f.read(4) == b'fLaC':
+            if _is_flac(f):
                 return True
-            f.seek(0)
             tag, nch, _, bits, _, _ = _riff_chunks(f)
         return nch >= 1 and ((tag == 1 and bits in (8, 16, 24, 32)) or (tag == 3 and bits in (32, 64)))
     except (OSError, ValueError, struct.error):

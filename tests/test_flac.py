@@ -435,3 +435,28 @@ def test_shard_tar_with_flac_members(tmp_path):
     got = list(tar_file_and_group([str(shard)]))
     assert [s['key'] for s in got] == ['u1', 'u2'] and [s['txt'] for s in got] == ['hello world', 'b']
     assert np.array_equal(got[0]['wav'], x) and np.array_equal(got[1]['wav'], y) and got[0]['sample_rate'] == 16000
+
+
+def test_id3v2_tag_in_front_of_the_stream(tmp_path):
+    """Taggers sometimes prepend an ID3v2 tag to a .flac file; libFLAC (behind torchaudio.load) skips it, so do read_wav,
+    the native ingest and the GPU pack (frame offsets are absolute: the kernel never sees the tag)."""
+    from openeat_b200.dataset import read_wav
+    from openeat_b200.ingest import FlacGpuIngest, NativeIngest
+    rng = np.random.default_rng(71)
+    x = speechlike(rng, 9000)
+    size = 301                                                     # tag body, sync-safe size field; 0xFF bytes inside must not fool the frame walk
+    tag = b'ID3\x04\x00\x00' + bytes([(size >> 21) & 127, (size >> 14) & 127, (size >> 7) & 127, size & 127]) + b'\xff\xf8' * 150 + b'\x00'
+    assert len(tag) == 10 + size
+    p = tmp_path / 'tagged.flac'
+    p.write_bytes(tag + lib_encode(x, block=1152))
+    got, sr = read_wav(str(p))
+    assert sr == 16000 and np.array_equal(got, x)
+    seg, _ = read_wav(str(p), '0.1', '0.3')
+    assert np.array_equal(seg, x[1600:4800])
+    buf, offs, lens, rates, loaded, _ = NativeIngest(threads=2, ring=2).load([str(p)])
+    assert loaded.all() and np.array_equal(buf.numpy()[offs[0]:offs[0] + lens[0]], x)
+    b = FlacGpuIngest(threads=2, ring=2).pack([str(p), str(p) + ',0.1,0.3'])
+    assert b.loaded.all()
+    out, err = emul_decode(b)
+    assert not err.any() and np.array_equal(out[b.offsets[0]:b.offsets[0] + 9000], x)
+    assert np.array_equal(out[b.offsets[1]:b.offsets[1] + b.lens[1]], x[1600:4800])
